@@ -295,6 +295,9 @@ def random_alignment(rng, n, L, p_seg, p_junk, junk_alphabet, lower):
             for r in range(n):
                 rows[r][p] = ch
     seqs = ["".join(r) for r in rows]
+    # readfasta right-strips every line (PolyFastA.py:245): a trailing blank would make the file ragged,
+    # which main() rejects before the hot path (PolyFastA.py:112,135-140)
+    seqs = [s.rstrip() + "-" * (len(s) - len(s.rstrip())) for s in seqs]
     if lower:
         seqs = ["".join(c.lower() if rng.random() < 0.3 else c for c in s) for s in seqs]
     return seqs
@@ -321,6 +324,7 @@ for ci in range(220):
         path = tf.name
     d = ref.readfasta(path, False)
     os.unlink(path)
+    assert ref.all_same([len(v) for v in d.values()]) and len(next(iter(d.values()))) == L
     rec = {"text": text, "seqlen": L, "pops": {}}
     for key in ("NA", "pop1", "pop2", "ind1", "s1"):
         dg = d if key == "NA" else {k: d[k] for k in d if key in k}
