@@ -1,0 +1,156 @@
+/* polyfasta_b200 -- C ABI of the B200-native PolyFastA hot path.
+ *
+ * The reference (PolyFastA.py, pure Python) has no FFI; its seams are the function calls inside
+ * print_result.no_header (PolyFastA.py:149,165,172-173,191).  Each entry point below names the reference
+ * code it replaces.  Plain pointers and sizes only; every call returns an int status (0 = PFA_OK); no
+ * C++ exception crosses the boundary; the library owns all device and pinned memory behind opaque
+ * handles; there is NO CPU fallback -- without a CUDA device every compute entry point fails with
+ * PFA_ERR_CUDA.  Calls on one handle are not re-entrant.
+ *
+ * Device layout: three site-major bit-planes over rows, b0 / b1 / v, each
+ * uint4[sites][Wq] with Wq = ceil(n/128).  v=1: A,C,G,T = b1b0 00,01,10,11.  v=0: '-','N','?' = 00,01,10
+ * and 11 = "escape" (any other byte; its identity is kept in a sorted exception list).
+ */
+#ifndef POLYFASTA_B200_H
+#define POLYFASTA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFA_OK 0
+#define PFA_ERR_CUDA 1      /* CUDA runtime error or no device; text via pfa_last_error */
+#define PFA_ERR_ARG 2
+#define PFA_ERR_NOT_FASTA 3 /* PolyFastA.py:246-248 "# file ... is not FASTA!" */
+#define PFA_ERR_RAGGED 4    /* PolyFastA.py:112,135-140 "# Sequences do not have the same length" */
+#define PFA_ERR_IO 5
+#define PFA_ERR_NOMEM 6
+#define PFA_ERR_NON_ASCII 7 /* bytes >= 0x80 in sequence lines: len() in code points != bytes; unsupported */
+
+typedef struct pfa_ctx pfa_ctx;     /* one CUDA device + stream + scratch */
+typedef struct pfa_fasta pfa_fasta; /* one parsed FASTA file on the host  */
+typedef struct pfa_aln pfa_aln;     /* one alignment (or column shard of one) resident in HBM */
+
+int pfa_version(void);
+int pfa_device_count(void);
+const char* pfa_global_error(void); /* error text of the last failed call that had no ctx */
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int pfa_ctx_create(int device, pfa_ctx** out);
+int pfa_ctx_destroy(pfa_ctx* ctx);
+const char* pfa_last_error(const pfa_ctx* ctx);
+int pfa_ctx_sync(pfa_ctx* ctx);
+/* run the library's work for this ctx on a caller-owned stream (cudaStream_t as void*; e.g. torch's
+ * current stream) so that a collective enqueued by the caller is ordered after the kernels. NULL restores
+ * the ctx's own stream. */
+int pfa_ctx_set_stream(pfa_ctx* ctx, void* cuda_stream);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t pfa_ctx_launch_count(const pfa_ctx* ctx);
+
+/* ---- ingest: replaces readfasta (PolyFastA.py:227-250) -------------------------------------------- */
+/* Parsing semantics of the reference: a line whose first byte is '>' starts a record, header = rest of
+ * the line right-stripped; a repeated header restarts that record in place; lines before the first
+ * non-empty header are dropped; sequence lines are right-stripped (upper-casing happens in the encoder
+ * and in pfa_fasta_copy_row).  Returns PFA_ERR_NOT_FASTA when the reference would. */
+int pfa_fasta_parse_file(const char* path, pfa_fasta** out);
+int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out);
+void pfa_fasta_free(pfa_fasta* f);
+int64_t pfa_fasta_nseq(const pfa_fasta* f);
+int64_t pfa_fasta_seqlen(const pfa_fasta* f); /* common length, or -1 when rows differ in length */
+int64_t pfa_fasta_row_len(const pfa_fasta* f, int64_t row);
+const char* pfa_fasta_header(const pfa_fasta* f, int64_t row, int64_t* len); /* not NUL-terminated */
+/* upper-cased copy of one row into caller memory (cap >= row_len) */
+int pfa_fasta_copy_row(const pfa_fasta* f, int64_t row, uint8_t* dst, int64_t cap);
+
+/* ---- alignment upload: host text -> packed planes in HBM (kernel K1) ------------------------------- */
+/* columns [col_begin, col_end) of a parsed file (the column shard of this GPU) */
+int pfa_aln_from_fasta(pfa_ctx* ctx, const pfa_fasta* f, int64_t col_begin, int64_t col_end, pfa_aln** out);
+/* same from a raw row-major byte matrix text[row*ld + col] in host memory (pinned or pageable) */
+int pfa_aln_from_rows(pfa_ctx* ctx, const uint8_t* text, int64_t n, int64_t L, int64_t ld,
+                      int64_t col_begin, int64_t col_end, pfa_aln** out);
+/* same from a byte matrix already in device memory */
+int pfa_aln_from_device_rows(pfa_ctx* ctx, const uint8_t* d_text, int64_t n, int64_t L, int64_t ld,
+                             int64_t col_begin, int64_t col_end, pfa_aln** out);
+/* deterministic synthetic alignment (pure ACGT), generated directly in packed form on the device;
+ * columns [col_begin, col_end) of the n x L alignment defined by (seed, p_seg_ppm, tri_ppm).
+ * The same generator exists on the host in polyfasta_b200/synth.py (numpy). */
+int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm,
+                      int64_t col_begin, int64_t col_end, pfa_aln** out);
+int pfa_aln_free(pfa_aln* a);
+int64_t pfa_aln_nseq(const pfa_aln* a);
+int64_t pfa_aln_nsites(const pfa_aln* a);        /* sites in this shard */
+int64_t pfa_aln_num_escapes(const pfa_aln* a);   /* entries in the exception list */
+int64_t pfa_aln_packed_bytes(const pfa_aln* a);  /* bytes of the three planes */
+int pfa_aln_has_invalid(const pfa_aln* a);       /* any non-ACGT symbol in the shard */
+/* debugging / tests: copy plane p (0=b0,1=b1,2=v) to the host, nsites*Wq*16 bytes */
+int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap);
+
+/* ---- populations: replaces the header-substring split (PolyFastA.py:123-134) ------------------------ */
+/* k row bit-masks, each words_per_mask = 4*ceil(n/128) uint32 (bit r%32 of word r/32 = row r).  Substring
+ * matching stays in Python; an empty population never reaches the library. k = 0 restores "all rows". */
+int pfa_aln_set_pops(pfa_aln* a, const uint32_t* masks, int k);
+int pfa_aln_num_pops(const pfa_aln* a);
+int64_t pfa_aln_pop_size(const pfa_aln* a, int pop);
+
+/* ---- K2 site scan: replaces getvarsites + the sums of nucleotide_diversity / wattersons_theta / getsfs
+ *      (PolyFastA.py:252-261, 274-282, 485-497) -------------------------------------------------------- */
+/* Layout of the int64 result vector: for pop q at offset pfa_site_offset(a,q): [S, H, sfs[0..n_q/2)].
+ * H = sum over columns of n^2 - sum_a c_a^2 (so pi_tot = H/(n(n-1))). */
+int64_t pfa_site_len(const pfa_aln* a);
+int64_t pfa_site_offset(const pfa_aln* a, int pop);
+/* asynchronous, result stays in device memory (d_out: int64[pfa_site_len]); the caller may all-reduce
+ * it (NCCL, sum) across column shards and then read it.  d_isvar (optional, may be NULL): uint8
+ * [k][nsites], 1 where the column is variable in that population. */
+int pfa_site_stats_device(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar);
+/* synchronous convenience: same, copied to host memory */
+int pfa_site_stats(pfa_aln* a, int64_t* out, uint8_t* isvar /* host, optional */);
+
+/* ---- K4 codon scan: replaces getvarCDSsites + get_syn_nonsyn_cod_sites + the var-site matching
+ *      (PolyFastA.py:165-170, 284-434) ------------------------------------------------------------------ */
+#define PFA_CDS_NSTOPS 0
+#define PFA_CDS_MISSING 1   /* already multiplied by 3 (PolyFastA.py:305) */
+#define PFA_CDS_SS 2        /* S_s: number of synonymous segregating positions */
+#define PFA_CDS_HS 3
+#define PFA_CDS_SN 4
+#define PFA_CDS_HN 5
+#define PFA_CDS_SUM3 6      /* sum3_by_len[l], l = 0..64 at [6+l]: sum of 3*syncodfreq over columns with l clean codons */
+#define PFA_CDS_LEN 71
+/* d_out: int64[k][PFA_CDS_LEN].  first_codon_phase: (global column of this shard's first site) % 3 must be 0.
+ * total_len: length of the WHOLE alignment (the trailing partial codon column belongs to the last shard).
+ * d_labels (optional): uint8 [k][nsites], 0 none / 1 synonymous / 2 nonsynonymous. */
+int pfa_cds_stats_device(pfa_aln* a, int64_t* d_out, uint8_t* d_labels);
+int pfa_cds_stats(pfa_aln* a, int64_t* out, uint8_t* labels /* host, optional */);
+/* host-side classifier tables, exposed for tests (no GPU needed):
+ * labels byte for two codon indices (16*b1+4*b2+b3, A=0 C=1 G=2 T=3): bits 0-1 pos0, 2-3 pos1, 4-5 pos2 */
+int pfa_codon_pair_labels(int codon_a, int codon_b);
+int pfa_codon_set_labels(uint64_t sense_codon_set);
+int pfa_codon_syn3(int codon);   /* 3*syncodfreq (PolyFastA.py:536-557), 0..4 */
+int pfa_codon_class(int codon);  /* id of the 3-char class of PolyFastA.py:324-329, 255 for stops */
+
+/* ---- K3 pairwise mismatches: replaces nucleotide_diversity3 (PolyFastA.py:468-480) -------------------- */
+/* d_out: int64[k] sum_{i<j} d_ij per population; d_matrix (optional): int32[n][n] over all rows. */
+int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
+int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix /* host, optional */);
+
+/* ---- K5 finalisation in fp64 on the device: replaces polymorphism / nucleotide_diversity /
+ *      wattersons_theta / Dvar / jukes_cantor_correction (PolyFastA.py:485-534) --------------------------- */
+typedef struct pfa_final_in {
+    int64_t n, S, H;
+    double seqlen; /* int seqlen, or the float ssites / nsites in CDS mode */
+    int32_t jc;
+    int32_t pad;
+} pfa_final_in;
+typedef struct pfa_final_out {
+    double pi_site, theta_site, D;
+    int32_t D_is_NA; /* Dv == 0 (PolyFastA.py:508-511) */
+    int32_t no_var;  /* S == 0: the row is (0,0,0,"NA") (PolyFastA.py:503-504) */
+} pfa_final_out;
+int pfa_finalize(pfa_ctx* ctx, const pfa_final_in* in, pfa_final_out* out, int count);
+/* synonymous-site count from the integer accumulators: sum_l sum3_by_len[l] / (3 l), fp64 on the device */
+int pfa_cds_ssites(pfa_ctx* ctx, const int64_t* cds_out /* [count][PFA_CDS_LEN] host */, double* ssites, int count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

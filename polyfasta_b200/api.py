@@ -1,0 +1,368 @@
+"""Host-side objects over the C ABI: Context (one GPU), Fasta (one parsed file), Alignment (packed planes in HBM).
+
+Everything that computes runs in libpolyfasta_b200.so on the GPU; this module only moves pointers."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import FinalIn, FinalOut, PFA_CDS_LEN, PolyFastaError, check, lib
+
+_default_ctx = {}
+
+
+class Context:
+    """one CUDA device + stream (pfa_ctx)"""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        check(lib().pfa_ctx_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise PolyFastaError(_lib.PFA_ERR_ARG, "context is closed")
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().pfa_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib().pfa_ctx_sync(self.handle), self.handle)
+
+    def set_stream(self, cuda_stream):
+        """run the library's kernels on a caller-owned stream (int / torch.cuda.Stream.cuda_stream); None restores"""
+        check(lib().pfa_ctx_set_stream(self.handle, ctypes.c_void_p(cuda_stream or 0)), self.handle)
+
+    @property
+    def launch_count(self):
+        return int(lib().pfa_ctx_launch_count(self.handle))
+
+    def finalize(self, items):
+        """items: iterable of (n, S, H, seqlen, jc) -> list of (S, pi_site, theta_site, D | "NA"), the tuple
+        polymorphism returns (PolyFastA.py:502-520); S == 0 gives (0, 0, 0, "NA").  fp64 on the device (K5)."""
+        items = list(items)
+        if not items:
+            return []
+        inp = (FinalIn * len(items))()
+        for i, (n, S, H, seqlen, jc) in enumerate(items):
+            inp[i] = FinalIn(int(n), int(S), int(H), float(seqlen), int(bool(jc)), 0)
+        out = (FinalOut * len(items))()
+        check(lib().pfa_finalize(self.handle, inp, out, len(items)), self.handle)
+        res = []
+        for (n, S, H, seqlen, jc), o in zip(items, out):
+            if o.no_var:
+                res.append((0, 0, 0, "NA"))
+            else:
+                res.append((int(S), o.pi_site, o.theta_site, "NA" if o.D_is_NA else o.D))
+        return res
+
+    def cds_ssites(self, cds_rows):
+        """[k][PFA_CDS_LEN] int64 -> synonymous-site counts (fp64 on the device)"""
+        arr = np.ascontiguousarray(cds_rows, dtype=np.int64).reshape(-1, PFA_CDS_LEN)
+        out = np.zeros(arr.shape[0], dtype=np.float64)
+        check(lib().pfa_cds_ssites(self.handle, arr.ctypes.data, out.ctypes.data, arr.shape[0]), self.handle)
+        return out
+
+
+def default_context(device=0):
+    ctx = _default_ctx.get(device)
+    if ctx is None or not ctx._h:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+class NotFasta(Exception):
+    """the reference would print '# file ... is not FASTA!' (PolyFastA.py:246-248)"""
+
+
+class Fasta:
+    """one parsed FASTA file on the host (pfa_fasta); parsing follows readfasta (PolyFastA.py:227-250)"""
+
+    def __init__(self, handle):
+        self._h = handle
+        L = lib()
+        self.nseq = int(L.pfa_fasta_nseq(handle))
+        self.seqlen = int(L.pfa_fasta_seqlen(handle))  # -1 when rows differ in length
+        self._headers = None
+
+    @classmethod
+    def from_file(cls, path):
+        h = ctypes.c_void_p()
+        rc = lib().pfa_fasta_parse_file(str(path).encode(), ctypes.byref(h))
+        return cls._wrap(rc, h, path)
+
+    @classmethod
+    def from_bytes(cls, data):
+        if isinstance(data, str):
+            data = data.encode("utf-8", "surrogateescape")
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(data, len(data)) if data else None
+        rc = lib().pfa_fasta_parse_buffer(buf, len(data), ctypes.byref(h))
+        return cls._wrap(rc, h, "<buffer>")
+
+    @classmethod
+    def _wrap(cls, rc, h, what):
+        if rc == _lib.PFA_ERR_NOT_FASTA:
+            raise NotFasta(what)
+        if rc == _lib.PFA_ERR_IO:
+            raise OSError("cannot read %s" % what)
+        if rc == _lib.PFA_ERR_NON_ASCII:
+            raise ValueError("%s: non-ASCII bytes in sequence lines are not supported" % what)
+        check(rc)
+        return cls(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def headers(self):
+        if self._headers is None:
+            L = lib()
+            out = []
+            n = ctypes.c_int64()
+            for i in range(self.nseq):
+                ptr = L.pfa_fasta_header(self._h, i, ctypes.byref(n))
+                out.append(ctypes.string_at(ptr, n.value).decode("utf-8", "surrogateescape") if n.value else "")
+            self._headers = out
+        return self._headers
+
+    def row_lengths(self):
+        L = lib()
+        return [int(L.pfa_fasta_row_len(self._h, i)) for i in range(self.nseq)]
+
+    def row(self, i):
+        """upper-cased sequence i as str"""
+        n = int(lib().pfa_fasta_row_len(self._h, i))
+        buf = ctypes.create_string_buffer(max(n, 1))
+        check(lib().pfa_fasta_copy_row(self._h, i, buf, n))
+        return buf.raw[:n].decode("latin-1")
+
+    def as_dict(self):
+        """{header: SEQUENCE}, what readfasta returns"""
+        return {h: self.row(i) for i, h in enumerate(self.headers)}
+
+    def close(self):
+        if self._h:
+            lib().pfa_fasta_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rows_to_masks(n, row_lists):
+    """list of row-index lists -> uint32 [k][4*ceil(n/128)] bit masks for pfa_aln_set_pops"""
+    wn = 4 * ((n + 127) // 128)
+    m = np.zeros((len(row_lists), max(wn, 1)), dtype=np.uint32)
+    for q, rows in enumerate(row_lists):
+        r = np.asarray(list(rows), dtype=np.int64)
+        if r.size:
+            np.bitwise_or.at(m[q], r >> 5, (np.uint32(1) << (r & 31).astype(np.uint32)))
+    return m
+
+
+class Alignment:
+    """one alignment, or one column shard of it, packed in HBM (pfa_aln)"""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._h = handle
+        L = lib()
+        self.n = int(L.pfa_aln_nseq(handle))
+        self.nsites = int(L.pfa_aln_nsites(handle))
+
+    # ---- constructors ----
+    @classmethod
+    def from_fasta(cls, ctx, fasta, col_begin=0, col_end=None):
+        if fasta.seqlen < 0:
+            raise PolyFastaError(_lib.PFA_ERR_RAGGED, "sequences do not have the same length")
+        col_end = fasta.seqlen if col_end is None else col_end
+        h = ctypes.c_void_p()
+        check(lib().pfa_aln_from_fasta(ctx.handle, fasta.handle, col_begin, col_end, ctypes.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_rows(cls, ctx, mat, col_begin=0, col_end=None):
+        """mat: uint8 [n][L] row-major host matrix (numpy array, or anything with __array_interface__)"""
+        mat = np.asarray(mat)
+        if mat.dtype != np.uint8 or mat.ndim != 2:
+            raise ValueError("expected a 2-D uint8 matrix")
+        if mat.shape[1] and mat.strides[1] != 1:
+            mat = np.ascontiguousarray(mat)
+        n, L = mat.shape
+        ld = mat.strides[0] if n > 1 else max(L, 1)
+        col_end = L if col_end is None else col_end
+        h = ctypes.c_void_p()
+        check(lib().pfa_aln_from_rows(ctx.handle, mat.ctypes.data, n, L, ld, col_begin, col_end, ctypes.byref(h)), ctx.handle)
+        a = cls(ctx, h)
+        return a
+
+    @classmethod
+    def from_host_ptr(cls, ctx, ptr, n, L, ld, col_begin=0, col_end=None):
+        """raw host pointer (e.g. a pinned torch tensor's data_ptr())"""
+        col_end = L if col_end is None else col_end
+        h = ctypes.c_void_p()
+        check(lib().pfa_aln_from_rows(ctx.handle, ctypes.c_void_p(ptr), n, L, ld, col_begin, col_end, ctypes.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_device_ptr(cls, ctx, ptr, n, L, ld, col_begin=0, col_end=None):
+        col_end = L if col_end is None else col_end
+        h = ctypes.c_void_p()
+        check(lib().pfa_aln_from_device_rows(ctx.handle, ctypes.c_void_p(ptr), n, L, ld, col_begin, col_end, ctypes.byref(h)),
+              ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_strings(cls, ctx, seqs, col_begin=0, col_end=None):
+        """list of equal-length str/bytes (any case)"""
+        n = len(seqs)
+        L = len(seqs[0]) if n else 0
+        mat = np.zeros((n, max(L, 1)), dtype=np.uint8)
+        for i, s in enumerate(seqs):
+            b = s.encode("latin-1") if isinstance(s, str) else bytes(s)
+            if len(b) != L:
+                raise PolyFastaError(_lib.PFA_ERR_RAGGED, "sequences do not have the same length")
+            if L:
+                mat[i, :L] = np.frombuffer(b, dtype=np.uint8)
+        return cls.from_rows(ctx, mat[:, :L] if L else mat[:, :0], col_begin, col_end)
+
+    @classmethod
+    def synthetic(cls, ctx, n, L, seed, p_seg_ppm=50000, tri_ppm=10000, col_begin=0, col_end=None):
+        col_end = L if col_end is None else col_end
+        h = ctypes.c_void_p()
+        check(lib().pfa_aln_synthetic(ctx.handle, n, L, seed, p_seg_ppm, tri_ppm, col_begin, col_end, ctypes.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    # ---- housekeeping ----
+    @property
+    def handle(self):
+        if not self._h:
+            raise PolyFastaError(_lib.PFA_ERR_ARG, "alignment is freed")
+        return self._h
+
+    def free(self):
+        if self._h:
+            lib().pfa_aln_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def num_escapes(self):
+        return int(lib().pfa_aln_num_escapes(self.handle))
+
+    @property
+    def has_invalid(self):
+        return bool(lib().pfa_aln_has_invalid(self.handle))
+
+    @property
+    def packed_bytes(self):
+        return int(lib().pfa_aln_packed_bytes(self.handle))
+
+    def plane(self, which):
+        """uint32 [nsites][4*Wq] copy of plane 0 (b0), 1 (b1) or 2 (v)"""
+        wn = 4 * ((self.n + 127) // 128)
+        out = np.zeros((self.nsites, wn), dtype=np.uint32)
+        check(lib().pfa_aln_copy_plane(self.handle, which, out.ctypes.data, out.nbytes), self.ctx.handle)
+        return out
+
+    # ---- populations ----
+    def set_pops(self, row_lists):
+        """row_lists: list of row-index iterables (one per population, in output order); None/[] = all rows"""
+        if not row_lists:
+            check(lib().pfa_aln_set_pops(self.handle, None, 0), self.ctx.handle)
+            return
+        m = rows_to_masks(self.n, row_lists)
+        check(lib().pfa_aln_set_pops(self.handle, m.ctypes.data, len(row_lists)), self.ctx.handle)
+
+    @property
+    def num_pops(self):
+        return int(lib().pfa_aln_num_pops(self.handle))
+
+    def pop_sizes(self):
+        return [int(lib().pfa_aln_pop_size(self.handle, q)) for q in range(self.num_pops)]
+
+    # ---- scans ----
+    def site_len(self):
+        return int(lib().pfa_site_len(self.handle))
+
+    def site_offsets(self):
+        return [int(lib().pfa_site_offset(self.handle, q)) for q in range(self.num_pops + 1)]
+
+    def unpack_site(self, vec):
+        """int64 result vector -> list of dict(n, S, H, sfs) per population"""
+        off = self.site_offsets()
+        sizes = self.pop_sizes()
+        return [{"n": sizes[q], "S": int(vec[off[q]]), "H": int(vec[off[q] + 1]),
+                 "sfs": [int(x) for x in vec[off[q] + 2: off[q + 1]]]} for q in range(len(sizes))]
+
+    def site_stats(self, want_isvar=False):
+        """K2 -> list of dict(n, S, H, sfs[, isvar]) per population"""
+        out = np.zeros(max(self.site_len(), 1), dtype=np.int64)
+        k = self.num_pops
+        isvar = np.zeros((k, max(self.nsites, 1)), dtype=np.uint8) if want_isvar else None
+        check(lib().pfa_site_stats(self.handle, out.ctypes.data, isvar.ctypes.data if want_isvar else None), self.ctx.handle)
+        res = self.unpack_site(out)
+        if want_isvar:
+            flat = isvar.reshape(-1)[: k * self.nsites].reshape(k, self.nsites) if self.nsites else isvar[:, :0]
+            for q in range(k):
+                res[q]["isvar"] = flat[q]
+        return res
+
+    def site_stats_device(self, d_out_ptr, d_isvar_ptr=None):
+        """asynchronous K2 into caller device memory (int64[site_len]); for the multi-GPU all-reduce"""
+        check(lib().pfa_site_stats_device(self.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_isvar_ptr or 0)),
+              self.ctx.handle)
+
+    @staticmethod
+    def unpack_cds(row):
+        return {"nstops": int(row[0]), "missing": int(row[1]), "S_s": int(row[2]), "H_s": int(row[3]), "S_n": int(row[4]),
+                "H_n": int(row[5]), "sum3_by_len": {l: int(row[6 + l]) for l in range(65) if row[6 + l]}}
+
+    def cds_stats(self, want_labels=False):
+        """K4 -> list of dict(nstops, missing, S_s, H_s, S_n, H_n, sum3_by_len, ssites[, labels]) per population"""
+        k = self.num_pops
+        out = np.zeros((k, PFA_CDS_LEN), dtype=np.int64)
+        labels = np.zeros((k, max(self.nsites, 1)), dtype=np.uint8) if want_labels else None
+        check(lib().pfa_cds_stats(self.handle, out.ctypes.data, labels.ctypes.data if want_labels else None), self.ctx.handle)
+        ss = self.ctx.cds_ssites(out)
+        res = []
+        for q in range(k):
+            d = self.unpack_cds(out[q])
+            d["ssites"] = float(ss[q])
+            d["raw"] = out[q].copy()
+            if want_labels:
+                d["labels"] = labels.reshape(-1)[: k * self.nsites].reshape(k, self.nsites)[q] if self.nsites else labels[q, :0]
+            res.append(d)
+        return res
+
+    def cds_stats_device(self, d_out_ptr, d_labels_ptr=None):
+        check(lib().pfa_cds_stats_device(self.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_labels_ptr or 0)),
+              self.ctx.handle)
+
+    def pairwise(self, want_matrix=False):
+        """K3 -> (list of sum_{i<j} d_ij per population, optional int32 [n][n] matrix over all rows)"""
+        k = self.num_pops
+        out = np.zeros(k, dtype=np.int64)
+        mat = np.zeros((self.n, self.n), dtype=np.int32) if want_matrix else None
+        check(lib().pfa_pairwise(self.handle, out.ctypes.data, mat.ctypes.data if want_matrix else None), self.ctx.handle)
+        return ([int(x) for x in out], mat) if want_matrix else [int(x) for x in out]

@@ -1,0 +1,495 @@
+// C ABI of the library: contexts, alignment upload, populations, result wrappers.  See include/polyfasta_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "pfa_common.cuh"
+#include "pfa_host.h"
+#include "pfa_sites.cuh"
+
+static thread_local std::string g_error;
+
+void pfa_set_global_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+int pfa_fail(pfa_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_error = buf;
+    return code;
+}
+
+static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out);
+static int aln_default_pop(pfa_aln* a);
+
+// run a *_device entry point into temporary device buffers and copy the results to the host
+template <typename F>
+static int run_to_host(pfa_aln* a, size_t out_bytes, void* out, size_t aux_bytes, void* aux, F launch) {
+    pfa_ctx* ctx = a->ctx;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *d_out = nullptr, *d_aux = nullptr;
+    PFA_CUDA(ctx, cudaMalloc(&d_out, std::max<size_t>(out_bytes, 8)));
+    if (aux) {
+        cudaError_t e = cudaMalloc(&d_aux, std::max<size_t>(aux_bytes, 8));
+        if (e != cudaSuccess) {
+            cudaFree(d_out);
+            return pfa_fail(ctx, PFA_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+        }
+    }
+    int rc = launch(d_out, d_aux);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && aux && aux_bytes) e = cudaMemcpyAsync(aux, d_aux, aux_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d_out);
+    cudaFree(d_aux);
+    if (rc) return rc;
+    if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(e));
+    return PFA_OK;
+}
+
+extern "C" {
+
+int pfa_version(void) { return 100; }
+const char* pfa_global_error(void) { return g_error.c_str(); }
+
+int pfa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pfa_ctx_create(int device, pfa_ctx** out) {
+    if (!out) return PFA_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        pfa_set_global_error("no CUDA device available (%s); polyfasta_b200 has no CPU fallback",
+                             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return PFA_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        pfa_set_global_error("device %d out of range (0..%d)", device, n - 1);
+        return PFA_ERR_ARG;
+    }
+    pfa_ctx* ctx = new (std::nothrow) pfa_ctx();
+    if (!ctx) return PFA_ERR_NOMEM;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        pfa_set_global_error("cannot initialise device %d: %s", device, cudaGetErrorString(e));
+        delete ctx;
+        return PFA_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    int rc = pfa_upload_codon_tables(ctx);
+    if (rc) {
+        pfa_set_global_error("%s", ctx->err.c_str());
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return PFA_OK;
+}
+
+int pfa_ctx_destroy(pfa_ctx* ctx) {
+    if (!ctx) return PFA_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return PFA_OK;
+}
+
+const char* pfa_last_error(const pfa_ctx* ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+
+int pfa_ctx_sync(pfa_ctx* ctx) {
+    if (!ctx) return PFA_ERR_ARG;
+    PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFA_OK;
+}
+
+int pfa_ctx_set_stream(pfa_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return PFA_ERR_ARG;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return PFA_OK;
+}
+
+int64_t pfa_ctx_launch_count(const pfa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- upload -------------------------------------------------------------------------------------------
+
+int pfa_aln_free(pfa_aln* a) {
+    if (!a) return PFA_OK;
+    cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->stream);
+    cudaFree(a->planes);
+    cudaFree(a->exc_keys);
+    cudaFree(a->exc_heads);
+    cudaFree(a->d_masks);
+    cudaFree(a->d_union);
+    cudaFree(a->d_pop_n);
+    cudaFree(a->rowmajor);
+    delete a;
+    return PFA_OK;
+}
+
+// encode columns [col_begin, col_end) of a text matrix; `dev` says where the matrix lives
+static int aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
+                         int64_t col_end, pfa_aln** out) {
+    if (!ctx || !out) return PFA_ERR_ARG;
+    *out = nullptr;
+    if (n < 0 || L < 0 || col_begin < 0 || col_end < col_begin || col_end > L || (n > 0 && L > 0 && (!text || ld < L)))
+        return pfa_fail(ctx, PFA_ERR_ARG, "bad alignment shape n=%lld L=%lld ld=%lld cols=[%lld,%lld)", (long long)n,
+                        (long long)L, (long long)ld, (long long)col_begin, (long long)col_end);
+    if (n >= (1ll << 24)) return pfa_fail(ctx, PFA_ERR_ARG, "more than 2^24-1 sequences are not supported");
+    if (col_end - col_begin >= (1ll << 32)) return pfa_fail(ctx, PFA_ERR_ARG, "a shard holds at most 2^32-1 sites");
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    pfa_aln* a = nullptr;
+    int rc = aln_alloc(ctx, n, L, col_begin, col_end, &a);
+    if (rc) return rc;
+    const int64_t ns = a->ns;
+    unsigned long long* d_count = nullptr;
+    int* d_inv = nullptr;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_encoded[2] = {nullptr, nullptr};
+    bool registered = false;
+    int64_t cap = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_count);
+        cudaFree(d_inv);
+        cudaFree(stage[0]);
+        cudaFree(stage[1]);
+        for (int i = 0; i < 2; ++i) {
+            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+            if (ev_encoded[i]) cudaEventDestroy(ev_encoded[i]);
+        }
+        if (cs) cudaStreamDestroy(cs);
+        if (registered) cudaHostUnregister(const_cast<uint8_t*>(text));
+    };
+#define UP(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            cleanup();                                                                                    \
+            pfa_aln_free(a);                                                                              \
+            return pfa_fail(ctx, PFA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));          \
+        }                                                                                                 \
+    } while (0)
+    if (ns > 0 && n > 0) {
+        UP(cudaMalloc(&d_count, sizeof(unsigned long long)));
+        UP(cudaMalloc(&d_inv, sizeof(int)));
+        // columns per chunk: ~256 MB of text, a multiple of 256 columns
+        int64_t chunk = ((256ll << 20) / n) & ~255ll;
+        if (chunk < 256) chunk = 256;
+        if (chunk > ns) chunk = ns;
+        const int64_t ldt = pfa_round_up(chunk, 256);
+        if (!dev) {
+            UP(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            const int nbuf = chunk < ns ? 2 : 1;
+            for (int i = 0; i < nbuf; ++i) {
+                UP(cudaMalloc(&stage[i], (size_t)(n * ldt)));
+                UP(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+                UP(cudaEventCreateWithFlags(&ev_encoded[i], cudaEventDisableTiming));
+            }
+            // pin large pageable inputs in place so that the 2-D copies run asynchronously at full PCIe rate
+            cudaPointerAttributes attr;
+            const bool is_pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+            const size_t span = (size_t)((n - 1) * ld + L);
+            if (!is_pinned && span >= (32u << 20)) {
+                registered = cudaHostRegister(const_cast<uint8_t*>(text), span, cudaHostRegisterReadOnly) == cudaSuccess ||
+                             cudaHostRegister(const_cast<uint8_t*>(text), span, cudaHostRegisterDefault) == cudaSuccess;
+                cudaGetLastError();
+            }
+        }
+        cap = std::max<int64_t>(1 << 16, n * ns / 256);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            cudaFree(a->exc_keys);
+            a->exc_keys = nullptr;
+            UP(cudaMalloc(&a->exc_keys, sizeof(unsigned long long) * (size_t)cap));
+            UP(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
+            UP(cudaMemsetAsync(d_inv, 0, sizeof(int), ctx->stream));
+            int64_t ci = 0;
+            for (int64_t c = 0; c < ns; c += chunk, ++ci) {
+                const int64_t cols = std::min(chunk, ns - c);
+                if (dev) {
+                    rc = pfa_encode_chunk(a, text + col_begin + c, ld, cols, c, d_count, cap, d_inv);
+                } else {
+                    const int b = (int)(ci & 1);
+                    if (ci >= 2) UP(cudaStreamWaitEvent(cs, ev_encoded[b], 0));
+                    UP(cudaMemcpy2DAsync(stage[b], (size_t)ldt, text + col_begin + c, (size_t)ld, (size_t)cols, (size_t)n,
+                                         cudaMemcpyHostToDevice, cs));
+                    UP(cudaEventRecord(ev_copied[b], cs));
+                    UP(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
+                    rc = pfa_encode_chunk(a, stage[b], ldt, cols, c, d_count, cap, d_inv);
+                    if (!rc) UP(cudaEventRecord(ev_encoded[b], ctx->stream));
+                }
+                if (rc) {
+                    cleanup();
+                    pfa_aln_free(a);
+                    return rc;
+                }
+            }
+            unsigned long long count = 0;
+            UP(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, ctx->stream));
+            UP(cudaMemcpyAsync(&a->has_invalid, d_inv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            UP(cudaStreamSynchronize(ctx->stream));
+            if ((int64_t)count <= cap) {
+                if (count >= (1ull << 31)) {
+                    cleanup();
+                    pfa_aln_free(a);
+                    return pfa_fail(ctx, PFA_ERR_ARG, "more than 2^31 non-ACGT/-/N/? symbols in one shard");
+                }
+                rc = pfa_finish_exceptions(a, (int64_t)count);
+                if (rc) {
+                    cleanup();
+                    pfa_aln_free(a);
+                    return rc;
+                }
+                break;
+            }
+            cap = (int64_t)count;  // the exception list overflowed: encode once more with the exact size
+        }
+    }
+#undef UP
+    cleanup();
+    rc = aln_default_pop(a);
+    if (rc) {
+        pfa_aln_free(a);
+        return rc;
+    }
+    *out = a;
+    return PFA_OK;
+}
+
+int pfa_aln_from_rows(pfa_ctx* ctx, const uint8_t* text, int64_t n, int64_t L, int64_t ld, int64_t col_begin, int64_t col_end,
+                      pfa_aln** out) {
+    return aln_from_text(ctx, text, false, n, L, ld, col_begin, col_end, out);
+}
+
+int pfa_aln_from_device_rows(pfa_ctx* ctx, const uint8_t* d_text, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
+                             int64_t col_end, pfa_aln** out) {
+    return aln_from_text(ctx, d_text, true, n, L, ld, col_begin, col_end, out);
+}
+
+int pfa_aln_from_fasta(pfa_ctx* ctx, const pfa_fasta* f, int64_t col_begin, int64_t col_end, pfa_aln** out) {
+    if (!ctx || !f || !out) return PFA_ERR_ARG;
+    if (f->seqlen < 0) return pfa_fail(ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
+    return aln_from_text(ctx, f->data, false, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), col_begin, col_end, out);
+}
+
+int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm, int64_t col_begin,
+                      int64_t col_end, pfa_aln** out) {
+    if (!ctx || !out) return PFA_ERR_ARG;
+    *out = nullptr;
+    if (n <= 0 || L <= 0 || col_begin < 0 || col_end < col_begin || col_end > L || n >= (1ll << 24))
+        return pfa_fail(ctx, PFA_ERR_ARG, "bad synthetic shape");
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    pfa_aln* a = nullptr;
+    int rc = aln_alloc(ctx, n, L, col_begin, col_end, &a);
+    if (rc) return rc;
+    rc = pfa_synth_fill(a, seed, p_seg_ppm, tri_ppm);
+    if (!rc) rc = aln_default_pop(a);
+    if (rc) {
+        pfa_aln_free(a);
+        return rc;
+    }
+    *out = a;
+    return PFA_OK;
+}
+
+int64_t pfa_aln_nseq(const pfa_aln* a) { return a ? a->n : 0; }
+int64_t pfa_aln_nsites(const pfa_aln* a) { return a ? a->ns : 0; }
+int64_t pfa_aln_num_escapes(const pfa_aln* a) { return a ? a->n_exc : 0; }
+int64_t pfa_aln_packed_bytes(const pfa_aln* a) { return a ? 3 * a->ns * (int64_t)a->Wq * 16 : 0; }
+int pfa_aln_has_invalid(const pfa_aln* a) { return a ? a->has_invalid : 0; }
+
+int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap) {
+    if (!a || plane < 0 || plane > 2 || !dst) return PFA_ERR_ARG;
+    const size_t bytes = (size_t)a->ns * a->Wq * 16;
+    if (cap < bytes) return pfa_fail(a->ctx, PFA_ERR_ARG, "plane buffer too small");
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    const uint4* src = plane == 0 ? a->b0 : plane == 1 ? a->b1 : a->v;
+    PFA_CUDA(a->ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, a->ctx->stream));
+    PFA_CUDA(a->ctx, cudaStreamSynchronize(a->ctx->stream));
+    return PFA_OK;
+}
+
+// ---- populations ---------------------------------------------------------------------------------------
+
+int pfa_aln_set_pops(pfa_aln* a, const uint32_t* masks, int k) {
+    if (!a || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
+    if (k == 0) return aln_default_pop(a);
+    pfa_ctx* ctx = a->ctx;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t Wn = (int64_t)a->Wq * 4;
+    std::vector<uint32_t> m((size_t)(k * Wn)), uni((size_t)Wn, 0u);
+    a->pop_n.assign((size_t)k, 0);
+    a->site_off.assign((size_t)k + 1, 0);
+    std::vector<int64_t> meta((size_t)(3 * k + 1));
+    int64_t sfs_total = 0;
+    for (int q = 0; q < k; ++q) {
+        int64_t cnt = 0;
+        for (int64_t w = 0; w < Wn; ++w) {
+            uint32_t x = masks[q * Wn + w];
+            const int64_t lo = w * 32;
+            if (lo >= a->n) x = 0;
+            else if (lo + 32 > a->n) x &= (1u << (a->n - lo)) - 1u;
+            m[(size_t)(q * Wn + w)] = x;
+            uni[(size_t)w] |= x;
+            cnt += __builtin_popcount(x);
+        }
+        a->pop_n[(size_t)q] = cnt;
+        a->site_off[(size_t)q + 1] = a->site_off[(size_t)q] + 2 + cnt / 2;
+        meta[(size_t)q] = cnt;
+        meta[(size_t)(k + q)] = a->site_off[(size_t)q];
+        meta[(size_t)(2 * k + q)] = sfs_total;
+        sfs_total += cnt / 2;
+    }
+    meta[(size_t)(3 * k)] = sfs_total;
+    cudaFree(a->d_masks);
+    cudaFree(a->d_union);
+    cudaFree(a->d_pop_n);
+    a->d_masks = a->d_union = nullptr;
+    a->d_pop_n = nullptr;
+    PFA_CUDA(ctx, cudaMalloc(&a->d_masks, sizeof(uint32_t) * (size_t)std::max<int64_t>(k * Wn, 4)));
+    PFA_CUDA(ctx, cudaMalloc(&a->d_union, sizeof(uint32_t) * (size_t)std::max<int64_t>(Wn, 4)));
+    PFA_CUDA(ctx, cudaMalloc(&a->d_pop_n, sizeof(int64_t) * meta.size()));
+    if (Wn) {
+        PFA_CUDA(ctx, cudaMemcpyAsync(a->d_masks, m.data(), sizeof(uint32_t) * m.size(), cudaMemcpyHostToDevice, ctx->stream));
+        PFA_CUDA(ctx, cudaMemcpyAsync(a->d_union, uni.data(), sizeof(uint32_t) * uni.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PFA_CUDA(ctx, cudaMemcpyAsync(a->d_pop_n, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    a->d_site_off = a->d_pop_n + k;
+    a->k = k;
+    return PFA_OK;
+}
+
+int pfa_aln_num_pops(const pfa_aln* a) { return a ? a->k : 0; }
+int64_t pfa_aln_pop_size(const pfa_aln* a, int pop) { return (a && pop >= 0 && pop < a->k) ? a->pop_n[(size_t)pop] : -1; }
+int64_t pfa_site_len(const pfa_aln* a) { return a ? a->site_off[(size_t)a->k] : 0; }
+int64_t pfa_site_offset(const pfa_aln* a, int pop) { return (a && pop >= 0 && pop <= a->k) ? a->site_off[(size_t)pop] : -1; }
+
+// ---- scans ----------------------------------------------------------------------------------------------
+
+int pfa_site_stats_device(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar) {
+    if (!a || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    return pfa_launch_site_scan(a, d_out, d_isvar);
+}
+
+int pfa_site_stats(pfa_aln* a, int64_t* out, uint8_t* isvar) {
+    if (!a || !out) return PFA_ERR_ARG;
+    return run_to_host(a, sizeof(int64_t) * (size_t)pfa_site_len(a), out, (size_t)(a->k * a->ns), isvar,
+                       [&](void* d_out, void* d_aux) { return pfa_launch_site_scan(a, (int64_t*)d_out, (uint8_t*)d_aux); });
+}
+
+int pfa_cds_stats_device(pfa_aln* a, int64_t* d_out, uint8_t* d_labels) {
+    if (!a || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    return pfa_launch_cds_scan(a, d_out, d_labels);
+}
+
+int pfa_cds_stats(pfa_aln* a, int64_t* out, uint8_t* labels) {
+    if (!a || !out) return PFA_ERR_ARG;
+    return run_to_host(a, sizeof(int64_t) * PFA_CDS_LEN * (size_t)a->k, out, (size_t)(a->k * a->ns), labels,
+                       [&](void* d_out, void* d_aux) { return pfa_launch_cds_scan(a, (int64_t*)d_out, (uint8_t*)d_aux); });
+}
+
+int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
+    if (!a || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    return pfa_launch_pairwise(a, d_out, d_matrix);
+}
+
+int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix) {
+    if (!a || !out) return PFA_ERR_ARG;
+    return run_to_host(a, sizeof(int64_t) * (size_t)a->k, out, sizeof(int32_t) * (size_t)(a->n * a->n), matrix,
+                       [&](void* d_out, void* d_aux) { return pfa_launch_pairwise(a, (int64_t*)d_out, (int32_t*)d_aux); });
+}
+
+}  // extern "C"
+
+// ---- helpers ---------------------------------------------------------------------------------------------
+
+static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out) {
+    pfa_aln* a = new (std::nothrow) pfa_aln();
+    if (!a) return pfa_fail(ctx, PFA_ERR_NOMEM, "out of host memory");
+    a->ctx = ctx;
+    a->n = n;
+    a->L_total = L;
+    a->col_begin = col_begin;
+    a->ns = col_end - col_begin;
+    a->Wq = (int)((n + 127) / 128);
+    a->plane_bytes = (size_t)pfa_round_up(std::max<int64_t>(a->ns * (int64_t)a->Wq * 16, 16), 256);
+    cudaError_t e = cudaMalloc(&a->planes, 3 * a->plane_bytes);
+    if (e != cudaSuccess) {
+        const size_t want = 3 * a->plane_bytes;
+        delete a;
+        return pfa_fail(ctx, PFA_ERR_CUDA, "cudaMalloc of %zu bytes for the packed alignment failed: %s", want,
+                        cudaGetErrorString(e));
+    }
+    a->b0 = a->planes;
+    a->b1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a->planes) + a->plane_bytes);
+    a->v = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a->planes) + 2 * a->plane_bytes);
+    // rows beyond n (padding up to a multiple of 128) must read as zero in every plane
+    e = cudaMemsetAsync(a->planes, 0, 3 * a->plane_bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        pfa_aln_free(a);
+        return pfa_fail(ctx, PFA_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    }
+    *out = a;
+    return PFA_OK;
+}
+
+static int aln_default_pop(pfa_aln* a) {
+    const int64_t Wn = (int64_t)a->Wq * 4;
+    std::vector<uint32_t> all((size_t)std::max<int64_t>(Wn, 1), 0u);
+    for (int64_t r = 0; r < a->n; ++r) all[(size_t)(r >> 5)] |= 1u << (r & 31);
+    return pfa_aln_set_pops(a, all.data(), 1);
+}
+
+void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args) {
+    args->b0 = a->b0;
+    args->b1 = a->b1;
+    args->v = a->v;
+    args->masks = a->d_masks;
+    args->umask = a->d_union;
+    args->pop_n = a->d_pop_n;
+    args->out_off = a->d_pop_n + a->k;
+    args->sfs_off = a->d_pop_n + 2 * a->k;
+    args->out = d_out;
+    args->isvar = d_isvar;
+    args->ns = a->ns;
+    args->Wq = a->Wq;
+    args->k = a->k;
+    int64_t bins = 0;
+    for (int q = 0; q < a->k; ++q) bins += a->pop_n[(size_t)q] / 2;
+    args->sfs_bins = (int)std::min<int64_t>(bins, 1 << 30);
+    args->sfs_in_smem = (16 * (int64_t)a->k + 4 * bins) <= 40 * 1024;
+}

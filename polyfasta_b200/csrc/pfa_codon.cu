@@ -1,0 +1,375 @@
+// K4: codon scan -- synonymous / nonsynonymous site and difference counting as the reference does it.
+//
+// Replaces getvarCDSsites (PolyFastA.py:284-315), get_syn_nonsyn_cod_sites (:319-434), syncodfreq (:536-557)
+// and the var-site matching of print_result (:169-170).  Everything the reference derives from one codon
+// column is a function of the SET of clean codons ([ACGT]{3}, stops included) its rows show, i.e. of a 64-bit
+// presence mask per population:
+//   nstops  += [mask & stops != 0]                                   (:293)
+//   missing += 3 when the mask is empty                              (:305; also the trailing partial column)
+//   sum3_by_len[popc(mask)] += sum_{c in mask} 3*syncodfreq(c)       (:307, kept as exact integers)
+//   labels of the three positions from the sense codons of the mask  (:311, tables in constant memory)
+//   S_s/H_s and S_n/H_n: for each labelled position the FULL column's n^2 - sum_a c_a^2 (:169-170)
+// A group of LPS lanes owns one codon column (three consecutive site records).  Pass 1 proves, with logic ops
+// only, that all three sites are monomorphic over the union of the populations -- then every population sees
+// the same single codon and the contribution is uniform.  Otherwise pass 2 builds the presence mask per
+// population by peeling distinct codons off each 32-row word, and counts the three columns with popcounts.
+#include "pfa_codon_rules.h"
+#include "pfa_sites.cuh"
+
+__constant__ uint8_t c_syn3[64];
+__constant__ uint8_t c_pair[64 * 64];
+__constant__ unsigned long long c_class_mask[24];
+__constant__ unsigned long long c_stop_mask;
+__constant__ int c_num_classes;
+
+int pfa_upload_codon_tables(pfa_ctx* ctx) {
+    const PfaCodonTables& t = pfa_codon_tables();
+    unsigned long long cm[24];
+    for (int i = 0; i < 24; ++i) cm[i] = t.class_mask[i];
+    const unsigned long long sm = t.stop_mask;
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(c_syn3, t.syn3, 64));
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(c_pair, t.pair, 64 * 64));
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(c_class_mask, cm, sizeof cm));
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(c_stop_mask, &sm, sizeof sm));
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(c_num_classes, &t.num_classes, sizeof(int)));
+    return PFA_OK;
+}
+
+struct PfaCdsArgs {
+    PfaSiteArgs s;
+    int64_t* out;      // [k][PFA_CDS_LEN]
+    uint8_t* labels;   // optional [k][ns]
+    int64_t ncf;       // complete codon columns in this shard
+    int has_partial;   // the shard ends with a partial codon column (1 or 2 sites)
+    int acc_in_smem;
+};
+
+// labels of the three codon positions from the set of sense codons of a column (PolyFastA.py:331-432)
+__device__ int pfa_labels_from_set(unsigned long long g) {
+    const int n = __popcll(g);
+    if (n < 2) return 0;
+    if (n == 2) return c_pair[(__ffsll((long long)g) - 1) * 64 + (63 - __clzll((long long)g))];
+    unsigned seen0 = 0, seen1 = 0, seen2 = 0;
+    for (unsigned long long t = g; t; t &= t - 1) {
+        const int c = __ffsll((long long)t) - 1;
+        seen0 |= 1u << (c >> 4);
+        seen1 |= 1u << ((c >> 2) & 3);
+        seen2 |= 1u << (c & 3);
+    }
+    const int nb[3] = {__popc(seen0), __popc(seen1), __popc(seen2)};
+    int top = 0;
+    for (int k = 0; k < c_num_classes; ++k) top = max(top, __popcll(g & c_class_mask[k]));
+    int last = nb[2] > 1 ? 2 : nb[1] > 1 ? 1 : 0;
+    int lab[3] = {0, 0, 0};
+    if (top >= 2) {  // some class repeats (:417-429)
+        for (int i = 0; i < last; ++i)
+            if (nb[i] > 1) lab[i] = 2;
+        if (top >= nb[last]) lab[last] = 1;
+    } else {  // :432
+        for (int i = 0; i < 3; ++i)
+            if (nb[i] > 1) lab[i] = 2;
+    }
+    return lab[0] | (lab[1] << 2) | (lab[2] << 4);
+}
+
+// presence mask of clean codons among the rows of one population, OR-reduced over the group
+template <int LPS, bool HAS_V>
+__device__ __forceinline__ unsigned long long pfa_codon_presence(const uint4* __restrict__ b0, const uint4* __restrict__ b1,
+                                                                  const uint4* __restrict__ v, int64_t site, int Wq,
+                                                                  const uint4* __restrict__ mq, int sub, unsigned gmask) {
+    unsigned long long P = 0;
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(b0 + site * Wq);
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(b1 + site * Wq);
+    const uint32_t* qv = reinterpret_cast<const uint32_t*>(v + site * Wq);
+    const uint32_t* qm = reinterpret_cast<const uint32_t*>(mq);
+    const int Wn = Wq * 4;
+    for (int j = sub; j < Wq; j += LPS) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int o = j * 4 + w;
+            uint32_t live = __ldg(qm + o);
+            if (!live) continue;
+            uint32_t x[6];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                x[2 * t] = __ldg(q1 + o + t * Wn);      // high bit of the base at codon position t
+                x[2 * t + 1] = __ldg(q0 + o + t * Wn);  // low bit
+                if (HAS_V) live &= __ldg(qv + o + t * Wn);
+            }
+            while (live) {  // peel one distinct codon per iteration
+                const int r = __ffs(live) - 1;
+                uint32_t match = live;
+                int c = 0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const uint32_t bit = (x[t] >> r) & 1u;
+                    c = (c << 1) | (int)bit;
+                    match &= x[t] ^ (bit - 1u);
+                }
+                P |= 1ull << c;
+                live &= ~match;
+            }
+        }
+    }
+    if (LPS > 1) {
+        uint32_t lo = (uint32_t)P, hi = (uint32_t)(P >> 32);
+        lo = pfa_group_or<LPS>(lo, gmask);
+        hi = pfa_group_or<LPS>(hi, gmask);
+        P = ((unsigned long long)hi << 32) | lo;
+    }
+    return P;
+}
+
+// everything one (codon column, population) contributes, given its presence mask and the class counts of its sites
+__device__ __forceinline__ void pfa_cds_contribute(unsigned long long P, const uint32_t cnt[3][PFA_NCLASS], int64_t nq,
+                                                   const uint32_t escd[3], const unsigned long long escsq[3],
+                                                   unsigned long long* acc, uint8_t* labels, int64_t site0) {
+    if (P & c_stop_mask) atomicAdd(&acc[PFA_CDS_NSTOPS], 1ull);
+    const int len = __popcll(P);
+    if (len == 0) {
+        atomicAdd(&acc[PFA_CDS_MISSING], 3ull);
+        return;
+    }
+    unsigned tot3 = 0;
+    for (unsigned long long t = P; t; t &= t - 1) tot3 += c_syn3[__ffsll((long long)t) - 1];
+    if (tot3) atomicAdd(&acc[PFA_CDS_SUM3 + len], (unsigned long long)tot3);
+    if (len < 2) return;
+    const int lab = pfa_labels_from_set(P & ~c_stop_mask);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int li = (lab >> (2 * i)) & 3;
+        if (!li) continue;
+        const PfaSiteResult r = pfa_site_result(cnt[i], nq, escd[i], escsq[i]);
+        atomicAdd(&acc[li == 1 ? PFA_CDS_SS : PFA_CDS_SN], 1ull);
+        atomicAdd(&acc[li == 1 ? PFA_CDS_HS : PFA_CDS_HN], r.h);
+        if (labels) labels[site0 + i] = (uint8_t)li;
+    }
+}
+
+template <int LPS, bool HAS_V>
+__global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const PfaCdsArgs a) {
+    extern __shared__ unsigned long long smem[];  // [3] uniform + [k][PFA_CDS_LEN] when acc_in_smem
+    const int nacc = 3 + (a.acc_in_smem ? a.s.k * PFA_CDS_LEN : 0);
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) smem[i] = 0ull;
+    __syncthreads();
+    unsigned long long* sm_acc = smem + 3;
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPS - 1);
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPS;
+    const int Wq = a.s.Wq;
+    unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;  // contributions identical for every population
+
+    for (int64_t cc = gid; cc < a.ncf; cc += ngroups) {
+        const int64_t site0 = cc * 3;
+        // ---- pass 1: are the three sites monomorphic over the union of the populations? ----
+        uint32_t acc[3][6];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc[t][i] = 0;
+        for (int j = sub; j < Wq; j += LPS) {
+            const uint4 m = __ldg(a.s.umask + j);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const uint4 x0 = pfa_ld_stream(a.s.b0 + (site0 + t) * Wq + j);
+                const uint4 x1 = pfa_ld_stream(a.s.b1 + (site0 + t) * Wq + j);
+                acc[t][0] |= (x0.x & m.x) | (x0.y & m.y) | (x0.z & m.z) | (x0.w & m.w);
+                acc[t][1] |= (~x0.x & m.x) | (~x0.y & m.y) | (~x0.z & m.z) | (~x0.w & m.w);
+                acc[t][2] |= (x1.x & m.x) | (x1.y & m.y) | (x1.z & m.z) | (x1.w & m.w);
+                acc[t][3] |= (~x1.x & m.x) | (~x1.y & m.y) | (~x1.z & m.z) | (~x1.w & m.w);
+                if (HAS_V) {
+                    const uint4 xv = pfa_ld_stream(a.s.v + (site0 + t) * Wq + j);
+                    acc[t][4] |= (xv.x & m.x) | (xv.y & m.y) | (xv.z & m.z) | (xv.w & m.w);
+                    acc[t][5] |= (~xv.x & m.x) | (~xv.y & m.y) | (~xv.z & m.z) | (~xv.w & m.w);
+                } else {
+                    acc[t][4] |= m.x | m.y | m.z | m.w;
+                }
+            }
+        }
+        unsigned f = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) f |= (acc[t][i] ? 1u : 0u) << (6 * t + i);
+        f = pfa_group_or<LPS>(f, gmask);
+        bool uniform = true, clean = true;
+        int codon = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const unsigned ft = (f >> (6 * t)) & 63u;
+            const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
+            const bool all_escape = (ft & 1u) && (ft & 4u) && !(ft & 16u);
+            uniform = uniform && mono && !all_escape;
+            clean = clean && (ft & 16u) && !(ft & 32u);
+            codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+        }
+        if (uniform) {
+            if (sub == 0) {
+                if (clean) {
+                    u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
+                    u_sum3 += c_syn3[codon];
+                } else {
+                    u_missing += 3;
+                }
+            }
+            continue;
+        }
+        // ---- pass 2: per population ----
+        for (int q = 0; q < a.s.k; ++q) {
+            const uint4* mq = a.s.masks + (int64_t)q * Wq;
+            uint32_t cnt[3][PFA_NCLASS];
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                pfa_class_counts<LPS, HAS_V>(a.s.b0 + (site0 + t) * Wq, a.s.b1 + (site0 + t) * Wq, a.s.v + (site0 + t) * Wq, mq, Wq,
+                                             sub, gmask, cnt[t]);
+            if (cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
+            const unsigned long long P = pfa_codon_presence<LPS, HAS_V>(a.s.b0, a.s.b1, a.s.v, site0, Wq, mq, sub, gmask);
+            if (sub != 0) continue;
+            const uint32_t escd[3] = {0, 0, 0};
+            const unsigned long long escsq[3] = {0, 0, 0};
+            unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
+                                                    : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
+            pfa_cds_contribute(P, cnt, a.s.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+        }
+    }
+    if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;  // :305 for the trailing 1-2 sites
+    // ---- flush ----
+    for (int off = 16; off; off >>= 1) {
+        u_nstops += __shfl_xor_sync(0xffffffffu, u_nstops, off);
+        u_missing += __shfl_xor_sync(0xffffffffu, u_missing, off);
+        u_sum3 += __shfl_xor_sync(0xffffffffu, u_sum3, off);
+    }
+    if (lane == 0) {
+        if (u_nstops) atomicAdd(&smem[0], (unsigned long long)u_nstops);
+        if (u_missing) atomicAdd(&smem[1], (unsigned long long)u_missing);
+        if (u_sum3) atomicAdd(&smem[2], (unsigned long long)u_sum3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.s.k * PFA_CDS_LEN; i += blockDim.x) {
+        const int e = i % PFA_CDS_LEN;
+        unsigned long long x = a.acc_in_smem ? sm_acc[i] : 0ull;
+        if (e == PFA_CDS_NSTOPS) x += smem[0];
+        if (e == PFA_CDS_MISSING) x += smem[1];
+        if (e == PFA_CDS_SUM3 + 1) x += smem[2];
+        if (x) atomicAdd(reinterpret_cast<unsigned long long*>(a.out) + i, x);
+    }
+}
+
+// per-site escape statistics of one population: number of distinct escape bytes and the sum of their squared counts
+__device__ __forceinline__ void pfa_escape_stats(const unsigned long long* __restrict__ keys, int64_t i0, int64_t i1,
+                                                 const uint32_t* __restrict__ mq, unsigned int* hist, int lane,
+                                                 uint32_t* distinct_out, unsigned long long* sq_out) {
+    for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+    __syncwarp();
+    for (int64_t i = i0 + lane; i < i1; i += 32) {
+        const unsigned long long key = keys[i];
+        const uint32_t row = (uint32_t)(key & 0xffffffull);
+        if ((mq[row >> 5] >> (row & 31)) & 1u) atomicAdd(&hist[(key >> 24) & 0xffu], 1u);
+    }
+    __syncwarp();
+    uint32_t distinct = 0;
+    unsigned long long sq = 0;
+    for (int b = lane; b < 256; b += 32) {
+        const unsigned long long c = hist[b];
+        distinct += c ? 1u : 0u;
+        sq += c * c;
+    }
+    for (int off = 16; off; off >>= 1) {
+        distinct += __shfl_xor_sync(0xffffffffu, distinct, off);
+        sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    }
+    __syncwarp();
+    *distinct_out = distinct;
+    *sq_out = sq;
+}
+
+// One warp per codon column that holds an escape symbol (owned by its first exception site).
+__global__ void __launch_bounds__(256) pfa_cds_escape_kernel(const PfaCdsArgs a, const unsigned long long* __restrict__ keys,
+                                                             int64_t n_exc, const int64_t* __restrict__ heads, int64_t n_heads) {
+    __shared__ unsigned int hist[8][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int Wq = a.s.Wq;
+    for (int64_t h = wid; h < n_heads; h += nwarps) {
+        const int64_t cc = (int64_t)(keys[heads[h]] >> 32) / 3;
+        if (cc >= a.ncf) continue;                                                    // trailing partial column
+        if (h > 0 && (int64_t)(keys[heads[h - 1]] >> 32) / 3 == cc) continue;        // not the first exception site of cc
+        int64_t seg0[3] = {0, 0, 0}, seg1[3] = {0, 0, 0};
+        for (int64_t hh = h; hh < n_heads && hh < h + 3; ++hh) {
+            const int64_t s = (int64_t)(keys[heads[hh]] >> 32);
+            if (s / 3 != cc) break;
+            seg0[s % 3] = heads[hh];
+            seg1[s % 3] = (hh + 1 < n_heads) ? heads[hh + 1] : n_exc;
+        }
+        const int64_t site0 = cc * 3;
+        for (int q = 0; q < a.s.k; ++q) {
+            const uint4* mq = a.s.masks + (int64_t)q * Wq;
+            uint32_t cnt[3][PFA_NCLASS];
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                pfa_class_counts<32, true>(a.s.b0 + (site0 + t) * Wq, a.s.b1 + (site0 + t) * Wq, a.s.v + (site0 + t) * Wq, mq, Wq, lane,
+                                           0xffffffffu, cnt[t]);
+            if (!(cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC])) continue;  // the main kernel counted it
+            uint32_t escd[3] = {0, 0, 0};
+            unsigned long long escsq[3] = {0, 0, 0};
+            for (int t = 0; t < 3; ++t)
+                if (cnt[t][PFA_C_ESC])
+                    pfa_escape_stats(keys, seg0[t], seg1[t], reinterpret_cast<const uint32_t*>(mq), hist[wib], lane, &escd[t], &escsq[t]);
+            const unsigned long long P = pfa_codon_presence<32, true>(a.s.b0, a.s.b1, a.s.v, site0, Wq, mq, lane, 0xffffffffu);
+            if (lane != 0) continue;
+            pfa_cds_contribute(P, cnt, a.s.pop_n[q], escd, escsq, reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN),
+                               a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+        }
+    }
+}
+
+template <int LPS>
+static void launch_cds(const PfaCdsArgs& args, bool has_v, dim3 grid, size_t smem, cudaStream_t st) {
+    if (has_v) pfa_cds_scan_kernel<LPS, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
+    else pfa_cds_scan_kernel<LPS, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
+}
+
+int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels) {
+    pfa_ctx* ctx = a->ctx;
+    if (a->col_begin % 3 != 0) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: the shard must start on a codon boundary");
+    const bool last = a->col_begin + a->ns == a->L_total;
+    if (a->ns % 3 != 0 && !last) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: only the last shard may end inside a codon");
+    PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * PFA_CDS_LEN * (size_t)a->k, ctx->stream));
+    if (d_labels && a->ns) PFA_CUDA(ctx, cudaMemsetAsync(d_labels, 0, (size_t)(a->k * a->ns), ctx->stream));
+    if (a->ns == 0 || a->n == 0) return PFA_OK;
+    PfaCdsArgs args;
+    pfa_fill_site_args(a, nullptr, nullptr, &args.s);
+    args.out = d_out;
+    args.labels = d_labels;
+    args.ncf = a->ns / 3;
+    args.has_partial = (a->ns % 3) != 0;
+    args.acc_in_smem = (int64_t)a->k * PFA_CDS_LEN * 8 <= 40 * 1024;
+    const size_t smem = 8 * (3 + (args.acc_in_smem ? (size_t)a->k * PFA_CDS_LEN : 0));
+    int lps = 1;
+    while (lps < 32 && (a->Wq + lps - 1) / lps > 4) lps *= 2;
+    const int64_t groups_per_block = PFA_SITE_THREADS / lps;
+    int64_t blocks = (std::max<int64_t>(args.ncf, 1) + groups_per_block - 1) / groups_per_block;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * (2048 / PFA_SITE_THREADS);
+    if (blocks > max_blocks) blocks = max_blocks;
+    dim3 grid((unsigned)blocks);
+    switch (lps) {
+        case 1: launch_cds<1>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 2: launch_cds<2>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 4: launch_cds<4>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 8: launch_cds<8>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 16: launch_cds<16>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        default: launch_cds<32>(args, a->has_invalid, grid, smem, ctx->stream); break;
+    }
+    PFA_LAUNCH_CHECK(ctx);
+    if (a->n_exc_sites > 0) {
+        int64_t eb = (a->n_exc_sites + 7) / 8;
+        if (eb > (int64_t)ctx->sm_count * 8) eb = (int64_t)ctx->sm_count * 8;
+        pfa_cds_escape_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, a->exc_keys, a->n_exc, a->exc_heads, a->n_exc_sites);
+        PFA_LAUNCH_CHECK(ctx);
+    }
+    return PFA_OK;
+}

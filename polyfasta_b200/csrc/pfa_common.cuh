@@ -1,0 +1,87 @@
+// Shared declarations of the polyfasta_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/polyfasta_b200.h"
+
+#define PFA_SM_COUNT_FALLBACK 148
+
+// ---- handles ----------------------------------------------------------------------------------------
+struct pfa_ctx {
+    int device = 0;
+    int sm_count = PFA_SM_COUNT_FALLBACK;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // own_stream or a caller-owned stream
+    std::string err;
+    int64_t launches = 0;
+    // small pinned + device scratch for finalisation and synchronous result copies
+    void* h_scratch = nullptr;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+struct pfa_aln {
+    pfa_ctx* ctx = nullptr;
+    int64_t n = 0;          // rows
+    int64_t L_total = 0;    // sites of the whole alignment
+    int64_t col_begin = 0;  // first global column of this shard
+    int64_t ns = 0;         // sites in this shard
+    int Wq = 0;             // uint4 per site per plane = ceil(n/128)
+    uint4* planes = nullptr;  // one allocation: b0 | b1 | v
+    uint4 *b0 = nullptr, *b1 = nullptr, *v = nullptr;
+    size_t plane_bytes = 0;  // bytes of ONE plane (ns*Wq*16, padded to 256)
+    int has_invalid = 0;
+    // exception list: sorted keys (site:32 | byte:8 | row:24), heads = first index of every distinct site
+    unsigned long long* exc_keys = nullptr;
+    int64_t n_exc = 0;
+    int64_t* exc_heads = nullptr;
+    int64_t n_exc_sites = 0;
+    // populations
+    int k = 1;
+    uint4* d_masks = nullptr;  // [k][Wq]
+    uint4* d_union = nullptr;  // [Wq]
+    int64_t* d_pop_n = nullptr;
+    int64_t* d_site_off = nullptr;
+    std::vector<int64_t> pop_n;
+    std::vector<int64_t> site_off;  // offsets into the site result vector, size k+1
+    // row-major copy for the pairwise kernel (built lazily): [plane][n][Wl] uint32, Wl = ceil(ns/32) padded to 4
+    uint32_t* rowmajor = nullptr;
+    int64_t Wl = 0;
+};
+
+// ---- error plumbing ----------------------------------------------------------------------------------
+int pfa_fail(pfa_ctx* ctx, int code, const char* fmt, ...);
+void pfa_set_global_error(const char* fmt, ...);
+
+#define PFA_CUDA(ctx, call)                                                                       \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return pfa_fail((ctx), PFA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define PFA_LAUNCH_CHECK(ctx)                                                                     \
+    do {                                                                                          \
+        (ctx)->launches++;                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess)                                                                   \
+            return pfa_fail((ctx), PFA_ERR_CUDA, "kernel launch failed: %s (%s:%d)",              \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+    } while (0)
+
+// ---- internal entry points implemented in the .cu files -----------------------------------------------
+int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t cols, int64_t site0,
+                     unsigned long long* d_exc_count, int64_t exc_cap, int* d_has_invalid);
+int pfa_finish_exceptions(pfa_aln* a, int64_t count);
+int pfa_synth_fill(pfa_aln* a, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm);
+int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar);
+int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels);
+int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
+int pfa_upload_codon_tables(pfa_ctx* ctx);
+
+static inline int64_t pfa_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -1,0 +1,201 @@
+// Host FASTA ingest with the reference's parsing semantics (replaces readfasta, PolyFastA.py:227-250).
+//
+// The reference iterates text-mode lines (universal newlines: "\n", "\r\n" and a lone "\r" all end a
+// line); a line whose first character is '>' opens a record whose header is the rest of the line,
+// right-stripped (:233,:242); the same header seen again restarts that record but keeps its position in
+// the dict (:234,:243); any other line is right-stripped, upper-cased and appended to the current record
+// iff the current header is non-empty (:235-236,:244-245).  If the LAST header seen is empty (or none was
+// seen) the file "is not FASTA" (:246-248).  Upper-casing is deferred to the device encoder (its LUT folds
+// case) and to pfa_fasta_copy_row.
+//
+// Output: rows in first-seen order in one arena; when all rows have the same length L the arena is the
+// row-major matrix text[row*L + col] that pfa_aln_from_fasta uploads.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "pfa_host.h"
+
+namespace {
+
+// str.rstrip() with no argument strips characters for which str.isspace() is true; in ASCII these are
+// \t \n \v \f \r, the separators 0x1c-0x1f and the blank.
+inline bool py_space(unsigned char c) { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); }
+
+struct Slice {
+    const unsigned char* p;
+    size_t len;
+};
+
+struct Record {
+    std::string header;
+    std::vector<Slice> parts;
+    int64_t len = 0;
+};
+
+}  // namespace
+
+static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
+    std::vector<Record> recs;
+    std::unordered_map<std::string, size_t> index;
+    bool seen_header = false, head_nonempty = false;
+    size_t cur = 0;
+    bool non_ascii = false;
+    size_t i = 0;
+    while (i < len) {
+        size_t e = i;
+        while (e < len && buf[e] != '\n' && buf[e] != '\r') ++e;
+        size_t next = e;
+        if (next < len) next += (buf[next] == '\r' && next + 1 < len && buf[next + 1] == '\n') ? 2 : 1;
+        // the line is buf[i, e) plus its terminator; never empty as a Python line, but may be empty here
+        size_t r = e;
+        while (r > i && py_space(buf[r - 1])) --r;
+        if (e > i && buf[i] == '>') {
+            std::string h(reinterpret_cast<const char*>(buf + i + 1), r > i + 1 ? r - (i + 1) : 0);
+            seen_header = true;
+            head_nonempty = !h.empty();
+            auto it = index.find(h);
+            if (it == index.end()) {
+                index.emplace(h, recs.size());
+                cur = recs.size();
+                recs.push_back(Record{h, {}, 0});
+            } else {
+                cur = it->second;
+                recs[cur].parts.clear();
+                recs[cur].len = 0;
+            }
+        } else if (seen_header && head_nonempty && r > i) {
+            recs[cur].parts.push_back(Slice{buf + i, r - i});
+            recs[cur].len += (int64_t)(r - i);
+        }
+        i = next;
+    }
+    if (!seen_header || !head_nonempty) return PFA_ERR_NOT_FASTA;
+
+    pfa_fasta* f = new pfa_fasta();
+    f->n = (int64_t)recs.size();
+    f->row_len.resize(recs.size());
+    f->row_off.resize(recs.size() + 1);
+    int64_t total = 0;
+    bool same = true;
+    for (size_t k = 0; k < recs.size(); ++k) {
+        f->row_len[k] = recs[k].len;
+        f->row_off[k] = total;
+        total += recs[k].len;
+        if (recs[k].len != recs[0].len) same = false;
+        f->header_off.push_back((int64_t)f->headers.size());
+        f->headers += recs[k].header;
+    }
+    f->row_off[recs.size()] = total;
+    f->header_off.push_back((int64_t)f->headers.size());
+    f->seqlen = same ? recs[0].len : -1;
+    f->data_bytes = (size_t)std::max<int64_t>(total, 1);
+    f->data = (unsigned char*)malloc(f->data_bytes);
+    if (!f->data) {
+        delete f;
+        return PFA_ERR_NOMEM;
+    }
+    // copy the line slices; rows are independent, so large files are copied by several threads
+    unsigned nthreads = total > (64ll << 20) ? std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::vector<char> bad(nthreads, 0);
+    auto work = [&](unsigned t) {
+        for (size_t k = t; k < recs.size(); k += nthreads) {
+            unsigned char* dst = f->data + f->row_off[k];
+            for (const Slice& s : recs[k].parts) {
+                memcpy(dst, s.p, s.len);
+                unsigned char acc = 0;
+                for (size_t b = 0; b < s.len; ++b) acc |= s.p[b];
+                if (acc & 0x80) bad[t] = 1;
+                dst += s.len;
+            }
+        }
+    };
+    if (nthreads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    for (char b : bad) non_ascii |= (b != 0);
+    if (non_ascii) {
+        pfa_fasta_free(f);
+        return PFA_ERR_NON_ASCII;
+    }
+    *out = f;
+    return PFA_OK;
+}
+
+extern "C" {
+
+int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out) {
+    if (!out || (!buf && len)) return PFA_ERR_ARG;
+    *out = nullptr;
+    return parse_impl(static_cast<const unsigned char*>(buf), len, out);
+}
+
+int pfa_fasta_parse_file(const char* path, pfa_fasta** out) {
+    if (!out || !path) return PFA_ERR_ARG;
+    *out = nullptr;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return PFA_ERR_IO;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) {
+        close(fd);
+        return PFA_ERR_IO;
+    }
+    int rc;
+    if (st.st_size == 0) {
+        rc = parse_impl(nullptr, 0, out);
+    } else {
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) {
+            close(fd);
+            return PFA_ERR_IO;
+        }
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        rc = parse_impl(static_cast<const unsigned char*>(m), (size_t)st.st_size, out);
+        munmap(m, (size_t)st.st_size);
+    }
+    close(fd);
+    return rc;
+}
+
+void pfa_fasta_free(pfa_fasta* f) {
+    if (!f) return;
+    if (f->unpin) f->unpin(f->data);
+    free(f->data);
+    delete f;
+}
+
+int64_t pfa_fasta_nseq(const pfa_fasta* f) { return f ? f->n : 0; }
+int64_t pfa_fasta_seqlen(const pfa_fasta* f) { return f ? f->seqlen : -1; }
+int64_t pfa_fasta_row_len(const pfa_fasta* f, int64_t row) {
+    return (f && row >= 0 && row < f->n) ? f->row_len[(size_t)row] : -1;
+}
+const char* pfa_fasta_header(const pfa_fasta* f, int64_t row, int64_t* len) {
+    if (!f || row < 0 || row >= f->n) return nullptr;
+    if (len) *len = f->header_off[(size_t)row + 1] - f->header_off[(size_t)row];
+    return f->headers.data() + f->header_off[(size_t)row];
+}
+int pfa_fasta_copy_row(const pfa_fasta* f, int64_t row, uint8_t* dst, int64_t cap) {
+    if (!f || row < 0 || row >= f->n || !dst || cap < f->row_len[(size_t)row]) return PFA_ERR_ARG;
+    const unsigned char* src = f->data + f->row_off[(size_t)row];
+    for (int64_t i = 0; i < f->row_len[(size_t)row]; ++i) {
+        unsigned char c = src[i];
+        dst[i] = (c >= 'a' && c <= 'z') ? (unsigned char)(c - 32) : c;  // str.upper() on ASCII
+    }
+    return PFA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// Host-only part of the library (no CUDA headers): the parsed FASTA file.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/polyfasta_b200.h"
+
+struct pfa_fasta {
+    int64_t n = 0;
+    int64_t seqlen = -1;             // common row length or -1
+    unsigned char* data = nullptr;   // rows back to back in first-seen order; a matrix [n][seqlen] when seqlen >= 0
+    size_t data_bytes = 0;
+    std::vector<int64_t> row_off;    // n+1
+    std::vector<int64_t> row_len;    // n
+    std::string headers;             // concatenated header bytes
+    std::vector<int64_t> header_off; // n+1
+    bool pinned = false;             // data registered with cudaHostRegister by the uploader
+    void (*unpin)(void*) = nullptr;
+};

@@ -1,0 +1,194 @@
+// K2: per-site allele counting over the packed alignment.
+//
+// Replaces getvarsites (PolyFastA.py:252-261) and the column sums inside nucleotide_diversity (:485-492),
+// wattersons_theta (:494-497) and getsfs (:274-282): one pass over the planes yields, for every population at
+// once, S = #columns with > 1 distinct character, H = sum_cols (n^2 - sum_a c_a^2) and the folded SFS.
+//
+// A group of LPS lanes owns one site; its lanes stride over the Wq 128-bit chunks of the site record.
+// Pass 1 (every site, 2 or 3 coalesced 128-bit loads per chunk, logic ops only) decides whether all rows
+// of the union of the populations carry the same symbol.  Monomorphic sites -- the overwhelming majority of
+// a real alignment -- end there.  Pass 2 (variable sites only; re-reads the record from L1/L2) counts the
+// symbol classes per population with popcounts and group shuffles.  Sites holding "escape" symbols (IUPAC
+// codes etc., which are distinct alleles in the reference) are finished by pfa_escape_sites_kernel from the
+// sorted exception list.
+#include "pfa_sites.cuh"
+
+template <int LPS, bool HAS_V>
+__global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const PfaSiteArgs a) {
+    extern __shared__ unsigned long long smem[];
+    unsigned long long* sm_SH = smem;                                       // [2k]
+    unsigned int* sm_sfs = reinterpret_cast<unsigned int*>(smem + 2 * a.k);  // [sfs_bins] when a.sfs_in_smem
+    const int nsm = 2 * a.k;
+    for (int i = threadIdx.x; i < nsm; i += blockDim.x) sm_SH[i] = 0ull;
+    if (a.sfs_in_smem)
+        for (int i = threadIdx.x; i < a.sfs_bins; i += blockDim.x) sm_sfs[i] = 0u;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPS - 1);
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPS;
+    const int Wq = a.Wq;
+
+    for (int64_t s = gid; s < a.ns; s += ngroups) {
+        const uint4* p0 = a.b0 + s * Wq;
+        const uint4* p1 = a.b1 + s * Wq;
+        const uint4* pv = a.v + s * Wq;
+        // ---- pass 1: is the column monomorphic over the union of the populations? ----
+        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll 2
+        for (int j = sub; j < Wq; j += LPS) {
+            const uint4 m = __ldg(a.umask + j);
+            const uint4 x0 = pfa_ld_stream(p0 + j);
+            const uint4 x1 = pfa_ld_stream(p1 + j);
+            o0 |= (x0.x & m.x) | (x0.y & m.y) | (x0.z & m.z) | (x0.w & m.w);
+            z0 |= (~x0.x & m.x) | (~x0.y & m.y) | (~x0.z & m.z) | (~x0.w & m.w);
+            o1 |= (x1.x & m.x) | (x1.y & m.y) | (x1.z & m.z) | (x1.w & m.w);
+            z1 |= (~x1.x & m.x) | (~x1.y & m.y) | (~x1.z & m.z) | (~x1.w & m.w);
+            if (HAS_V) {
+                const uint4 xv = pfa_ld_stream(pv + j);
+                ov |= (xv.x & m.x) | (xv.y & m.y) | (xv.z & m.z) | (xv.w & m.w);
+                zv |= (~xv.x & m.x) | (~xv.y & m.y) | (~xv.z & m.z) | (~xv.w & m.w);
+            } else {
+                ov |= m.x | m.y | m.z | m.w;
+            }
+        }
+        unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+        f = pfa_group_or<LPS>(f, gmask);
+        const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
+        const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);  // every row shows the escape class
+        if (mono && !all_escape) {
+            if (a.isvar && sub == 0)
+                for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
+            continue;
+        }
+        // ---- pass 2: class counts per population ----
+        for (int q = 0; q < a.k; ++q) {
+            uint32_t c[PFA_NCLASS];
+            pfa_class_counts<LPS, HAS_V>(p0, p1, pv, a.masks + (int64_t)q * Wq, Wq, sub, gmask, c);
+            if (sub != 0) continue;
+            const int64_t nq = a.pop_n[q];
+            PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
+            if (r.has_escape) continue;  // finished by pfa_escape_sites_kernel
+            if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
+            if (r.isvar) {
+                atomicAdd(&sm_SH[2 * q], 1ull);
+                atomicAdd(&sm_SH[2 * q + 1], r.h);
+                if (r.sfs_bin >= 0) {
+                    if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
+                    else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
+        if (sm_SH[2 * q]) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q]), sm_SH[2 * q]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 1), sm_SH[2 * q + 1]);
+        }
+    }
+    if (a.sfs_in_smem) {
+        for (int q = 0; q < a.k; ++q) {
+            const int nb = (int)(a.pop_n[q] / 2);
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+                const unsigned int cnt = sm_sfs[a.sfs_off[q] + i];
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + i), (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// One warp per site that holds at least one escape symbol.  For every population with an escape row at
+// this site the column is counted in full: the seven packed classes from the planes plus one count per
+// distinct escape byte from the exception list (sorted by site, byte, row).
+__global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs a, const unsigned long long* __restrict__ keys,
+                                                               int64_t n_exc, const int64_t* __restrict__ heads, int64_t n_heads) {
+    __shared__ unsigned int hist[8][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t h = wid; h < n_heads; h += nwarps) {
+        const int64_t i0 = heads[h], i1 = (h + 1 < n_heads) ? heads[h + 1] : n_exc;
+        const int64_t s = (int64_t)(keys[i0] >> 32);
+        const uint4* p0 = a.b0 + s * a.Wq;
+        const uint4* p1 = a.b1 + s * a.Wq;
+        const uint4* pv = a.v + s * a.Wq;
+        for (int q = 0; q < a.k; ++q) {
+            uint32_t c[PFA_NCLASS];
+            pfa_class_counts<32, true>(p0, p1, pv, a.masks + (int64_t)q * a.Wq, a.Wq, lane, 0xffffffffu, c);
+            if (c[PFA_C_ESC] == 0) continue;  // warp-uniform: the main kernel already counted this (site, pop)
+            for (int b = lane; b < 256; b += 32) hist[wib][b] = 0u;
+            __syncwarp();
+            const uint32_t* mq = reinterpret_cast<const uint32_t*>(a.masks + (int64_t)q * a.Wq);
+            for (int64_t i = i0 + lane; i < i1; i += 32) {
+                const unsigned long long key = keys[i];
+                const uint32_t row = (uint32_t)(key & 0xffffffull);
+                if ((mq[row >> 5] >> (row & 31)) & 1u) atomicAdd(&hist[wib][(key >> 24) & 0xffu], 1u);
+            }
+            __syncwarp();
+            uint32_t distinct = 0;
+            unsigned long long sq = 0;
+            for (int b = lane; b < 256; b += 32) {
+                const unsigned long long cnt = hist[wib][b];
+                distinct += cnt ? 1u : 0u;
+                sq += cnt * cnt;
+            }
+            for (int off = 16; off; off >>= 1) {
+                distinct += __shfl_xor_sync(0xffffffffu, distinct, off);
+                sq += __shfl_xor_sync(0xffffffffu, sq, off);
+            }
+            __syncwarp();
+            if (lane != 0) continue;
+            PfaSiteResult r = pfa_site_result(c, a.pop_n[q], distinct, sq);
+            if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
+            if (r.isvar) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q]), 1ull);
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 1), r.h);
+                if (r.sfs_bin >= 0)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
+            }
+        }
+    }
+}
+
+template <int LPS>
+static void launch_scan(const PfaSiteArgs& args, bool has_v, dim3 grid, size_t smem, cudaStream_t st) {
+    if (has_v) pfa_site_scan_kernel<LPS, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
+    else pfa_site_scan_kernel<LPS, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
+}
+
+int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar) {
+    pfa_ctx* ctx = a->ctx;
+    const int64_t out_len = a->site_off[a->k];
+    PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
+    if (a->ns == 0 || a->n == 0) return PFA_OK;
+    PfaSiteArgs args;
+    pfa_fill_site_args(a, d_out, d_isvar, &args);
+    // lanes per site: the smallest power of two that leaves every lane at most ~5 chunks
+    int lps = 1;
+    while (lps < 32 && (a->Wq + lps - 1) / lps > 5) lps *= 2;
+    const size_t smem = sizeof(unsigned long long) * 2 * (size_t)a->k + (args.sfs_in_smem ? sizeof(unsigned int) * (size_t)args.sfs_bins : 0);
+    const int64_t groups_per_block = PFA_SITE_THREADS / lps;
+    int64_t blocks = (a->ns + groups_per_block - 1) / groups_per_block;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * (2048 / PFA_SITE_THREADS);
+    if (blocks > max_blocks) blocks = max_blocks;
+    dim3 grid((unsigned)blocks);
+    switch (lps) {
+        case 1: launch_scan<1>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 2: launch_scan<2>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 4: launch_scan<4>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 8: launch_scan<8>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        case 16: launch_scan<16>(args, a->has_invalid, grid, smem, ctx->stream); break;
+        default: launch_scan<32>(args, a->has_invalid, grid, smem, ctx->stream); break;
+    }
+    PFA_LAUNCH_CHECK(ctx);
+    if (a->n_exc_sites > 0) {
+        int64_t eb = (a->n_exc_sites + 7) / 8;
+        if (eb > (int64_t)ctx->sm_count * 8) eb = (int64_t)ctx->sm_count * 8;
+        pfa_escape_sites_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, a->exc_keys, a->n_exc, a->exc_heads, a->n_exc_sites);
+        PFA_LAUNCH_CHECK(ctx);
+    }
+    return PFA_OK;
+}

@@ -1,0 +1,138 @@
+// Device helpers shared by the site scan (K2), the escape-site kernel and the codon scan (K4).
+#pragma once
+#include "pfa_common.cuh"
+
+#define PFA_SITE_THREADS 256
+// packed symbol classes counted with popcounts; the gap class '-' is n_pop minus the others
+#define PFA_C_A 0
+#define PFA_C_C 1
+#define PFA_C_G 2
+#define PFA_C_T 3
+#define PFA_C_N 4
+#define PFA_C_Q 5
+#define PFA_C_ESC 6
+#define PFA_NCLASS 7
+
+struct PfaSiteArgs {
+    const uint4* b0;
+    const uint4* b1;
+    const uint4* v;
+    const uint4* masks;  // [k][Wq]
+    const uint4* umask;  // [Wq] union of the populations
+    const int64_t* pop_n;    // [k]
+    const int64_t* out_off;  // [k] offset of pop q in the int64 result vector ([S, H, sfs...])
+    const int64_t* sfs_off;  // [k] offset of pop q's bins in the shared-memory histogram
+    int64_t* out;
+    uint8_t* isvar;  // optional [k][ns]
+    int64_t ns;
+    int Wq;
+    int k;
+    int sfs_in_smem;
+    int sfs_bins;  // total bins over all populations
+};
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (every byte of the planes is used once)
+__device__ __forceinline__ uint4 pfa_ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <int LPS>
+__device__ __forceinline__ unsigned pfa_group_or(unsigned x, unsigned gmask) {
+    if (LPS == 32) return __reduce_or_sync(0xffffffffu, x);
+#pragma unroll
+    for (int off = LPS / 2; off; off >>= 1) x |= __shfl_xor_sync(gmask, x, off);
+    return x;
+}
+
+template <int LPS>
+__device__ __forceinline__ uint32_t pfa_group_add(uint32_t x, unsigned gmask) {
+    if (LPS == 32) return __reduce_add_sync(0xffffffffu, x);
+#pragma unroll
+    for (int off = LPS / 2; off; off >>= 1) x += __shfl_xor_sync(gmask, x, off);
+    return x;
+}
+
+// counts of the seven packed classes among the rows of one population at one site, summed over the group
+template <int LPS, bool HAS_V>
+__device__ __forceinline__ void pfa_class_counts(const uint4* __restrict__ p0, const uint4* __restrict__ p1,
+                                                 const uint4* __restrict__ pv, const uint4* __restrict__ mq, int Wq,
+                                                 int sub, unsigned gmask, uint32_t c[PFA_NCLASS]) {
+#pragma unroll
+    for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+    for (int j = sub; j < Wq; j += LPS) {
+        const uint4 m4 = __ldg(mq + j), a4 = __ldg(p0 + j), b4 = __ldg(p1 + j);
+        uint4 v4 = m4;
+        if (HAS_V) v4 = __ldg(pv + j);
+        const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w}, x0[4] = {a4.x, a4.y, a4.z, a4.w}, x1[4] = {b4.x, b4.y, b4.z, b4.w},
+                       xv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t vm = HAS_V ? (xv[w] & m[w]) : m[w];
+            const uint32_t hi = vm & x1[w], lo = vm & ~x1[w];
+            c[PFA_C_T] += __popc(hi & x0[w]);
+            c[PFA_C_G] += __popc(hi & ~x0[w]);
+            c[PFA_C_C] += __popc(lo & x0[w]);
+            c[PFA_C_A] += __popc(lo & ~x0[w]);
+            if (HAS_V) {
+                const uint32_t im = ~xv[w] & m[w];
+                const uint32_t ihi = im & x1[w];
+                c[PFA_C_ESC] += __popc(ihi & x0[w]);
+                c[PFA_C_Q] += __popc(ihi & ~x0[w]);
+                c[PFA_C_N] += __popc(im & ~x1[w] & x0[w]);
+            }
+        }
+    }
+    if (LPS > 1) {
+#pragma unroll
+        for (int i = 0; i < PFA_NCLASS; ++i)
+            if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
+    }
+}
+
+struct PfaSiteResult {
+    int isvar;
+    int has_escape;
+    int sfs_bin;  // -1: fewer than two alleles among A,C,G,T (getsfs is undefined there and skipped)
+    unsigned long long h;
+};
+
+// (#distinct characters > 1, n^2 - sum_a c_a^2, folded-SFS bin) of one column for one population
+// (PolyFastA.py:258, :486-489, :279-281).  esc_distinct / esc_sq describe the escape bytes of the column.
+__device__ __forceinline__ PfaSiteResult pfa_site_result(const uint32_t c[PFA_NCLASS], int64_t nq, uint32_t esc_distinct,
+                                                          unsigned long long esc_sq) {
+    PfaSiteResult r;
+    unsigned long long sum = 0, sq = esc_sq;
+    int distinct = (int)esc_distinct;
+#pragma unroll
+    for (int i = 0; i < PFA_NCLASS; ++i) {
+        sum += c[i];
+        if (i != PFA_C_ESC) {
+            sq += (unsigned long long)c[i] * c[i];
+            distinct += c[i] ? 1 : 0;
+        }
+    }
+    const unsigned long long gap = (unsigned long long)nq - sum;
+    sq += gap * gap;
+    distinct += gap ? 1 : 0;
+    r.has_escape = c[PFA_C_ESC] != 0;
+    r.isvar = distinct > 1;
+    r.h = r.isvar ? (unsigned long long)nq * (unsigned long long)nq - sq : 0ull;
+    // second largest count among the alleles that are exactly A, C, G, T
+    uint32_t m1 = 0, m2 = 0;
+    int present = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t x = c[i];
+        present += x ? 1 : 0;
+        if (x > m1) { m2 = m1; m1 = x; }
+        else if (x > m2) m2 = x;
+    }
+    r.sfs_bin = (present >= 2) ? (int)m2 - 1 : -1;
+    return r;
+}
+
+void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args);

@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the golden vectors produced by the unmodified
+reference, (b) the CPU oracles on seeded inputs, (c) size-independent properties at the benchmark's full size.
+Integers are compared bit-exactly; fp64 statistics within rel 1e-12 (D: see test_oracle_golden.check_poly)."""
+import io
+import math
+import os
+import random
+import subprocess
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+import polyfasta_b200 as pf
+from polyfasta_b200 import cli, synth
+from conftest import GOLDEN, ROOT, load_golden
+from oracle import c_oracle as co
+from oracle import polyfasta_oracle as orc
+from test_oracle_golden import check_poly, close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return pf.default_context(0)
+
+
+def _pops_present(heads, keys):
+    plan = [(k, list(range(len(heads))) if k == "NA" else orc.pop_rows(heads, k)) for k in keys]
+    return [(k, r) for k, r in plan if r]
+
+
+def _check_alignment(ctx, heads, seqs, L, pops, file, check_rows=True):
+    present = _pops_present(heads, [k for k, rec in pops.items() if rec is not None])
+    if not present:
+        return
+    aln = pf.Alignment.from_strings(ctx, seqs)
+    aln.set_pops([r for _, r in present])
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    pw = aln.pairwise() if len(seqs) <= 64 else None
+    aln.free()
+    for q, (key, rows) in enumerate(present):
+        rec = pops[key]
+        st = site[q]
+        assert (st["n"], st["S"], st["H"]) == (rec["n"], rec["S"], rec["H"]), (file, key)
+        assert np.flatnonzero(st["isvar"]).tolist() == rec["pos"], (file, key)
+        assert st["sfs"] == (rec["sfs"] if rec["S"] else [0] * (rec["n"] // 2)), (file, key)
+        if pw is not None:
+            assert 2 * pw[q] == rec["H"], (file, key)
+        for jc in (0, 1):
+            got = ctx.finalize([(st["n"], st["S"], st["H"], L, jc)])[0]
+            check_poly(got, rec["poly_jc%d" % jc], st["n"], st["S"], st["H"])
+        c = rec.get("cds")
+        if c is None:
+            continue
+        g = cds[q]
+        for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n"):
+            assert g[k] == c[k], (file, key, k)
+        assert np.flatnonzero(g["labels"] == 1).tolist() == sorted(c["S_pos"]), (file, key)
+        assert np.flatnonzero(g["labels"] == 2).tolist() == sorted(c["N_pos"]), (file, key)
+        assert {str(k): v for k, v in g["sum3_by_len"].items()} == {k: v for k, v in c["sum3_by_len"].items() if v}
+        assert close(g["ssites"], c["count_syn"]), (file, key)
+        if check_rows:
+            for is_cds in (0, 1):
+                for jc in (0, 1):
+                    want = rec["row_cds%d_jc%d" % (is_cds, jc)].rstrip("\n")
+                    got = cli.format_rows(ctx, file, L, bool(is_cds), bool(jc), [(key, len(rows))], [st], [g] if is_cds else None)[0]
+                    _rows_close(got, want)
+
+
+def _rows_close(got, want):
+    g, w = got.split(","), want.split(",")
+    assert len(g) == len(w), (got, want)
+    for x, y in zip(g, w):
+        if x != y:
+            assert math.isclose(float(x), float(y), rel_tol=2e-11), (got, want)
+
+
+def test_example_loci(ctx):
+    """C1/C2: the shipped loci, whole file and header-substring populations, against the reference's own numbers"""
+    for fn, entry in load_golden("kat_examples.json").items():
+        f = pf.Fasta.from_file(os.path.join(GOLDEN, "example_theta_0.01", fn))
+        seqs = [f.row(i) for i in range(f.nseq)]
+        _check_alignment(ctx, f.headers, seqs, entry["seqlen"], entry["pops"], fn)
+
+
+def test_random_cases(ctx):
+    """220 random alignments with gaps / N / IUPAC / '?' / lower case / stops"""
+    for ci, case in enumerate(load_golden("random_cases.json")):
+        f = pf.Fasta.from_bytes(case["text"])
+        seqs = [f.row(i) for i in range(f.nseq)]
+        _check_alignment(ctx, f.headers, seqs, case["seqlen"], case["pops"], "case%d.fa" % ci)
+
+
+def test_finalize_cases(ctx):
+    recs = load_golden("finalize_cases.json")
+    got = ctx.finalize([(r["n"], r["S"], r["H"], r["seqlen"], r["jc"]) for r in recs])
+    for g, r in zip(got, recs):
+        check_poly(g, r["out"], r["n"], r["S"], r["H"])
+
+
+def test_cli_golden(tmp_path):
+    """the drop-in command line against the reference's captured stdout / --out files"""
+    env = dict(os.environ, PYTHONPATH=ROOT, PYTHONHASHSEED="0")
+    for rec in load_golden("cli_examples.json"):
+        args = list(rec["args"])
+        outp = str(tmp_path / "out.csv")
+        if "@OUT@" in args:
+            with open(outp, "w") as f:
+                f.write("PRE-EXISTING LINE\n")
+            args[args.index("@OUT@")] = outp
+        stdin = None
+        if rec["stdin"]:
+            with open(os.path.join(GOLDEN, "example_theta_0.01", "file1.fa"), "rb") as f:
+                stdin = f.read()
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "PolyFastA.py")] + args, input=stdin, capture_output=True,
+                           env=env, cwd=GOLDEN)
+        assert p.returncode == rec["rc"], (args, p.stderr.decode())
+        _text_close(p.stdout.decode().replace(outp, "@OUT@"), rec["stdout"], args)
+        if "outfile" in rec:
+            with open(outp) as f:
+                _text_close(f.read(), rec["outfile"], args)
+
+
+def _text_close(got, want, what):
+    gl, wl = got.split("\n"), want.split("\n")
+    assert len(gl) == len(wl), (what, got, want)
+    for g, w in zip(gl, wl):
+        if g != w:
+            _rows_close(g, w)
+
+
+def test_cli_pops(tmp_path):
+    """-p: rows per key in key order, '# Pop ... not found' rows, overlapping keys (reference rows via print_result)"""
+    kat = load_golden("kat_examples.json")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "PolyFastA.py"), "-d", "example_theta_0.01", "-p",
+                        "indiv1,nothere,indiv2", "--jc", "-s"], capture_output=True, text=True, env=env, cwd=GOLDEN)
+    assert p.returncode == 0, p.stderr
+    want = []
+    for fn in sorted(kat):
+        want.append(kat[fn]["pops"]["indiv1"]["row_cds0_jc1"].rstrip("\n"))
+        want.append("# Pop nothere string was not found in fasta headers.")
+        want.append(kat[fn]["pops"]["indiv2"]["row_cds0_jc1"].rstrip("\n"))
+    _text_close(p.stdout, "\n".join(want) + "\n", "pops")
+
+
+def _random_text(rng, n, L, p_var=0.05, p_junk=0.01, junk=b"-N?RYKM.", lower=0.1):
+    anc = rng.integers(0, 4, L)
+    mat = np.repeat(anc[None, :], n, axis=0)
+    var = rng.random(L) < p_var
+    k = rng.integers(1, n, L)
+    der = (anc + rng.integers(1, 4, L)) % 4
+    perm_rank = rng.random((n, L)).argsort(axis=0)
+    mat = np.where(var[None, :] & (perm_rank < k[None, :]), der[None, :], mat)
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[mat]
+    j = rng.random((n, L)) < p_junk
+    text = np.where(j, np.frombuffer(junk, dtype=np.uint8)[rng.integers(0, len(junk), (n, L))], text)
+    lo = rng.random((n, L)) < lower
+    text = np.where(lo & (text >= 65) & (text <= 90), text + 32, text).astype(np.uint8)
+    return np.ascontiguousarray(text)
+
+
+def _upper(mat):
+    return np.where((mat >= 97) & (mat <= 122), mat - 32, mat).astype(np.uint8)
+
+
+@pytest.mark.parametrize("n,L", [(1, 50), (2, 333), (31, 1000), (32, 999), (33, 1001), (127, 700), (128, 701), (129, 650),
+                                 (300, 5000), (1000, 6001), (2049, 3000), (5000, 1500), (10001, 600)])
+def test_against_c_oracle(ctx, n, L):
+    """seeded alignments of many shapes (word / chunk boundary cases for n), three overlapping populations"""
+    rng = np.random.default_rng(n * 1000003 + L)
+    text = _random_text(rng, n, L)
+    up = _upper(text)
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n))]
+    pops = [p for p in pops if p]
+    aln = pf.Alignment.from_rows(ctx, text)
+    aln.set_pops(pops)
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    aln.free()
+    for q, rows in enumerate(pops):
+        want = co.site_stats(up, rows, per_site=True)
+        assert (site[q]["S"], site[q]["H"], site[q]["sfs"]) == (want["S"], want["H"], want["sfs"]), (n, L, q)
+        assert np.array_equal(site[q]["isvar"], want["isvar"])
+        wc = co.cds_stats(up, rows, want_labels=True)
+        for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
+            assert cds[q][k] == wc[k], (n, L, q, k)
+        assert np.array_equal(cds[q]["labels"], wc["labels"])
+        assert math.isclose(cds[q]["ssites"], wc["ssites"], rel_tol=1e-12) or cds[q]["ssites"] == wc["ssites"]
+
+
+def test_gappy_and_escape_heavy(ctx):
+    """every column holds non-ACGT symbols; many distinct escape bytes per column; whole-column escapes"""
+    rng = np.random.default_rng(77)
+    n, L = 150, 900
+    text = _random_text(rng, n, L, p_var=0.3, p_junk=0.4, junk=b"-N?RYKMSWBDHV.* x", lower=0.3)
+    text[:, 10] = ord("R")
+    text[:, 11] = ord("-")
+    text[: n // 2, 12] = ord("Y")
+    text[n // 2:, 12] = ord("r")
+    up = _upper(text)
+    pops = [list(range(n)), list(range(0, n, 3)), list(range(5, 40))]
+    aln = pf.Alignment.from_rows(ctx, text)
+    assert aln.num_escapes > 0 and aln.has_invalid
+    aln.set_pops(pops)
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    pw = aln.pairwise()
+    aln.free()
+    for q, rows in enumerate(pops):
+        want = co.site_stats(up, rows, per_site=True)
+        assert (site[q]["S"], site[q]["H"], site[q]["sfs"]) == (want["S"], want["H"], want["sfs"])
+        assert np.array_equal(site[q]["isvar"], want["isvar"])
+        wc = co.cds_stats(up, rows, want_labels=True)
+        for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
+            assert cds[q][k] == wc[k], (q, k)
+        assert np.array_equal(cds[q]["labels"], wc["labels"])
+        assert 2 * pw[q] == want["H"]
+
+
+def test_column_shards_add_up(ctx):
+    """the integer vectors of column shards (codon-aligned) sum to the whole: what the multi-GPU all-reduce relies on"""
+    rng = np.random.default_rng(5)
+    n, L = 400, 3001
+    text = _random_text(rng, n, L)
+    pops = [list(range(n)), list(range(0, n, 2))]
+    whole = pf.Alignment.from_rows(ctx, text)
+    whole.set_pops(pops)
+    ws, wc = whole.site_stats(), whole.cds_stats()
+    whole.free()
+    for parts in (2, 4, 8):
+        per = (L // parts) // 3 * 3
+        bounds = [i * per for i in range(parts)] + [L]
+        acc_s = None
+        acc_c = None
+        for i in range(parts):
+            sh = pf.Alignment.from_rows(ctx, text, bounds[i], bounds[i + 1])
+            sh.set_pops(pops)
+            s, c = sh.site_stats(), sh.cds_stats()
+            sh.free()
+            vs = [np.array([x["S"], x["H"]] + x["sfs"]) for x in s]
+            vc = [x["raw"] for x in c]
+            acc_s = vs if acc_s is None else [a + b for a, b in zip(acc_s, vs)]
+            acc_c = vc if acc_c is None else [a + b for a, b in zip(acc_c, vc)]
+        for q in range(len(pops)):
+            assert acc_s[q].tolist() == [ws[q]["S"], ws[q]["H"]] + ws[q]["sfs"]
+            assert np.array_equal(acc_c[q], wc[q]["raw"])
+
+
+def test_synthetic_generator_matches_numpy_twin(ctx):
+    """device generator == numpy twin (planes bit for bit), and the kernels == the closed form"""
+    for n, L, seed in [(20, 1000, 1), (100, 5000, 5), (129, 777, 9), (1000, 3000, 4)]:
+        dev = pf.Alignment.synthetic(ctx, n, L, seed, 100000, 50000)
+        host = pf.Alignment.from_rows(ctx, synth.text_matrix(seed, n, L, 100000, 50000))
+        for pl in range(3):
+            assert np.array_equal(dev.plane(pl), host.plane(pl)), (n, L, pl)
+        got = dev.site_stats()[0]
+        want = synth.expected_site_stats(seed, n, L, 100000, 50000)
+        assert (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"])
+        dev.free()
+        host.free()
+
+
+def test_full_size_closed_form(ctx):
+    """C4's row count (10,000) at 2 Mb (2e10 bases): the site scan against the generator's closed form, whole and in
+    8 column shards; the same check runs at the full 10 Mb inside bench.py"""
+    n, L, seed = 10000, 2_000_000, 4
+    want = synth.expected_site_stats(seed, n, L)
+    a = pf.Alignment.synthetic(ctx, n, L, seed)
+    got = a.site_stats()[0]
+    a.free()
+    assert (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"])
+    tot = np.zeros(2 + n // 2, dtype=np.int64)
+    per = L // 8
+    for i in range(8):
+        sh = pf.Alignment.synthetic(ctx, n, L, seed, col_begin=i * per, col_end=L if i == 7 else (i + 1) * per)
+        r = sh.site_stats()[0]
+        sh.free()
+        tot += np.array([r["S"], r["H"]] + r["sfs"])
+    assert tot.tolist() == [want["S"], want["H"]] + want["sfs"]
+
+
+def test_mirror_api_reads_like_the_reference(ctx):
+    kat = load_golden("kat_examples.json")["file1.fa"]
+    d = pf.readfasta(os.path.join(GOLDEN, "example_theta_0.01", "file1.fa"), False)
+    pos, var = pf.getvarsites(d, 1000)
+    rec = kat["pops"]["NA"]
+    assert pos == rec["pos"] and len(var) == 87 and len(var[0]) == 20
+    check_poly(pf.polymorphism(var, 1000, False), rec["poly_jc0"], 20, rec["S"], rec["H"])
+    assert pf.getsfs(var) == rec["sfs_ref"]
+    cs, S, N, nstops, missing = pf.getvarCDSsites(d, 1000)
+    c = rec["cds"]
+    assert (S, N, nstops, missing) == (sorted(c["S_pos"]), sorted(c["N_pos"]), c["nstops"], c["missing"])
+    assert close(cs, c["count_syn"])
+    haplo = list(map(list, zip(*var)))
+    assert pf.nucleotide_diversity3(haplo) * (20 * 19 // 2) * 2 == pytest.approx(rec["H"], rel=1e-15)
+
+
+def test_edge_shapes(ctx):
+    """empty alignment, single row, single site, no variation"""
+    a = pf.Alignment.from_strings(ctx, ["", ""])
+    assert a.site_stats()[0]["S"] == 0 and a.cds_stats()[0]["missing"] == 0
+    a.free()
+    a = pf.Alignment.from_strings(ctx, ["ACGTAC"])
+    s = a.site_stats()[0]
+    assert (s["n"], s["S"], s["H"], s["sfs"]) == (1, 0, 0, [])
+    a.free()
+    a = pf.Alignment.from_strings(ctx, ["A", "C", "A"])
+    s = a.site_stats()[0]
+    assert (s["S"], s["H"], s["sfs"]) == (1, 4, [1])
+    c = a.cds_stats()[0]
+    assert c["missing"] == 3 and c["nstops"] == 0
+    a.free()
+    assert ctx.finalize([(5, 0, 0, 10, False)]) == [(0, 0, 0, "NA")]

@@ -1,0 +1,121 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol, the
+FASTA parser follows the reference's readfasta on the golden corner cases, and compute fails loudly without a GPU."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+import polyfasta_b200 as pf
+from polyfasta_b200 import _lib
+from conftest import GOLDEN, ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    with open(os.path.join(ROOT, "include", "polyfasta_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(pfa_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pfa_final_in", "pfa_final_out"}
+    assert declared == set(_lib.EXPORTS)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert L.pfa_version() >= 100
+
+
+def test_ingest_cases_match_reference():
+    for name, rec in load_golden("ingest_cases.json").items():
+        if "ret" in rec:
+            with pytest.raises(pf.NotFasta):
+                pf.Fasta.from_bytes(rec["text"])
+            continue
+        f = pf.Fasta.from_bytes(rec["text"])
+        assert f.headers == rec["keys"], name
+        assert [f.row(i) for i in range(f.nseq)] == rec["seqs"], name
+        lens = {len(s) for s in rec["seqs"]}
+        assert f.seqlen == (lens.pop() if len(lens) == 1 else -1), name
+        f.close()
+
+
+def test_readfasta_mirror(tmp_path, capsys):
+    p = tmp_path / "x.fa"
+    p.write_text(">a\nacgt\n>b\nAC-N\n")
+    assert pf.readfasta(str(p), False) == {"a": "ACGT", "b": "AC-N"}
+    q = tmp_path / "bad.fa"
+    q.write_text("no header here\n")
+    assert pf.readfasta(str(q), False) == 1
+    assert capsys.readouterr().out == f"# file {q} is not FASTA!\n"
+
+
+def test_example_files_parse():
+    kat = load_golden("kat_examples.json")
+    for fn, entry in kat.items():
+        f = pf.Fasta.from_file(os.path.join(GOLDEN, "example_theta_0.01", fn))
+        assert f.headers == entry["headers"] and f.seqlen == entry["seqlen"] and f.nseq == 20
+
+
+def test_non_ascii_sequence_rejected():
+    with pytest.raises(ValueError):
+        pf.Fasta.from_bytes(">a\nAC\xc3\xa9T\n".encode("latin-1"))
+
+
+def test_codon_tables_match_reference():
+    """the product's own classifier tables (host side of K4) against the reference's exhaustive vectors"""
+    L = _lib.lib()
+    g = load_golden("codon_classifier.json")
+    bases = "ACGT"
+    idx = lambda c: 16 * bases.index(c[0]) + 4 * bases.index(c[1]) + bases.index(c[2])  # noqa: E731
+    for c, v in g["syn3"].items():
+        assert L.pfa_codon_syn3(idx(c)) == v, c
+    stops = {"TAA", "TAG", "TGA"}
+    for key, (S, N) in g["pairs"].items():
+        a, b = key[:3], key[3:]
+        lab = L.pfa_codon_pair_labels(idx(a), idx(b))
+        if a in stops or b in stops:
+            continue
+        got_s = [i for i in range(3) if (lab >> (2 * i)) & 3 == 1]
+        got_n = [i for i in range(3) if (lab >> (2 * i)) & 3 == 2]
+        assert (got_s, got_n) == (S, N), key
+    for cods, S, N in g["multi"]:
+        m = 0
+        for c in cods:
+            if c not in stops:
+                m |= 1 << idx(c)
+        lab = L.pfa_codon_set_labels(m)
+        got_s = [i for i in range(3) if (lab >> (2 * i)) & 3 == 1]
+        got_n = [i for i in range(3) if (lab >> (2 * i)) & 3 == 2]
+        assert (got_s, got_n) == (S, N), cods
+
+
+def test_compute_fails_loudly_without_gpu():
+    if _lib.lib().pfa_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pf.PolyFastaError):
+        pf.Context(0)
+    with pytest.raises(pf.PolyFastaError):
+        pf.getvarsites({"a": "ACGT", "b": "ACGA"}, 4)
+
+
+def test_cli_argument_errors():
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, os.path.join(ROOT, "PolyFastA.py")]
+    p = subprocess.run(cmd + ["-f", "a.fa", "-d", "somedir"], capture_output=True, text=True, env=env)
+    assert p.returncode == 2 and "Run with either --file/-f or --dir/-d, but not both" in p.stderr
+    p = subprocess.run(cmd + ["-h"], capture_output=True, text=True, env=env)
+    assert p.returncode == 0
+    for flag in ("--file", "--dir", "--pops", "--out", "--pipe", "--cds", "--silent", "--name", "--jc"):
+        assert flag in p.stdout
+    p = subprocess.run(cmd, input="n\n", capture_output=True, text=True, env=env)
+    assert p.returncode == 2 and "Both --file/-f and --dir/-d were not found." in p.stdout
+
+
+def test_synth_twin_closed_form_small():
+    """numpy twin: the closed-form counts equal a brute-force recount of the generated text (oracle)"""
+    from oracle import c_oracle as co
+    from polyfasta_b200 import synth
+    for n, L in [(2, 200), (3, 500), (20, 3000), (101, 2000), (257, 700)]:
+        mat = synth.text_matrix(11, n, L, 200000, 100000)
+        want = co.site_stats(mat)
+        got = synth.expected_site_stats(11, n, L, 200000, 100000)
+        assert (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"]), (n, L)
