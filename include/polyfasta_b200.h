@@ -77,12 +77,18 @@ int pfa_aln_from_device_rows(pfa_ctx* ctx, const uint8_t* d_text, int64_t n, int
  * The same generator exists on the host in polyfasta_b200/synth.py (numpy). */
 int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm,
                       int64_t col_begin, int64_t col_end, pfa_aln** out);
+/* the same synthetic alignment as upper-case text d_text[row*ld + (col-col_begin)] in DEVICE memory (benchmark input
+ * for the end-to-end leg: copied to pinned host memory, then uploaded like any other alignment) */
+int pfa_synth_text_device(pfa_ctx* ctx, uint8_t* d_text, int64_t ld, int64_t n, uint64_t seed, uint32_t p_seg_ppm,
+                          uint32_t tri_ppm, int64_t col_begin, int64_t col_end);
 int pfa_aln_free(pfa_aln* a);
 int64_t pfa_aln_nseq(const pfa_aln* a);
 int64_t pfa_aln_nsites(const pfa_aln* a);        /* sites in this shard */
 int64_t pfa_aln_num_escapes(const pfa_aln* a);   /* entries in the exception list */
 int64_t pfa_aln_packed_bytes(const pfa_aln* a);  /* bytes of the three planes */
 int pfa_aln_has_invalid(const pfa_aln* a);       /* any non-ACGT symbol in the shard */
+/* benchmarking: force the scans to read the validity plane even though the shard is pure ACGT (flag != 0) */
+int pfa_aln_force_validity(pfa_aln* a, int flag);
 /* debugging / tests: copy plane p (0=b0,1=b1,2=v) to the host, nsites*Wq*16 bytes */
 int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap);
 

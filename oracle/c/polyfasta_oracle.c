@@ -238,6 +238,56 @@ int orc_finalize(int64_t n, int64_t S, int64_t H, double seqlen, int jc, double 
     return 1;
 }
 
+/* C twin of the synthetic alignment used by the benchmark (same integer recipe as polyfasta_b200/synth.py):
+ * writes columns [col_begin, col_end) as upper-case text, out[row*ld + (col - col_begin)]. */
+static uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+void orc_synth_text(uint8_t* out, int64_t ld, int64_t n, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm,
+                    int64_t col_begin, int64_t col_end, uint64_t mult, int nthreads) {
+    static const char B[4] = {'A', 'C', 'G', 'T'};
+    uint64_t nb = 0;
+    for (uint64_t x = (uint64_t)n - 1; x; x >>= 1) ++nb;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t col = col_begin; col < col_end; ++col) {
+        const uint64_t h1 = mix64(seed ^ mix64((uint64_t)col));
+        uint32_t anc = (uint32_t)(h1 & 3u), der1 = anc, der2 = anc;
+        uint64_t k1 = 0, k2 = 0, Bo = 0;
+        if (n >= 2 && ((h1 >> 8) % 1000000ull) < p_seg_ppm) {
+            const uint64_t h2 = mix64(h1 + 1), h3 = mix64(h1 + 2);
+            uint64_t r = ((uint64_t)n - 1) >> (h2 % nb);
+            if (r < 1) r = 1;
+            k1 = 1 + (h2 >> 8) % r;
+            const uint32_t o1 = 1u + (uint32_t)((h2 >> 40) % 3ull);
+            der1 = (anc + o1) & 3u;
+            if (n >= 3 && k1 + 2 <= (uint64_t)n && ((h3 >> 8) % 1000000ull) < tri_ppm) {
+                uint64_t r2 = ((uint64_t)n - 1) >> 2;
+                if (r2 < 1) r2 = 1;
+                if (r2 > (uint64_t)n - 1 - k1) r2 = (uint64_t)n - 1 - k1;
+                k2 = 1 + (h3 >> 32) % r2;
+                der2 = (anc + 1u + ((o1 - 1u) + 1u + (uint32_t)(h3 & 1ull)) % 3u) & 3u;
+            }
+            Bo = mix64(h1 + 3) % (uint64_t)n;
+        }
+        uint8_t* dst = out + (col - col_begin);
+        if (!k1) {
+            for (int64_t r = 0; r < n; ++r) dst[r * ld] = (uint8_t)B[anc];
+        } else {
+            for (int64_t r = 0; r < n; ++r) {
+                const uint64_t pos = (mult * (uint64_t)r + Bo) % (uint64_t)n;
+                dst[r * ld] = (uint8_t)B[pos < k1 ? der1 : (pos >= (uint64_t)n - k2 ? der2 : anc)];
+            }
+        }
+    }
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

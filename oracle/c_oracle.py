@@ -31,6 +31,8 @@ def lib():
         L.orc_pairwise_sum.argtypes = [p, i64, i64, p, i64, p, ctypes.c_int]
         L.orc_pairwise_sum.restype = i64
         L.orc_finalize.argtypes = [i64, i64, i64, ctypes.c_double, ctypes.c_int, p, p]
+        L.orc_synth_text.argtypes = [p, i64, i64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, i64, i64, ctypes.c_uint64, ctypes.c_int]
+        L.orc_synth_text.restype = None
         _lib = L
     return _lib
 
@@ -104,3 +106,16 @@ def finalize(n, S, H, seqlen, jc):
     if not lib().orc_finalize(n, S, H, float(seqlen), int(bool(jc)), out, ctypes.byref(na)):
         return 0, 0, 0, "NA"
     return S, out[0], out[1], ("NA" if na.value else out[2])
+
+
+def synth_text(seed, n, L, p_seg_ppm=50000, tri_ppm=10000, col_begin=0, col_end=None, threads=0):
+    """C twin of polyfasta_b200.synth.text_matrix (fast enough for the benchmark's CPU sample)"""
+    col_end = L if col_end is None else col_end
+    out = np.empty((n, col_end - col_begin), dtype=np.uint8)
+    mult = next((p for p in (7919, 7927, 7933, 7937, 7949, 7951, 7963, 7993, 8009, 8011, 8017, 8039) if n % p), 1)
+    lib().orc_synth_text(out.ctypes.data, out.strides[0], n, seed, p_seg_ppm, tri_ppm, col_begin, col_end, mult, threads)
+    return out
+
+
+def num_threads():
+    return int(lib().orc_num_threads())

@@ -17,7 +17,7 @@ EXPORTS = [
     "pfa_ctx_create", "pfa_ctx_destroy", "pfa_last_error", "pfa_ctx_sync", "pfa_ctx_set_stream", "pfa_ctx_launch_count",
     "pfa_fasta_parse_file", "pfa_fasta_parse_buffer", "pfa_fasta_free", "pfa_fasta_nseq", "pfa_fasta_seqlen",
     "pfa_fasta_row_len", "pfa_fasta_header", "pfa_fasta_copy_row",
-    "pfa_aln_from_fasta", "pfa_aln_from_rows", "pfa_aln_from_device_rows", "pfa_aln_synthetic", "pfa_aln_free",
+    "pfa_aln_from_fasta", "pfa_aln_from_rows", "pfa_aln_from_device_rows", "pfa_aln_synthetic", "pfa_synth_text_device", "pfa_aln_force_validity", "pfa_aln_free",
     "pfa_aln_nseq", "pfa_aln_nsites", "pfa_aln_num_escapes", "pfa_aln_packed_bytes", "pfa_aln_has_invalid",
     "pfa_aln_copy_plane", "pfa_aln_set_pops", "pfa_aln_num_pops", "pfa_aln_pop_size",
     "pfa_site_len", "pfa_site_offset", "pfa_site_stats_device", "pfa_site_stats",
@@ -78,6 +78,8 @@ def lib():
         "pfa_aln_from_rows": (c.c_int, [p, p, i64, i64, i64, i64, i64, c.POINTER(p)]),
         "pfa_aln_from_device_rows": (c.c_int, [p, p, i64, i64, i64, i64, i64, c.POINTER(p)]),
         "pfa_aln_synthetic": (c.c_int, [p, i64, i64, c.c_uint64, c.c_uint32, c.c_uint32, i64, i64, c.POINTER(p)]),
+        "pfa_synth_text_device": (c.c_int, [p, p, i64, i64, c.c_uint64, c.c_uint32, c.c_uint32, i64, i64]),
+        "pfa_aln_force_validity": (c.c_int, [p, c.c_int]),
         "pfa_aln_free": (c.c_int, [p]),
         "pfa_aln_nseq": (i64, [p]),
         "pfa_aln_nsites": (i64, [p]),

@@ -74,6 +74,12 @@ class Context:
         return out
 
 
+def synth_text_device(ctx, d_ptr, ld, n, seed, p_seg_ppm=50000, tri_ppm=10000, col_begin=0, col_end=0):
+    """fill device memory with the synthetic alignment as text (benchmark input)"""
+    check(lib().pfa_synth_text_device(ctx.handle, ctypes.c_void_p(d_ptr), ld, n, seed, p_seg_ppm, tri_ppm, col_begin, col_end),
+          ctx.handle)
+
+
 def default_context(device=0):
     ctx = _default_ctx.get(device)
     if ctx is None or not ctx._h:
@@ -273,6 +279,10 @@ class Alignment:
     @property
     def has_invalid(self):
         return bool(lib().pfa_aln_has_invalid(self.handle))
+
+    def force_validity(self, flag=True):
+        """benchmarking: make the scans read the validity plane even for a pure-ACGT shard"""
+        check(lib().pfa_aln_force_validity(self.handle, int(bool(flag))), self.ctx.handle)
 
     @property
     def packed_bytes(self):

@@ -327,6 +327,12 @@ int64_t pfa_aln_nsites(const pfa_aln* a) { return a ? a->ns : 0; }
 int64_t pfa_aln_num_escapes(const pfa_aln* a) { return a ? a->n_exc : 0; }
 int64_t pfa_aln_packed_bytes(const pfa_aln* a) { return a ? 3 * a->ns * (int64_t)a->Wq * 16 : 0; }
 int pfa_aln_has_invalid(const pfa_aln* a) { return a ? a->has_invalid : 0; }
+int pfa_aln_force_validity(pfa_aln* a, int flag) {
+    if (!a) return PFA_ERR_ARG;
+    if (flag) a->has_invalid |= 2;
+    else a->has_invalid &= 1;
+    return PFA_OK;
+}
 
 int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap) {
     if (!a || plane < 0 || plane > 2 || !dst) return PFA_ERR_ARG;

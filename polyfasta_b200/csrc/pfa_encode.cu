@@ -200,3 +200,43 @@ int pfa_synth_fill(pfa_aln* a, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_p
     }
     return PFA_OK;
 }
+
+// the same synthetic alignment as upper-case text in device memory (input of the end-to-end benchmark leg):
+// one thread writes 16 consecutive sites of one row
+__global__ void __launch_bounds__(256) pfa_synth_text_kernel(uint8_t* __restrict__ text, int64_t ld, int64_t n, int64_t cols,
+                                                             int64_t col_begin, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm,
+                                                             uint64_t mult) {
+    const int64_t groups = (cols + 15) / 16;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = t / groups, g = t % groups;
+    if (row >= n) return;
+    uint8_t out[16];
+    const int64_t c0 = g * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const pfa_synth_site sp = pfa_synth_site_params(seed, (uint64_t)(col_begin + c0 + i), (uint64_t)n, p_seg_ppm, tri_ppm);
+        const uint32_t b = sp.k1 ? pfa_synth_base(sp, (uint64_t)row, (uint64_t)n, mult) : sp.anc;
+        out[i] = (uint8_t)("ACGT"[b]);
+    }
+    uint8_t* dst = text + row * ld + c0;
+    if (c0 + 16 <= cols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+    } else {
+        for (int i = 0; i < 16 && c0 + i < cols; ++i) dst[i] = out[i];
+    }
+}
+
+extern "C" int pfa_synth_text_device(pfa_ctx* ctx, uint8_t* d_text, int64_t ld, int64_t n, uint64_t seed, uint32_t p_seg_ppm,
+                                     uint32_t tri_ppm, int64_t col_begin, int64_t col_end) {
+    if (!ctx || !d_text || n <= 0 || col_end < col_begin || ld < col_end - col_begin) return PFA_ERR_ARG;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t cols = col_end - col_begin;
+    if (!cols) return PFA_OK;
+    const int64_t groups = (cols + 15) / 16;
+    const int64_t blocks = (n * groups + 255) / 256;
+    if (blocks >= ((int64_t)1 << 31)) return pfa_fail(ctx, PFA_ERR_ARG, "synthetic text: n * cols too large for one launch");
+    pfa_synth_text_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_text, ld, n, cols, col_begin, seed, p_seg_ppm, tri_ppm,
+                                                                     pfa_synth_multiplier((uint64_t)n));
+    PFA_LAUNCH_CHECK(ctx);
+    return PFA_OK;
+}

@@ -74,9 +74,15 @@ def _check_alignment(ctx, heads, seqs, L, pops, file, check_rows=True):
 def _rows_close(got, want):
     g, w = got.split(","), want.split(",")
     assert len(g) == len(w), (got, want)
-    for x, y in zip(g, w):
+    for i, (x, y) in enumerate(zip(g, w)):
         if x != y:
-            assert math.isclose(float(x), float(y), rel_tol=2e-11), (got, want)
+            if len(g) == 14 and i in (1, 2):
+                # sites_S / sites_N are printed as round(x, 2) (PolyFastA.py:178): when the exact value is a tie such
+                # as 8.875 the reference's running float sum (:307) decides the last digit.  The unrounded values are
+                # compared to 1e-12 separately (ssites); here one unit in the last printed place is allowed.
+                assert abs(float(x) - float(y)) <= 0.01 + 1e-9, (got, want)
+            else:
+                assert math.isclose(float(x), float(y), rel_tol=2e-11), (got, want)
 
 
 def test_example_loci(ctx):
@@ -152,7 +158,7 @@ def _random_text(rng, n, L, p_var=0.05, p_junk=0.01, junk=b"-N?RYKM.", lower=0.1
     anc = rng.integers(0, 4, L)
     mat = np.repeat(anc[None, :], n, axis=0)
     var = rng.random(L) < p_var
-    k = rng.integers(1, n, L)
+    k = rng.integers(1, max(n, 2), L)
     der = (anc + rng.integers(1, 4, L)) % 4
     perm_rank = rng.random((n, L)).argsort(axis=0)
     mat = np.where(var[None, :] & (perm_rank < k[None, :]), der[None, :], mat)
