@@ -155,7 +155,7 @@ def main():
     import torch
     import torch.distributed as dist
     import polyfasta_b200 as pf
-    from polyfasta_b200 import api, synth
+    from polyfasta_b200 import api, parallel, synth
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -166,8 +166,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     def shard(total, r):
-        per = (total // world) // 3 * 3
-        return r * per, (total if r == world - 1 else (r + 1) * per)
+        return parallel.shard_columns(total, world, r)
 
     def barrier():
         if world > 1:
@@ -235,6 +234,7 @@ def main():
         parity = "S, H and the folded SFS of the %d x %d alignment equal the generator's closed form (S=%d)" % (n, L, want["S"])
     fin = ctx.finalize([(n, int(result[0]), int(result[1]), L, True)])[0]
     aln.free()
+    ctx.trim()
 
     # ---- end to end from host text ----
     e2e = None

@@ -8,7 +8,7 @@
  * PFA_ERR_CUDA.  Calls on one handle are not re-entrant.
  *
  * Device layout: three site-major bit-planes over rows, b0 / b1 / v, each
- * uint4[sites][Wq] with Wq = ceil(n/128).  v=1: A,C,G,T = b1b0 00,01,10,11.  v=0: '-','N','?' = 00,01,10
+ * uint4[sites][Wq] with Wq = ceil(n/128) (rounded up to an even number from 16 on: whole 32-byte sectors).  v=1: A,C,G,T = b1b0 00,01,10,11.  v=0: '-','N','?' = 00,01,10
  * and 11 = "escape" (any other byte; its identity is kept in a sorted exception list).
  */
 #ifndef POLYFASTA_B200_H
@@ -41,6 +41,8 @@ int pfa_ctx_create(int device, pfa_ctx** out);
 int pfa_ctx_destroy(pfa_ctx* ctx);
 const char* pfa_last_error(const pfa_ctx* ctx);
 int pfa_ctx_sync(pfa_ctx* ctx);
+/* device memory freed by the library stays in the device's stream-ordered pool for reuse; this returns it to the driver */
+int pfa_ctx_trim(pfa_ctx* ctx);
 /* run the library's work for this ctx on a caller-owned stream (cudaStream_t as void*; e.g. torch's
  * current stream) so that a collective enqueued by the caller is ordered after the kernels. NULL restores
  * the ctx's own stream. */
@@ -93,8 +95,9 @@ int pfa_aln_force_validity(pfa_aln* a, int flag);
 int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap);
 
 /* ---- populations: replaces the header-substring split (PolyFastA.py:123-134) ------------------------ */
-/* k row bit-masks, each words_per_mask = 4*ceil(n/128) uint32 (bit r%32 of word r/32 = row r).  Substring
- * matching stays in Python; an empty population never reaches the library. k = 0 restores "all rows". */
+/* k row bit-masks, each pfa_aln_mask_words(a) uint32 long (bit r%32 of word r/32 = row r; the words of a site record,
+ * 4*Wq).  Substring matching stays in Python; an empty population never reaches the library. k = 0 restores "all rows". */
+int64_t pfa_aln_mask_words(const pfa_aln* a);
 int pfa_aln_set_pops(pfa_aln* a, const uint32_t* masks, int k);
 int pfa_aln_num_pops(const pfa_aln* a);
 int64_t pfa_aln_pop_size(const pfa_aln* a, int pop);

@@ -14,12 +14,12 @@ PFA_CDS_LEN = 71
 # every symbol include/polyfasta_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "pfa_version", "pfa_device_count", "pfa_global_error",
-    "pfa_ctx_create", "pfa_ctx_destroy", "pfa_last_error", "pfa_ctx_sync", "pfa_ctx_set_stream", "pfa_ctx_launch_count",
+    "pfa_ctx_create", "pfa_ctx_destroy", "pfa_last_error", "pfa_ctx_sync", "pfa_ctx_trim", "pfa_ctx_set_stream", "pfa_ctx_launch_count",
     "pfa_fasta_parse_file", "pfa_fasta_parse_buffer", "pfa_fasta_free", "pfa_fasta_nseq", "pfa_fasta_seqlen",
     "pfa_fasta_row_len", "pfa_fasta_header", "pfa_fasta_copy_row",
     "pfa_aln_from_fasta", "pfa_aln_from_rows", "pfa_aln_from_device_rows", "pfa_aln_synthetic", "pfa_synth_text_device", "pfa_aln_force_validity", "pfa_aln_free",
     "pfa_aln_nseq", "pfa_aln_nsites", "pfa_aln_num_escapes", "pfa_aln_packed_bytes", "pfa_aln_has_invalid",
-    "pfa_aln_copy_plane", "pfa_aln_set_pops", "pfa_aln_num_pops", "pfa_aln_pop_size",
+    "pfa_aln_copy_plane", "pfa_aln_mask_words", "pfa_aln_set_pops", "pfa_aln_num_pops", "pfa_aln_pop_size",
     "pfa_site_len", "pfa_site_offset", "pfa_site_stats_device", "pfa_site_stats",
     "pfa_cds_stats_device", "pfa_cds_stats", "pfa_codon_pair_labels", "pfa_codon_set_labels", "pfa_codon_syn3",
     "pfa_codon_class", "pfa_pairwise_device", "pfa_pairwise", "pfa_finalize", "pfa_cds_ssites",
@@ -64,6 +64,7 @@ def lib():
         "pfa_ctx_destroy": (c.c_int, [p]),
         "pfa_last_error": (c.c_char_p, [p]),
         "pfa_ctx_sync": (c.c_int, [p]),
+        "pfa_ctx_trim": (c.c_int, [p]),
         "pfa_ctx_set_stream": (c.c_int, [p, p]),
         "pfa_ctx_launch_count": (i64, [p]),
         "pfa_fasta_parse_file": (c.c_int, [c.c_char_p, c.POINTER(p)]),
@@ -87,6 +88,7 @@ def lib():
         "pfa_aln_packed_bytes": (i64, [p]),
         "pfa_aln_has_invalid": (c.c_int, [p]),
         "pfa_aln_copy_plane": (c.c_int, [p, c.c_int, p, sz]),
+        "pfa_aln_mask_words": (i64, [p]),
         "pfa_aln_set_pops": (c.c_int, [p, p, c.c_int]),
         "pfa_aln_num_pops": (c.c_int, [p]),
         "pfa_aln_pop_size": (i64, [p, c.c_int]),

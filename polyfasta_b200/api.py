@@ -39,6 +39,10 @@ class Context:
     def sync(self):
         check(lib().pfa_ctx_sync(self.handle), self.handle)
 
+    def trim(self):
+        """return the library's cached device memory to the driver"""
+        check(lib().pfa_ctx_trim(self.handle), self.handle)
+
     def set_stream(self, cuda_stream):
         """run the library's kernels on a caller-owned stream (int / torch.cuda.Stream.cuda_stream); None restores"""
         check(lib().pfa_ctx_set_stream(self.handle, ctypes.c_void_p(cuda_stream or 0)), self.handle)
@@ -170,9 +174,8 @@ class Fasta:
             pass
 
 
-def rows_to_masks(n, row_lists):
-    """list of row-index lists -> uint32 [k][4*ceil(n/128)] bit masks for pfa_aln_set_pops"""
-    wn = 4 * ((n + 127) // 128)
+def rows_to_masks(wn, row_lists):
+    """list of row-index lists -> uint32 [k][wn] bit masks for pfa_aln_set_pops (wn = pfa_aln_mask_words)"""
     m = np.zeros((len(row_lists), max(wn, 1)), dtype=np.uint32)
     for q, rows in enumerate(row_lists):
         r = np.asarray(list(rows), dtype=np.int64)
@@ -290,8 +293,7 @@ class Alignment:
 
     def plane(self, which):
         """uint32 [nsites][4*Wq] copy of plane 0 (b0), 1 (b1) or 2 (v)"""
-        wn = 4 * ((self.n + 127) // 128)
-        out = np.zeros((self.nsites, wn), dtype=np.uint32)
+        out = np.zeros((self.nsites, self.mask_words), dtype=np.uint32)
         check(lib().pfa_aln_copy_plane(self.handle, which, out.ctypes.data, out.nbytes), self.ctx.handle)
         return out
 
@@ -301,8 +303,12 @@ class Alignment:
         if not row_lists:
             check(lib().pfa_aln_set_pops(self.handle, None, 0), self.ctx.handle)
             return
-        m = rows_to_masks(self.n, row_lists)
+        m = rows_to_masks(self.mask_words, row_lists)
         check(lib().pfa_aln_set_pops(self.handle, m.ctypes.data, len(row_lists)), self.ctx.handle)
+
+    @property
+    def mask_words(self):
+        return int(lib().pfa_aln_mask_words(self.handle))
 
     @property
     def num_pops(self):

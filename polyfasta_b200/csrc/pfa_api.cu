@@ -39,11 +39,11 @@ static int run_to_host(pfa_aln* a, size_t out_bytes, void* out, size_t aux_bytes
     pfa_ctx* ctx = a->ctx;
     PFA_CUDA(ctx, cudaSetDevice(ctx->device));
     void *d_out = nullptr, *d_aux = nullptr;
-    PFA_CUDA(ctx, cudaMalloc(&d_out, std::max<size_t>(out_bytes, 8)));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &d_out, std::max<size_t>(out_bytes, 8)));
     if (aux) {
-        cudaError_t e = cudaMalloc(&d_aux, std::max<size_t>(aux_bytes, 8));
+        cudaError_t e = pfa_dmalloc(ctx, &d_aux, std::max<size_t>(aux_bytes, 8));
         if (e != cudaSuccess) {
-            cudaFree(d_out);
+            pfa_dfree(ctx, d_out);
             return pfa_fail(ctx, PFA_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
         }
     }
@@ -54,8 +54,8 @@ static int run_to_host(pfa_aln* a, size_t out_bytes, void* out, size_t aux_bytes
         if (e == cudaSuccess && aux && aux_bytes) e = cudaMemcpyAsync(aux, d_aux, aux_bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(d_out);
-    cudaFree(d_aux);
+    pfa_dfree(ctx, d_out);
+    pfa_dfree(ctx, d_aux);
     if (rc) return rc;
     if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(e));
     return PFA_OK;
@@ -99,6 +99,18 @@ int pfa_ctx_create(int device, pfa_ctx** out) {
         return PFA_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_encoded[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming);
+    cudaGetLastError();
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     int rc = pfa_upload_codon_tables(ctx);
@@ -118,8 +130,24 @@ int pfa_ctx_destroy(pfa_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_encoded[i]) cudaEventDestroy(ctx->ev_encoded[i]);
+    }
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return PFA_OK;
+}
+
+int pfa_ctx_trim(pfa_ctx* ctx) {
+    if (!ctx) return PFA_ERR_ARG;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    PFA_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    PFA_CUDA(ctx, cudaMemPoolTrimTo(pool, 0));
     return PFA_OK;
 }
 
@@ -133,6 +161,7 @@ int pfa_ctx_sync(pfa_ctx* ctx) {
 
 int pfa_ctx_set_stream(pfa_ctx* ctx, void* cuda_stream) {
     if (!ctx) return PFA_ERR_ARG;
+    PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // stream-ordered allocations must not straddle two streams
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return PFA_OK;
 }
@@ -143,15 +172,15 @@ int64_t pfa_ctx_launch_count(const pfa_ctx* ctx) { return ctx ? ctx->launches : 
 
 int pfa_aln_free(pfa_aln* a) {
     if (!a) return PFA_OK;
-    cudaSetDevice(a->ctx->device);
-    cudaStreamSynchronize(a->ctx->stream);
-    cudaFree(a->planes);
-    cudaFree(a->exc_keys);
-    cudaFree(a->exc_heads);
-    cudaFree(a->d_masks);
-    cudaFree(a->d_union);
-    cudaFree(a->d_pop_n);
-    cudaFree(a->rowmajor);
+    pfa_ctx* ctx = a->ctx;
+    cudaSetDevice(ctx->device);
+    pfa_dfree(ctx, a->planes);
+    pfa_dfree(ctx, a->exc_keys);
+    pfa_dfree(ctx, a->exc_heads);
+    pfa_dfree(ctx, a->d_masks);
+    pfa_dfree(ctx, a->d_union);
+    pfa_dfree(ctx, a->d_pop_n);
+    pfa_dfree(ctx, a->rowmajor);
     delete a;
     return PFA_OK;
 }
@@ -174,20 +203,16 @@ static int aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n,
     unsigned long long* d_count = nullptr;
     int* d_inv = nullptr;
     uint8_t* stage[2] = {nullptr, nullptr};
-    cudaStream_t cs = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_encoded[2] = {nullptr, nullptr};
+    cudaStream_t cs = ctx->copy_stream;
+    cudaEvent_t* ev_copied = ctx->ev_copied;
+    cudaEvent_t* ev_encoded = ctx->ev_encoded;
     bool registered = false;
     int64_t cap = 0;
     auto cleanup = [&]() {
-        cudaFree(d_count);
-        cudaFree(d_inv);
-        cudaFree(stage[0]);
-        cudaFree(stage[1]);
-        for (int i = 0; i < 2; ++i) {
-            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
-            if (ev_encoded[i]) cudaEventDestroy(ev_encoded[i]);
-        }
-        if (cs) cudaStreamDestroy(cs);
+        pfa_dfree(ctx, d_count);
+        pfa_dfree(ctx, d_inv);
+        pfa_dfree(ctx, stage[0]);
+        pfa_dfree(ctx, stage[1]);
         if (registered) cudaHostUnregister(const_cast<uint8_t*>(text));
     };
 #define UP(call)                                                                                          \
@@ -200,21 +225,19 @@ static int aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n,
         }                                                                                                 \
     } while (0)
     if (ns > 0 && n > 0) {
-        UP(cudaMalloc(&d_count, sizeof(unsigned long long)));
-        UP(cudaMalloc(&d_inv, sizeof(int)));
+        UP(pfa_dmalloc(ctx, &d_count, sizeof(unsigned long long)));
+        UP(pfa_dmalloc(ctx, &d_inv, sizeof(int)));
         // columns per chunk: ~256 MB of text, a multiple of 256 columns
         int64_t chunk = ((256ll << 20) / n) & ~255ll;
         if (chunk < 256) chunk = 256;
         if (chunk > ns) chunk = ns;
         const int64_t ldt = pfa_round_up(chunk, 256);
         if (!dev) {
-            UP(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
             const int nbuf = chunk < ns ? 2 : 1;
-            for (int i = 0; i < nbuf; ++i) {
-                UP(cudaMalloc(&stage[i], (size_t)(n * ldt)));
-                UP(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
-                UP(cudaEventCreateWithFlags(&ev_encoded[i], cudaEventDisableTiming));
-            }
+            for (int i = 0; i < nbuf; ++i) UP(pfa_dmalloc(ctx, &stage[i], (size_t)(n * ldt)));
+            // the copy stream may touch the staging buffers only after their (stream-ordered) allocation
+            UP(cudaEventRecord(ctx->ev_ready, ctx->stream));
+            UP(cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
             // pin large pageable inputs in place so that the 2-D copies run asynchronously at full PCIe rate
             cudaPointerAttributes attr;
             const bool is_pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -228,9 +251,9 @@ static int aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n,
         }
         cap = std::max<int64_t>(1 << 16, n * ns / 256);
         for (int attempt = 0; attempt < 2; ++attempt) {
-            cudaFree(a->exc_keys);
+            pfa_dfree(ctx, a->exc_keys);
             a->exc_keys = nullptr;
-            UP(cudaMalloc(&a->exc_keys, sizeof(unsigned long long) * (size_t)cap));
+            UP(pfa_dmalloc(ctx, &a->exc_keys, sizeof(unsigned long long) * (size_t)cap));
             UP(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
             UP(cudaMemsetAsync(d_inv, 0, sizeof(int), ctx->stream));
             int64_t ci = 0;
@@ -377,14 +400,14 @@ int pfa_aln_set_pops(pfa_aln* a, const uint32_t* masks, int k) {
         sfs_total += cnt / 2;
     }
     meta[(size_t)(3 * k)] = sfs_total;
-    cudaFree(a->d_masks);
-    cudaFree(a->d_union);
-    cudaFree(a->d_pop_n);
+    pfa_dfree(ctx, a->d_masks);
+    pfa_dfree(ctx, a->d_union);
+    pfa_dfree(ctx, a->d_pop_n);
     a->d_masks = a->d_union = nullptr;
     a->d_pop_n = nullptr;
-    PFA_CUDA(ctx, cudaMalloc(&a->d_masks, sizeof(uint32_t) * (size_t)std::max<int64_t>(k * Wn, 4)));
-    PFA_CUDA(ctx, cudaMalloc(&a->d_union, sizeof(uint32_t) * (size_t)std::max<int64_t>(Wn, 4)));
-    PFA_CUDA(ctx, cudaMalloc(&a->d_pop_n, sizeof(int64_t) * meta.size()));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &a->d_masks, sizeof(uint32_t) * (size_t)std::max<int64_t>(k * Wn, 4)));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &a->d_union, sizeof(uint32_t) * (size_t)std::max<int64_t>(Wn, 4)));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &a->d_pop_n, sizeof(int64_t) * meta.size()));
     if (Wn) {
         PFA_CUDA(ctx, cudaMemcpyAsync(a->d_masks, m.data(), sizeof(uint32_t) * m.size(), cudaMemcpyHostToDevice, ctx->stream));
         PFA_CUDA(ctx, cudaMemcpyAsync(a->d_union, uni.data(), sizeof(uint32_t) * uni.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -397,6 +420,7 @@ int pfa_aln_set_pops(pfa_aln* a, const uint32_t* masks, int k) {
 }
 
 int pfa_aln_num_pops(const pfa_aln* a) { return a ? a->k : 0; }
+int64_t pfa_aln_mask_words(const pfa_aln* a) { return a ? (int64_t)a->Wq * 4 : 0; }
 int64_t pfa_aln_pop_size(const pfa_aln* a, int pop) { return (a && pop >= 0 && pop < a->k) ? a->pop_n[(size_t)pop] : -1; }
 int64_t pfa_site_len(const pfa_aln* a) { return a ? a->site_off[(size_t)a->k] : 0; }
 int64_t pfa_site_offset(const pfa_aln* a, int pop) { return (a && pop >= 0 && pop <= a->k) ? a->site_off[(size_t)pop] : -1; }
@@ -452,8 +476,10 @@ static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int6
     a->col_begin = col_begin;
     a->ns = col_end - col_begin;
     a->Wq = (int)((n + 127) / 128);
+    // long site records are padded to whole 32-byte sectors so that no sector is shared by two sites
+    if (a->Wq >= 16 && (a->Wq & 1)) a->Wq++;
     a->plane_bytes = (size_t)pfa_round_up(std::max<int64_t>(a->ns * (int64_t)a->Wq * 16, 16), 256);
-    cudaError_t e = cudaMalloc(&a->planes, 3 * a->plane_bytes);
+    cudaError_t e = pfa_dmalloc(ctx, &a->planes, 3 * a->plane_bytes);
     if (e != cudaSuccess) {
         const size_t want = 3 * a->plane_bytes;
         delete a;

@@ -22,6 +22,9 @@ struct pfa_ctx {
     void* h_scratch = nullptr;
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    // upload pipeline: copy stream + events, created once per context
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_encoded[2] = {nullptr, nullptr}, ev_ready = nullptr;
 };
 
 struct pfa_aln {
@@ -83,5 +86,15 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar);
 int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels);
 int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_upload_codon_tables(pfa_ctx* ctx);
+
+// Device memory comes from the device's stream-ordered pool (release threshold = keep): allocating and freeing the planes
+// of one alignment after another (--dir mode, benchmark loops) reuses the same blocks without synchronising the device.
+template <typename T>
+static inline cudaError_t pfa_dmalloc(pfa_ctx* ctx, T** p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, ctx->stream);
+}
+static inline void pfa_dfree(pfa_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 
 static inline int64_t pfa_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

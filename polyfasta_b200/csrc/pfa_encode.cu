@@ -115,37 +115,37 @@ int pfa_finish_exceptions(pfa_aln* a, int64_t count) {
     a->n_exc_sites = 0;
     if (count == 0) return PFA_OK;
     unsigned long long* sorted = nullptr;
-    PFA_CUDA(ctx, cudaMalloc(&sorted, sizeof(unsigned long long) * (size_t)count));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &sorted, sizeof(unsigned long long) * (size_t)count));
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, a->exc_keys, sorted, (int)count, 0, 64, ctx->stream);
     void* tmp = nullptr;
-    PFA_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &tmp, tmp_bytes));
     PFA_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, a->exc_keys, sorted, (int)count, 0, 64, ctx->stream));
     ctx->launches += 4;
     PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
-    cudaFree(a->exc_keys);
+    pfa_dfree(ctx, tmp);
+    pfa_dfree(ctx, a->exc_keys);
     a->exc_keys = sorted;
 
     uint8_t* flags = nullptr;
     int64_t* d_num = nullptr;
-    PFA_CUDA(ctx, cudaMalloc(&flags, (size_t)count));
-    PFA_CUDA(ctx, cudaMalloc(&a->exc_heads, sizeof(int64_t) * (size_t)count));
-    PFA_CUDA(ctx, cudaMalloc(&d_num, sizeof(int64_t)));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &flags, (size_t)count));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &a->exc_heads, sizeof(int64_t) * (size_t)count));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &d_num, sizeof(int64_t)));
     pfa_head_flags_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(sorted, count, flags);
     PFA_LAUNCH_CHECK(ctx);
     cub::CountingInputIterator<int64_t> idx(0);
     tmp_bytes = 0;
     cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, flags, a->exc_heads, d_num, (int)count, ctx->stream);
-    PFA_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &tmp, tmp_bytes));
     PFA_CUDA(ctx, cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, flags, a->exc_heads, d_num, (int)count, ctx->stream));
     ctx->launches += 2;
     int64_t num = 0;
     PFA_CUDA(ctx, cudaMemcpyAsync(&num, d_num, sizeof(num), cudaMemcpyDeviceToHost, ctx->stream));
     PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
-    cudaFree(flags);
-    cudaFree(d_num);
+    pfa_dfree(ctx, tmp);
+    pfa_dfree(ctx, flags);
+    pfa_dfree(ctx, d_num);
     a->n_exc_sites = num;
     return PFA_OK;
 }

@@ -151,7 +151,7 @@ int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     int32_t* D = d_matrix;
     bool own = false;
     if (!D) {
-        PFA_CUDA(ctx, cudaMalloc(&D, sizeof(int32_t) * (size_t)(n * n)));
+        PFA_CUDA(ctx, pfa_dmalloc(ctx, &D, sizeof(int32_t) * (size_t)(n * n)));
         own = true;
     }
     const int Wn = a->Wq * 4;
@@ -161,7 +161,7 @@ int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     if (e == cudaSuccess && a->ns > 0) {
         if (!a->rowmajor) {
             a->Wl = pfa_round_up((a->ns + 31) / 32, 4);
-            e = cudaMalloc(&a->rowmajor, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl));
+            e = pfa_dmalloc(ctx, &a->rowmajor, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl));
             if (e == cudaSuccess) e = cudaMemsetAsync(a->rowmajor, 0, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl), ctx->stream);
             if (e == cudaSuccess) {
                 const int64_t sw = (a->ns + 31) / 32;
@@ -193,7 +193,7 @@ int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     if (e != cudaSuccess) rc = pfa_fail(ctx, PFA_ERR_CUDA, "pairwise failed: %s", cudaGetErrorString(e));
     if (own) {
         cudaStreamSynchronize(ctx->stream);
-        cudaFree(D);
+        pfa_dfree(ctx, D);
     }
     return rc;
 }

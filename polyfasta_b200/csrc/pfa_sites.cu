@@ -11,6 +11,8 @@
 // symbol classes per population with popcounts and group shuffles.  Sites holding "escape" symbols (IUPAC
 // codes etc., which are distinct alleles in the reference) are finished by pfa_escape_sites_kernel from the
 // sorted exception list.
+#include <cstdlib>
+
 #include "pfa_sites.cuh"
 
 template <int LPS, bool HAS_V>
@@ -71,6 +73,140 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
             const int64_t nq = a.pop_n[q];
             PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
             if (r.has_escape) continue;  // finished by pfa_escape_sites_kernel
+            if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
+            if (r.isvar) {
+                atomicAdd(&sm_SH[2 * q], 1ull);
+                atomicAdd(&sm_SH[2 * q + 1], r.h);
+                if (r.sfs_bin >= 0) {
+                    if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
+                    else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
+        if (sm_SH[2 * q]) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q]), sm_SH[2 * q]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 1), sm_SH[2 * q + 1]);
+        }
+    }
+    if (a.sfs_in_smem) {
+        for (int q = 0; q < a.k; ++q) {
+            const int nb = (int)(a.pop_n[q] / 2);
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+                const unsigned int cnt = sm_sfs[a.sfs_off[q] + i];
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + i), (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// Register-resident variant for Wq <= 5*32 chunks: every lane owns ITER fixed chunks of the site record, loads them
+// once (all loads of a site are issued back to back: 2-3 * ITER independent 128-bit requests per lane), keeps its slice
+// of the union mask in registers for the whole kernel, and both passes work on registers -- each byte of the planes
+// crosses L2 exactly once.
+template <int LPS, int ITER, bool HAS_V>
+__global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(const PfaSiteArgs a) {
+    extern __shared__ unsigned long long smem[];
+    unsigned long long* sm_SH = smem;
+    unsigned int* sm_sfs = reinterpret_cast<unsigned int*>(smem + 2 * a.k);
+    for (int i = threadIdx.x; i < 2 * a.k; i += blockDim.x) sm_SH[i] = 0ull;
+    if (a.sfs_in_smem)
+        for (int i = threadIdx.x; i < a.sfs_bins; i += blockDim.x) sm_sfs[i] = 0u;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPS - 1);
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPS;
+    const int Wq = a.Wq;
+    const bool one_pop = a.k == 1;
+
+    uint4 um[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int j = sub + LPS * i;
+        um[i] = j < Wq ? __ldg(a.umask + j) : make_uint4(0, 0, 0, 0);
+    }
+
+    for (int64_t s = gid; s < a.ns; s += ngroups) {
+        const uint4* p0 = a.b0 + s * Wq;
+        const uint4* p1 = a.b1 + s * Wq;
+        const uint4* pv = a.v + s * Wq;
+        uint4 x0[ITER], x1[ITER], xv[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int j = sub + LPS * i;
+            x0[i] = x1[i] = make_uint4(0, 0, 0, 0);
+            xv[i] = um[i];
+            if (j < Wq) {
+                x0[i] = pfa_ld_stream(p0 + j);
+                x1[i] = pfa_ld_stream(p1 + j);
+                if (HAS_V) xv[i] = pfa_ld_stream(pv + j);
+            }
+        }
+        // ---- pass 1 on registers ----
+        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const uint4 m = um[i];
+            o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
+            z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
+            o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
+            z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
+            ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
+            if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
+        }
+        unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+        f = pfa_group_or<LPS>(f, gmask);
+        const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
+        const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
+        if (mono && !all_escape) {
+            if (a.isvar && sub == 0)
+                for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
+            continue;
+        }
+        // ---- pass 2 on registers ----
+        for (int q = 0; q < a.k; ++q) {
+            uint32_t c[PFA_NCLASS];
+#pragma unroll
+            for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+            const uint4* mq = a.masks + (int64_t)q * Wq;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                uint4 m4 = um[i];
+                if (!one_pop) m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+                const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
+                               w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w}, wv[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t vm = HAS_V ? (wv[w] & m[w]) : m[w];
+                    const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
+                    c[PFA_C_T] += __popc(hi & w0[w]);
+                    c[PFA_C_G] += __popc(hi & ~w0[w]);
+                    c[PFA_C_C] += __popc(lo & w0[w]);
+                    c[PFA_C_A] += __popc(lo & ~w0[w]);
+                    if (HAS_V) {
+                        const uint32_t im = ~wv[w] & m[w];
+                        const uint32_t ihi = im & w1[w];
+                        c[PFA_C_ESC] += __popc(ihi & w0[w]);
+                        c[PFA_C_Q] += __popc(ihi & ~w0[w]);
+                        c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
+                    }
+                }
+            }
+            if (LPS > 1) {
+#pragma unroll
+                for (int i = 0; i < PFA_NCLASS; ++i)
+                    if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
+            }
+            if (sub != 0) continue;
+            const int64_t nq = a.pop_n[q];
+            PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
+            if (r.has_escape) continue;
             if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
             if (r.isvar) {
                 atomicAdd(&sm_SH[2 * q], 1ull);
@@ -166,23 +302,43 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar) {
     if (a->ns == 0 || a->n == 0) return PFA_OK;
     PfaSiteArgs args;
     pfa_fill_site_args(a, d_out, d_isvar, &args);
-    // lanes per site: the smallest power of two that leaves every lane at most ~5 chunks
+    // lanes per site: the smallest power of two that leaves every lane at most 5 chunks
     int lps = 1;
     while (lps < 32 && (a->Wq + lps - 1) / lps > 5) lps *= 2;
+    const int iter = (a->Wq + lps - 1) / lps;
     const size_t smem = sizeof(unsigned long long) * 2 * (size_t)a->k + (args.sfs_in_smem ? sizeof(unsigned int) * (size_t)args.sfs_bins : 0);
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;
     int64_t blocks = (a->ns + groups_per_block - 1) / groups_per_block;
-    const int64_t max_blocks = (int64_t)ctx->sm_count * (2048 / PFA_SITE_THREADS);
+    const bool hv = a->has_invalid != 0;
+    const bool generic = iter > 5 || getenv("PFA_GENERIC_SCAN") != nullptr;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * (generic ? 4 : 2);
     if (blocks > max_blocks) blocks = max_blocks;
     dim3 grid((unsigned)blocks);
-    switch (lps) {
-        case 1: launch_scan<1>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 2: launch_scan<2>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 4: launch_scan<4>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 8: launch_scan<8>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 16: launch_scan<16>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        default: launch_scan<32>(args, a->has_invalid, grid, smem, ctx->stream); break;
+    cudaStream_t st = ctx->stream;
+#define PFA_REG_CASE(L_, I_)                                                                                          \
+    if (lps == L_ && iter == I_) {                                                                                    \
+        if (hv) pfa_site_scan_reg_kernel<L_, I_, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                    \
+        else pfa_site_scan_reg_kernel<L_, I_, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                      \
+    } else
+    if (generic) {
+        switch (lps) {
+            case 1: launch_scan<1>(args, hv, grid, smem, st); break;
+            case 2: launch_scan<2>(args, hv, grid, smem, st); break;
+            case 4: launch_scan<4>(args, hv, grid, smem, st); break;
+            case 8: launch_scan<8>(args, hv, grid, smem, st); break;
+            case 16: launch_scan<16>(args, hv, grid, smem, st); break;
+            default: launch_scan<32>(args, hv, grid, smem, st); break;
+        }
+    } else {
+        PFA_REG_CASE(1, 1) PFA_REG_CASE(1, 2) PFA_REG_CASE(1, 3) PFA_REG_CASE(1, 4) PFA_REG_CASE(1, 5)
+        PFA_REG_CASE(2, 3) PFA_REG_CASE(2, 4) PFA_REG_CASE(2, 5)
+        PFA_REG_CASE(4, 3) PFA_REG_CASE(4, 4) PFA_REG_CASE(4, 5)
+        PFA_REG_CASE(8, 3) PFA_REG_CASE(8, 4) PFA_REG_CASE(8, 5)
+        PFA_REG_CASE(16, 3) PFA_REG_CASE(16, 4) PFA_REG_CASE(16, 5)
+        PFA_REG_CASE(32, 3) PFA_REG_CASE(32, 4) PFA_REG_CASE(32, 5)
+        return pfa_fail(ctx, PFA_ERR_ARG, "site scan: no kernel for lps=%d iter=%d", lps, iter);
     }
+#undef PFA_REG_CASE
     PFA_LAUNCH_CHECK(ctx);
     if (a->n_exc_sites > 0) {
         int64_t eb = (a->n_exc_sites + 7) / 8;

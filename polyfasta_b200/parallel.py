@@ -1,0 +1,43 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink), work split by columns or by loci.
+
+Two ways the path shards:
+  * within one alignment: contiguous, codon-aligned column ranges per rank; every rank scans its range and the int64
+    vectors ([S, H, SFS...] per population, or the PFA_CDS_LEN codon accumulators) are summed with ONE all-reduce --
+    integer sums, so the result is bit-identical for any number of ranks;
+  * across loci (--dir): locus i (in the reference's sorted() order, PolyFastA.py:104) goes to rank i mod world, no
+    collective; rank 0 gathers the finished rows and prints them in sorted order.
+"""
+
+
+def shard_columns(total, world, rank, multiple=3):
+    """[begin, end) of rank's column range: boundaries are multiples of `multiple` (codon-aligned so that --cds shards
+    never split a codon); the last rank takes the remainder, including a trailing partial codon."""
+    per = (total // world) // multiple * multiple
+    begin = rank * per
+    end = total if rank == world - 1 else (rank + 1) * per
+    return begin, end
+
+
+def round_robin(items, world, rank):
+    """the loci of this rank: sorted() order, item i -> rank i mod world"""
+    return [(i, x) for i, x in enumerate(sorted(items)) if i % world == rank]
+
+
+def allreduce_sum(tensor):
+    """in-place sum over ranks of an int64 count vector (NCCL on GPU tensors, gloo on CPU tensors); no-op when not distributed"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+def gather_rows(rows):
+    """--dir mode: every rank contributes [(locus_index, text), ...]; rank 0 gets them back merged in index order"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return sorted(rows)
+    out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(rows, out, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    return sorted(r for part in out for r in part)
