@@ -64,43 +64,64 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    """SM clock and throttle reasons sampled through NVML every few ms DURING the timed region (B200_PROFILING.md)"""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.sm_max, self.power = [], 0, None, []
         self.stop_flag = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(self.period)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        names = []
+        if self.h is not None:
+            nv = self.nv
+            for nm, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                            ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+                if self.reasons & bit:
+                    names.append(nm)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max, "reasons": names,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
+
+
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def cpu_oracle_rate(n, sample_sites, seconds, min_passes=2):
     """the oracle port (C + OpenMP, all host threads) on columns [0, sample_sites) of the workload -> bases/s"""
     from oracle import c_oracle as co
     co.build()
-    threads = co.num_threads()
-    mat = co.synth_text(SEED, n, N_SITES, P_SEG_PPM, TRI_PPM, 0, sample_sites)
+    threads = host_threads()
+    mat = co.synth_text(SEED, n, N_SITES, P_SEG_PPM, TRI_PPM, 0, sample_sites, threads=threads)
     co.site_stats(mat, threads=threads)  # warm-up
     t0 = time.perf_counter()
     passes = 0
@@ -117,9 +138,9 @@ def run_reference(args, rank):
         return
     from oracle import c_oracle as co
     co.build()
-    threads = co.num_threads()
+    threads = host_threads()
     n, sample = args.n, args.cpu_sample_sites
-    mat = co.synth_text(SEED, n, args.sites, P_SEG_PPM, TRI_PPM, 0, sample)
+    mat = co.synth_text(SEED, n, args.sites, P_SEG_PPM, TRI_PPM, 0, sample, threads=threads)
     for _ in range(args.warmup):
         co.site_stats(mat, threads=threads)
     t0 = time.perf_counter()
@@ -139,11 +160,20 @@ def run_reference(args, rank):
         "gpu_launches": 0,
         "note": "the reference is pure Python (not on this box); its own functions ran at ~1e7 bases/s on one core in the build container (BASELINE.md)",
     }
-    print(json.dumps(line))
+    print_json(line)
 
 
 def main():
     args = parse_args()
+    # rank 0 prints exactly ONE line on stdout; anything a library writes to fd 1 (NCCL's version banner) goes to stderr
+    global print_json
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def print_json(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -307,7 +337,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "parity": parity,
             "result": {"S": int(result[0]), "H": int(result[1]), "pi_site_jc": fin[1], "theta_site": fin[2], "tajimasD": fin[3]},
         }
-        print(json.dumps(line))
+        print_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
