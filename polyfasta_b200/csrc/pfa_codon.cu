@@ -13,6 +13,8 @@
 // only, that all three sites are monomorphic over the union of the populations -- then every population sees
 // the same single codon and the contribution is uniform.  Otherwise pass 2 builds the presence mask per
 // population by peeling distinct codons off each 32-row word, and counts the three columns with popcounts.
+#include <cstdlib>
+
 #include "pfa_codon_rules.h"
 #include "pfa_sites.cuh"
 
@@ -258,6 +260,189 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const Pf
     }
 }
 
+// Register-resident variant (Wq <= 3*32 chunks): the three site records of a codon column are loaded once -- all
+// loads back to back -- and pass 1, the class counts and the codon peeling of pass 2 all work on registers.
+__device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 0 ? x.x : w == 1 ? x.y : w == 2 ? x.z : x.w; }
+
+template <int LPS, int ITER, bool HAS_V>
+__global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds_scan_reg_kernel(const PfaCdsArgs a) {
+    extern __shared__ unsigned long long smem[];
+    const int nacc = 3 + (a.acc_in_smem ? a.s.k * PFA_CDS_LEN : 0);
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) smem[i] = 0ull;
+    __syncthreads();
+    unsigned long long* sm_acc = smem + 3;
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPS - 1);
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPS;
+    const int Wq = a.s.Wq;
+    const bool one_pop = a.s.k == 1;
+    unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;
+
+    uint4 um[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int j = sub + LPS * i;
+        um[i] = j < Wq ? __ldg(a.s.umask + j) : make_uint4(0, 0, 0, 0);
+    }
+
+    for (int64_t cc = gid; cc < a.ncf; cc += ngroups) {
+        const int64_t site0 = cc * 3;
+        uint4 x0[3][ITER], x1[3][ITER], xv[3][ITER];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                x0[t][i] = x1[t][i] = make_uint4(0, 0, 0, 0);
+                xv[t][i] = um[i];
+                if (j < Wq) {
+                    x0[t][i] = pfa_ld_stream(a.s.b0 + (site0 + t) * Wq + j);
+                    x1[t][i] = pfa_ld_stream(a.s.b1 + (site0 + t) * Wq + j);
+                    if (HAS_V) xv[t][i] = pfa_ld_stream(a.s.v + (site0 + t) * Wq + j);
+                }
+            }
+        // ---- pass 1 ----
+        unsigned f = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const uint4 m = um[i];
+                o0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
+                z0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
+                o1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
+                z1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
+                ov |= (xv[t][i].x & m.x) | (xv[t][i].y & m.y) | (xv[t][i].z & m.z) | (xv[t][i].w & m.w);
+                if (HAS_V) zv |= (~xv[t][i].x & m.x) | (~xv[t][i].y & m.y) | (~xv[t][i].z & m.z) | (~xv[t][i].w & m.w);
+            }
+            f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
+        }
+        f = pfa_group_or<LPS>(f, gmask);
+        bool uniform = true, clean = true;
+        int codon = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const unsigned ft = (f >> (6 * t)) & 63u;
+            const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
+            const bool all_escape = (ft & 1u) && (ft & 4u) && !(ft & 16u);
+            uniform = uniform && mono && !all_escape;
+            clean = clean && (ft & 16u) && !(ft & 32u);
+            codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+        }
+        if (uniform) {
+            if (sub == 0) {
+                if (clean) {
+                    u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
+                    u_sum3 += c_syn3[codon];
+                } else {
+                    u_missing += 3;
+                }
+            }
+            continue;
+        }
+        // ---- pass 2 ----
+        for (int q = 0; q < a.s.k; ++q) {
+            const uint4* mq = a.s.masks + (int64_t)q * Wq;
+            uint4 m4[ITER];
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                m4[i] = um[i];
+                if (!one_pop) m4[i] = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+            }
+            uint32_t cnt[3][PFA_NCLASS];
+            unsigned long long P = 0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int c = 0; c < PFA_NCLASS; ++c) cnt[t][c] = 0;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t m = pfa_u4(m4[i], w);
+                    uint32_t live = m;
+                    uint32_t x[6];
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const uint32_t w0 = pfa_u4(x0[t][i], w), w1 = pfa_u4(x1[t][i], w), wv = pfa_u4(xv[t][i], w);
+                        const uint32_t vm = HAS_V ? (wv & m) : m;
+                        const uint32_t hi = vm & w1, lo = vm & ~w1;
+                        cnt[t][PFA_C_T] += __popc(hi & w0);
+                        cnt[t][PFA_C_G] += __popc(hi & ~w0);
+                        cnt[t][PFA_C_C] += __popc(lo & w0);
+                        cnt[t][PFA_C_A] += __popc(lo & ~w0);
+                        if (HAS_V) {
+                            const uint32_t im = ~wv & m;
+                            const uint32_t ihi = im & w1;
+                            cnt[t][PFA_C_ESC] += __popc(ihi & w0);
+                            cnt[t][PFA_C_Q] += __popc(ihi & ~w0);
+                            cnt[t][PFA_C_N] += __popc(im & ~w1 & w0);
+                            live &= wv;
+                        }
+                        x[2 * t] = w1;
+                        x[2 * t + 1] = w0;
+                    }
+                    while (live) {  // peel one distinct codon per iteration
+                        const int r = __ffs(live) - 1;
+                        uint32_t match = live;
+                        int c = 0;
+#pragma unroll
+                        for (int t = 0; t < 6; ++t) {
+                            const uint32_t bit = (x[t] >> r) & 1u;
+                            c = (c << 1) | (int)bit;
+                            match &= x[t] ^ (bit - 1u);
+                        }
+                        P |= 1ull << c;
+                        live &= ~match;
+                    }
+                }
+            if (LPS > 1) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int c = 0; c < PFA_NCLASS; ++c)
+                        if (HAS_V || c < 4) cnt[t][c] = pfa_group_add<LPS>(cnt[t][c], gmask);
+                uint32_t lo = (uint32_t)P, hi = (uint32_t)(P >> 32);
+                lo = pfa_group_or<LPS>(lo, gmask);
+                hi = pfa_group_or<LPS>(hi, gmask);
+                P = ((unsigned long long)hi << 32) | lo;
+            }
+            if (cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
+            if (sub != 0) continue;
+            const uint32_t escd[3] = {0, 0, 0};
+            const unsigned long long escsq[3] = {0, 0, 0};
+            unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
+                                                    : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
+            pfa_cds_contribute(P, cnt, a.s.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+        }
+    }
+    if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
+    for (int off = 16; off; off >>= 1) {
+        u_nstops += __shfl_xor_sync(0xffffffffu, u_nstops, off);
+        u_missing += __shfl_xor_sync(0xffffffffu, u_missing, off);
+        u_sum3 += __shfl_xor_sync(0xffffffffu, u_sum3, off);
+    }
+    if (lane == 0) {
+        if (u_nstops) atomicAdd(&smem[0], (unsigned long long)u_nstops);
+        if (u_missing) atomicAdd(&smem[1], (unsigned long long)u_missing);
+        if (u_sum3) atomicAdd(&smem[2], (unsigned long long)u_sum3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.s.k * PFA_CDS_LEN; i += blockDim.x) {
+        const int e = i % PFA_CDS_LEN;
+        unsigned long long x = a.acc_in_smem ? sm_acc[i] : 0ull;
+        if (e == PFA_CDS_NSTOPS) x += smem[0];
+        if (e == PFA_CDS_MISSING) x += smem[1];
+        if (e == PFA_CDS_SUM3 + 1) x += smem[2];
+        if (x) atomicAdd(reinterpret_cast<unsigned long long*>(a.out) + i, x);
+    }
+}
+
 // per-site escape statistics of one population: number of distinct escape bytes and the sum of their squared counts
 __device__ __forceinline__ void pfa_escape_stats(const unsigned long long* __restrict__ keys, int64_t i0, int64_t i1,
                                                  const uint32_t* __restrict__ mq, unsigned int* hist, int lane,
@@ -350,20 +535,40 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels) {
     args.acc_in_smem = (int64_t)a->k * PFA_CDS_LEN * 8 <= 40 * 1024;
     const size_t smem = 8 * (3 + (args.acc_in_smem ? (size_t)a->k * PFA_CDS_LEN : 0));
     int lps = 1;
-    while (lps < 32 && (a->Wq + lps - 1) / lps > 4) lps *= 2;
+    while (lps < 32 && (a->Wq + lps - 1) / lps > 2) lps *= 2;
+    int iter = (a->Wq + lps - 1) / lps;
+    const bool hv = a->has_invalid != 0;
+    const bool generic = iter > 3 || getenv("PFA_GENERIC_SCAN") != nullptr;
+    if (generic) {
+        lps = 1;
+        while (lps < 32 && (a->Wq + lps - 1) / lps > 4) lps *= 2;
+    }
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;
     int64_t blocks = (std::max<int64_t>(args.ncf, 1) + groups_per_block - 1) / groups_per_block;
-    const int64_t max_blocks = (int64_t)ctx->sm_count * (2048 / PFA_SITE_THREADS);
+    const int64_t max_blocks = (int64_t)ctx->sm_count * (generic ? 4 : (iter >= 3 ? 1 : 2));
     if (blocks > max_blocks) blocks = max_blocks;
     dim3 grid((unsigned)blocks);
-    switch (lps) {
-        case 1: launch_cds<1>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 2: launch_cds<2>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 4: launch_cds<4>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 8: launch_cds<8>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        case 16: launch_cds<16>(args, a->has_invalid, grid, smem, ctx->stream); break;
-        default: launch_cds<32>(args, a->has_invalid, grid, smem, ctx->stream); break;
+    cudaStream_t st = ctx->stream;
+#define PFA_CDS_CASE(L_, I_)                                                                                          \
+    if (lps == L_ && iter == I_) {                                                                                    \
+        if (hv) pfa_cds_scan_reg_kernel<L_, I_, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                     \
+        else pfa_cds_scan_reg_kernel<L_, I_, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                       \
+    } else
+    if (generic) {
+        switch (lps) {
+            case 1: launch_cds<1>(args, hv, grid, smem, st); break;
+            case 2: launch_cds<2>(args, hv, grid, smem, st); break;
+            case 4: launch_cds<4>(args, hv, grid, smem, st); break;
+            case 8: launch_cds<8>(args, hv, grid, smem, st); break;
+            case 16: launch_cds<16>(args, hv, grid, smem, st); break;
+            default: launch_cds<32>(args, hv, grid, smem, st); break;
+        }
+    } else {
+        PFA_CDS_CASE(1, 1) PFA_CDS_CASE(1, 2) PFA_CDS_CASE(2, 2) PFA_CDS_CASE(4, 2) PFA_CDS_CASE(8, 2) PFA_CDS_CASE(16, 2)
+        PFA_CDS_CASE(32, 2) PFA_CDS_CASE(32, 3)
+        return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: no kernel for lps=%d iter=%d", lps, iter);
     }
+#undef PFA_CDS_CASE
     PFA_LAUNCH_CHECK(ctx);
     if (a->n_exc_sites > 0) {
         int64_t eb = (a->n_exc_sites + 7) / 8;
