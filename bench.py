@@ -253,6 +253,14 @@ def main():
     algo_bytes = n * my_sites * planes_read / 8.0
     peak, peak_kind = measured_peak()
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get("C4 n=%d sites=%d gpus=%d planes=%d" % (n, L, world, planes_read))
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
 
     # ---- parity at full size: the generator's closed form (numpy) ----
     parity = "skipped"
@@ -332,8 +340,8 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB of planes read per GPU per step)" % (algo_bytes / 1e9),
                        "planes_read": planes_read, "seed": SEED, "p_seg_ppm": P_SEG_PPM, "tri_ppm": TRI_PPM},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                         "kernel": "pfa_site_scan_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
+                         "traffic": traffic, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                         "kernel": "pfa_site_scan_reg_kernel<16,5,HAS_V>" if n == N_SEQ else "pfa_site_scan_*", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "parity": parity,
             "result": {"S": int(result[0]), "H": int(result[1]), "pi_site_jc": fin[1], "theta_site": fin[2], "tajimasD": fin[3]},
         }
