@@ -142,6 +142,30 @@ int pfa_codon_class(int codon);  /* id of the 3-char class of PolyFastA.py:324-3
 int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix /* host, optional */);
 
+/* ---- batched path for many small loci: replaces the per-file loop of --dir mode (PolyFastA.py:93-94,104) ------------- */
+/* A batch is filled on the host (rows are copied into one pinned blob), then pfa_batch_run does ONE upload, three segmented
+ * launches (K1b encode, K2b site scan, K5b finalise; + the escape kernel when needed) and ONE synchronisation.  Non-CDS
+ * statistics only; loci with more than 16,384 sequences go through pfa_aln_*. */
+typedef struct pfa_batch pfa_batch;
+int64_t pfa_mask_words_for(int64_t n); /* words of one population mask for an alignment of n rows */
+int pfa_batch_create(pfa_ctx* ctx, pfa_batch** out);
+int pfa_batch_destroy(pfa_batch* b);
+int pfa_batch_clear(pfa_batch* b);
+int64_t pfa_batch_size(const pfa_batch* b);
+int64_t pfa_batch_text_bytes(const pfa_batch* b);
+/* masks: k * pfa_mask_words_for(n) uint32 (k = 0: one population of all rows); *index receives the locus number */
+int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k, int64_t* index);
+int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k,
+                       int64_t* index);
+int pfa_batch_run(pfa_batch* b, int jc);
+int pfa_batch_num_pops(const pfa_batch* b, int64_t locus);
+/* counts = {n, S, H}; sfs (optional) n/2 bins; fin (optional) the K5 output of that (locus, population) */
+int pfa_batch_result(const pfa_batch* b, int64_t locus, int pop, int64_t counts[3], int64_t* sfs, void* fin /* pfa_final_out* */);
+/* ingest helpers for --dir: parse many files with `threads` host threads (status[i] = PFA_OK / PFA_ERR_NOT_FASTA / ...), and
+ * build the row mask of the headers containing `key` (PolyFastA.py:125); returns the number of matching rows */
+int pfa_fasta_parse_files(const char* const* paths, int count, int threads, pfa_fasta** out, int* status);
+int64_t pfa_fasta_match_mask(const pfa_fasta* f, const char* key, int64_t key_len, uint32_t* mask, int64_t mask_words);
+
 /* ---- K5 finalisation in fp64 on the device: replaces polymorphism / nucleotide_diversity /
  *      wattersons_theta / Dvar / jukes_cantor_correction (PolyFastA.py:485-534) --------------------------- */
 typedef struct pfa_final_in {

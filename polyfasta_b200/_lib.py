@@ -23,6 +23,9 @@ EXPORTS = [
     "pfa_site_len", "pfa_site_offset", "pfa_site_stats_device", "pfa_site_stats",
     "pfa_cds_stats_device", "pfa_cds_stats", "pfa_codon_pair_labels", "pfa_codon_set_labels", "pfa_codon_syn3",
     "pfa_codon_class", "pfa_pairwise_device", "pfa_pairwise", "pfa_finalize", "pfa_cds_ssites",
+    "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
+    "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
+    "pfa_fasta_parse_files", "pfa_fasta_match_mask",
 ]
 
 
@@ -106,6 +109,19 @@ def lib():
         "pfa_pairwise": (c.c_int, [p, p, p]),
         "pfa_finalize": (c.c_int, [p, c.POINTER(FinalIn), c.POINTER(FinalOut), c.c_int]),
         "pfa_cds_ssites": (c.c_int, [p, p, p, c.c_int]),
+        "pfa_mask_words_for": (i64, [i64]),
+        "pfa_batch_create": (c.c_int, [p, c.POINTER(p)]),
+        "pfa_batch_destroy": (c.c_int, [p]),
+        "pfa_batch_clear": (c.c_int, [p]),
+        "pfa_batch_size": (i64, [p]),
+        "pfa_batch_text_bytes": (i64, [p]),
+        "pfa_batch_add": (c.c_int, [p, p, p, c.c_int, c.POINTER(i64)]),
+        "pfa_batch_add_rows": (c.c_int, [p, p, i64, i64, i64, p, c.c_int, c.POINTER(i64)]),
+        "pfa_batch_run": (c.c_int, [p, c.c_int]),
+        "pfa_batch_num_pops": (c.c_int, [p, i64]),
+        "pfa_batch_result": (c.c_int, [p, i64, c.c_int, c.POINTER(i64), p, c.POINTER(FinalOut)]),
+        "pfa_fasta_parse_files": (c.c_int, [c.POINTER(c.c_char_p), c.c_int, c.c_int, c.POINTER(p), c.POINTER(c.c_int)]),
+        "pfa_fasta_match_mask": (i64, [p, c.c_char_p, i64, p, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

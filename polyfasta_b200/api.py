@@ -382,3 +382,112 @@ class Alignment:
         mat = np.zeros((self.n, self.n), dtype=np.int32) if want_matrix else None
         check(lib().pfa_pairwise(self.handle, out.ctypes.data, mat.ctypes.data if want_matrix else None), self.ctx.handle)
         return ([int(x) for x in out], mat) if want_matrix else [int(x) for x in out]
+
+
+def parse_files(paths, threads=0):
+    """parse many FASTA files with host threads -> list of Fasta | NotFasta | OSError | ValueError instances, in order"""
+    n = len(paths)
+    if n == 0:
+        return []
+    arr = (ctypes.c_char_p * n)(*[str(x).encode() for x in paths])
+    out = (ctypes.c_void_p * n)()
+    status = (ctypes.c_int * n)()
+    check(lib().pfa_fasta_parse_files(arr, n, threads, out, status))
+    res = []
+    for i in range(n):
+        rc = status[i]
+        if rc == _lib.PFA_OK:
+            res.append(Fasta(ctypes.c_void_p(out[i])))
+        elif rc == _lib.PFA_ERR_NOT_FASTA:
+            res.append(NotFasta(paths[i]))
+        elif rc == _lib.PFA_ERR_IO:
+            res.append(OSError("cannot read %s" % paths[i]))
+        elif rc == _lib.PFA_ERR_NON_ASCII:
+            res.append(ValueError("%s: non-ASCII bytes in sequence lines are not supported" % paths[i]))
+        else:
+            res.append(PolyFastaError(rc, "parse failed: %s" % paths[i]))
+    return res
+
+
+def match_mask(fasta, key):
+    """(mask uint32[mask_words_for(n)], number of rows) of the headers containing `key` (PolyFastA.py:125)"""
+    words = int(lib().pfa_mask_words_for(fasta.nseq))
+    m = np.zeros(max(words, 1), dtype=np.uint32)
+    kb = key.encode("utf-8", "surrogateescape")
+    hits = int(lib().pfa_fasta_match_mask(fasta.handle, kb, len(kb), m.ctypes.data, words))
+    return m, hits
+
+
+class Batch:
+    """many small loci, one upload + three segmented launches + one synchronisation (pfa_batch); non-CDS statistics"""
+
+    MAX_ROWS = 16384          # Wq <= 128: the batched site kernel keeps a site record in registers
+    MAX_LOCUS_BYTES = 64 << 20
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        check(lib().pfa_batch_create(ctx.handle, ctypes.byref(self._h)), ctx.handle)
+
+    def close(self):
+        if self._h:
+            lib().pfa_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        check(lib().pfa_batch_clear(self._h), self.ctx.handle)
+
+    def __len__(self):
+        return int(lib().pfa_batch_size(self._h))
+
+    @property
+    def text_bytes(self):
+        return int(lib().pfa_batch_text_bytes(self._h))
+
+    @classmethod
+    def fits(cls, fasta):
+        return fasta.seqlen >= 0 and fasta.nseq <= cls.MAX_ROWS and fasta.nseq * max(fasta.seqlen, 1) <= cls.MAX_LOCUS_BYTES
+
+    def add(self, fasta, masks=None):
+        """masks: None (all rows) or uint32 [k][mask_words_for(n)]; returns the locus index"""
+        idx = ctypes.c_int64()
+        if masks is None:
+            check(lib().pfa_batch_add(self._h, fasta.handle, None, 0, ctypes.byref(idx)), self.ctx.handle)
+        else:
+            m = np.ascontiguousarray(masks, dtype=np.uint32)
+            check(lib().pfa_batch_add(self._h, fasta.handle, m.ctypes.data, m.shape[0], ctypes.byref(idx)), self.ctx.handle)
+        return idx.value
+
+    def add_rows(self, mat, row_lists=None):
+        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        n, L = mat.shape
+        idx = ctypes.c_int64()
+        if row_lists:
+            m = rows_to_masks(int(lib().pfa_mask_words_for(n)), row_lists)
+            check(lib().pfa_batch_add_rows(self._h, mat.ctypes.data, n, L, max(L, 1), m.ctypes.data, len(row_lists), ctypes.byref(idx)),
+                  self.ctx.handle)
+        else:
+            check(lib().pfa_batch_add_rows(self._h, mat.ctypes.data, n, L, max(L, 1), None, 0, ctypes.byref(idx)), self.ctx.handle)
+        return idx.value
+
+    def run(self, jc=False):
+        check(lib().pfa_batch_run(self._h, int(bool(jc))), self.ctx.handle)
+
+    def result(self, locus, pop=0, want_sfs=False):
+        """dict(n, S, H[, sfs], poly) with poly = the tuple polymorphism returns"""
+        counts = (ctypes.c_int64 * 3)()
+        fin = FinalOut()
+        check(lib().pfa_batch_result(self._h, locus, pop, counts, None, ctypes.byref(fin)), self.ctx.handle)
+        res = {"n": counts[0], "S": counts[1], "H": counts[2]}
+        if want_sfs:
+            sfs = np.zeros(max(counts[0] // 2, 1), dtype=np.int64)
+            check(lib().pfa_batch_result(self._h, locus, pop, counts, sfs.ctypes.data, None), self.ctx.handle)
+            res["sfs"] = sfs[: counts[0] // 2].tolist()
+        res["poly"] = (0, 0, 0, "NA") if fin.no_var else (counts[1], fin.pi_site, fin.theta_site, "NA" if fin.D_is_NA else fin.D)
+        return res

@@ -143,36 +143,148 @@ def format_rows(ctx, file, seqlen, cds, jc, pops, site, cdsst):
     return lines
 
 
-def process_alignment(ctx, fasta, file, cds, jc, popkeys, sink):
-    """one file: equal-length check, %3 warning, population split, GPU scans, rows (PolyFastA.py:109-140)"""
-    if fasta.seqlen < 0:
-        sink.note(f"# Sequences do not have the same length: {file}")
-        return
-    seqlen = fasta.seqlen
-    if cds and seqlen % 3 != 0:
-        sink.note(f"# CDS sequence length is not a multiple of 3: {file}")
+BATCH_FILES = int(os.environ.get("POLYFASTA_BATCH_FILES", "512"))   # loci per batched GPU pass
+BATCH_BYTES = 1 << 30          # ... or this much text
+
+
+def plan_populations(fasta, popkeys):
+    """[(label, mask | None, rows)]: header-substring split (PolyFastA.py:123-125); no keys = one population 'NA'"""
     if popkeys is None:
-        plan = [("NA", list(range(fasta.nseq)))]
-    else:
-        heads = fasta.headers
-        plan = [(key, [i for i, h in enumerate(heads) if key in h]) for key in popkeys]
-    found = [(label, rows) for label, rows in plan if rows]
-    lines = []
-    if found:
-        aln = api.Alignment.from_fasta(ctx, fasta)
+        return [("NA", None, fasta.nseq)]
+    plan = []
+    for key in popkeys:
+        mask, hits = api.match_mask(fasta, key)
+        plan.append((key, mask, hits))
+    return plan
+
+
+def single_alignment_rows(ctx, fasta, file, cds, jc, found):
+    """rows of one alignment through the single-alignment kernels (large alignments, and --cds)"""
+    import numpy as np
+    aln = api.Alignment.from_fasta(ctx, fasta)
+    try:
+        if found[0][1] is not None:
+            m = np.stack([mask for _, mask, _ in found])
+            api.check(api.lib().pfa_aln_set_pops(aln.handle, m.ctypes.data, len(found)), ctx.handle)
+        site = aln.site_stats()
+        cdsst = aln.cds_stats() if cds else None
+    finally:
+        aln.free()
+    return format_rows(ctx, file, fasta.seqlen, cds, jc, [(label, rows) for label, _, rows in found], site, cdsst)
+
+
+def process_chunk(ctx, batch, items, cds, jc, popkeys):
+    """items: [(path, Fasta | exception)] in output order -> ordered actions ('stdout' | 'note' | 'row', ...).
+    Small non-CDS loci of the chunk share ONE batched GPU pass; everything else goes through the single-alignment path."""
+    actions = []
+    pending = []   # (position in actions, locus, pop, file, seqlen, label, n)
+    batch.clear()
+    for path, fasta in items:
+        file = path.split("/")[-1]
+        if isinstance(fasta, api.NotFasta):
+            actions.append(("stdout", f"# file {path} is not FASTA!"))                         # PolyFastA.py:247
+            continue
+        if isinstance(fasta, Exception):
+            actions.append(("raise", fasta))
+            break
+        if fasta.seqlen < 0:
+            actions.append(("note", f"# Sequences do not have the same length: {file}"))        # :135-140
+            continue
+        if cds and fasta.seqlen % 3 != 0:
+            actions.append(("note", f"# CDS sequence length is not a multiple of 3: {file}"))   # :114-119
+        plan = plan_populations(fasta, popkeys)
+        found = [p for p in plan if p[2] > 0]
+        rows = iter(())
+        if found and (cds or not api.Batch.fits(fasta)):
+            rows = iter(single_alignment_rows(ctx, fasta, file, cds, jc, found))
+        elif found:
+            import numpy as np
+            masks = None if found[0][1] is None else np.stack([m for _, m, _ in found])
+            locus = batch.add(fasta, masks)
+        q = 0
+        for label, mask, hits in plan:
+            if hits == 0:
+                actions.append(("note", f"# Pop {label} string was not found in fasta headers."))   # :126-132
+            elif cds or not api.Batch.fits(fasta):
+                actions.append(("row", next(rows), file, label))
+            else:
+                pending.append((len(actions), locus, q, file, fasta.seqlen, label, hits))
+                actions.append(None)
+                q += 1
+    if pending:
+        batch.run(jc)
+        for pos, locus, q, file, seqlen, label, n in pending:
+            r = batch.result(locus, q)
+            if r["S"] == 0:
+                line = f"{file},{seqlen},{label},{n},0,0,0,NA"                                     # :187/:189
+            else:
+                p = r["poly"]
+                line = f"{file},{seqlen},{label},{n},{p[0]},{p[1]},{p[2]},{p[3]}"                  # :196/:198
+            actions[pos] = ("row", line, file, label)
+    for _, fasta in items:
+        if isinstance(fasta, api.Fasta):
+            fasta.close()
+    return actions
+
+
+def emit(actions, sink):
+    for a in actions:
+        if a[0] == "stdout":
+            print(a[1])
+        elif a[0] == "note":
+            sink.note(a[1])
+        elif a[0] == "row":
+            sink.row(a[1], a[2], a[3])
+        elif a[0] == "raise":
+            raise a[1]
+
+
+def devices_from_env():
+    """POLYFASTA_DEVICES=0,1,... (or POLYFASTA_DEVICE=0): the GPUs the --dir loci are spread over, round-robin by chunk"""
+    spec = os.environ.get("POLYFASTA_DEVICES") or os.environ.get("POLYFASTA_DEVICE") or "0"
+    return [int(x) for x in spec.split(",") if x.strip() != ""]
+
+
+def run_files(paths, cds, jc, popkeys, sink):
+    """the per-file loop of PolyFastA.py:104-140 over sorted paths, in chunks; chunk i runs on device i mod G and the
+    rows are emitted in the reference's order"""
+    from concurrent.futures import ThreadPoolExecutor
+    devs = devices_from_env()
+    chunks, cur, cur_bytes = [], [], 0
+    for p in paths:
         try:
-            aln.set_pops([rows for _, rows in found])
-            site = aln.site_stats()
-            cdsst = aln.cds_stats() if cds else None
-        finally:
-            aln.free()
-        lines = format_rows(ctx, file, seqlen, cds, jc, [(label, len(rows)) for label, rows in found], site, cdsst)
-    it = iter(lines)
-    for label, rows in plan:
-        if not rows:
-            sink.note(f"# Pop {label} string was not found in fasta headers.")
-        else:
-            sink.row(next(it), file, label)
+            sz = os.path.getsize(p)
+        except OSError:
+            sz = 0
+        if cur and (len(cur) >= BATCH_FILES or cur_bytes + sz > BATCH_BYTES):
+            chunks.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += sz
+    if cur:
+        chunks.append(cur)
+    state = {}
+
+    def work(ci):
+        slot = ci % len(devs)   # one context + batch per listed device slot (a context is not re-entrant)
+        if slot not in state:
+            ctx = api.Context(devs[slot])
+            state[slot] = (ctx, api.Batch(ctx))
+        ctx, batch = state[slot]
+        fastas = api.parse_files(chunks[ci], threads=max(1, (os.cpu_count() or 1) // len(devs)))
+        return process_chunk(ctx, batch, list(zip(chunks[ci], fastas)), cds, jc, popkeys)
+
+    if len(devs) == 1 or len(chunks) == 1:
+        for ci in range(len(chunks)):
+            emit(work(ci), sink)
+    else:
+        # one worker thread per device (a context is not re-entrant); ctypes releases the GIL during library calls
+        pools = [ThreadPoolExecutor(max_workers=1) for _ in devs]
+        futs = [pools[ci % len(devs)].submit(work, ci) for ci in range(len(chunks))]
+        for f in futs:
+            emit(f.result(), sink)
+        for pl in pools:
+            pl.shutdown()
 
 
 def main(argv=None):
@@ -193,24 +305,22 @@ def main(argv=None):
     if not args.silent:
         sink.header(args.cds)
     popkeys = args.pops.split(",") if args.pops else None
-    ctx = None
-    for path in sorted(args.file):
-        if len(args.file) > 0 and args.pipe and not (args.file[0] == "stdin" or args.file[0] == args.name):
+    paths = sorted(args.file)
+    if paths and args.pipe:
+        if not (args.file[0] == "stdin" or args.file[0] == args.name):
             parser.error("A FASTA file or multiple files cannot be used with the --pipe argument.")
-        try:
-            if args.pipe:
-                fasta = api.Fasta.from_bytes(sys.stdin.buffer.read())
-            else:
-                fasta = api.Fasta.from_file(path)
-        except api.NotFasta:
-            print(f"# file {path} is not FASTA!")
-            continue
-        if ctx is None:
-            ctx = api.default_context(int(os.environ.get("POLYFASTA_DEVICE", "0")))
-        try:
-            process_alignment(ctx, fasta, path.split("/")[-1], args.cds, args.jc, popkeys, sink)
-        finally:
-            fasta.close()
+        data = sys.stdin.buffer.read()
+        ctx = api.default_context(devices_from_env()[0])
+        batch = api.Batch(ctx)
+        for path in paths:   # the reference reads stdin once per listed name; the second read is empty
+            try:
+                fasta = api.Fasta.from_bytes(data)
+            except api.NotFasta as e:
+                fasta = e
+            emit(process_chunk(ctx, batch, [(path, fasta)], args.cds, args.jc, popkeys), sink)
+            data = b""
+    elif paths:
+        run_files(paths, args.cds, args.jc, popkeys, sink)
     if len(args.out) != 0 and not args.silent:
         print("")
     return 0

@@ -475,9 +475,8 @@ static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int6
     a->L_total = L;
     a->col_begin = col_begin;
     a->ns = col_end - col_begin;
-    a->Wq = (int)((n + 127) / 128);
-    // long site records are padded to whole 32-byte sectors so that no sector is shared by two sites
-    if (a->Wq >= 16 && (a->Wq & 1)) a->Wq++;
+    // ceil(n/128), long site records padded to whole 32-byte sectors so that no sector is shared by two sites
+    a->Wq = (int)(pfa_mask_words_for(n) / 4);
     a->plane_bytes = (size_t)pfa_round_up(std::max<int64_t>(a->ns * (int64_t)a->Wq * 16, 16), 256);
     cudaError_t e = pfa_dmalloc(ctx, &a->planes, 3 * a->plane_bytes);
     if (e != cudaSuccess) {

@@ -1,0 +1,567 @@
+// Batched path for many small loci (the reference's --dir loop, PolyFastA.py:93-94,104): instead of one upload, three
+// launches and several synchronisations PER FILE, a batch of loci is copied to the GPU as one pinned blob and processed by
+// three segmented launches -- K1b encode, K2b site scan, K5b finalise -- with ONE synchronisation.  A locus keeps its own
+// shape (n, L), populations and result slots; kernels find the locus of a tile / site group by binary search in a prefix
+// table.  The arithmetic is the same device code as the single-alignment kernels (pfa_sites.cuh, pfa_finalize.cu).
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "pfa_host.h"
+#include "pfa_sites.cuh"
+
+struct PfaLocusDesc {
+    long long text_off;   // byte offset of the locus' text matrix in the blob
+    long long plane_off;  // uint4 offset of its first site record in each plane
+    long long mask_off;   // uint4 offset of its masks ([k][Wq], then the union [Wq])
+    long long site_base;  // global index of its first site (exception keys, group prefix)
+    long long tile_base;  // first K1b tile
+    long long pop_base;   // first (locus, population) slot
+    int n, L, ld, Wq, k, pad;
+};
+
+struct PfaPopSlot {
+    long long n;        // rows in the population
+    long long out_off;  // offset of [S, H, sfs...] in the batch result vector
+    long long locus;
+    double seqlen;
+};
+
+struct pfa_batch {
+    pfa_ctx* ctx = nullptr;
+    std::vector<PfaLocusDesc> desc;
+    std::vector<PfaPopSlot> pops;
+    std::vector<uint32_t> masks;  // per locus: k masks then the union, each 4*Wq words
+    unsigned char* h_text = nullptr;  // pinned
+    size_t h_text_cap = 0, h_text_used = 0;
+    long long n_sites = 0, n_tiles = 0, plane_u4 = 0, mask_u4 = 0, out_len = 0;
+    int max_Wq = 0;
+    // results (host)
+    std::vector<int64_t> out;
+    std::vector<pfa_final_out> fin;
+    bool ran = false;
+};
+
+static int grow_text(pfa_batch* b, size_t need) {
+    if (need <= b->h_text_cap) return PFA_OK;
+    size_t cap = std::max<size_t>(need, std::max<size_t>(b->h_text_cap * 2, 64u << 20));
+    unsigned char* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return pfa_fail(b->ctx, PFA_ERR_NOMEM, "cannot pin %zu bytes", cap);
+    if (b->h_text_used) memcpy(p, b->h_text, b->h_text_used);
+    if (b->h_text) cudaFreeHost(b->h_text);
+    b->h_text = p;
+    b->h_text_cap = cap;
+    return PFA_OK;
+}
+
+static inline int wq_of(int64_t n) {
+    int wq = (int)((n + 127) / 128);
+    if (wq >= 16 && (wq & 1)) wq++;
+    return wq;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ int pfa_find_locus(const long long* __restrict__ base, int nloci, long long x) {
+    // largest i with base[i] <= x ; base has nloci + 1 entries
+    int lo = 0, hi = nloci;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (base[mid] <= x) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ unsigned pfa_classify_byte(unsigned c) {
+    if (c >= 'a' && c <= 'z') c -= 32;
+    switch (c) {
+        case 'A': return 4 | 0;
+        case 'C': return 4 | 1;
+        case 'G': return 4 | 2;
+        case 'T': return 4 | 3;
+        case '-': return 0;
+        case 'N': return 1;
+        case '?': return 2;
+        default: return 8 | 3;
+    }
+}
+
+// K1b: one warp = 32 rows x 32 sites of one locus (see pfa_encode_kernel)
+__global__ void __launch_bounds__(256) pfa_batch_encode_kernel(const uint8_t* __restrict__ text, const PfaLocusDesc* __restrict__ desc,
+                                                               const long long* __restrict__ tile_base, int nloci, long long n_tiles,
+                                                               uint32_t* __restrict__ b0, uint32_t* __restrict__ b1, uint32_t* __restrict__ v,
+                                                               unsigned long long* __restrict__ exc_keys, unsigned long long* __restrict__ exc_count,
+                                                               long long exc_cap, int* __restrict__ locus_invalid) {
+    __shared__ uint8_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (uint8_t)pfa_classify_byte(i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int li = pfa_find_locus(tile_base, nloci, tile);
+    const PfaLocusDesc d = desc[li];
+    const long long t = tile - d.tile_base;
+    const int sgs = (d.L + 31) / 32;
+    const int w = (int)(t / sgs);
+    const long long c0 = (t % sgs) * 32;
+    const long long row = (long long)w * 32 + lane;
+    const bool live = row < d.n;
+    uint32_t bytes[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bytes[i] = 0x2d2d2d2du;
+    if (live) {
+        const uint8_t* src = text + d.text_off + row * d.ld + c0;
+        if (c0 + 32 <= d.L) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            const uint4 a = __ldg(s4), b = __ldg(s4 + 1);
+            bytes[0] = a.x; bytes[1] = a.y; bytes[2] = a.z; bytes[3] = a.w;
+            bytes[4] = b.x; bytes[5] = b.y; bytes[6] = b.z; bytes[7] = b.w;
+        } else {
+            const int lim = (int)(d.L - c0);
+            for (int i = 0; i < lim; ++i) {
+                const uint32_t c = src[i];
+                bytes[i >> 2] = (bytes[i >> 2] & ~(0xffu << (8 * (i & 3)))) | (c << (8 * (i & 3)));
+            }
+        }
+    }
+    uint32_t my0 = 0, my1 = 0, myv = 0;
+    bool any_invalid = false;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+        const unsigned c = (bytes[s >> 2] >> (8 * (s & 3))) & 0xffu;
+        const unsigned code = live ? lut[c] : 0u;
+        const uint32_t w0 = __ballot_sync(0xffffffffu, code & 1u);
+        const uint32_t w1 = __ballot_sync(0xffffffffu, code & 2u);
+        const uint32_t wv = __ballot_sync(0xffffffffu, code & 4u);
+        if (lane == s) { my0 = w0; my1 = w1; myv = wv; }
+        const bool in_range = c0 + s < d.L;
+        if (live && in_range && !(code & 4u)) any_invalid = true;
+        if (live && in_range && (code & 8u)) {
+            const unsigned up = (c >= 'a' && c <= 'z') ? c - 32 : c;
+            const unsigned long long slot = atomicAdd(exc_count, 1ull);
+            if ((long long)slot < exc_cap)
+                exc_keys[slot] = ((unsigned long long)(d.site_base + c0 + s) << 32) | ((unsigned long long)up << 24) | (unsigned long long)row;
+        }
+    }
+    if (__any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(locus_invalid + li, 1);
+    if (c0 + lane < d.L) {
+        const long long o = (d.plane_off + (c0 + lane) * d.Wq) * 4 + w;
+        b0[o] = my0; b1[o] = my1; v[o] = myv;
+    }
+}
+
+struct PfaBatchArgs {
+    const uint4* b0;
+    const uint4* b1;
+    const uint4* v;
+    const uint4* masks;
+    const PfaLocusDesc* desc;
+    const PfaPopSlot* pops;
+    const long long* site_base;  // nloci + 1
+    const int* locus_invalid;
+    long long* out;
+    long long n_sites;
+    int nloci;
+};
+
+// K2b: a group of LPS lanes owns one site of one locus; same two passes as pfa_site_scan_reg_kernel, accumulators in global
+// memory (only variable columns touch them)
+template <int LPS, int ITER>
+__global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_batch_site_kernel(const PfaBatchArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPS - 1);
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
+    const long long ngroups = (long long)gridDim.x * blockDim.x / LPS;
+    for (long long g = gid; g < a.n_sites; g += ngroups) {
+        const int li = pfa_find_locus(a.site_base, a.nloci, g);
+        const PfaLocusDesc d = a.desc[li];
+        const long long s = g - d.site_base;
+        const int Wq = d.Wq;
+        const bool hv = a.locus_invalid[li] != 0;
+        const uint4* um = a.masks + d.mask_off + (long long)d.k * Wq;
+        const uint4* p0 = a.b0 + d.plane_off + s * Wq;
+        const uint4* p1 = a.b1 + d.plane_off + s * Wq;
+        const uint4* pv = a.v + d.plane_off + s * Wq;
+        uint4 x0[ITER], x1[ITER], xv[ITER], m[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int j = sub + LPS * i;
+            x0[i] = x1[i] = xv[i] = m[i] = make_uint4(0, 0, 0, 0);
+            if (j < Wq) {
+                m[i] = __ldg(um + j);
+                x0[i] = pfa_ld_stream(p0 + j);
+                x1[i] = pfa_ld_stream(p1 + j);
+                xv[i] = hv ? pfa_ld_stream(pv + j) : m[i];
+            }
+        }
+        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            o0 |= (x0[i].x & m[i].x) | (x0[i].y & m[i].y) | (x0[i].z & m[i].z) | (x0[i].w & m[i].w);
+            z0 |= (~x0[i].x & m[i].x) | (~x0[i].y & m[i].y) | (~x0[i].z & m[i].z) | (~x0[i].w & m[i].w);
+            o1 |= (x1[i].x & m[i].x) | (x1[i].y & m[i].y) | (x1[i].z & m[i].z) | (x1[i].w & m[i].w);
+            z1 |= (~x1[i].x & m[i].x) | (~x1[i].y & m[i].y) | (~x1[i].z & m[i].z) | (~x1[i].w & m[i].w);
+            ov |= (xv[i].x & m[i].x) | (xv[i].y & m[i].y) | (xv[i].z & m[i].z) | (xv[i].w & m[i].w);
+            zv |= (~xv[i].x & m[i].x) | (~xv[i].y & m[i].y) | (~xv[i].z & m[i].z) | (~xv[i].w & m[i].w);
+        }
+        unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+        f = pfa_group_or<LPS>(f, gmask);
+        const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
+        const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
+        if (mono && !all_escape) continue;
+        for (int q = 0; q < d.k; ++q) {
+            uint32_t c[PFA_NCLASS];
+#pragma unroll
+            for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+            const uint4* mq = a.masks + d.mask_off + (long long)q * Wq;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                const uint4 m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
+                               w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w}, wv[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t vm = wv[w] & mm[w];
+                    const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
+                    c[PFA_C_T] += __popc(hi & w0[w]);
+                    c[PFA_C_G] += __popc(hi & ~w0[w]);
+                    c[PFA_C_C] += __popc(lo & w0[w]);
+                    c[PFA_C_A] += __popc(lo & ~w0[w]);
+                    const uint32_t im = ~wv[w] & mm[w];
+                    const uint32_t ihi = im & w1[w];
+                    c[PFA_C_ESC] += __popc(ihi & w0[w]);
+                    c[PFA_C_Q] += __popc(ihi & ~w0[w]);
+                    c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
+                }
+            }
+            if (LPS > 1) {
+#pragma unroll
+                for (int i = 0; i < PFA_NCLASS; ++i) c[i] = pfa_group_add<LPS>(c[i], gmask);
+            }
+            if (sub != 0) continue;
+            const PfaPopSlot ps = a.pops[d.pop_base + q];
+            const PfaSiteResult r = pfa_site_result(c, ps.n, 0u, 0ull);
+            if (r.has_escape || !r.isvar) continue;
+            unsigned long long* o = reinterpret_cast<unsigned long long*>(a.out + ps.out_off);
+            atomicAdd(o, 1ull);
+            atomicAdd(o + 1, r.h);
+            if (r.sfs_bin >= 0) atomicAdd(o + 2 + r.sfs_bin, 1ull);
+        }
+    }
+}
+
+// sites with escape symbols: one warp per distinct (global) site of the sorted exception list
+__global__ void __launch_bounds__(256) pfa_batch_escape_kernel(const PfaBatchArgs a, const unsigned long long* __restrict__ keys, long long n_exc,
+                                                               const long long* __restrict__ heads, long long n_heads) {
+    __shared__ unsigned int hist[8][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long h = wid; h < n_heads; h += nwarps) {
+        const long long i0 = heads[h], i1 = (h + 1 < n_heads) ? heads[h + 1] : n_exc;
+        const long long g = (long long)(keys[i0] >> 32);
+        const int li = pfa_find_locus(a.site_base, a.nloci, g);
+        const PfaLocusDesc d = a.desc[li];
+        const long long s = g - d.site_base;
+        const int Wq = d.Wq;
+        for (int q = 0; q < d.k; ++q) {
+            const uint4* mq = a.masks + d.mask_off + (long long)q * Wq;
+            uint32_t c[PFA_NCLASS];
+            pfa_class_counts<32, true>(a.b0 + d.plane_off + s * Wq, a.b1 + d.plane_off + s * Wq, a.v + d.plane_off + s * Wq, mq, Wq, lane,
+                                       0xffffffffu, c);
+            if (c[PFA_C_ESC] == 0) continue;
+            for (int b = lane; b < 256; b += 32) hist[wib][b] = 0u;
+            __syncwarp();
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(mq);
+            for (long long i = i0 + lane; i < i1; i += 32) {
+                const unsigned long long key = keys[i];
+                const uint32_t row = (uint32_t)(key & 0xffffffull);
+                if ((mw[row >> 5] >> (row & 31)) & 1u) atomicAdd(&hist[wib][(key >> 24) & 0xffu], 1u);
+            }
+            __syncwarp();
+            uint32_t distinct = 0;
+            unsigned long long sq = 0;
+            for (int b = lane; b < 256; b += 32) {
+                const unsigned long long cnt = hist[wib][b];
+                distinct += cnt ? 1u : 0u;
+                sq += cnt * cnt;
+            }
+            for (int off = 16; off; off >>= 1) {
+                distinct += __shfl_xor_sync(0xffffffffu, distinct, off);
+                sq += __shfl_xor_sync(0xffffffffu, sq, off);
+            }
+            __syncwarp();
+            if (lane != 0) continue;
+            const PfaPopSlot ps = a.pops[d.pop_base + q];
+            const PfaSiteResult r = pfa_site_result(c, ps.n, distinct, sq);
+            if (!r.isvar) continue;
+            unsigned long long* o = reinterpret_cast<unsigned long long*>(a.out + ps.out_off);
+            atomicAdd(o, 1ull);
+            atomicAdd(o + 1, r.h);
+            if (r.sfs_bin >= 0) atomicAdd(o + 2 + r.sfs_bin, 1ull);
+        }
+    }
+}
+
+// K5b input straight from the device result vector: no host round trip between the scan and the finalisation
+__global__ void pfa_batch_final_in_kernel(const PfaPopSlot* __restrict__ pops, const long long* __restrict__ out, int jc, long long n_pops,
+                                          pfa_final_in* __restrict__ fin_in) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pops) return;
+    const PfaPopSlot p = pops[i];
+    pfa_final_in f;
+    f.n = p.n;
+    f.S = out[p.out_off];
+    f.H = out[p.out_off + 1];
+    f.seqlen = p.seqlen;
+    f.jc = jc;
+    f.pad = 0;
+    fin_in[i] = f;
+}
+
+
+// ---- host --------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int64_t pfa_mask_words_for(int64_t n) { return (int64_t)wq_of(n) * 4; }
+
+int pfa_batch_create(pfa_ctx* ctx, pfa_batch** out) {
+    if (!ctx || !out) return PFA_ERR_ARG;
+    pfa_batch* b = new (std::nothrow) pfa_batch();
+    if (!b) return PFA_ERR_NOMEM;
+    b->ctx = ctx;
+    *out = b;
+    return PFA_OK;
+}
+
+int pfa_batch_clear(pfa_batch* b) {
+    if (!b) return PFA_ERR_ARG;
+    b->desc.clear();
+    b->pops.clear();
+    b->masks.clear();
+    b->h_text_used = 0;
+    b->n_sites = b->n_tiles = b->plane_u4 = b->mask_u4 = b->out_len = 0;
+    b->max_Wq = 0;
+    b->ran = false;
+    return PFA_OK;
+}
+
+int pfa_batch_destroy(pfa_batch* b) {
+    if (!b) return PFA_OK;
+    if (b->h_text) cudaFreeHost(b->h_text);
+    delete b;
+    return PFA_OK;
+}
+
+int64_t pfa_batch_size(const pfa_batch* b) { return b ? (int64_t)b->desc.size() : 0; }
+int64_t pfa_batch_text_bytes(const pfa_batch* b) { return b ? (int64_t)b->h_text_used : 0; }
+
+int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k, int64_t* index) {
+    if (!b || n <= 0 || L < 0 || (L > 0 && (!text || ld < L)) || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
+    if (n >= (1ll << 24) || L >= (1ll << 31)) return pfa_fail(b->ctx, PFA_ERR_ARG, "locus too large for the batched path");
+    PfaLocusDesc d;
+    d.n = (int)n;
+    d.L = (int)L;
+    d.ld = (int)pfa_round_up(std::max<int64_t>(L, 1), 32);
+    d.Wq = wq_of(n);
+    d.k = k > 0 ? k : 1;
+    d.pad = 0;
+    d.text_off = (long long)pfa_round_up((int64_t)b->h_text_used, 256);
+    const size_t need = (size_t)d.text_off + (size_t)n * d.ld;
+    int rc = grow_text(b, need);
+    if (rc) return rc;
+    for (int64_t r = 0; r < n; ++r) memcpy(b->h_text + d.text_off + r * d.ld, text + r * ld, (size_t)L);
+    b->h_text_used = need;
+    d.plane_off = b->plane_u4;
+    d.mask_off = b->mask_u4;
+    d.site_base = b->n_sites;
+    d.tile_base = b->n_tiles;
+    d.pop_base = (long long)b->pops.size();
+    const int64_t Wn = (int64_t)d.Wq * 4;
+    // masks: k population masks, then their union
+    const size_t m0 = b->masks.size();
+    b->masks.resize(m0 + (size_t)((d.k + 1) * Wn), 0u);
+    uint32_t* mk = b->masks.data() + m0;
+    uint32_t* uni = mk + (size_t)d.k * Wn;
+    for (int q = 0; q < d.k; ++q) {
+        int64_t cnt = 0;
+        for (int64_t w = 0; w < Wn; ++w) {
+            uint32_t x = k > 0 ? masks[q * Wn + w] : 0xffffffffu;
+            const int64_t lo = w * 32;
+            if (lo >= n) x = 0;
+            else if (lo + 32 > n) x &= (1u << (n - lo)) - 1u;
+            mk[q * Wn + w] = x;
+            uni[w] |= x;
+            cnt += __builtin_popcount(x);
+        }
+        if (cnt == 0) {
+            b->masks.resize(m0);
+            return pfa_fail(b->ctx, PFA_ERR_ARG, "empty population in batch");
+        }
+        PfaPopSlot ps;
+        ps.n = cnt;
+        ps.out_off = b->out_len;
+        ps.locus = (long long)b->desc.size();
+        ps.seqlen = (double)L;
+        b->pops.push_back(ps);
+        b->out_len += 2 + cnt / 2;
+    }
+    b->plane_u4 += (long long)L * d.Wq;
+    b->mask_u4 += (long long)(d.k + 1) * d.Wq;
+    b->n_sites += L;
+    b->n_tiles += ((n + 31) / 32) * ((L + 31) / 32);
+    b->max_Wq = std::max(b->max_Wq, d.Wq);
+    if (index) *index = (int64_t)b->desc.size();
+    b->desc.push_back(d);
+    b->ran = false;
+    return PFA_OK;
+}
+
+int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k, int64_t* index) {
+    if (!b || !f) return PFA_ERR_ARG;
+    if (f->seqlen < 0) return pfa_fail(b->ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
+    return pfa_batch_add_rows(b, f->data, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), masks, k, index);
+}
+
+int pfa_batch_run(pfa_batch* b, int jc) {
+    if (!b) return PFA_ERR_ARG;
+    pfa_ctx* ctx = b->ctx;
+    const int nloci = (int)b->desc.size();
+    const long long npops = (long long)b->pops.size();
+    b->out.assign((size_t)b->out_len, 0);
+    b->fin.assign((size_t)npops, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
+    b->ran = true;
+    if (nloci == 0) return PFA_OK;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<long long> site_base((size_t)nloci + 1), tile_base((size_t)nloci + 1);
+    for (int i = 0; i < nloci; ++i) {
+        site_base[(size_t)i] = b->desc[(size_t)i].site_base;
+        tile_base[(size_t)i] = b->desc[(size_t)i].tile_base;
+    }
+    site_base[(size_t)nloci] = b->n_sites;
+    tile_base[(size_t)nloci] = b->n_tiles;
+
+    uint8_t* d_text = nullptr;
+    PfaLocusDesc* d_desc = nullptr;
+    PfaPopSlot* d_pops = nullptr;
+    long long *d_site_base = nullptr, *d_tile_base = nullptr, *d_out = nullptr;
+    uint4 *d_planes = nullptr, *d_masks = nullptr;
+    int* d_inv = nullptr;
+    unsigned long long *d_count = nullptr, *d_keys = nullptr;
+    pfa_final_in* d_fin_in = nullptr;
+    pfa_final_out* d_fin_out = nullptr;
+    int64_t* heads = nullptr;
+    const size_t plane_bytes = (size_t)pfa_round_up(std::max<long long>(b->plane_u4, 1) * 16, 256);
+    long long cap = std::max<long long>(1 << 16, (long long)(b->h_text_used / 64));
+    int rc = PFA_OK;
+    cudaError_t e = cudaSuccess;
+#define BR(call)                                                                       \
+    do {                                                                               \
+        if (e == cudaSuccess) e = (call);                                              \
+    } while (0)
+    BR(pfa_dmalloc(ctx, &d_text, b->h_text_used));
+    BR(pfa_dmalloc(ctx, &d_desc, sizeof(PfaLocusDesc) * (size_t)nloci));
+    BR(pfa_dmalloc(ctx, &d_pops, sizeof(PfaPopSlot) * (size_t)npops));
+    BR(pfa_dmalloc(ctx, &d_site_base, sizeof(long long) * ((size_t)nloci + 1)));
+    BR(pfa_dmalloc(ctx, &d_tile_base, sizeof(long long) * ((size_t)nloci + 1)));
+    BR(pfa_dmalloc(ctx, &d_out, sizeof(long long) * (size_t)std::max<long long>(b->out_len, 1)));
+    BR(pfa_dmalloc(ctx, &d_planes, 3 * plane_bytes));
+    BR(pfa_dmalloc(ctx, &d_masks, sizeof(uint32_t) * std::max<size_t>(b->masks.size(), 4)));
+    BR(pfa_dmalloc(ctx, &d_inv, sizeof(int) * (size_t)nloci));
+    BR(pfa_dmalloc(ctx, &d_count, sizeof(unsigned long long)));
+    BR(pfa_dmalloc(ctx, &d_keys, sizeof(unsigned long long) * (size_t)cap));
+    BR(pfa_dmalloc(ctx, &d_fin_in, sizeof(pfa_final_in) * (size_t)npops));
+    BR(pfa_dmalloc(ctx, &d_fin_out, sizeof(pfa_final_out) * (size_t)npops));
+    BR(cudaMemcpyAsync(d_text, b->h_text, b->h_text_used, cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d_desc, b->desc.data(), sizeof(PfaLocusDesc) * (size_t)nloci, cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d_pops, b->pops.data(), sizeof(PfaPopSlot) * (size_t)npops, cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d_site_base, site_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d_tile_base, tile_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d_masks, b->masks.data(), sizeof(uint32_t) * b->masks.size(), cudaMemcpyHostToDevice, st));
+    BR(cudaMemsetAsync(d_out, 0, sizeof(long long) * (size_t)std::max<long long>(b->out_len, 1), st));
+    BR(cudaMemsetAsync(d_planes, 0, 3 * plane_bytes, st));
+    BR(cudaMemsetAsync(d_inv, 0, sizeof(int) * (size_t)nloci, st));
+    BR(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    if (e == cudaSuccess && b->n_tiles > 0) {
+        uint4* p0 = d_planes;
+        uint4* p1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d_planes) + plane_bytes);
+        uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d_planes) + 2 * plane_bytes);
+        pfa_batch_encode_kernel<<<(unsigned)((b->n_tiles + 7) / 8), 256, 0, st>>>(d_text, d_desc, d_tile_base, nloci, b->n_tiles, (uint32_t*)p0,
+                                                                                (uint32_t*)p1, (uint32_t*)pv, d_keys, d_count, cap, d_inv);
+        ctx->launches++;
+        PfaBatchArgs args{p0, p1, pv, d_masks, d_desc, d_pops, d_site_base, d_inv, d_out, b->n_sites, nloci};
+        int lps = 1;
+        while (lps < 32 && (b->max_Wq + lps - 1) / lps > 4) lps *= 2;
+        const int iter = (b->max_Wq + lps - 1) / lps;
+        long long blocks = (b->n_sites * lps + PFA_SITE_THREADS - 1) / PFA_SITE_THREADS;
+        blocks = std::min<long long>(std::max<long long>(blocks, 1), (long long)ctx->sm_count * 4);
+#define PFA_B_CASE(L_, I_) \
+    if (lps == L_ && iter == I_) pfa_batch_site_kernel<L_, I_><<<(unsigned)blocks, PFA_SITE_THREADS, 0, st>>>(args); else
+        PFA_B_CASE(1, 1) PFA_B_CASE(1, 2) PFA_B_CASE(1, 3) PFA_B_CASE(1, 4) PFA_B_CASE(2, 3) PFA_B_CASE(2, 4) PFA_B_CASE(4, 3) PFA_B_CASE(4, 4)
+        PFA_B_CASE(8, 3) PFA_B_CASE(8, 4) PFA_B_CASE(16, 3) PFA_B_CASE(16, 4) PFA_B_CASE(32, 3) PFA_B_CASE(32, 4)
+        rc = pfa_fail(ctx, PFA_ERR_ARG, "batched path: a locus has too many sequences (Wq=%d); use the single-alignment path", b->max_Wq);
+#undef PFA_B_CASE
+        ctx->launches++;
+        e = cudaGetLastError();
+        // exception list: one small synchronisation per batch
+        unsigned long long count = 0;
+        BR(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, st));
+        BR(cudaStreamSynchronize(st));
+        if (e == cudaSuccess && !rc && count > 0) {
+            if ((long long)count > cap) rc = pfa_fail(ctx, PFA_ERR_ARG, "batched path: too many non-ACGT/-/N/? symbols (%llu); use the single-alignment path", count);
+            int64_t n_heads = 0;
+            if (!rc) rc = pfa_sort_exceptions(ctx, &d_keys, (int64_t)count, &heads, &n_heads);
+            if (!rc && n_heads > 0) {
+                long long eb = std::min<long long>((n_heads + 7) / 8, (long long)ctx->sm_count * 8);
+                pfa_batch_escape_kernel<<<(unsigned)eb, 256, 0, st>>>(args, d_keys, (long long)count, (const long long*)heads, n_heads);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+        }
+    }
+    if (e == cudaSuccess && !rc) {
+        pfa_batch_final_in_kernel<<<(unsigned)((npops + 127) / 128), 128, 0, st>>>(d_pops, d_out, jc, npops, d_fin_in);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) rc = pfa_launch_finalize(ctx, d_fin_in, d_fin_out, (int)npops);
+        if (rc) e = cudaErrorUnknown;
+        BR(cudaMemcpyAsync(b->out.data(), d_out, sizeof(long long) * (size_t)b->out_len, cudaMemcpyDeviceToHost, st));
+        BR(cudaMemcpyAsync(b->fin.data(), d_fin_out, sizeof(pfa_final_out) * (size_t)npops, cudaMemcpyDeviceToHost, st));
+        BR(cudaStreamSynchronize(st));
+    }
+#undef BR
+    pfa_dfree(ctx, d_text); pfa_dfree(ctx, d_desc); pfa_dfree(ctx, d_pops); pfa_dfree(ctx, d_site_base); pfa_dfree(ctx, d_tile_base);
+    pfa_dfree(ctx, d_out); pfa_dfree(ctx, d_planes); pfa_dfree(ctx, d_masks); pfa_dfree(ctx, d_inv); pfa_dfree(ctx, d_count);
+    pfa_dfree(ctx, d_keys); pfa_dfree(ctx, d_fin_in); pfa_dfree(ctx, d_fin_out); pfa_dfree(ctx, heads);
+    if (rc) return rc;
+    if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "batched run failed: %s", cudaGetErrorString(e));
+    return PFA_OK;
+}
+
+int pfa_batch_num_pops(const pfa_batch* b, int64_t locus) {
+    return (b && locus >= 0 && locus < (int64_t)b->desc.size()) ? b->desc[(size_t)locus].k : -1;
+}
+
+/* result of (locus, pop): counts[0..2] = n, S, H ; sfs copied when sfs != NULL (n/2 bins); fin = K5 output */
+int pfa_batch_result(const pfa_batch* b, int64_t locus, int pop, int64_t counts[3], int64_t* sfs, void* fin) {
+    if (!b || !b->ran || locus < 0 || locus >= (int64_t)b->desc.size()) return PFA_ERR_ARG;
+    const PfaLocusDesc& d = b->desc[(size_t)locus];
+    if (pop < 0 || pop >= d.k) return PFA_ERR_ARG;
+    const PfaPopSlot& ps = b->pops[(size_t)(d.pop_base + pop)];
+    if (counts) {
+        counts[0] = ps.n;
+        counts[1] = b->out[(size_t)ps.out_off];
+        counts[2] = b->out[(size_t)ps.out_off + 1];
+    }
+    if (sfs)
+        for (long long i = 0; i < ps.n / 2; ++i) sfs[i] = b->out[(size_t)(ps.out_off + 2 + i)];
+    if (fin) *static_cast<pfa_final_out*>(fin) = b->fin[(size_t)(d.pop_base + pop)];
+    return PFA_OK;
+}
+
+}  // extern "C"

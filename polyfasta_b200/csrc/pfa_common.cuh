@@ -81,6 +81,8 @@ void pfa_set_global_error(const char* fmt, ...);
 int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t cols, int64_t site0,
                      unsigned long long* d_exc_count, int64_t exc_cap, int* d_has_invalid);
 int pfa_finish_exceptions(pfa_aln* a, int64_t count);
+int pfa_sort_exceptions(pfa_ctx* ctx, unsigned long long** keys, int64_t count, int64_t** heads, int64_t* n_heads);
+int pfa_launch_finalize(pfa_ctx* ctx, const pfa_final_in* d_in, pfa_final_out* d_out, int count);
 int pfa_synth_fill(pfa_aln* a, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm);
 int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar);
 int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels);

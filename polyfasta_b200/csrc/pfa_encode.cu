@@ -109,36 +109,36 @@ __global__ void pfa_head_flags_kernel(const unsigned long long* __restrict__ key
     if (i < n) flags[i] = (i == 0) || ((keys[i] >> 32) != (keys[i - 1] >> 32));
 }
 
-int pfa_finish_exceptions(pfa_aln* a, int64_t count) {
-    pfa_ctx* ctx = a->ctx;
-    a->n_exc = count;
-    a->n_exc_sites = 0;
+// sorts `count` keys in place (the buffer is replaced) and returns the index of the first key of every distinct site
+int pfa_sort_exceptions(pfa_ctx* ctx, unsigned long long** keys, int64_t count, int64_t** heads_out, int64_t* n_heads) {
+    *heads_out = nullptr;
+    *n_heads = 0;
     if (count == 0) return PFA_OK;
     unsigned long long* sorted = nullptr;
     PFA_CUDA(ctx, pfa_dmalloc(ctx, &sorted, sizeof(unsigned long long) * (size_t)count));
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, a->exc_keys, sorted, (int)count, 0, 64, ctx->stream);
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, *keys, sorted, (int)count, 0, 64, ctx->stream);
     void* tmp = nullptr;
     PFA_CUDA(ctx, pfa_dmalloc(ctx, &tmp, tmp_bytes));
-    PFA_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, a->exc_keys, sorted, (int)count, 0, 64, ctx->stream));
+    PFA_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, *keys, sorted, (int)count, 0, 64, ctx->stream));
     ctx->launches += 4;
-    PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     pfa_dfree(ctx, tmp);
-    pfa_dfree(ctx, a->exc_keys);
-    a->exc_keys = sorted;
+    pfa_dfree(ctx, *keys);
+    *keys = sorted;
 
     uint8_t* flags = nullptr;
     int64_t* d_num = nullptr;
+    int64_t* heads = nullptr;
     PFA_CUDA(ctx, pfa_dmalloc(ctx, &flags, (size_t)count));
-    PFA_CUDA(ctx, pfa_dmalloc(ctx, &a->exc_heads, sizeof(int64_t) * (size_t)count));
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &heads, sizeof(int64_t) * (size_t)count));
     PFA_CUDA(ctx, pfa_dmalloc(ctx, &d_num, sizeof(int64_t)));
     pfa_head_flags_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(sorted, count, flags);
     PFA_LAUNCH_CHECK(ctx);
     cub::CountingInputIterator<int64_t> idx(0);
     tmp_bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, flags, a->exc_heads, d_num, (int)count, ctx->stream);
+    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, flags, heads, d_num, (int)count, ctx->stream);
     PFA_CUDA(ctx, pfa_dmalloc(ctx, &tmp, tmp_bytes));
-    PFA_CUDA(ctx, cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, flags, a->exc_heads, d_num, (int)count, ctx->stream));
+    PFA_CUDA(ctx, cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, flags, heads, d_num, (int)count, ctx->stream));
     ctx->launches += 2;
     int64_t num = 0;
     PFA_CUDA(ctx, cudaMemcpyAsync(&num, d_num, sizeof(num), cudaMemcpyDeviceToHost, ctx->stream));
@@ -146,8 +146,15 @@ int pfa_finish_exceptions(pfa_aln* a, int64_t count) {
     pfa_dfree(ctx, tmp);
     pfa_dfree(ctx, flags);
     pfa_dfree(ctx, d_num);
-    a->n_exc_sites = num;
+    *heads_out = heads;
+    *n_heads = num;
     return PFA_OK;
+}
+
+int pfa_finish_exceptions(pfa_aln* a, int64_t count) {
+    a->n_exc = count;
+    a->n_exc_sites = 0;
+    return pfa_sort_exceptions(a->ctx, &a->exc_keys, count, &a->exc_heads, &a->n_exc_sites);
 }
 
 // ---- synthetic generator: the planes of columns [col_begin, col_begin+ns) written directly ---------------

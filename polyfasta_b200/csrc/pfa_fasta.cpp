@@ -52,9 +52,18 @@ static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
     size_t cur = 0;
     bool non_ascii = false;
     size_t i = 0;
+    // a '\r' anywhere switches to the byte-wise scan (a lone '\r' ends a line under universal newlines); otherwise lines
+    // end at '\n' only and memchr finds them at memory speed
+    const bool has_cr = len && memchr(buf, '\r', len) != nullptr;
     while (i < len) {
-        size_t e = i;
-        while (e < len && buf[e] != '\n' && buf[e] != '\r') ++e;
+        size_t e;
+        if (has_cr) {
+            e = i;
+            while (e < len && buf[e] != '\n' && buf[e] != '\r') ++e;
+        } else {
+            const void* nl = memchr(buf + i, '\n', len - i);
+            e = nl ? (size_t)(static_cast<const unsigned char*>(nl) - buf) : len;
+        }
         size_t next = e;
         if (next < len) next += (buf[next] == '\r' && next + 1 < len && buf[next + 1] == '\n') ? 2 : 1;
         // the line is buf[i, e) plus its terminator; never empty as a Python line, but may be empty here
@@ -158,17 +167,65 @@ int pfa_fasta_parse_file(const char* path, pfa_fasta** out) {
     if (st.st_size == 0) {
         rc = parse_impl(nullptr, 0, out);
     } else {
-        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m == MAP_FAILED) {
+        // read() into a private buffer: for the many small files of --dir this beats mmap (no page fault per 4 KB)
+        const size_t size = (size_t)st.st_size;
+        unsigned char* tmp = (unsigned char*)malloc(size);
+        if (!tmp) {
             close(fd);
-            return PFA_ERR_IO;
+            return PFA_ERR_NOMEM;
         }
-        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
-        rc = parse_impl(static_cast<const unsigned char*>(m), (size_t)st.st_size, out);
-        munmap(m, (size_t)st.st_size);
+        size_t got = 0;
+        while (got < size) {
+            const ssize_t r = read(fd, tmp + got, size - got);
+            if (r < 0) {
+                free(tmp);
+                close(fd);
+                return PFA_ERR_IO;
+            }
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        rc = parse_impl(tmp, got, out);
+        free(tmp);
     }
     close(fd);
     return rc;
+}
+
+int pfa_fasta_parse_files(const char* const* paths, int count, int threads, pfa_fasta** out, int* status) {
+    if (count < 0 || (count > 0 && (!paths || !out || !status))) return PFA_ERR_ARG;
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = std::min(threads, std::max(count, 1));
+    auto work = [&](int t) {
+        for (int i = t; i < count; i += threads) {
+            out[i] = nullptr;
+            status[i] = pfa_fasta_parse_file(paths[i], &out[i]);
+        }
+    };
+    if (threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    return PFA_OK;
+}
+
+int64_t pfa_fasta_match_mask(const pfa_fasta* f, const char* key, int64_t key_len, uint32_t* mask, int64_t mask_words) {
+    if (!f || !mask || key_len < 0 || (key_len > 0 && !key) || mask_words * 32 < f->n) return -1;
+    memset(mask, 0, sizeof(uint32_t) * (size_t)mask_words);
+    int64_t hits = 0;
+    for (int64_t r = 0; r < f->n; ++r) {
+        const char* h = f->headers.data() + f->header_off[(size_t)r];
+        const size_t hl = (size_t)(f->header_off[(size_t)r + 1] - f->header_off[(size_t)r]);
+        const bool hit = key_len == 0 || (hl >= (size_t)key_len && memmem(h, hl, key, (size_t)key_len) != nullptr);
+        if (hit) {
+            mask[r >> 5] |= 1u << (r & 31);
+            ++hits;
+        }
+    }
+    return hits;
 }
 
 void pfa_fasta_free(pfa_fasta* f) {

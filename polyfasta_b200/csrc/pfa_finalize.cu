@@ -101,6 +101,14 @@ __global__ void pfa_ssites_kernel(const int64_t* __restrict__ cds, double* __res
     ssites[e] = s;
 }
 
+// device-to-device finalisation of `count` entries (used by the batched path: inputs never leave the GPU)
+int pfa_launch_finalize(pfa_ctx* ctx, const pfa_final_in* d_in, pfa_final_out* d_out, int count) {
+    if (count <= 0) return PFA_OK;
+    pfa_finalize_kernel<<<count, 256, 0, ctx->stream>>>(d_in, d_out, count);
+    PFA_LAUNCH_CHECK(ctx);
+    return PFA_OK;
+}
+
 static int ensure_scratch(pfa_ctx* ctx, size_t bytes) {
     if (ctx->scratch_bytes >= bytes) return PFA_OK;
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);

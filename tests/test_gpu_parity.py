@@ -322,3 +322,76 @@ def test_edge_shapes(ctx):
     assert c["missing"] == 3 and c["nstops"] == 0
     a.free()
     assert ctx.finalize([(5, 0, 0, 10, False)]) == [(0, 0, 0, "NA")]
+
+
+def test_batch_path_matches_single_alignment_path(ctx):
+    """the batched --dir path (K1b/K2b/K5b, one sync) == the single-alignment kernels == the C oracle, for loci of mixed
+    shapes, populations and symbol content in one batch"""
+    rng = np.random.default_rng(123)
+    shapes = [(20, 1000), (100, 5000), (3, 7), (1, 40), (33, 65), (128, 300), (129, 301), (700, 900), (2100, 257), (16, 0), (50, 31)]
+    batch = pf.api.Batch(ctx)
+    loci = []
+    for i, (n, L) in enumerate(shapes):
+        text = _random_text(rng, n, L, p_junk=(0.0 if i % 3 == 0 else 0.02)) if L else np.zeros((n, 0), dtype=np.uint8)
+        pops = None if i % 2 == 0 else [p for p in (list(range(0, n, 2)), list(range(n // 2, n)), list(range(n))) if p]
+        loci.append((text, pops, batch.add_rows(text, pops)))
+    batch.run(jc=True)
+    for text, pops, idx in loci:
+        n, L = text.shape
+        up = _upper(text)
+        for q, rows in enumerate(pops or [list(range(n))]):
+            got = batch.result(idx, q, want_sfs=True)
+            want = co.site_stats(up, rows) if L else {"S": 0, "H": 0, "sfs": [0] * (len(rows) // 2)}
+            assert (got["n"], got["S"], got["H"], got["sfs"]) == (len(rows), want["S"], want["H"], want["sfs"]), (n, L, q)
+            ref = ctx.finalize([(len(rows), want["S"], want["H"], L, True)])[0]
+            assert got["poly"] == ref, (n, L, q)
+    # reuse of the same batch object
+    batch.clear()
+    idx = batch.add_rows(loci[1][0], None)
+    batch.run(jc=False)
+    assert batch.result(idx)["S"] == co.site_stats(_upper(loci[1][0]))["S"]
+    batch.close()
+
+
+def test_batch_golden_examples(ctx):
+    """C2: the 10 shipped loci in ONE batch, with the substring populations, against the reference's rows"""
+    kat = load_golden("kat_examples.json")
+    batch = pf.api.Batch(ctx)
+    slots = []
+    for fn in sorted(kat):
+        f = pf.Fasta.from_file(os.path.join(GOLDEN, "example_theta_0.01", fn))
+        masks = np.stack([pf.api.match_mask(f, key)[0] for key in ("indiv1", "indiv2", "indiv")])
+        slots.append((fn, batch.add(f, masks)))
+    batch.run(jc=True)
+    for fn, idx in slots:
+        for q, key in enumerate(("indiv1", "indiv2", "indiv")):
+            rec = kat[fn]["pops"][key]
+            got = batch.result(idx, q, want_sfs=True)
+            assert (got["n"], got["S"], got["H"]) == (rec["n"], rec["S"], rec["H"])
+            check_poly(got["poly"], rec["poly_jc1"], rec["n"], rec["S"], rec["H"])
+    batch.close()
+
+
+def test_cli_dir_on_two_contexts(tmp_path):
+    """--dir with POLYFASTA_DEVICES naming two contexts (the same GPU twice on a 1-GPU box): chunks are processed by two
+    worker threads and the rows still come out in the reference's sorted() order"""
+    import polyfasta_b200.cli as cli_mod
+    d = tmp_path / "loci"
+    d.mkdir()
+    rng = np.random.default_rng(8)
+    want = {}
+    for i in range(23):
+        n, L = int(rng.integers(2, 40)), int(rng.integers(10, 400))
+        text = _upper(_random_text(rng, n, L, lower=0.0))
+        with open(d / ("locus%d.fa" % i), "w") as f:
+            for r in range(n):
+                f.write(">s%d\n%s\n" % (r, text[r].tobytes().decode()))
+        rows = [text[r].tobytes().decode() for r in range(n)]
+        want["locus%d.fa" % i] = orc.noncds_row("locus%d.fa" % i, L, "NA", rows, True)
+    env = dict(os.environ, PYTHONPATH=ROOT, POLYFASTA_DEVICES="0,0", POLYFASTA_BATCH_FILES="4")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "PolyFastA.py"), "-d", str(d), "--jc", "-s"], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.strip().split("\n")
+    assert [ln.split(",")[0] for ln in lines] == sorted(want)
+    for ln in lines:
+        _rows_close(ln, want[ln.split(",")[0]])
