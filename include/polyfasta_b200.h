@@ -157,6 +157,14 @@ int64_t pfa_batch_text_bytes(const pfa_batch* b);
 int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k, int64_t* index);
 int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k,
                        int64_t* index);
+/* --dir in one native call: read + parse (reference semantics) + header-substring split + append of `count` files with
+ * `threads` host threads, rows copied straight into the pinned blob.  status[i]: PFA_OK, PFA_ERR_NOT_FASTA, PFA_ERR_RAGGED,
+ * PFA_ERR_IO, PFA_ERR_NON_ASCII or PFA_BATCH_TOO_BIG (not added: use pfa_aln_*); shape[2i], shape[2i+1] = n, L;
+ * locus[i] = index in the batch or -1; hits[i*max(nkeys,1)+j] = rows whose header contains keys[j] (populations without a
+ * match are not added; nkeys = 0: one population of all rows). */
+#define PFA_BATCH_TOO_BIG 100
+int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const char* const* keys, int nkeys, int threads,
+                        int* status, int64_t* shape, int64_t* locus, int64_t* hits);
 int pfa_batch_run(pfa_batch* b, int jc);
 int pfa_batch_num_pops(const pfa_batch* b, int64_t locus);
 /* counts = {n, S, H}; sfs (optional) n/2 bins; fin (optional) the K5 output of that (locus, population) */

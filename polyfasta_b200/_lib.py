@@ -10,6 +10,7 @@ SO_PATH = os.path.join(_HERE, "libpolyfasta_b200.so")
 
 PFA_OK, PFA_ERR_CUDA, PFA_ERR_ARG, PFA_ERR_NOT_FASTA, PFA_ERR_RAGGED, PFA_ERR_IO, PFA_ERR_NOMEM, PFA_ERR_NON_ASCII = range(8)
 PFA_CDS_LEN = 71
+PFA_BATCH_TOO_BIG = 100
 
 # every symbol include/polyfasta_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
@@ -24,7 +25,7 @@ EXPORTS = [
     "pfa_cds_stats_device", "pfa_cds_stats", "pfa_codon_pair_labels", "pfa_codon_set_labels", "pfa_codon_syn3",
     "pfa_codon_class", "pfa_pairwise_device", "pfa_pairwise", "pfa_finalize", "pfa_cds_ssites",
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
-    "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
+    "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
 ]
 
@@ -117,6 +118,8 @@ def lib():
         "pfa_batch_text_bytes": (i64, [p]),
         "pfa_batch_add": (c.c_int, [p, p, p, c.c_int, c.POINTER(i64)]),
         "pfa_batch_add_rows": (c.c_int, [p, p, i64, i64, i64, p, c.c_int, c.POINTER(i64)]),
+        "pfa_batch_add_files": (c.c_int, [p, c.POINTER(c.c_char_p), c.c_int, c.POINTER(c.c_char_p), c.c_int, c.c_int,
+                                          c.POINTER(c.c_int), c.POINTER(i64), c.POINTER(i64), c.POINTER(i64)]),
         "pfa_batch_run": (c.c_int, [p, c.c_int]),
         "pfa_batch_num_pops": (c.c_int, [p, i64]),
         "pfa_batch_result": (c.c_int, [p, i64, c.c_int, c.POINTER(i64), p, c.POINTER(FinalOut)]),

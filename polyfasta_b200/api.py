@@ -476,6 +476,23 @@ class Batch:
             check(lib().pfa_batch_add_rows(self._h, mat.ctypes.data, n, L, max(L, 1), None, 0, ctypes.byref(idx)), self.ctx.handle)
         return idx.value
 
+    def add_files(self, paths, keys=(), threads=0):
+        """read + parse + population split + append of many files in one native call (host threads).
+        -> list of dict(status, n, L, locus, hits[list per key, or [n] without keys])"""
+        n = len(paths)
+        if n == 0:
+            return []
+        nk = max(len(keys), 1)
+        parr = (ctypes.c_char_p * n)(*[str(x).encode() for x in paths])
+        karr = (ctypes.c_char_p * max(len(keys), 1))(*[k.encode("utf-8", "surrogateescape") for k in keys]) if keys else None
+        status = (ctypes.c_int * n)()
+        shape = (ctypes.c_int64 * (2 * n))()
+        locus = (ctypes.c_int64 * n)()
+        hits = (ctypes.c_int64 * (n * nk))()
+        check(lib().pfa_batch_add_files(self._h, parr, n, karr, len(keys), threads, status, shape, locus, hits), self.ctx.handle)
+        return [{"status": status[i], "n": shape[2 * i], "L": shape[2 * i + 1], "locus": locus[i],
+                 "hits": [hits[i * nk + j] for j in range(nk)]} for i in range(n)]
+
     def run(self, jc=False):
         check(lib().pfa_batch_run(self._h, int(bool(jc))), self.ctx.handle)
 

@@ -227,6 +227,69 @@ def process_chunk(ctx, batch, items, cds, jc, popkeys):
     return actions
 
 
+def noncds_line(file, seqlen, label, n, r):
+    if r["S"] == 0:
+        return f"{file},{seqlen},{label},{n},0,0,0,NA"                                         # PolyFastA.py:187/:189
+    p = r["poly"]
+    return f"{file},{seqlen},{label},{n},{p[0]},{p[1]},{p[2]},{p[3]}"                          # :196/:198
+
+
+def process_chunk_native(ctx, batch, paths, jc, popkeys, threads):
+    """non-CDS --dir chunk: ONE native call reads, parses, splits and stages every file (host threads), ONE batched GPU pass
+    computes every (locus, population), then the rows are formatted in order"""
+    from ._lib import PFA_BATCH_TOO_BIG, PFA_ERR_IO, PFA_ERR_NON_ASCII, PFA_ERR_NOT_FASTA, PFA_ERR_RAGGED, PFA_OK
+    import time
+    t0 = time.perf_counter()
+    batch.clear()
+    info = batch.add_files(paths, popkeys or (), threads)
+    t1 = time.perf_counter()
+    labels = popkeys if popkeys is not None else ["NA"]
+    actions, pending = [], []
+    for path, fi in zip(paths, info):
+        file = path.split("/")[-1]
+        st = fi["status"]
+        if st == PFA_ERR_NOT_FASTA:
+            actions.append(("stdout", f"# file {path} is not FASTA!"))
+        elif st == PFA_ERR_IO:
+            actions.append(("raise", OSError("cannot read %s" % path)))
+            break
+        elif st == PFA_ERR_NON_ASCII:
+            actions.append(("raise", ValueError("%s: non-ASCII bytes in sequence lines are not supported" % path)))
+            break
+        elif st == PFA_ERR_RAGGED:
+            actions.append(("note", f"# Sequences do not have the same length: {file}"))
+        elif st == PFA_BATCH_TOO_BIG:
+            sub = api.Batch(ctx)
+            try:
+                actions.extend(process_chunk(ctx, sub, [(path, api.parse_files([path])[0])], False, jc, popkeys))
+            finally:
+                sub.close()
+        elif st == PFA_OK:
+            q = 0
+            for label, hits in zip(labels, fi["hits"]):
+                if hits == 0:
+                    actions.append(("note", f"# Pop {label} string was not found in fasta headers."))
+                else:
+                    pending.append((len(actions), fi["locus"], q, file, fi["L"], label, hits))
+                    actions.append(None)
+                    q += 1
+        else:
+            actions.append(("raise", api.PolyFastaError(st, "cannot process %s" % path)))
+            break
+    t2 = time.perf_counter()
+    if pending:
+        batch.run(jc)
+        t3 = time.perf_counter()
+        for pos, locus, q, file, seqlen, label, n in pending:
+            actions[pos] = ("row", noncds_line(file, seqlen, label, n, batch.result(locus, q)), file, label)
+    else:
+        t3 = t2
+    if os.environ.get("POLYFASTA_TIMING"):
+        print("chunk of %d files: add_files %.1f ms (%d threads), plan %.1f ms, gpu run %.1f ms, rows %.1f ms" %
+              (len(paths), (t1 - t0) * 1e3, threads, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3), file=sys.stderr)
+    return [a for a in actions if a is not None]
+
+
 def emit(actions, sink):
     for a in actions:
         if a[0] == "stdout":
@@ -263,6 +326,8 @@ def run_files(paths, cds, jc, popkeys, sink):
         cur_bytes += sz
     if cur:
         chunks.append(cur)
+    if len(chunks) > 1 and os.environ.get("POLYFASTA_DOUBLE_BUFFER", "1") != "0":
+        devs = [d for d in devs for _ in (0, 1)]   # two slots per GPU: host staging of chunk i+1 overlaps the GPU pass of chunk i
     state = {}
 
     def work(ci):
@@ -271,7 +336,10 @@ def run_files(paths, cds, jc, popkeys, sink):
             ctx = api.Context(devs[slot])
             state[slot] = (ctx, api.Batch(ctx))
         ctx, batch = state[slot]
-        fastas = api.parse_files(chunks[ci], threads=max(1, (os.cpu_count() or 1) // len(devs)))
+        threads = max(1, (os.cpu_count() or 1) // len(devs))
+        if not cds:
+            return process_chunk_native(ctx, batch, chunks[ci], jc, popkeys, threads)
+        fastas = api.parse_files(chunks[ci], threads=threads)
         return process_chunk(ctx, batch, list(zip(chunks[ci], fastas)), cds, jc, popkeys)
 
     if len(devs) == 1 or len(chunks) == 1:

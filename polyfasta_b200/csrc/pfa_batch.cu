@@ -3,9 +3,13 @@
 // three segmented launches -- K1b encode, K2b site scan, K5b finalise -- with ONE synchronisation.  A locus keeps its own
 // shape (n, L), populations and result slots; kernels find the locus of a tile / site group by binary search in a prefix
 // table.  The arithmetic is the same device code as the single-alignment kernels (pfa_sites.cuh, pfa_finalize.cu).
+#include <sys/stat.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "pfa_host.h"
 #include "pfa_sites.cuh"
@@ -27,8 +31,17 @@ struct PfaPopSlot {
     double seqlen;
 };
 
+// one locus as added on the host; the device layout (PfaLocusDesc / PfaPopSlot) is derived from these in pfa_batch_run
+struct PfaBatchEntry {
+    long long text_off = 0;
+    int n = 0, L = 0, ld = 0, Wq = 0, k = 0;
+    std::vector<uint32_t> masks;    // [k][4*Wq]
+    std::vector<long long> pop_n;   // [k]
+};
+
 struct pfa_batch {
     pfa_ctx* ctx = nullptr;
+    std::vector<PfaBatchEntry> entries;
     std::vector<PfaLocusDesc> desc;
     std::vector<PfaPopSlot> pops;
     std::vector<uint32_t> masks;  // per locus: k masks then the union, each 4*Wq words
@@ -46,7 +59,10 @@ static int grow_text(pfa_batch* b, size_t need) {
     if (need <= b->h_text_cap) return PFA_OK;
     size_t cap = std::max<size_t>(need, std::max<size_t>(b->h_text_cap * 2, 64u << 20));
     unsigned char* p = nullptr;
-    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return pfa_fail(b->ctx, PFA_ERR_NOMEM, "cannot pin %zu bytes", cap);
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return pfa_fail(b->ctx, PFA_ERR_NOMEM, "cannot pin %zu bytes", cap);
+    }
     if (b->h_text_used) memcpy(p, b->h_text, b->h_text_used);
     if (b->h_text) cudaFreeHost(b->h_text);
     b->h_text = p;
@@ -340,12 +356,8 @@ int pfa_batch_create(pfa_ctx* ctx, pfa_batch** out) {
 
 int pfa_batch_clear(pfa_batch* b) {
     if (!b) return PFA_ERR_ARG;
-    b->desc.clear();
-    b->pops.clear();
-    b->masks.clear();
+    b->entries.clear();
     b->h_text_used = 0;
-    b->n_sites = b->n_tiles = b->plane_u4 = b->mask_u4 = b->out_len = 0;
-    b->max_Wq = 0;
     b->ran = false;
     return PFA_OK;
 }
@@ -357,66 +369,95 @@ int pfa_batch_destroy(pfa_batch* b) {
     return PFA_OK;
 }
 
-int64_t pfa_batch_size(const pfa_batch* b) { return b ? (int64_t)b->desc.size() : 0; }
+int64_t pfa_batch_size(const pfa_batch* b) { return b ? (int64_t)b->entries.size() : 0; }
 int64_t pfa_batch_text_bytes(const pfa_batch* b) { return b ? (int64_t)b->h_text_used : 0; }
 
-int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k, int64_t* index) {
-    if (!b || n <= 0 || L < 0 || (L > 0 && (!text || ld < L)) || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
-    if (n >= (1ll << 24) || L >= (1ll << 31)) return pfa_fail(b->ctx, PFA_ERR_ARG, "locus too large for the batched path");
-    PfaLocusDesc d;
-    d.n = (int)n;
-    d.L = (int)L;
-    d.ld = (int)pfa_round_up(std::max<int64_t>(L, 1), 32);
-    d.Wq = wq_of(n);
-    d.k = k > 0 ? k : 1;
-    d.pad = 0;
-    d.text_off = (long long)pfa_round_up((int64_t)b->h_text_used, 256);
-    const size_t need = (size_t)d.text_off + (size_t)n * d.ld;
-    int rc = grow_text(b, need);
-    if (rc) return rc;
-    for (int64_t r = 0; r < n; ++r) memcpy(b->h_text + d.text_off + r * d.ld, text + r * ld, (size_t)L);
-    b->h_text_used = need;
-    d.plane_off = b->plane_u4;
-    d.mask_off = b->mask_u4;
-    d.site_base = b->n_sites;
-    d.tile_base = b->n_tiles;
-    d.pop_base = (long long)b->pops.size();
-    const int64_t Wn = (int64_t)d.Wq * 4;
-    // masks: k population masks, then their union
-    const size_t m0 = b->masks.size();
-    b->masks.resize(m0 + (size_t)((d.k + 1) * Wn), 0u);
-    uint32_t* mk = b->masks.data() + m0;
-    uint32_t* uni = mk + (size_t)d.k * Wn;
-    for (int q = 0; q < d.k; ++q) {
-        int64_t cnt = 0;
+}  // extern "C"
+
+// trims the masks to n rows, counts the populations; false when one is empty
+static bool entry_set_masks(PfaBatchEntry* e, const uint32_t* masks, int k) {
+    const int64_t Wn = (int64_t)e->Wq * 4, n = e->n;
+    e->k = k > 0 ? k : 1;
+    e->masks.assign((size_t)(e->k * Wn), 0u);
+    e->pop_n.assign((size_t)e->k, 0);
+    for (int q = 0; q < e->k; ++q) {
+        long long cnt = 0;
         for (int64_t w = 0; w < Wn; ++w) {
             uint32_t x = k > 0 ? masks[q * Wn + w] : 0xffffffffu;
             const int64_t lo = w * 32;
             if (lo >= n) x = 0;
             else if (lo + 32 > n) x &= (1u << (n - lo)) - 1u;
-            mk[q * Wn + w] = x;
-            uni[w] |= x;
+            e->masks[(size_t)(q * Wn + w)] = x;
             cnt += __builtin_popcount(x);
         }
-        if (cnt == 0) {
-            b->masks.resize(m0);
-            return pfa_fail(b->ctx, PFA_ERR_ARG, "empty population in batch");
-        }
-        PfaPopSlot ps;
-        ps.n = cnt;
-        ps.out_off = b->out_len;
-        ps.locus = (long long)b->desc.size();
-        ps.seqlen = (double)L;
-        b->pops.push_back(ps);
-        b->out_len += 2 + cnt / 2;
+        if (cnt == 0) return false;
+        e->pop_n[(size_t)q] = cnt;
     }
-    b->plane_u4 += (long long)L * d.Wq;
-    b->mask_u4 += (long long)(d.k + 1) * d.Wq;
-    b->n_sites += L;
-    b->n_tiles += ((n + 31) / 32) * ((L + 31) / 32);
-    b->max_Wq = std::max(b->max_Wq, d.Wq);
-    if (index) *index = (int64_t)b->desc.size();
-    b->desc.push_back(d);
+    return true;
+}
+
+// device layout of the current entries
+static void build_layout(pfa_batch* b) {
+    b->desc.clear();
+    b->pops.clear();
+    b->masks.clear();
+    b->n_sites = b->n_tiles = b->plane_u4 = b->mask_u4 = b->out_len = 0;
+    b->max_Wq = 0;
+    for (size_t i = 0; i < b->entries.size(); ++i) {
+        const PfaBatchEntry& e = b->entries[i];
+        PfaLocusDesc d;
+        d.text_off = e.text_off;
+        d.plane_off = b->plane_u4;
+        d.mask_off = b->mask_u4;
+        d.site_base = b->n_sites;
+        d.tile_base = b->n_tiles;
+        d.pop_base = (long long)b->pops.size();
+        d.n = e.n; d.L = e.L; d.ld = e.ld; d.Wq = e.Wq; d.k = e.k; d.pad = 0;
+        const int64_t Wn = (int64_t)e.Wq * 4;
+        const size_t m0 = b->masks.size();
+        b->masks.resize(m0 + (size_t)((e.k + 1) * Wn), 0u);
+        memcpy(b->masks.data() + m0, e.masks.data(), sizeof(uint32_t) * (size_t)(e.k * Wn));
+        uint32_t* uni = b->masks.data() + m0 + (size_t)e.k * Wn;
+        for (int q = 0; q < e.k; ++q) {
+            for (int64_t w = 0; w < Wn; ++w) uni[w] |= e.masks[(size_t)(q * Wn + w)];
+            PfaPopSlot ps;
+            ps.n = e.pop_n[(size_t)q];
+            ps.out_off = b->out_len;
+            ps.locus = (long long)i;
+            ps.seqlen = (double)e.L;
+            b->pops.push_back(ps);
+            b->out_len += 2 + ps.n / 2;
+        }
+        b->plane_u4 += (long long)e.L * e.Wq;
+        b->mask_u4 += (long long)(e.k + 1) * e.Wq;
+        b->n_sites += e.L;
+        b->n_tiles += (long long)((e.n + 31) / 32) * ((e.L + 31) / 32);
+        b->max_Wq = std::max(b->max_Wq, e.Wq);
+        b->desc.push_back(d);
+    }
+}
+
+#define PFA_BATCH_MAX_WQ 128
+
+extern "C" {
+
+int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k, int64_t* index) {
+    if (!b || n <= 0 || L < 0 || (L > 0 && (!text || ld < L)) || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
+    if (L >= (1ll << 31) || wq_of(n) > PFA_BATCH_MAX_WQ) return pfa_fail(b->ctx, PFA_ERR_ARG, "locus too large for the batched path");
+    PfaBatchEntry e;
+    e.n = (int)n;
+    e.L = (int)L;
+    e.ld = (int)pfa_round_up(std::max<int64_t>(L, 1), 32);
+    e.Wq = wq_of(n);
+    if (!entry_set_masks(&e, masks, k)) return pfa_fail(b->ctx, PFA_ERR_ARG, "empty population in batch");
+    e.text_off = (long long)pfa_round_up((int64_t)b->h_text_used, 256);
+    const size_t need = (size_t)e.text_off + (size_t)n * e.ld;
+    int rc = grow_text(b, need);
+    if (rc) return rc;
+    for (int64_t r = 0; r < n; ++r) memcpy(b->h_text + e.text_off + r * e.ld, text + r * ld, (size_t)L);
+    b->h_text_used = need;
+    if (index) *index = (int64_t)b->entries.size();
+    b->entries.push_back(std::move(e));
     b->ran = false;
     return PFA_OK;
 }
@@ -427,9 +468,110 @@ int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k
     return pfa_batch_add_rows(b, f->data, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), masks, k, index);
 }
 
+// --dir in one native call: read, parse (reference semantics), split by header-substring keys and append `count` files with
+// `threads` host threads; rows are copied straight into the pinned blob.  Per file: status[i] (PFA_OK, PFA_ERR_NOT_FASTA,
+// PFA_ERR_RAGGED, PFA_ERR_IO, PFA_ERR_NON_ASCII, or PFA_BATCH_TOO_BIG = not added, use the single-alignment path),
+// shape[2i] = n, shape[2i+1] = L, locus[i] = its index in the batch or -1, hits[i*max(nkeys,1) + j] = rows matching key j
+// (populations without a match are not added; with nkeys = 0 the one population is all rows).
+int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const char* const* keys, int nkeys, int threads, int* status,
+                        int64_t* shape, int64_t* locus, int64_t* hits) {
+    if (!b || count < 0 || nkeys < 0 || (count > 0 && (!paths || !status || !shape || !locus || !hits)) || (nkeys > 0 && !keys))
+        return PFA_ERR_ARG;
+    if (count == 0) return PFA_OK;
+    // size the blob once: the rows of a file never need more than its size plus the padding of every row to 32 bytes
+    std::vector<size_t> fsize((size_t)count, 0);
+    size_t bound = (size_t)pfa_round_up((int64_t)b->h_text_used, 256);
+    for (int i = 0; i < count; ++i) {
+        struct stat st;
+        if (stat(paths[i], &st) == 0 && !S_ISDIR(st.st_mode)) fsize[(size_t)i] = (size_t)st.st_size;
+        bound += fsize[(size_t)i] + fsize[(size_t)i] / 8 + 4096;
+    }
+    int rc = grow_text(b, bound);
+    if (rc) return rc;
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = std::min(threads, count);
+    const int nk = std::max(nkeys, 1);
+    std::vector<PfaBatchEntry> slots((size_t)count);
+    std::atomic<size_t> cursor((size_t)pfa_round_up((int64_t)b->h_text_used, 256));
+    std::vector<size_t> klen((size_t)nkeys);
+    for (int j = 0; j < nkeys; ++j) klen[(size_t)j] = strlen(keys[j]);
+    auto work = [&](int t) {
+        std::vector<unsigned char> buf;
+        PfaParsed parsed;
+        for (int i = t; i < count; i += threads) {
+            locus[i] = -1;
+            shape[2 * i] = shape[2 * i + 1] = 0;
+            for (int j = 0; j < nk; ++j) hits[(size_t)i * nk + j] = 0;
+            size_t len = 0;
+            int st = pfa_read_file(paths[i], &buf, &len);
+            if (!st) st = pfa_parse_lines(buf.data(), len, &parsed);
+            if (st) { status[i] = st; continue; }
+            const int64_t n = (int64_t)parsed.recs.size(), L = parsed.seqlen;
+            shape[2 * i] = n;
+            shape[2 * i + 1] = L;
+            if (L < 0) { status[i] = PFA_ERR_RAGGED; continue; }
+            PfaBatchEntry& e = slots[(size_t)i];
+            e.n = (int)n; e.L = (int)L; e.Wq = wq_of(n);
+            e.ld = (int)pfa_round_up(std::max<int64_t>(L, 1), 32);
+            // populations: header substring match per key (PolyFastA.py:125), empty ones dropped
+            const int64_t Wn = (int64_t)e.Wq * 4;
+            std::vector<uint32_t> m;
+            int kfound = 0;
+            if (nkeys == 0) {
+                hits[(size_t)i * nk] = n;
+            } else {
+                for (int j = 0; j < nkeys; ++j) {
+                    std::vector<uint32_t> mj((size_t)Wn, 0u);
+                    int64_t h = 0;
+                    for (int64_t r = 0; r < n; ++r) {
+                        const std::string& hd = parsed.recs[(size_t)r].header;
+                        if (klen[(size_t)j] == 0 || (hd.size() >= klen[(size_t)j] && memmem(hd.data(), hd.size(), keys[j], klen[(size_t)j]))) {
+                            mj[(size_t)(r >> 5)] |= 1u << (r & 31);
+                            ++h;
+                        }
+                    }
+                    hits[(size_t)i * nk + j] = h;
+                    if (h) { m.insert(m.end(), mj.begin(), mj.end()); ++kfound; }
+                }
+                if (kfound == 0) { status[i] = PFA_OK; continue; }   // nothing to compute: every key prints its note
+            }
+            if (n >= (1ll << 24) || L >= (1ll << 31) || e.Wq > PFA_BATCH_MAX_WQ || (size_t)n * (size_t)e.ld > (64u << 20)) {
+                status[i] = PFA_BATCH_TOO_BIG;
+                continue;
+            }
+            const size_t need = (size_t)pfa_round_up((int64_t)((size_t)n * e.ld), 256);
+            const size_t off = cursor.fetch_add(need);
+            if (off + need > b->h_text_cap) { status[i] = PFA_BATCH_TOO_BIG; continue; }
+            bool ascii = true;
+            for (int64_t r = 0; r < n; ++r) ascii &= pfa_copy_record(parsed.recs[(size_t)r], b->h_text + off + (size_t)r * e.ld);
+            if (!ascii) { status[i] = PFA_ERR_NON_ASCII; continue; }
+            e.text_off = (long long)off;
+            entry_set_masks(&e, nkeys ? m.data() : nullptr, nkeys ? kfound : 0);
+            locus[i] = 0;  // placeholder: numbered in file order below
+            status[i] = PFA_OK;
+        }
+    };
+    if (threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    b->h_text_used = std::min(cursor.load(), b->h_text_cap);
+    for (int i = 0; i < count; ++i)
+        if (locus[i] == 0) {
+            locus[i] = (int64_t)b->entries.size();
+            b->entries.push_back(std::move(slots[(size_t)i]));
+        }
+    b->ran = false;
+    return PFA_OK;
+}
+
 int pfa_batch_run(pfa_batch* b, int jc) {
     if (!b) return PFA_ERR_ARG;
     pfa_ctx* ctx = b->ctx;
+    build_layout(b);
     const int nloci = (int)b->desc.size();
     const long long npops = (long long)b->pops.size();
     b->out.assign((size_t)b->out_len, 0);
@@ -544,7 +686,7 @@ int pfa_batch_run(pfa_batch* b, int jc) {
 }
 
 int pfa_batch_num_pops(const pfa_batch* b, int64_t locus) {
-    return (b && locus >= 0 && locus < (int64_t)b->desc.size()) ? b->desc[(size_t)locus].k : -1;
+    return (b && locus >= 0 && locus < (int64_t)b->entries.size()) ? b->entries[(size_t)locus].k : -1;
 }
 
 /* result of (locus, pop): counts[0..2] = n, S, H ; sfs copied when sfs != NULL (n/2 bins); fin = K5 output */

@@ -27,30 +27,18 @@
 #include "pfa_host.h"
 
 namespace {
-
 // str.rstrip() with no argument strips characters for which str.isspace() is true; in ASCII these are
 // \t \n \v \f \r, the separators 0x1c-0x1f and the blank.
 inline bool py_space(unsigned char c) { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); }
-
-struct Slice {
-    const unsigned char* p;
-    size_t len;
-};
-
-struct Record {
-    std::string header;
-    std::vector<Slice> parts;
-    int64_t len = 0;
-};
-
 }  // namespace
 
-static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
-    std::vector<Record> recs;
+// line scan: records with their line slices (pointing into buf), lengths, and whether all rows have one length
+int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out) {
+    std::vector<PfaRecord>& recs = out->recs;
+    recs.clear();
     std::unordered_map<std::string, size_t> index;
     bool seen_header = false, head_nonempty = false;
     size_t cur = 0;
-    bool non_ascii = false;
     size_t i = 0;
     // a '\r' anywhere switches to the byte-wise scan (a lone '\r' ends a line under universal newlines); otherwise lines
     // end at '\n' only and memchr finds them at memory speed
@@ -77,57 +65,72 @@ static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
             if (it == index.end()) {
                 index.emplace(h, recs.size());
                 cur = recs.size();
-                recs.push_back(Record{h, {}, 0});
+                recs.push_back(PfaRecord{h, {}, 0});
             } else {
                 cur = it->second;
                 recs[cur].parts.clear();
                 recs[cur].len = 0;
             }
         } else if (seen_header && head_nonempty && r > i) {
-            recs[cur].parts.push_back(Slice{buf + i, r - i});
+            recs[cur].parts.push_back(PfaSlice{buf + i, r - i});
             recs[cur].len += (int64_t)(r - i);
         }
         i = next;
     }
     if (!seen_header || !head_nonempty) return PFA_ERR_NOT_FASTA;
+    out->total = 0;
+    out->same = true;
+    for (const PfaRecord& rec : recs) {
+        out->total += rec.len;
+        if (rec.len != recs[0].len) out->same = false;
+    }
+    out->seqlen = out->same ? recs[0].len : -1;
+    return PFA_OK;
+}
 
+// copy the line slices of one record to dst; returns false when a byte >= 0x80 was seen
+bool pfa_copy_record(const PfaRecord& rec, unsigned char* dst) {
+    unsigned char acc = 0;
+    for (const PfaSlice& s : rec.parts) {
+        memcpy(dst, s.p, s.len);
+        for (size_t b = 0; b < s.len; ++b) acc |= s.p[b];
+        dst += s.len;
+    }
+    return !(acc & 0x80);
+}
+
+static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
+    PfaParsed parsed;
+    int rc = pfa_parse_lines(buf, len, &parsed);
+    if (rc) return rc;
+    const std::vector<PfaRecord>& recs = parsed.recs;
     pfa_fasta* f = new pfa_fasta();
     f->n = (int64_t)recs.size();
     f->row_len.resize(recs.size());
     f->row_off.resize(recs.size() + 1);
     int64_t total = 0;
-    bool same = true;
     for (size_t k = 0; k < recs.size(); ++k) {
         f->row_len[k] = recs[k].len;
         f->row_off[k] = total;
         total += recs[k].len;
-        if (recs[k].len != recs[0].len) same = false;
         f->header_off.push_back((int64_t)f->headers.size());
         f->headers += recs[k].header;
     }
     f->row_off[recs.size()] = total;
     f->header_off.push_back((int64_t)f->headers.size());
-    f->seqlen = same ? recs[0].len : -1;
+    f->seqlen = parsed.seqlen;
     f->data_bytes = (size_t)std::max<int64_t>(total, 1);
     f->data = (unsigned char*)malloc(f->data_bytes);
     if (!f->data) {
         delete f;
         return PFA_ERR_NOMEM;
     }
-    // copy the line slices; rows are independent, so large files are copied by several threads
+    // rows are independent, so large files are copied by several threads
     unsigned nthreads = total > (64ll << 20) ? std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
     std::vector<char> bad(nthreads, 0);
     auto work = [&](unsigned t) {
-        for (size_t k = t; k < recs.size(); k += nthreads) {
-            unsigned char* dst = f->data + f->row_off[k];
-            for (const Slice& s : recs[k].parts) {
-                memcpy(dst, s.p, s.len);
-                unsigned char acc = 0;
-                for (size_t b = 0; b < s.len; ++b) acc |= s.p[b];
-                if (acc & 0x80) bad[t] = 1;
-                dst += s.len;
-            }
-        }
+        for (size_t k = t; k < recs.size(); k += nthreads)
+            if (!pfa_copy_record(recs[k], f->data + f->row_off[k])) bad[t] = 1;
     };
     if (nthreads == 1) {
         work(0);
@@ -136,12 +139,39 @@ static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
         for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(work, t);
         for (auto& x : th) x.join();
     }
+    bool non_ascii = false;
     for (char b : bad) non_ascii |= (b != 0);
     if (non_ascii) {
         pfa_fasta_free(f);
         return PFA_ERR_NON_ASCII;
     }
     *out = f;
+    return PFA_OK;
+}
+
+// whole file into a reusable buffer (read() rather than mmap: no page fault per 4 KB for the many small files of --dir)
+int pfa_read_file(const char* path, std::vector<unsigned char>* buf, size_t* len) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return PFA_ERR_IO;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) {
+        close(fd);
+        return PFA_ERR_IO;
+    }
+    const size_t size = (size_t)st.st_size;
+    if (buf->size() < size) buf->resize(size);
+    size_t got = 0;
+    while (got < size) {
+        const ssize_t r = read(fd, buf->data() + got, size - got);
+        if (r < 0) {
+            close(fd);
+            return PFA_ERR_IO;
+        }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    *len = got;  // the buffer keeps its size so that the next, equally large file does not zero-fill it again
     return PFA_OK;
 }
 
@@ -156,40 +186,11 @@ int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out) {
 int pfa_fasta_parse_file(const char* path, pfa_fasta** out) {
     if (!out || !path) return PFA_ERR_ARG;
     *out = nullptr;
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) return PFA_ERR_IO;
-    struct stat st;
-    if (fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) {
-        close(fd);
-        return PFA_ERR_IO;
-    }
-    int rc;
-    if (st.st_size == 0) {
-        rc = parse_impl(nullptr, 0, out);
-    } else {
-        // read() into a private buffer: for the many small files of --dir this beats mmap (no page fault per 4 KB)
-        const size_t size = (size_t)st.st_size;
-        unsigned char* tmp = (unsigned char*)malloc(size);
-        if (!tmp) {
-            close(fd);
-            return PFA_ERR_NOMEM;
-        }
-        size_t got = 0;
-        while (got < size) {
-            const ssize_t r = read(fd, tmp + got, size - got);
-            if (r < 0) {
-                free(tmp);
-                close(fd);
-                return PFA_ERR_IO;
-            }
-            if (r == 0) break;
-            got += (size_t)r;
-        }
-        rc = parse_impl(tmp, got, out);
-        free(tmp);
-    }
-    close(fd);
-    return rc;
+    static thread_local std::vector<unsigned char> buf;  // warm across the files one thread parses
+    size_t n = 0;
+    int rc = pfa_read_file(path, &buf, &n);
+    if (rc) return rc;
+    return parse_impl(buf.data(), n, out);
 }
 
 int pfa_fasta_parse_files(const char* const* paths, int count, int threads, pfa_fasta** out, int* status) {

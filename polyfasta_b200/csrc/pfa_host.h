@@ -19,3 +19,23 @@ struct pfa_fasta {
     bool pinned = false;             // data registered with cudaHostRegister by the uploader
     void (*unpin)(void*) = nullptr;
 };
+
+// ---- parser internals shared with the batched path --------------------------------------------------------------------
+struct PfaSlice {
+    const unsigned char* p;
+    size_t len;
+};
+struct PfaRecord {
+    std::string header;
+    std::vector<PfaSlice> parts;
+    int64_t len = 0;
+};
+struct PfaParsed {
+    std::vector<PfaRecord> recs;
+    int64_t total = 0;
+    int64_t seqlen = -1;
+    bool same = true;
+};
+int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out);
+bool pfa_copy_record(const PfaRecord& rec, unsigned char* dst);
+int pfa_read_file(const char* path, std::vector<unsigned char>* buf, size_t* len);
