@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = the scan kernel's last block sums the shard vectors over NVLink peer memory (pfa_xchg, the product "
+                         "path); 'nccl' = scan kernel + torch.distributed all_reduce (comparison only)")
     ap.add_argument("--force-validity", action="store_true", help="make the scan read the validity plane too (0.375 B/base)")
     return ap.parse_args()
 
@@ -217,15 +220,20 @@ def main():
             aln.force_validity(True)
         planes_read = 3 if (aln.has_invalid or args.force_validity) else 2
         out = torch.zeros(aln.site_len(), dtype=torch.int64, device="cuda")
+        fused = world > 1 and args.collective == "fused"
+        xchg = parallel.connect_exchange(ctx, aln.site_len()) if fused else None
         ctx.sync()
 
         def step(ev=None):
             if ev:
                 ev[0].record(stream)
-            aln.site_stats_device(out.data_ptr())
+            if fused:
+                aln.site_stats_xchg(xchg, out.data_ptr())     # ONE launch: K2 + sum over the shards of all ranks
+            else:
+                aln.site_stats_device(out.data_ptr())
             if ev:
                 ev[1].record(stream)
-            if world > 1:
+            if world > 1 and not fused:
                 dist.all_reduce(out)
 
         for _ in range(args.warmup):
@@ -236,6 +244,14 @@ def main():
         sampler.start()
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            # device-side rendezvous on the timing stream: the ranks leave the host barrier up to a millisecond apart, and
+            # without it the first timed step of the early ranks would just measure that host skew
+            sync_word = torch.zeros(1, dtype=torch.int64, device="cuda")
+            if fused:
+                xchg.allreduce(sync_word.data_ptr(), 1)
+            else:
+                dist.all_reduce(sync_word)
         t_start.record(stream)
         for i in range(args.steps):
             step(kev[i])
@@ -247,6 +263,15 @@ def main():
         elapsed_ms = max_over_ranks(t_start.elapsed_time(t_end))
         kernel_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in kev) / args.steps)
         result = out.cpu().numpy().copy()
+        if fused and xchg.timed_out():
+            raise SystemExit("the NVLink exchange timed out on rank %d (a rank did not arrive)" % rank)
+        if os.environ.get("PFA_XCHG_STAMPS"):
+            per = [a.elapsed_time(b) for a, b in kev]
+            gaps = [kev[i][0].elapsed_time(kev[i + 1][0]) for i in range(args.steps - 1)]
+            sys.stderr.write("rank %d kernel ms per step %s\nrank %d step-to-step ms %s\n" %
+                             (rank, ["%.3f" % x for x in per], rank, ["%.3f" % x for x in gaps]))
+            if fused:
+                sys.stderr.write("rank %d exchange stages (ns): %s\n" % (rank, xchg.stamps()))
 
     value = n * L * args.steps / (elapsed_ms * 1e-3)
     my_sites = c1 - c0
@@ -294,9 +319,12 @@ def main():
 
             def e2e_step():
                 a = pf.Alignment.from_host_ptr(ctx, h_text.data_ptr(), n, cols, ld)   # H2D (pinned, chunked) + K1
-                a.site_stats_device(out.data_ptr())                                  # K2
-                if world > 1:
-                    dist.all_reduce(out)
+                if fused:
+                    a.site_stats_xchg(xchg, out.data_ptr())                          # K2 + sum over shards (NVLink)
+                else:
+                    a.site_stats_device(out.data_ptr())                              # K2
+                    if world > 1:
+                        dist.all_reduce(out)
                 h_out.copy_(out, non_blocking=True)                                  # D2H
                 stream.synchronize()
                 r = ctx.finalize([(n, int(h_out[0]), int(h_out[1]), es, True)])[0]   # K5
@@ -336,7 +364,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": "C4: synthetic non-coding alignment %d seqs x %d sites, site scan (S, H, folded SFS)" % (n, L),
-                       "parallelism": "columns split in %d contiguous ranges + 1 NCCL int64 all-reduce per step" % world if world > 1 else "1 GPU",
+                       "parallelism": ("columns split in %d contiguous ranges; " % world + ("the scan kernel's last block sums the int64 shard vectors "
+                                       "over NVLink peer memory (fused, no collective call)" if fused else "1 NCCL int64 all-reduce per step"))
+                       if world > 1 else "1 GPU",
                        "l2": "inputs larger than L2 (%.1f GB of planes read per GPU per step)" % (algo_bytes / 1e9),
                        "planes_read": planes_read, "seed": SEED, "p_seg_ppm": P_SEG_PPM, "tri_ppm": TRI_PPM},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -142,6 +142,35 @@ int pfa_codon_class(int codon);  /* id of the 3-char class of PolyFastA.py:324-3
 int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix /* host, optional */);
 
+/* ---- column shards on several GPUs: the sum of the per-shard vectors, fused into the scan kernels ------------------------
+ * an alignment split in contiguous column ranges, one process per GPU; every statistic is a sum of exact
+ * integers over the shards.  A pfa_xchg owns one "symmetric" device buffer per rank; the ranks map each other's buffer
+ * (CUDA IPC over NVLink / NVSwitch peer access) and the LAST block of K2 / K4 adds the shard's vector into every
+ * rank's buffer with system-scope 64-bit reductions, signals, waits for the other ranks and writes the total to d_out:
+ * one launch per scan, no collective library on the data path.  All ranks must issue the same sequence of exchanges
+ * (same lengths); a rank that never arrives makes the others time out after 4 s (pfa_xchg_status), not hang.
+ * Usage: create on every rank -> export -> all-gather the handles on the host -> connect -> host barrier -> scans. */
+typedef struct pfa_xchg pfa_xchg;
+#define PFA_XCHG_HANDLE_BYTES 64
+int pfa_xchg_create(pfa_ctx* ctx, int64_t cap_words, pfa_xchg** out); /* cap_words: longest vector (int64 words) */
+int pfa_xchg_destroy(pfa_xchg* x);
+int64_t pfa_xchg_capacity(const pfa_xchg* x);
+int pfa_xchg_export(pfa_xchg* x, void* handle /* PFA_XCHG_HANDLE_BYTES */);
+int pfa_xchg_connect(pfa_xchg* x, int rank, int world, const void* handles /* world * PFA_XCHG_HANDLE_BYTES, by rank */);
+/* same with the buffers already addressable (several ranks in ONE process: tests) */
+void* pfa_xchg_base(const pfa_xchg* x);
+int pfa_xchg_connect_ptrs(pfa_xchg* x, int rank, int world, void* const* bases);
+int pfa_xchg_status(pfa_xchg* x, int* timed_out); /* synchronises the ctx stream */
+/* profiling: %globaltimer (ns) of the last exchange on this rank: [0] last block entered, [1] vector pushed to all ranks,
+ * [2] pushes acknowledged (fence), [3] all ranks have signalled, [4] total copied to d_out, [5] block 0 of K2 started */
+int pfa_xchg_stamps(pfa_xchg* x, uint64_t out[8]);
+/* K2 / K4 + the sum over shards: d_out (device, this rank) receives the vector of the WHOLE alignment, laid out as
+ * by pfa_site_stats_device / pfa_cds_stats_device.  d_isvar / d_labels stay per shard. */
+int pfa_site_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_isvar);
+int pfa_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_labels);
+/* the same exchange on its own for a vector produced by another kernel (K3 pairwise sums): in place on d_buf */
+int pfa_xchg_allreduce(pfa_xchg* x, int64_t* d_buf, int64_t len);
+
 /* ---- batched path for many small loci: replaces the per-file loop of --dir mode (PolyFastA.py:93-94,104) ------------- */
 /* A batch is filled on the host (rows are copied into one pinned blob), then pfa_batch_run does ONE upload, three segmented
  * launches (K1b encode, K2b site scan, K5b finalise; + the escape kernel when needed) and ONE synchronisation.  Non-CDS

@@ -27,6 +27,8 @@ EXPORTS = [
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
     "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
+    "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
+    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce",
 ]
 
 
@@ -125,6 +127,18 @@ def lib():
         "pfa_batch_result": (c.c_int, [p, i64, c.c_int, c.POINTER(i64), p, c.POINTER(FinalOut)]),
         "pfa_fasta_parse_files": (c.c_int, [c.POINTER(c.c_char_p), c.c_int, c.c_int, c.POINTER(p), c.POINTER(c.c_int)]),
         "pfa_fasta_match_mask": (i64, [p, c.c_char_p, i64, p, i64]),
+        "pfa_xchg_create": (c.c_int, [p, i64, c.POINTER(p)]),
+        "pfa_xchg_destroy": (c.c_int, [p]),
+        "pfa_xchg_capacity": (i64, [p]),
+        "pfa_xchg_export": (c.c_int, [p, p]),
+        "pfa_xchg_connect": (c.c_int, [p, c.c_int, c.c_int, p]),
+        "pfa_xchg_base": (p, [p]),
+        "pfa_xchg_connect_ptrs": (c.c_int, [p, c.c_int, c.c_int, c.POINTER(p)]),
+        "pfa_xchg_status": (c.c_int, [p, c.POINTER(c.c_int)]),
+        "pfa_xchg_stamps": (c.c_int, [p, c.POINTER(c.c_uint64)]),
+        "pfa_site_stats_xchg": (c.c_int, [p, p, p, p]),
+        "pfa_cds_stats_xchg": (c.c_int, [p, p, p, p]),
+        "pfa_xchg_allreduce": (c.c_int, [p, p, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -349,6 +349,16 @@ class Alignment:
         check(lib().pfa_site_stats_device(self.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_isvar_ptr or 0)),
               self.ctx.handle)
 
+    def site_stats_xchg(self, xchg, d_out_ptr, d_isvar_ptr=None):
+        """K2 fused with the sum over the column shards of all ranks (one launch): d_out gets the whole alignment's vector"""
+        check(lib().pfa_site_stats_xchg(self.handle, xchg.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_isvar_ptr or 0)),
+              self.ctx.handle)
+
+    def cds_stats_xchg(self, xchg, d_out_ptr, d_labels_ptr=None):
+        """K4 fused with the sum over the column shards of all ranks"""
+        check(lib().pfa_cds_stats_xchg(self.handle, xchg.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_labels_ptr or 0)),
+              self.ctx.handle)
+
     @staticmethod
     def unpack_cds(row):
         return {"nstops": int(row[0]), "missing": int(row[1]), "S_s": int(row[2]), "H_s": int(row[3]), "S_n": int(row[4]),
@@ -382,6 +392,80 @@ class Alignment:
         mat = np.zeros((self.n, self.n), dtype=np.int32) if want_matrix else None
         check(lib().pfa_pairwise(self.handle, out.ctypes.data, mat.ctypes.data if want_matrix else None), self.ctx.handle)
         return ([int(x) for x in out], mat) if want_matrix else [int(x) for x in out]
+
+
+class Exchange:
+    """sum of the per-shard vectors over NVLink peer memory, fused into the scan kernels (pfa_xchg).  One per rank;
+    polyfasta_b200.parallel.connect_exchange builds and connects it across the ranks of a torch.distributed group."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx, cap_words):
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        check(lib().pfa_xchg_create(ctx.handle, int(cap_words), ctypes.byref(self._h)), ctx.handle)
+        self.rank, self.world = 0, 0
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise PolyFastaError(_lib.PFA_ERR_ARG, "exchange is closed")
+        return self._h
+
+    @property
+    def capacity(self):
+        return int(lib().pfa_xchg_capacity(self.handle))
+
+    def export(self):
+        """the CUDA IPC handle of this rank's buffer (bytes), to be all-gathered by the host"""
+        buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+        check(lib().pfa_xchg_export(self.handle, buf), self.ctx.handle)
+        return buf.raw
+
+    def connect(self, rank, world, handles):
+        """handles: the exported handles of all ranks, in rank order"""
+        blob = b"".join(handles)
+        if len(blob) != world * self.HANDLE_BYTES:
+            raise ValueError("expected %d handles of %d bytes" % (world, self.HANDLE_BYTES))
+        check(lib().pfa_xchg_connect(self.handle, rank, world, ctypes.create_string_buffer(blob, len(blob))), self.ctx.handle)
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def connect_local(exchanges):
+        """several ranks inside ONE process (tests): exchanges[r] is rank r; the buffers must be addressable from every
+        device involved (same device, or peer access enabled)"""
+        world = len(exchanges)
+        bases = (ctypes.c_void_p * world)(*[lib().pfa_xchg_base(x.handle) for x in exchanges])
+        for r, x in enumerate(exchanges):
+            check(lib().pfa_xchg_connect_ptrs(x.handle, r, world, bases), x.ctx.handle)
+            x.rank, x.world = r, world
+
+    def timed_out(self):
+        """True when a wait gave up because a rank never arrived (synchronises the stream)"""
+        st = ctypes.c_int()
+        check(lib().pfa_xchg_status(self.handle, ctypes.byref(st)), self.ctx.handle)
+        return bool(st.value)
+
+    def stamps(self):
+        """ns between the stages of the last exchange on this rank: dict(scan, push, fence, wait, copy); scan = first block's start to the last block's arrival (K2 only)"""
+        t = (ctypes.c_uint64 * 8)()
+        check(lib().pfa_xchg_stamps(self.handle, t), self.ctx.handle)
+        return {"scan": t[0] - t[5] if t[5] else None, "push": t[1] - t[0], "fence": t[2] - t[1], "wait": t[3] - t[2], "copy": t[4] - t[3]}
+
+    def allreduce(self, d_ptr, length):
+        """in-place sum over ranks of an int64 device vector produced elsewhere (K3 pairwise sums)"""
+        check(lib().pfa_xchg_allreduce(self.handle, ctypes.c_void_p(d_ptr), int(length)), self.ctx.handle)
+
+    def close(self):
+        if self._h:
+            lib().pfa_xchg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def parse_files(paths, threads=0):

@@ -451,6 +451,18 @@ int pfa_cds_stats(pfa_aln* a, int64_t* out, uint8_t* labels) {
                        [&](void* d_out, void* d_aux) { return pfa_launch_cds_scan(a, (int64_t*)d_out, (uint8_t*)d_aux); });
 }
 
+int pfa_site_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_isvar) {
+    if (!a || !x || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    return pfa_launch_site_scan(a, d_out, d_isvar, x);
+}
+
+int pfa_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_labels) {
+    if (!a || !x || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    return pfa_launch_cds_scan(a, d_out, d_labels, x);
+}
+
 int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     if (!a || !d_out) return PFA_ERR_ARG;
     PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
@@ -506,6 +518,7 @@ static int aln_default_pop(pfa_aln* a) {
 }
 
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args) {
+    memset(&args->x, 0, sizeof args->x);
     args->b0 = a->b0;
     args->b1 = a->b1;
     args->v = a->v;

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const Pf
         if (e == PFA_CDS_SUM3 + 1) x += smem[2];
         if (x) atomicAdd(reinterpret_cast<unsigned long long*>(a.out) + i, x);
     }
+    if (a.s.x.world) pfa_xchg_epilogue(a.s.x);
 }
 
 // Register-resident variant (Wq <= 3*32 chunks): the three site records of a codon column are loaded once -- all
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
         if (e == PFA_CDS_SUM3 + 1) x += smem[2];
         if (x) atomicAdd(reinterpret_cast<unsigned long long*>(a.out) + i, x);
     }
+    if (a.s.x.world) pfa_xchg_epilogue(a.s.x);
 }
 
 // per-site escape statistics of one population: number of distinct escape bytes and the sum of their squared counts
@@ -518,17 +520,27 @@ static void launch_cds(const PfaCdsArgs& args, bool has_v, dim3 grid, size_t sme
     else pfa_cds_scan_kernel<LPS, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
 }
 
-int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels) {
+static int launch_cds_escape(pfa_aln* a, const PfaCdsArgs& args) {
+    pfa_ctx* ctx = a->ctx;
+    int64_t eb = (a->n_exc_sites + 7) / 8;
+    if (eb > (int64_t)ctx->sm_count * 8) eb = (int64_t)ctx->sm_count * 8;
+    pfa_cds_escape_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, a->exc_keys, a->n_exc, a->exc_heads, a->n_exc_sites);
+    PFA_LAUNCH_CHECK(ctx);
+    return PFA_OK;
+}
+
+int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg* x) {
     pfa_ctx* ctx = a->ctx;
     if (a->col_begin % 3 != 0) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: the shard must start on a codon boundary");
     const bool last = a->col_begin + a->ns == a->L_total;
     if (a->ns % 3 != 0 && !last) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: only the last shard may end inside a codon");
-    PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * PFA_CDS_LEN * (size_t)a->k, ctx->stream));
+    const int64_t out_len = (int64_t)PFA_CDS_LEN * a->k;
+    if (!x) PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
     if (d_labels && a->ns) PFA_CUDA(ctx, cudaMemsetAsync(d_labels, 0, (size_t)(a->k * a->ns), ctx->stream));
-    if (a->ns == 0 || a->n == 0) return PFA_OK;
+    if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, out_len, d_out) : PFA_OK;
     PfaCdsArgs args;
     pfa_fill_site_args(a, nullptr, nullptr, &args.s);
-    args.out = d_out;
+    args.out = x ? reinterpret_cast<int64_t*>(pfa_xchg_partial(x)) : d_out;
     args.labels = d_labels;
     args.ncf = a->ns / 3;
     args.has_partial = (a->ns % 3) != 0;
@@ -542,6 +554,14 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels) {
     if (generic) {
         lps = 1;
         while (lps < 32 && (a->Wq + lps - 1) / lps > 4) lps *= 2;
+    }
+    if (x) {  // escape columns first: the scan kernel's last block runs the exchange over the complete shard vector
+        if (a->n_exc_sites > 0) {
+            int rc = launch_cds_escape(a, args);
+            if (rc) return rc;
+        }
+        int rc = pfa_xchg_fill(x, out_len, d_out, &args.s.x);
+        if (rc) return rc;
     }
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;
     int64_t blocks = (std::max<int64_t>(args.ncf, 1) + groups_per_block - 1) / groups_per_block;
@@ -570,11 +590,6 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels) {
     }
 #undef PFA_CDS_CASE
     PFA_LAUNCH_CHECK(ctx);
-    if (a->n_exc_sites > 0) {
-        int64_t eb = (a->n_exc_sites + 7) / 8;
-        if (eb > (int64_t)ctx->sm_count * 8) eb = (int64_t)ctx->sm_count * 8;
-        pfa_cds_escape_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, a->exc_keys, a->n_exc, a->exc_heads, a->n_exc_sites);
-        PFA_LAUNCH_CHECK(ctx);
-    }
+    if (!x && a->n_exc_sites > 0) return launch_cds_escape(a, args);
     return PFA_OK;
 }

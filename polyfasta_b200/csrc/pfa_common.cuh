@@ -84,8 +84,14 @@ int pfa_finish_exceptions(pfa_aln* a, int64_t count);
 int pfa_sort_exceptions(pfa_ctx* ctx, unsigned long long** keys, int64_t count, int64_t** heads, int64_t* n_heads);
 int pfa_launch_finalize(pfa_ctx* ctx, const pfa_final_in* d_in, pfa_final_out* d_out, int count);
 int pfa_synth_fill(pfa_aln* a, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm);
-int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar);
-int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels);
+struct pfa_xchg;
+struct PfaXchgDev;
+// x != nullptr: fused with the sum over the column shards of all ranks (pfa_xchg.cu); d_out receives the reduced vector
+int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg* x = nullptr);
+int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg* x = nullptr);
+int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev);
+unsigned long long* pfa_xchg_partial(pfa_xchg* x);
+int pfa_xchg_launch_only(pfa_xchg* x, const int64_t* d_src, int64_t len, int64_t* d_out);
 int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_upload_codon_tables(pfa_ctx* ctx);
 

@@ -18,6 +18,7 @@
 template <int LPS, bool HAS_V>
 __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const PfaSiteArgs a) {
     extern __shared__ unsigned long long smem[];
+    if (a.x.world && blockIdx.x == 0 && threadIdx.x == 0) a.x.stamps[5] = pfa_globaltimer();
     unsigned long long* sm_SH = smem;                                       // [2k]
     unsigned int* sm_sfs = reinterpret_cast<unsigned int*>(smem + 2 * a.k);  // [sfs_bins] when a.sfs_in_smem
     const int nsm = 2 * a.k;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
             }
         }
     }
+    if (a.x.world) pfa_xchg_epilogue(a.x);
 }
 
 // Register-resident variant for Wq <= 5*32 chunks: every lane owns ITER fixed chunks of the site record, loads them
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
 template <int LPS, int ITER, bool HAS_V>
 __global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(const PfaSiteArgs a) {
     extern __shared__ unsigned long long smem[];
+    if (a.x.world && blockIdx.x == 0 && threadIdx.x == 0) a.x.stamps[5] = pfa_globaltimer();
     unsigned long long* sm_SH = smem;
     unsigned int* sm_sfs = reinterpret_cast<unsigned int*>(smem + 2 * a.k);
     for (int i = threadIdx.x; i < 2 * a.k; i += blockDim.x) sm_SH[i] = 0ull;
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(
             }
         }
     }
+    if (a.x.world) pfa_xchg_epilogue(a.x);
 }
 
 // One warp per site that holds at least one escape symbol.  For every population with an escape row at
@@ -295,13 +299,33 @@ static void launch_scan(const PfaSiteArgs& args, bool has_v, dim3 grid, size_t s
     else pfa_site_scan_kernel<LPS, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
 }
 
-int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar) {
+static int launch_escape_sites(pfa_aln* a, const PfaSiteArgs& args) {
+    pfa_ctx* ctx = a->ctx;
+    int64_t eb = (a->n_exc_sites + 7) / 8;
+    if (eb > (int64_t)ctx->sm_count * 8) eb = (int64_t)ctx->sm_count * 8;
+    pfa_escape_sites_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, a->exc_keys, a->n_exc, a->exc_heads, a->n_exc_sites);
+    PFA_LAUNCH_CHECK(ctx);
+    return PFA_OK;
+}
+
+int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg* x) {
     pfa_ctx* ctx = a->ctx;
     const int64_t out_len = a->site_off[a->k];
-    PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
-    if (a->ns == 0 || a->n == 0) return PFA_OK;
+    if (!x) PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
+    if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, out_len, d_out) : PFA_OK;
     PfaSiteArgs args;
     pfa_fill_site_args(a, d_out, d_isvar, &args);
+    if (x) {
+        // the blocks add into the exchange's partial vector (zero between launches); the escape kernel goes FIRST so that
+        // the scan kernel's last block sees the complete shard vector when it runs the exchange
+        args.out = reinterpret_cast<int64_t*>(pfa_xchg_partial(x));
+        if (a->n_exc_sites > 0) {
+            int rc = launch_escape_sites(a, args);
+            if (rc) return rc;
+        }
+        int rc = pfa_xchg_fill(x, out_len, d_out, &args.x);
+        if (rc) return rc;
+    }
     // lanes per site: the smallest power of two that leaves every lane at most 5 chunks
     int lps = 1;
     while (lps < 32 && (a->Wq + lps - 1) / lps > 5) lps *= 2;
@@ -340,11 +364,6 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar) {
     }
 #undef PFA_REG_CASE
     PFA_LAUNCH_CHECK(ctx);
-    if (a->n_exc_sites > 0) {
-        int64_t eb = (a->n_exc_sites + 7) / 8;
-        if (eb > (int64_t)ctx->sm_count * 8) eb = (int64_t)ctx->sm_count * 8;
-        pfa_escape_sites_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, a->exc_keys, a->n_exc, a->exc_heads, a->n_exc_sites);
-        PFA_LAUNCH_CHECK(ctx);
-    }
+    if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
     return PFA_OK;
 }

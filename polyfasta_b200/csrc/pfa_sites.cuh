@@ -1,6 +1,7 @@
 // Device helpers shared by the site scan (K2), the escape-site kernel and the codon scan (K4).
 #pragma once
 #include "pfa_common.cuh"
+#include "pfa_xchg.cuh"
 
 #define PFA_SITE_THREADS 256
 // packed symbol classes counted with popcounts; the gap class '-' is n_pop minus the others
@@ -29,6 +30,7 @@ struct PfaSiteArgs {
     int k;
     int sfs_in_smem;
     int sfs_bins;  // total bins over all populations
+    PfaXchgDev x;  // x.world > 0: the last block sums `out` over the column shards of all GPUs (pfa_xchg.cuh)
 };
 
 // streaming 128-bit load: read-only path, do not allocate in L1 (every byte of the planes is used once)

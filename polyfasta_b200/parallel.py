@@ -31,6 +31,24 @@ def allreduce_sum(tensor):
     return tensor
 
 
+def connect_exchange(ctx, cap_words, group=None):
+    """one api.Exchange per rank, connected over the ranks of `group`: the CUDA IPC handles of the symmetric buffers travel
+    through all_gather_object (host plumbing); afterwards Alignment.site_stats_xchg / cds_stats_xchg sum the shard vectors
+    inside the scan kernel over NVLink, without a collective call.  Collective: every rank of the group must call it."""
+    import torch.distributed as dist
+    from . import api
+    x = api.Exchange(ctx, cap_words)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        x.connect(0, 1, [x.export()])
+        return x
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, x.export(), group=group)
+    x.connect(rank, world, handles)
+    dist.barrier(group=group)  # every rank has mapped every buffer before the first kernel touches one
+    return x
+
+
 def gather_rows(rows):
     """--dir mode: every rank contributes [(locus_index, text), ...]; rank 0 gets them back merged in index order"""
     import torch.distributed as dist
