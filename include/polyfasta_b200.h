@@ -47,6 +47,13 @@ int pfa_ctx_trim(pfa_ctx* ctx);
  * current stream) so that a collective enqueued by the caller is ordered after the kernels. NULL restores
  * the ctx's own stream. */
 int pfa_ctx_set_stream(pfa_ctx* ctx, void* cuda_stream);
+/* host threads the ingest may use to pack column chunks (0 = the PFA_HOST_THREADS environment variable, else all hardware
+ * threads); with several ranks on one box give every rank its share */
+int pfa_ctx_set_host_threads(pfa_ctx* ctx, int threads);
+/* the last upload of this ctx: out[0] column chunks shipped as text (K1), out[1] chunks packed 4 bases/byte on the host
+ * (pfa_encode_packed_kernel), out[2] chunks the packer found dirty (non-ACGT) and handed back, out[3] host threads,
+ * out[4] bytes copied host->device as text, out[5] bytes copied host->device packed */
+int pfa_ctx_ingest_stats(const pfa_ctx* ctx, int64_t out[6]);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t pfa_ctx_launch_count(const pfa_ctx* ctx);
 
@@ -64,6 +71,14 @@ int64_t pfa_fasta_row_len(const pfa_fasta* f, int64_t row);
 const char* pfa_fasta_header(const pfa_fasta* f, int64_t row, int64_t* len); /* not NUL-terminated */
 /* upper-cased copy of one row into caller memory (cap >= row_len) */
 int pfa_fasta_copy_row(const pfa_fasta* f, int64_t row, uint8_t* dst, int64_t cap);
+
+/* host packer of the ingest, exposed for tests: cols bases of one text row -> ceil(cols/4) bytes, base j of a byte at bits
+ * 2j..2j+1, code = (byte >> 1) & 3 (A 0, C 1, T 2, G 3, either case).  Returns 1 when the row holds any other byte (such
+ * column chunks are uploaded as text and encoded by K1 instead), 0 when clean, < 0 on bad arguments / unsupported variant.
+ * variant: 0 = best for this CPU, 1 = scalar, 2 = AVX2, 3 = AVX-512BW. */
+int pfa_host_pack2(const uint8_t* src, int64_t cols, uint8_t* dst, int variant);
+/* a whole matrix text[row*ld + col] -> dst[row*ldp + col/4] with `threads` host threads (0 = all); returns the dirty rows */
+int64_t pfa_host_pack2_rows(const uint8_t* text, int64_t n, int64_t cols, int64_t ld, uint8_t* dst, int64_t ldp, int threads);
 
 /* ---- alignment upload: host text -> packed planes in HBM (kernel K1) ------------------------------- */
 /* columns [col_begin, col_end) of a parsed file (the column shard of this GPU) */

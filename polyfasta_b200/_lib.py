@@ -16,6 +16,7 @@ PFA_BATCH_TOO_BIG = 100
 EXPORTS = [
     "pfa_version", "pfa_device_count", "pfa_global_error",
     "pfa_ctx_create", "pfa_ctx_destroy", "pfa_last_error", "pfa_ctx_sync", "pfa_ctx_trim", "pfa_ctx_set_stream", "pfa_ctx_launch_count",
+    "pfa_ctx_set_host_threads", "pfa_ctx_ingest_stats",
     "pfa_fasta_parse_file", "pfa_fasta_parse_buffer", "pfa_fasta_free", "pfa_fasta_nseq", "pfa_fasta_seqlen",
     "pfa_fasta_row_len", "pfa_fasta_header", "pfa_fasta_copy_row",
     "pfa_aln_from_fasta", "pfa_aln_from_rows", "pfa_aln_from_device_rows", "pfa_aln_synthetic", "pfa_synth_text_device", "pfa_aln_force_validity", "pfa_aln_free",
@@ -27,6 +28,7 @@ EXPORTS = [
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
     "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
+    "pfa_host_pack2", "pfa_host_pack2_rows",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
     "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce",
 ]
@@ -73,6 +75,8 @@ def lib():
         "pfa_ctx_trim": (c.c_int, [p]),
         "pfa_ctx_set_stream": (c.c_int, [p, p]),
         "pfa_ctx_launch_count": (i64, [p]),
+        "pfa_ctx_set_host_threads": (c.c_int, [p, c.c_int]),
+        "pfa_ctx_ingest_stats": (c.c_int, [p, c.POINTER(i64)]),
         "pfa_fasta_parse_file": (c.c_int, [c.c_char_p, c.POINTER(p)]),
         "pfa_fasta_parse_buffer": (c.c_int, [p, sz, c.POINTER(p)]),
         "pfa_fasta_free": (None, [p]),
@@ -127,6 +131,8 @@ def lib():
         "pfa_batch_result": (c.c_int, [p, i64, c.c_int, c.POINTER(i64), p, c.POINTER(FinalOut)]),
         "pfa_fasta_parse_files": (c.c_int, [c.POINTER(c.c_char_p), c.c_int, c.c_int, c.POINTER(p), c.POINTER(c.c_int)]),
         "pfa_fasta_match_mask": (i64, [p, c.c_char_p, i64, p, i64]),
+        "pfa_host_pack2": (c.c_int, [p, i64, p, c.c_int]),
+        "pfa_host_pack2_rows": (i64, [p, i64, i64, i64, p, i64, c.c_int]),
         "pfa_xchg_create": (c.c_int, [p, i64, c.POINTER(p)]),
         "pfa_xchg_destroy": (c.c_int, [p]),
         "pfa_xchg_capacity": (i64, [p]),

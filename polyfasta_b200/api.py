@@ -47,6 +47,17 @@ class Context:
         """run the library's kernels on a caller-owned stream (int / torch.cuda.Stream.cuda_stream); None restores"""
         check(lib().pfa_ctx_set_stream(self.handle, ctypes.c_void_p(cuda_stream or 0)), self.handle)
 
+    def set_host_threads(self, threads):
+        """host threads the ingest may use to pack column chunks (0 = PFA_HOST_THREADS or all hardware threads)"""
+        check(lib().pfa_ctx_set_host_threads(self.handle, int(threads)), self.handle)
+
+    def ingest_stats(self):
+        """the last upload: dict(raw_chunks, packed_chunks, dirty_chunks, threads, h2d_text_bytes, h2d_packed_bytes)"""
+        out = (ctypes.c_int64 * 6)()
+        check(lib().pfa_ctx_ingest_stats(self.handle, out), self.handle)
+        return {"raw_chunks": out[0], "packed_chunks": out[1], "dirty_chunks": out[2], "threads": out[3],
+                "h2d_text_bytes": out[4], "h2d_packed_bytes": out[5]}
+
     @property
     def launch_count(self):
         return int(lib().pfa_ctx_launch_count(self.handle))

@@ -30,8 +30,6 @@ int pfa_fail(pfa_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out);
-static int aln_default_pop(pfa_aln* a);
 
 // run a *_device entry point into temporary device buffers and copy the results to the host
 template <typename F>
@@ -107,9 +105,14 @@ int pfa_ctx_create(int device, pfa_ctx** out) {
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ctx->ev_encoded[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_encoded[i], cudaEventDisableTiming | cudaEventBlockingSync);  // the ingest lanes sleep on these
     }
     cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->enc_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->pack_stream, cudaStreamNonBlocking);
+    for (auto& ev : ctx->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync);
+    for (auto& ev : ctx->ev_slot_copied) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& ev : ctx->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaGetLastError();
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -135,6 +138,12 @@ int pfa_ctx_destroy(pfa_ctx* ctx) {
         if (ctx->ev_encoded[i]) cudaEventDestroy(ctx->ev_encoded[i]);
     }
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    for (auto& ev : ctx->ev_slot) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_slot_copied) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_join) if (ev) cudaEventDestroy(ev);
+    if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
+    if (ctx->enc_stream) cudaStreamDestroy(ctx->enc_stream);
+    if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -166,7 +175,7 @@ int pfa_ctx_set_stream(pfa_ctx* ctx, void* cuda_stream) {
     return PFA_OK;
 }
 
-int64_t pfa_ctx_launch_count(const pfa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t pfa_ctx_launch_count(const pfa_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 // ---- upload -------------------------------------------------------------------------------------------
 
@@ -185,144 +194,20 @@ int pfa_aln_free(pfa_aln* a) {
     return PFA_OK;
 }
 
-// encode columns [col_begin, col_end) of a text matrix; `dev` says where the matrix lives
-static int aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
-                         int64_t col_end, pfa_aln** out) {
-    if (!ctx || !out) return PFA_ERR_ARG;
-    *out = nullptr;
-    if (n < 0 || L < 0 || col_begin < 0 || col_end < col_begin || col_end > L || (n > 0 && L > 0 && (!text || ld < L)))
-        return pfa_fail(ctx, PFA_ERR_ARG, "bad alignment shape n=%lld L=%lld ld=%lld cols=[%lld,%lld)", (long long)n,
-                        (long long)L, (long long)ld, (long long)col_begin, (long long)col_end);
-    if (n >= (1ll << 24)) return pfa_fail(ctx, PFA_ERR_ARG, "more than 2^24-1 sequences are not supported");
-    if (col_end - col_begin >= (1ll << 32)) return pfa_fail(ctx, PFA_ERR_ARG, "a shard holds at most 2^32-1 sites");
-    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
-    pfa_aln* a = nullptr;
-    int rc = aln_alloc(ctx, n, L, col_begin, col_end, &a);
-    if (rc) return rc;
-    const int64_t ns = a->ns;
-    unsigned long long* d_count = nullptr;
-    int* d_inv = nullptr;
-    uint8_t* stage[2] = {nullptr, nullptr};
-    cudaStream_t cs = ctx->copy_stream;
-    cudaEvent_t* ev_copied = ctx->ev_copied;
-    cudaEvent_t* ev_encoded = ctx->ev_encoded;
-    bool registered = false;
-    int64_t cap = 0;
-    auto cleanup = [&]() {
-        pfa_dfree(ctx, d_count);
-        pfa_dfree(ctx, d_inv);
-        pfa_dfree(ctx, stage[0]);
-        pfa_dfree(ctx, stage[1]);
-        if (registered) cudaHostUnregister(const_cast<uint8_t*>(text));
-    };
-#define UP(call)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e__ = (call);                                                                         \
-        if (e__ != cudaSuccess) {                                                                         \
-            cleanup();                                                                                    \
-            pfa_aln_free(a);                                                                              \
-            return pfa_fail(ctx, PFA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));          \
-        }                                                                                                 \
-    } while (0)
-    if (ns > 0 && n > 0) {
-        UP(pfa_dmalloc(ctx, &d_count, sizeof(unsigned long long)));
-        UP(pfa_dmalloc(ctx, &d_inv, sizeof(int)));
-        // columns per chunk: ~256 MB of text, a multiple of 256 columns
-        int64_t chunk = ((256ll << 20) / n) & ~255ll;
-        if (chunk < 256) chunk = 256;
-        if (chunk > ns) chunk = ns;
-        const int64_t ldt = pfa_round_up(chunk, 256);
-        if (!dev) {
-            const int nbuf = chunk < ns ? 2 : 1;
-            for (int i = 0; i < nbuf; ++i) UP(pfa_dmalloc(ctx, &stage[i], (size_t)(n * ldt)));
-            // the copy stream may touch the staging buffers only after their (stream-ordered) allocation
-            UP(cudaEventRecord(ctx->ev_ready, ctx->stream));
-            UP(cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
-            // pin large pageable inputs in place so that the 2-D copies run asynchronously at full PCIe rate
-            cudaPointerAttributes attr;
-            const bool is_pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-            cudaGetLastError();
-            const size_t span = (size_t)((n - 1) * ld + L);
-            if (!is_pinned && span >= (32u << 20)) {
-                registered = cudaHostRegister(const_cast<uint8_t*>(text), span, cudaHostRegisterReadOnly) == cudaSuccess ||
-                             cudaHostRegister(const_cast<uint8_t*>(text), span, cudaHostRegisterDefault) == cudaSuccess;
-                cudaGetLastError();
-            }
-        }
-        cap = std::max<int64_t>(1 << 16, n * ns / 256);
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            pfa_dfree(ctx, a->exc_keys);
-            a->exc_keys = nullptr;
-            UP(pfa_dmalloc(ctx, &a->exc_keys, sizeof(unsigned long long) * (size_t)cap));
-            UP(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
-            UP(cudaMemsetAsync(d_inv, 0, sizeof(int), ctx->stream));
-            int64_t ci = 0;
-            for (int64_t c = 0; c < ns; c += chunk, ++ci) {
-                const int64_t cols = std::min(chunk, ns - c);
-                if (dev) {
-                    rc = pfa_encode_chunk(a, text + col_begin + c, ld, cols, c, d_count, cap, d_inv);
-                } else {
-                    const int b = (int)(ci & 1);
-                    if (ci >= 2) UP(cudaStreamWaitEvent(cs, ev_encoded[b], 0));
-                    UP(cudaMemcpy2DAsync(stage[b], (size_t)ldt, text + col_begin + c, (size_t)ld, (size_t)cols, (size_t)n,
-                                         cudaMemcpyHostToDevice, cs));
-                    UP(cudaEventRecord(ev_copied[b], cs));
-                    UP(cudaStreamWaitEvent(ctx->stream, ev_copied[b], 0));
-                    rc = pfa_encode_chunk(a, stage[b], ldt, cols, c, d_count, cap, d_inv);
-                    if (!rc) UP(cudaEventRecord(ev_encoded[b], ctx->stream));
-                }
-                if (rc) {
-                    cleanup();
-                    pfa_aln_free(a);
-                    return rc;
-                }
-            }
-            unsigned long long count = 0;
-            UP(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, ctx->stream));
-            UP(cudaMemcpyAsync(&a->has_invalid, d_inv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            UP(cudaStreamSynchronize(ctx->stream));
-            if ((int64_t)count <= cap) {
-                if (count >= (1ull << 31)) {
-                    cleanup();
-                    pfa_aln_free(a);
-                    return pfa_fail(ctx, PFA_ERR_ARG, "more than 2^31 non-ACGT/-/N/? symbols in one shard");
-                }
-                rc = pfa_finish_exceptions(a, (int64_t)count);
-                if (rc) {
-                    cleanup();
-                    pfa_aln_free(a);
-                    return rc;
-                }
-                break;
-            }
-            cap = (int64_t)count;  // the exception list overflowed: encode once more with the exact size
-        }
-    }
-#undef UP
-    cleanup();
-    rc = aln_default_pop(a);
-    if (rc) {
-        pfa_aln_free(a);
-        return rc;
-    }
-    *out = a;
-    return PFA_OK;
-}
-
 int pfa_aln_from_rows(pfa_ctx* ctx, const uint8_t* text, int64_t n, int64_t L, int64_t ld, int64_t col_begin, int64_t col_end,
                       pfa_aln** out) {
-    return aln_from_text(ctx, text, false, n, L, ld, col_begin, col_end, out);
+    return pfa_aln_from_text(ctx, text, false, n, L, ld, col_begin, col_end, out);
 }
 
 int pfa_aln_from_device_rows(pfa_ctx* ctx, const uint8_t* d_text, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
                              int64_t col_end, pfa_aln** out) {
-    return aln_from_text(ctx, d_text, true, n, L, ld, col_begin, col_end, out);
+    return pfa_aln_from_text(ctx, d_text, true, n, L, ld, col_begin, col_end, out);
 }
 
 int pfa_aln_from_fasta(pfa_ctx* ctx, const pfa_fasta* f, int64_t col_begin, int64_t col_end, pfa_aln** out) {
     if (!ctx || !f || !out) return PFA_ERR_ARG;
     if (f->seqlen < 0) return pfa_fail(ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
-    return aln_from_text(ctx, f->data, false, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), col_begin, col_end, out);
+    return pfa_aln_from_text(ctx, f->data, false, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), col_begin, col_end, out);
 }
 
 int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm, int64_t col_begin,
@@ -333,10 +218,10 @@ int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_
         return pfa_fail(ctx, PFA_ERR_ARG, "bad synthetic shape");
     PFA_CUDA(ctx, cudaSetDevice(ctx->device));
     pfa_aln* a = nullptr;
-    int rc = aln_alloc(ctx, n, L, col_begin, col_end, &a);
+    int rc = pfa_aln_alloc(ctx, n, L, col_begin, col_end, &a);
     if (rc) return rc;
     rc = pfa_synth_fill(a, seed, p_seg_ppm, tri_ppm);
-    if (!rc) rc = aln_default_pop(a);
+    if (!rc) rc = pfa_aln_default_pop(a);
     if (rc) {
         pfa_aln_free(a);
         return rc;
@@ -372,7 +257,7 @@ int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap) {
 
 int pfa_aln_set_pops(pfa_aln* a, const uint32_t* masks, int k) {
     if (!a || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
-    if (k == 0) return aln_default_pop(a);
+    if (k == 0) return pfa_aln_default_pop(a);
     pfa_ctx* ctx = a->ctx;
     PFA_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t Wn = (int64_t)a->Wq * 4;
@@ -479,7 +364,7 @@ int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix) {
 
 // ---- helpers ---------------------------------------------------------------------------------------------
 
-static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out) {
+int pfa_aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out) {
     pfa_aln* a = new (std::nothrow) pfa_aln();
     if (!a) return pfa_fail(ctx, PFA_ERR_NOMEM, "out of host memory");
     a->ctx = ctx;
@@ -510,7 +395,7 @@ static int aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int6
     return PFA_OK;
 }
 
-static int aln_default_pop(pfa_aln* a) {
+int pfa_aln_default_pop(pfa_aln* a) {
     const int64_t Wn = (int64_t)a->Wq * 4;
     std::vector<uint32_t> all((size_t)std::max<int64_t>(Wn, 1), 0u);
     for (int64_t r = 0; r < a->n; ++r) all[(size_t)(r >> 5)] |= 1u << (r & 31);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -17,7 +18,7 @@ struct pfa_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // own_stream or a caller-owned stream
     std::string err;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};  // kernels launched (the packed ingest lane launches from its own thread)
     // small pinned + device scratch for finalisation and synchronous result copies
     void* h_scratch = nullptr;
     void* d_scratch = nullptr;
@@ -25,6 +26,14 @@ struct pfa_ctx {
     // upload pipeline: copy stream + events, created once per context
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_encoded[2] = {nullptr, nullptr}, ev_ready = nullptr;
+    // hybrid ingest (pfa_ingest.cu): encode stream of the raw lane, copy + encode stream of the packed lane, one event per
+    // packed staging slot, pinned staging for the host-packed chunks (kept between uploads)
+    cudaStream_t enc_stream = nullptr, pack_stream = nullptr;
+    cudaEvent_t ev_slot[3] = {nullptr, nullptr, nullptr}, ev_slot_copied[3] = {nullptr, nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    void* pack_pinned = nullptr;
+    size_t pack_pinned_bytes = 0;
+    int host_threads = 0;  // host threads the ingest may use; 0 = PFA_HOST_THREADS or all hardware threads
+    int64_t ingest_stats[6] = {0, 0, 0, 0, 0, 0};  // last upload: chunks sent as text, chunks packed on the host, dirty chunks, threads, H2D bytes as text, H2D bytes packed
 };
 
 struct pfa_aln {
@@ -79,7 +88,7 @@ void pfa_set_global_error(const char* fmt, ...);
 
 // ---- internal entry points implemented in the .cu files -----------------------------------------------
 int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t cols, int64_t site0,
-                     unsigned long long* d_exc_count, int64_t exc_cap, int* d_has_invalid);
+                     unsigned long long* d_exc_count, int64_t exc_cap, int* d_has_invalid, cudaStream_t st = nullptr);
 int pfa_finish_exceptions(pfa_aln* a, int64_t count);
 int pfa_sort_exceptions(pfa_ctx* ctx, unsigned long long** keys, int64_t count, int64_t** heads, int64_t* n_heads);
 int pfa_launch_finalize(pfa_ctx* ctx, const pfa_final_in* d_in, pfa_final_out* d_out, int count);
@@ -94,6 +103,12 @@ unsigned long long* pfa_xchg_partial(pfa_xchg* x);
 int pfa_xchg_launch_only(pfa_xchg* x, const int64_t* d_src, int64_t len, int64_t* d_out);
 int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_upload_codon_tables(pfa_ctx* ctx);
+int pfa_aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out);
+int pfa_aln_default_pop(pfa_aln* a);
+// upload + encode of columns [col_begin, col_end) of a text matrix (pfa_ingest.cu); `dev`: the matrix is in device memory
+int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
+                      int64_t col_end, pfa_aln** out);
+int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, int64_t cols, int64_t site0, cudaStream_t st);
 
 // Device memory comes from the device's stream-ordered pool (release threshold = keep): allocating and freeing the planes
 // of one alignment after another (--dir mode, benchmark loops) reuses the same blocks without synchronising the device.

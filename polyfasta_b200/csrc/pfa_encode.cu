@@ -90,15 +90,64 @@ __global__ void __launch_bounds__(256) pfa_encode_kernel(const uint8_t* __restri
 }
 
 int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t cols, int64_t site0,
-                     unsigned long long* d_exc_count, int64_t exc_cap, int* d_has_invalid) {
+                     unsigned long long* d_exc_count, int64_t exc_cap, int* d_has_invalid, cudaStream_t st) {
     pfa_ctx* ctx = a->ctx;
     if (cols <= 0 || a->n <= 0) return PFA_OK;
+    if (!st) st = ctx->stream;
     const int64_t groups = (cols + 31) / 32;
     const int vec_ok = (reinterpret_cast<uintptr_t>(d_text) % 16 == 0) && (ldt % 16 == 0);
     dim3 grid((unsigned)((groups + 7) / 8), (unsigned)((a->n + 31) / 32));
-    pfa_encode_kernel<<<grid, 256, 0, ctx->stream>>>(d_text, ldt, a->n, cols, site0, (uint32_t*)a->b0, (uint32_t*)a->b1,
+    pfa_encode_kernel<<<grid, 256, 0, st>>>(d_text, ldt, a->n, cols, site0, (uint32_t*)a->b0, (uint32_t*)a->b1,
                                                      (uint32_t*)a->v, a->Wq * 4, a->exc_keys, d_exc_count, exc_cap,
                                                      d_has_invalid, vec_ok);
+    PFA_LAUNCH_CHECK(ctx);
+    return PFA_OK;
+}
+
+// Same transposition for a chunk the HOST has packed (pfa_pack.cpp): 4 bases per byte, code t = A 0, C 1, T 2, G 3, all
+// rows clean.  One warp = 32 rows x 64 sites: lane j reads 16 bytes of row 32*w+j; b1 = t1, b0 = t0 ^ t1 turns the host
+// code into the planes' A 00, C 01, G 10, T 11; the validity word is the live-row mask.
+__global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* __restrict__ packed, int64_t ldp, int64_t n,
+                                                                int64_t cols, int64_t site0, uint32_t* __restrict__ b0,
+                                                                uint32_t* __restrict__ b1, uint32_t* __restrict__ v, int Wn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t sg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // group of 64 sites
+    const int64_t w = blockIdx.y;
+    const int64_t c0 = sg * 64;
+    if (c0 >= cols) return;
+    const int64_t row = w * 32 + lane;
+    const bool live = row < n;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (live) x = __ldg(reinterpret_cast<const uint4*>(packed + row * ldp + (c0 >> 2)));
+    const uint32_t wv = __ballot_sync(0xffffffffu, live);
+    const uint32_t words[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // sites c0 + 32h + s
+        uint32_t my0 = 0, my1 = 0;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const uint32_t t = (words[2 * h + (s >> 4)] >> (2 * (s & 15))) & 3u;
+            const uint32_t w1 = __ballot_sync(0xffffffffu, t & 2u);
+            const uint32_t w0 = __ballot_sync(0xffffffffu, (t ^ (t >> 1)) & 1u);
+            if (lane == s) { my0 = w0; my1 = w1; }
+        }
+        const int64_t c = c0 + 32 * h + lane;
+        if (c < cols) {
+            const int64_t o = (site0 + c) * (int64_t)Wn + w;
+            b0[o] = my0; b1[o] = my1; v[o] = wv;
+        }
+    }
+}
+
+int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, int64_t cols, int64_t site0, cudaStream_t st) {
+    pfa_ctx* ctx = a->ctx;
+    if (cols <= 0 || a->n <= 0) return PFA_OK;
+    if (ldp % 16 != 0 || reinterpret_cast<uintptr_t>(d_packed) % 16 != 0 || ldp * 4 < pfa_round_up(cols, 64))
+        return pfa_fail(ctx, PFA_ERR_ARG, "packed chunk: rows must be 16-byte aligned and padded to 64 bases");
+    const int64_t groups = (cols + 63) / 64;
+    dim3 grid((unsigned)((groups + 7) / 8), (unsigned)((a->n + 31) / 32));
+    pfa_encode_packed_kernel<<<grid, 256, 0, st>>>(d_packed, ldp, a->n, cols, site0, (uint32_t*)a->b0, (uint32_t*)a->b1,
+                                                   (uint32_t*)a->v, a->Wq * 4);
     PFA_LAUNCH_CHECK(ctx);
     return PFA_OK;
 }

@@ -39,3 +39,7 @@ struct PfaParsed {
 int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out);
 bool pfa_copy_record(const PfaRecord& rec, unsigned char* dst);
 int pfa_read_file(const char* path, std::vector<unsigned char>* buf, size_t* len);
+
+// ---- host packer (pfa_pack.cpp): cols bases of one text row -> ceil(cols/4) bytes, 4 bases per byte, code (byte >> 1) & 3
+// (A 0, C 1, T 2, G 3, either case); returns 1 when the row holds any other byte (the chunk then travels as text)
+int pfa_pack2_row(const uint8_t* src, int64_t cols, uint8_t* dst);

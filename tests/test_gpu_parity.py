@@ -395,3 +395,55 @@ def test_cli_dir_on_two_contexts(tmp_path):
     assert [ln.split(",")[0] for ln in lines] == sorted(want)
     for ln in lines:
         _rows_close(ln, want[ln.split(",")[0]])
+
+
+def _planes(a):
+    return [a.plane(i) for i in range(3)]
+
+
+@pytest.mark.parametrize("n,L,c0,c1", [(33, 70000, 0, None), (260, 40001, 0, None), (1000, 9000, 1200, 8190), (129, 30011, 3, 30011)])
+def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1):
+    """large host inputs are split in column chunks between a raw lane (text over PCIe, K1) and a packed lane (host threads
+    pack 4 bases per byte, pfa_encode_packed_kernel); chunks holding non-ACGT symbols fall back to the raw lane.  The planes,
+    the exception list and every statistic must not depend on which lane a chunk took."""
+    rng = np.random.default_rng(n + L)
+    clean = _random_text(rng, n, L, p_junk=0.0)
+    some = clean.copy()
+    some[rng.integers(0, n, 40), rng.integers(L // 2, L, 40)] = np.frombuffer(b"-NR?n", dtype=np.uint8)[rng.integers(0, 5, 40)]
+    gappy = _random_text(rng, n, L, p_junk=0.05)
+    monkeypatch.setenv("PFA_INGEST_CHUNK_MB", "1")
+    pops = [list(range(n)), list(range(0, n, 2))]
+    for name, text in (("clean", clean), ("some", some), ("gappy", gappy)):
+        monkeypatch.setenv("PFA_INGEST_HYBRID", "0")
+        plain = pf.Alignment.from_rows(ctx, text, c0, c1)
+        # mode 2: every chunk is offered to the packer first (deterministic); mode 1: the lanes race for the chunks
+        monkeypatch.setenv("PFA_INGEST_HYBRID", "2")
+        hyb = pf.Alignment.from_rows(ctx, text, c0, c1)
+        st = ctx.ingest_stats()
+        assert st["raw_chunks"] + st["packed_chunks"] >= 2, st
+        if name == "clean":
+            assert st["raw_chunks"] == 0 and st["dirty_chunks"] == 0, st
+        if name == "some":
+            assert st["packed_chunks"] > 0 and 0 < st["dirty_chunks"] <= st["raw_chunks"], st
+        if name == "gappy":
+            assert st["packed_chunks"] == 0 and st["dirty_chunks"] >= 1, st
+        monkeypatch.setenv("PFA_INGEST_HYBRID", "1")
+        race = pf.Alignment.from_rows(ctx, text, c0, c1)
+        for x, y, z in zip(_planes(plain), _planes(hyb), _planes(race)):
+            assert np.array_equal(x, y) and np.array_equal(x, z), name
+        assert race.num_escapes == plain.num_escapes
+        race.free()
+        assert plain.num_escapes == hyb.num_escapes and plain.has_invalid == hyb.has_invalid
+        plain.set_pops(pops)
+        hyb.set_pops(pops)
+        a, b = plain.site_stats(), hyb.site_stats()
+        ca, cb = plain.cds_stats(), hyb.cds_stats()
+        for q in range(2):
+            assert (a[q]["S"], a[q]["H"], a[q]["sfs"]) == (b[q]["S"], b[q]["H"], b[q]["sfs"])
+            assert np.array_equal(ca[q]["raw"], cb[q]["raw"])
+        if name == "some":
+            up = _upper(text[:, c0:c1])
+            want = co.site_stats(up, pops[1])
+            assert (b[1]["S"], b[1]["H"], b[1]["sfs"]) == (want["S"], want["H"], want["sfs"])
+        plain.free()
+        hyb.free()

@@ -5,6 +5,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 import polyfasta_b200 as pf
@@ -119,3 +120,60 @@ def test_synth_twin_closed_form_small():
         want = co.site_stats(mat)
         got = synth.expected_site_stats(11, n, L, 200000, 100000)
         assert (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"]), (n, L)
+
+
+def _pack_ref(row):
+    lut = np.full(256, 255, np.uint8)
+    for i, ch in enumerate(b"ACTG"):
+        lut[ch] = i
+        lut[ch | 32] = i
+    c = lut[row]
+    dirty = bool((c == 255).any())
+    c = np.concatenate([c & 3, np.zeros((-len(c)) % 4, np.uint8)]).reshape(-1, 4)
+    return (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8), dirty
+
+
+def test_host_packer_variants_agree_with_numpy():
+    """the ingest's host packer (4 bases per byte, A0 C1 T2 G3, either case; anything else marks the row dirty):
+    scalar, AVX2 and AVX-512 variants against a numpy restatement, all tail lengths"""
+    from polyfasta_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    txt = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, 1500)].copy()
+    ran = 0
+    for variant in (0, 1, 2, 3):
+        for cols in list(range(0, 140)) + [255, 256, 257, 1000, 1499]:
+            dst = np.full(cols // 4 + 2, 0xEE, np.uint8)
+            r = L.pfa_host_pack2(txt.ctypes.data, cols, dst.ctypes.data, variant)
+            if r == -2:
+                break  # this CPU lacks the instruction set
+            want, _ = _pack_ref(txt[:cols])
+            assert r == 0 and np.array_equal(dst[: (cols + 3) // 4], want), (variant, cols)
+            assert dst[(cols + 3) // 4] == 0xEE                      # nothing written past the row
+        else:
+            ran += 1
+            for pos in (0, 3, 63, 64, 65, 127, 128, 200, 299):
+                for bad in b"N-nRr?.* \x00\x01\xc1\xe1!@[`{":
+                    t = txt[:300].copy()
+                    t[pos] = bad
+                    dst = np.zeros(80, np.uint8)
+                    assert L.pfa_host_pack2(t.ctypes.data, 300, dst.ctypes.data, variant) == 1, (variant, pos, bad)
+    assert ran >= 2  # the scalar variant and the dispatcher always run
+
+
+def test_host_packer_matrix_threads():
+    from polyfasta_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    n, cols, ld = 37, 1001, 1100
+    txt = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, (n, ld))].copy()
+    txt[5, 1000] = ord("N")   # inside the packed range: one dirty row
+    txt[7, 1001] = ord("N")   # outside it: ignored
+    ldp = 256
+    dst = np.zeros((n, ldp), np.uint8)
+    for threads in (1, 3, 0):
+        assert L.pfa_host_pack2_rows(txt.ctypes.data, n, cols, ld, dst.ctypes.data, ldp, threads) == 1
+        for r in range(n):
+            want, dirty = _pack_ref(txt[r, :cols])
+            assert dirty == (r == 5)
+            assert np.array_equal(dst[r, : (cols + 3) // 4], want)
