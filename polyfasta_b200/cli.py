@@ -178,7 +178,9 @@ def process_chunk(ctx, batch, items, cds, jc, popkeys):
     Small non-CDS loci of the chunk share ONE batched GPU pass; everything else goes through the single-alignment path."""
     actions = []
     pending = []   # (position in actions, locus, pop, file, seqlen, label, n)
-    batch.clear()
+    own_batch = None
+    if batch is not None:
+        batch.clear()
     for path, fasta in items:
         file = path.split("/")[-1]
         if isinstance(fasta, api.NotFasta):
@@ -200,6 +202,8 @@ def process_chunk(ctx, batch, items, cds, jc, popkeys):
         elif found:
             import numpy as np
             masks = None if found[0][1] is None else np.stack([m for _, m, _ in found])
+            if batch is None:   # a caller that expected only large alignments: stage the small one in a batch of our own
+                batch = own_batch = api.Batch(ctx)
             locus = batch.add(fasta, masks)
         q = 0
         for label, mask, hits in plan:
@@ -224,6 +228,8 @@ def process_chunk(ctx, batch, items, cds, jc, popkeys):
     for _, fasta in items:
         if isinstance(fasta, api.Fasta):
             fasta.close()
+    if own_batch is not None:
+        own_batch.close()
     return actions
 
 
@@ -241,7 +247,15 @@ def process_chunk_native(ctx, batch, paths, jc, popkeys, threads):
     import time
     t0 = time.perf_counter()
     batch.clear()
-    info = batch.add_files(paths, popkeys or (), threads)
+    # files too large for the batched kernels skip the native staging (it would read and parse them only to refuse them)
+    def _size(p):
+        try:
+            return os.path.getsize(p)
+        except OSError:
+            return 0
+    big = [_size(p) > api.Batch.MAX_LOCUS_BYTES for p in paths]
+    small_info = iter(batch.add_files([p for p, b in zip(paths, big) if not b], popkeys or (), threads))
+    info = [{"status": PFA_BATCH_TOO_BIG} if b else next(small_info) for b in big]
     t1 = time.perf_counter()
     labels = popkeys if popkeys is not None else ["NA"]
     actions, pending = [], []
@@ -259,11 +273,7 @@ def process_chunk_native(ctx, batch, paths, jc, popkeys, threads):
         elif st == PFA_ERR_RAGGED:
             actions.append(("note", f"# Sequences do not have the same length: {file}"))
         elif st == PFA_BATCH_TOO_BIG:
-            sub = api.Batch(ctx)
-            try:
-                actions.extend(process_chunk(ctx, sub, [(path, api.parse_files([path])[0])], False, jc, popkeys))
-            finally:
-                sub.close()
+            actions.extend(process_chunk(ctx, None, [(path, api.parse_files([path], threads=threads)[0])], False, jc, popkeys))
         elif st == PFA_OK:
             q = 0
             for label, hits in zip(labels, fi["hits"]):

@@ -142,6 +142,7 @@ int pfa_ctx_destroy(pfa_ctx* ctx) {
     for (auto& ev : ctx->ev_slot_copied) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_join) if (ev) cudaEventDestroy(ev);
     if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
+    if (ctx->raw_pinned) cudaFreeHost(ctx->raw_pinned);
     if (ctx->enc_stream) cudaStreamDestroy(ctx->enc_stream);
     if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -207,7 +208,8 @@ int pfa_aln_from_device_rows(pfa_ctx* ctx, const uint8_t* d_text, int64_t n, int
 int pfa_aln_from_fasta(pfa_ctx* ctx, const pfa_fasta* f, int64_t col_begin, int64_t col_end, pfa_aln** out) {
     if (!ctx || !f || !out) return PFA_ERR_ARG;
     if (f->seqlen < 0) return pfa_fail(ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
-    return pfa_aln_from_text(ctx, f->data, false, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), col_begin, col_end, out);
+    return pfa_aln_from_text(ctx, f->data, false, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), col_begin, col_end, out,
+                             f->in_place ? f->row_off.data() : nullptr);
 }
 
 int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm, int64_t col_begin,

@@ -465,6 +465,11 @@ int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, 
 int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k, int64_t* index) {
     if (!b || !f) return PFA_ERR_ARG;
     if (f->seqlen < 0) return pfa_fail(b->ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
+    if (f->in_place) {  // a large file whose rows are slices of the file buffer: gather them into a matrix first (rare here)
+        std::vector<uint8_t> mat((size_t)std::max<int64_t>(f->n * f->seqlen, 1));
+        for (int64_t r = 0; r < f->n; ++r) memcpy(mat.data() + r * f->seqlen, f->data + f->row_off[(size_t)r], (size_t)f->seqlen);
+        return pfa_batch_add_rows(b, mat.data(), f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), masks, k, index);
+    }
     return pfa_batch_add_rows(b, f->data, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), masks, k, index);
 }
 

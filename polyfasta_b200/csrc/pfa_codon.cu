@@ -148,6 +148,27 @@ __device__ __forceinline__ void pfa_cds_contribute(unsigned long long P, const u
     }
 }
 
+// the same for a column in which only position tv varies (c = class counts of that site): no other position can be labelled
+__device__ __forceinline__ void pfa_cds_contribute_one(unsigned long long P, const uint32_t c[PFA_NCLASS], int tv, int64_t nq,
+                                                       unsigned long long* acc, uint8_t* labels, int64_t site0) {
+    if (P & c_stop_mask) atomicAdd(&acc[PFA_CDS_NSTOPS], 1ull);
+    const int len = __popcll(P);
+    if (len == 0) {
+        atomicAdd(&acc[PFA_CDS_MISSING], 3ull);
+        return;
+    }
+    unsigned tot3 = 0;
+    for (unsigned long long t = P; t; t &= t - 1) tot3 += c_syn3[__ffsll((long long)t) - 1];
+    if (tot3) atomicAdd(&acc[PFA_CDS_SUM3 + len], (unsigned long long)tot3);
+    if (len < 2) return;
+    const int li = (pfa_labels_from_set(P & ~c_stop_mask) >> (2 * tv)) & 3;
+    if (!li) return;
+    const PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
+    atomicAdd(&acc[li == 1 ? PFA_CDS_SS : PFA_CDS_SN], 1ull);
+    atomicAdd(&acc[li == 1 ? PFA_CDS_HS : PFA_CDS_HN], r.h);
+    if (labels) labels[site0 + tv] = (uint8_t)li;
+}
+
 template <int LPS, bool HAS_V>
 __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const PfaCdsArgs a) {
     extern __shared__ unsigned long long smem[];  // [3] uniform + [k][PFA_CDS_LEN] when acc_in_smem
@@ -345,7 +366,75 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
             }
             continue;
         }
-        // ---- pass 2 ----
+        // ---- pass 2, common case: exactly ONE of the three sites varies and the other two show one valid base.  Then the
+        // clean codons of a population are that fixed pair combined with the bases present at the variable site, so the
+        // presence mask follows from the four base counts of ONE column (no codon peeling, a third of the popcounts); only
+        // the variable position can carry a label (a label needs codons that differ there). ----
+        int nvar = 0, tv = 0, fixed = 0;
+        bool fixed_valid = true;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const unsigned ft = (f >> (6 * t)) & 63u;
+            const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
+            if (!mono) {
+                ++nvar;
+                tv = t;
+            } else {
+                fixed_valid = fixed_valid && (ft & 16u) && !(ft & 32u);
+                fixed |= (((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0)) << (2 * (2 - t));
+            }
+        }
+        if (nvar == 1 && fixed_valid) {
+            for (int q = 0; q < a.s.k; ++q) {
+                const uint4* mq = a.s.masks + (int64_t)q * Wq;
+                uint32_t c[PFA_NCLASS];
+#pragma unroll
+                for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+#pragma unroll
+                for (int i = 0; i < ITER; ++i) {
+                    const int j = sub + LPS * i;
+                    uint4 m4 = um[i];
+                    if (!one_pop) m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+                    const uint4 s0 = tv == 0 ? x0[0][i] : tv == 1 ? x0[1][i] : x0[2][i];
+                    const uint4 s1 = tv == 0 ? x1[0][i] : tv == 1 ? x1[1][i] : x1[2][i];
+                    const uint4 sv = tv == 0 ? xv[0][i] : tv == 1 ? xv[1][i] : xv[2][i];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t m = pfa_u4(m4, w), w0 = pfa_u4(s0, w), w1 = pfa_u4(s1, w), wv = pfa_u4(sv, w);
+                        const uint32_t vm = HAS_V ? (wv & m) : m;
+                        const uint32_t hi = vm & w1, lo = vm & ~w1;
+                        c[PFA_C_T] += __popc(hi & w0);
+                        c[PFA_C_G] += __popc(hi & ~w0);
+                        c[PFA_C_C] += __popc(lo & w0);
+                        c[PFA_C_A] += __popc(lo & ~w0);
+                        if (HAS_V) {
+                            const uint32_t im = ~wv & m;
+                            const uint32_t ihi = im & w1;
+                            c[PFA_C_ESC] += __popc(ihi & w0);
+                            c[PFA_C_Q] += __popc(ihi & ~w0);
+                            c[PFA_C_N] += __popc(im & ~w1 & w0);
+                        }
+                    }
+                }
+                if (LPS > 1) {
+#pragma unroll
+                    for (int i = 0; i < PFA_NCLASS; ++i)
+                        if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
+                }
+                if (c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
+                if (sub != 0) continue;
+                const int shift = 2 * (2 - tv);
+                unsigned long long P = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (c[b]) P |= 1ull << (fixed | (b << shift));
+                unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
+                                                        : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
+                pfa_cds_contribute_one(P, c, tv, a.s.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+            }
+            continue;
+        }
+        // ---- pass 2, general case ----
         for (int q = 0; q < a.s.k; ++q) {
             const uint4* mq = a.s.masks + (int64_t)q * Wq;
             uint4 m4[ITER];

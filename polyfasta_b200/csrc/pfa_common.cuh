@@ -32,6 +32,8 @@ struct pfa_ctx {
     cudaEvent_t ev_slot[3] = {nullptr, nullptr, nullptr}, ev_slot_copied[3] = {nullptr, nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     void* pack_pinned = nullptr;
     size_t pack_pinned_bytes = 0;
+    void* raw_pinned = nullptr;  // bounce buffers for text chunks of a pageable source
+    size_t raw_pinned_bytes = 0;
     int host_threads = 0;  // host threads the ingest may use; 0 = PFA_HOST_THREADS or all hardware threads
     int64_t ingest_stats[6] = {0, 0, 0, 0, 0, 0};  // last upload: chunks sent as text, chunks packed on the host, dirty chunks, threads, H2D bytes as text, H2D bytes packed
 };
@@ -106,8 +108,9 @@ int pfa_upload_codon_tables(pfa_ctx* ctx);
 int pfa_aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out);
 int pfa_aln_default_pop(pfa_aln* a);
 // upload + encode of columns [col_begin, col_end) of a text matrix (pfa_ingest.cu); `dev`: the matrix is in device memory
+// row_off (host sources only, optional): row r starts at text + row_off[r] instead of text + r * ld
 int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
-                      int64_t col_end, pfa_aln** out);
+                      int64_t col_end, pfa_aln** out, const int64_t* row_off = nullptr);
 int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, int64_t cols, int64_t site0, cudaStream_t st);
 
 // Device memory comes from the device's stream-ordered pool (release threshold = keep): allocating and freeing the planes

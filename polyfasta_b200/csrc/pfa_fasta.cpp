@@ -13,11 +13,14 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <stdint.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -27,55 +30,139 @@
 #include "pfa_host.h"
 
 namespace {
+unsigned big_threads() { return std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())); }
+
+// fn(t, nthreads) on nthreads threads
+template <typename F>
+void parallel_run(unsigned nthreads, F fn) {
+    if (nthreads <= 1) {
+        fn(0u, 1u);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(fn, t, nthreads);
+    for (auto& x : th) x.join();
+}
+
+// does the buffer hold byte c?  large buffers are searched by several threads
+bool pfa_parallel_memchr(const unsigned char* buf, int c, size_t len) {
+    if (len < (64u << 20)) return memchr(buf, c, len) != nullptr;  // small: one call
+    const unsigned nt = big_threads();
+    std::vector<char> hit(nt, 0);
+    parallel_run(nt, [&](unsigned t, unsigned n) {
+        const size_t lo = len * t / n, hi = len * (t + 1) / n;
+        hit[t] = memchr(buf + lo, c, hi - lo) != nullptr;
+    });
+    for (char h : hit)
+        if (h) return true;
+    return false;
+}
+
 // str.rstrip() with no argument strips characters for which str.isspace() is true; in ASCII these are
 // \t \n \v \f \r, the separators 0x1c-0x1f and the blank.
 inline bool py_space(unsigned char c) { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); }
 }  // namespace
 
-// line scan: records with their line slices (pointing into buf), lengths, and whether all rows have one length
-int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out) {
-    std::vector<PfaRecord>& recs = out->recs;
-    recs.clear();
-    std::unordered_map<std::string, size_t> index;
-    bool seen_header = false, head_nonempty = false;
-    size_t cur = 0;
-    size_t i = 0;
-    // a '\r' anywhere switches to the byte-wise scan (a lone '\r' ends a line under universal newlines); otherwise lines
-    // end at '\n' only and memchr finds them at memory speed
-    const bool has_cr = len && memchr(buf, '\r', len) != nullptr;
-    while (i < len) {
-        size_t e;
-        if (has_cr) {
-            e = i;
-            while (e < len && buf[e] != '\n' && buf[e] != '\r') ++e;
-        } else {
-            const void* nl = memchr(buf + i, '\n', len - i);
-            e = nl ? (size_t)(static_cast<const unsigned char*>(nl) - buf) : len;
-        }
-        size_t next = e;
-        if (next < len) next += (buf[next] == '\r' && next + 1 < len && buf[next + 1] == '\n') ? 2 : 1;
-        // the line is buf[i, e) plus its terminator; never empty as a Python line, but may be empty here
+// inputs of at least this many bytes are read, scanned and compacted by several threads (PFA_BIG_FILE_MIN overrides: tests)
+static size_t big_min() {
+    const char* s = getenv("PFA_BIG_FILE_MIN");
+    return s ? (size_t)atoll(s) : (size_t)(64u << 20);
+}
+
+// end of the line that starts at i (index of its terminator, or len) and the start of the next line
+static inline void line_end(const unsigned char* buf, size_t len, size_t i, bool has_cr, size_t* e, size_t* next) {
+    if (has_cr) {
+        size_t x = i;
+        while (x < len && buf[x] != '\n' && buf[x] != '\r') ++x;
+        *e = x;
+    } else {
+        const void* nl = memchr(buf + i, '\n', len - i);
+        *e = nl ? (size_t)(static_cast<const unsigned char*>(nl) - buf) : len;
+    }
+    *next = *e;
+    if (*next < len) *next += (buf[*next] == '\r' && *next + 1 < len && buf[*next + 1] == '\n') ? 2 : 1;
+}
+
+// one segment of the buffer scanned on its own: the sequence lines in front of its first header (they continue the last
+// record of the previous segment) and its records in file order, not yet merged by header
+struct PfaSegment {
+    std::vector<PfaSlice> lead;
+    int64_t lead_len = 0;
+    std::vector<PfaRecord> recs;
+};
+
+static void scan_segment(const unsigned char* buf, size_t len, size_t lo, size_t hi, bool has_cr, PfaSegment* seg) {
+    size_t i = lo;
+    bool in_rec = false, keep = false;
+    while (i < hi) {
+        size_t e, next;
+        line_end(buf, len, i, has_cr, &e, &next);
         size_t r = e;
         while (r > i && py_space(buf[r - 1])) --r;
         if (e > i && buf[i] == '>') {
-            std::string h(reinterpret_cast<const char*>(buf + i + 1), r > i + 1 ? r - (i + 1) : 0);
-            seen_header = true;
-            head_nonempty = !h.empty();
-            auto it = index.find(h);
-            if (it == index.end()) {
-                index.emplace(h, recs.size());
-                cur = recs.size();
-                recs.push_back(PfaRecord{h, {}, 0});
-            } else {
-                cur = it->second;
-                recs[cur].parts.clear();
-                recs[cur].len = 0;
+            seg->recs.push_back(PfaRecord{std::string(reinterpret_cast<const char*>(buf + i + 1), r > i + 1 ? r - (i + 1) : 0), {}, 0});
+            in_rec = true;
+            keep = !seg->recs.back().header.empty();
+        } else if (r > i) {
+            if (!in_rec) {
+                seg->lead.push_back(PfaSlice{buf + i, r - i});
+                seg->lead_len += (int64_t)(r - i);
+            } else if (keep) {
+                seg->recs.back().parts.push_back(PfaSlice{buf + i, r - i});
+                seg->recs.back().len += (int64_t)(r - i);
             }
-        } else if (seen_header && head_nonempty && r > i) {
-            recs[cur].parts.push_back(PfaSlice{buf + i, r - i});
-            recs[cur].len += (int64_t)(r - i);
         }
         i = next;
+    }
+}
+
+// line scan: records with their line slices (pointing into buf), lengths, and whether all rows have one length.
+// The reference's state machine (PolyFastA.py:232-245) runs over the records of the segments in file order: a header seen
+// again restarts its record in place, the lines after an empty header are dropped, lines before any header are ignored.
+int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out) {
+    std::vector<PfaRecord>& recs = out->recs;
+    recs.clear();
+    // a '\r' anywhere switches to the byte-wise line scan (a lone '\r' ends a line under universal newlines); otherwise
+    // lines end at '\n' only and memchr finds them at memory speed
+    const bool has_cr = len && pfa_parallel_memchr(buf, '\r', len);
+    unsigned nseg = (len >= big_min() && !has_cr) ? big_threads() : 1;
+    if (const char* s = getenv("PFA_PARSE_SEGMENTS")) nseg = has_cr ? 1u : (unsigned)std::max(1, atoi(s));
+    // segment boundaries on line starts
+    std::vector<size_t> start(nseg + 1, len);
+    start[0] = 0;
+    for (unsigned t = 1; t < nseg; ++t) {
+        const size_t lo = std::max(start[t - 1], len / nseg * t);
+        if (lo == 0 || lo >= len) {
+            start[t] = std::min(lo, len);
+            continue;
+        }
+        const void* nl = memchr(buf + lo - 1, '\n', len - (lo - 1));
+        start[t] = nl ? (size_t)(static_cast<const unsigned char*>(nl) - buf) + 1 : len;
+    }
+    std::vector<PfaSegment> segs(nseg);
+    parallel_run(nseg, [&](unsigned t, unsigned) { scan_segment(buf, len, start[t], start[t + 1], has_cr, &segs[t]); });
+    std::unordered_map<std::string, size_t> index;
+    bool seen_header = false, head_nonempty = false;
+    size_t cur = 0;
+    for (PfaSegment& seg : segs) {
+        if (seen_header && head_nonempty && !seg.lead.empty()) {
+            recs[cur].parts.insert(recs[cur].parts.end(), seg.lead.begin(), seg.lead.end());
+            recs[cur].len += seg.lead_len;
+        }
+        for (PfaRecord& r : seg.recs) {
+            seen_header = true;
+            head_nonempty = !r.header.empty();
+            auto it = index.find(r.header);
+            if (it == index.end()) {
+                index.emplace(r.header, recs.size());
+                cur = recs.size();
+                recs.push_back(std::move(r));
+            } else {
+                cur = it->second;
+                recs[cur].parts = std::move(r.parts);
+                recs[cur].len = r.len;
+            }
+        }
     }
     if (!seen_header || !head_nonempty) return PFA_ERR_NOT_FASTA;
     out->total = 0;
@@ -88,21 +175,57 @@ int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out) {
     return PFA_OK;
 }
 
-// copy the line slices of one record to dst; returns false when a byte >= 0x80 was seen
+// OR of all bytes of a slice, eight at a time
+static inline unsigned char or_bytes(const unsigned char* p, size_t n) {
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w0, w1, w2, w3;
+        memcpy(&w0, p + i, 8);
+        memcpy(&w1, p + i + 8, 8);
+        memcpy(&w2, p + i + 16, 8);
+        memcpy(&w3, p + i + 24, 8);
+        a0 |= w0; a1 |= w1; a2 |= w2; a3 |= w3;
+    }
+    uint64_t a = a0 | a1 | a2 | a3;
+    unsigned char r = 0;
+    for (; i < n; ++i) r |= p[i];
+    a |= a >> 32;
+    a |= a >> 16;
+    a |= a >> 8;
+    return (unsigned char)(r | (unsigned char)a);
+}
+
+// copy the line slices of one record to dst (memmove: dst may be the start of the record's own span in the same buffer);
+// returns false when a byte >= 0x80 was seen
 bool pfa_copy_record(const PfaRecord& rec, unsigned char* dst) {
     unsigned char acc = 0;
     for (const PfaSlice& s : rec.parts) {
-        memcpy(dst, s.p, s.len);
-        for (size_t b = 0; b < s.len; ++b) acc |= s.p[b];
+        acc |= or_bytes(s.p, s.len);
+        if (dst != s.p) memmove(dst, s.p, s.len);
         dst += s.len;
     }
     return !(acc & 0x80);
 }
 
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
     PfaParsed parsed;
+    const double t0 = now_ms();
     int rc = pfa_parse_lines(buf, len, &parsed);
     if (rc) return rc;
+    const double t1 = now_ms();
+    struct Trace {
+        double t0, t1;
+        size_t len;
+        ~Trace() {
+            if (getenv("PFA_PARSE_TRACE"))
+                fprintf(stderr, "[pfa parse] %zu bytes: line scan %.1f ms, rows -> matrix %.1f ms\n", len, t1 - t0, now_ms() - t1);
+        }
+    } trace{t0, t1, len};
     const std::vector<PfaRecord>& recs = parsed.recs;
     pfa_fasta* f = new pfa_fasta();
     f->n = (int64_t)recs.size();
@@ -125,8 +248,11 @@ static int parse_impl(const unsigned char* buf, size_t len, pfa_fasta** out) {
         delete f;
         return PFA_ERR_NOMEM;
     }
+#ifdef MADV_HUGEPAGE
+    if (f->data_bytes >= (64u << 20)) madvise(f->data, f->data_bytes, MADV_HUGEPAGE);
+#endif
     // rows are independent, so large files are copied by several threads
-    unsigned nthreads = total > (64ll << 20) ? std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    unsigned nthreads = total > (64ll << 20) ? big_threads() : 1;
     std::vector<char> bad(nthreads, 0);
     auto work = [&](unsigned t) {
         for (size_t k = t; k < recs.size(); k += nthreads)
@@ -183,9 +309,86 @@ int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out) {
     return parse_impl(static_cast<const unsigned char*>(buf), len, out);
 }
 
+// large files: no zero-filled vector, the slices of the file are read (and their pages touched) by several threads
+static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return PFA_ERR_IO;
+    unsigned char* buf = static_cast<unsigned char*>(malloc(size));
+    if (!buf) {
+        close(fd);
+        return PFA_ERR_NOMEM;
+    }
+#ifdef MADV_HUGEPAGE
+    madvise(buf, size, MADV_HUGEPAGE);
+#endif
+    const unsigned nt = big_threads();
+    std::vector<char> bad(nt, 0);
+    parallel_run(nt, [&](unsigned t, unsigned n) {
+        size_t lo = size * t / n;
+        const size_t hi = size * (t + 1) / n;
+        while (lo < hi) {
+            const ssize_t r = pread(fd, buf + lo, hi - lo, (off_t)lo);
+            if (r <= 0) {
+                bad[t] = 1;
+                return;
+            }
+            lo += (size_t)r;
+        }
+    });
+    close(fd);
+    for (char b : bad)
+        if (b) {
+            free(buf);
+            return PFA_ERR_IO;
+        }
+    // no second copy: every record is compacted where its lines were (the lines of a record lie between its header and
+    // the next one, so the records' spans are disjoint and the rows move independently, in parallel)
+    const double t0 = now_ms();
+    PfaParsed parsed;
+    int rc = pfa_parse_lines(buf, size, &parsed);
+    if (rc) {
+        free(buf);
+        return rc;
+    }
+    const double t1 = now_ms();
+    const std::vector<PfaRecord>& recs = parsed.recs;
+    pfa_fasta* f = new pfa_fasta();
+    f->n = (int64_t)recs.size();
+    f->in_place = true;
+    f->data = buf;
+    f->data_bytes = size;
+    f->seqlen = parsed.seqlen;
+    f->row_len.resize(recs.size());
+    f->row_off.resize(recs.size() + 1);
+    for (size_t k = 0; k < recs.size(); ++k) {
+        f->row_len[k] = recs[k].len;
+        f->row_off[k] = recs[k].parts.empty() ? 0 : (int64_t)(recs[k].parts[0].p - buf);
+        f->header_off.push_back((int64_t)f->headers.size());
+        f->headers += recs[k].header;
+    }
+    f->row_off[recs.size()] = (int64_t)size;
+    f->header_off.push_back((int64_t)f->headers.size());
+    std::vector<char> non_ascii(nt, 0);
+    parallel_run(nt, [&](unsigned t, unsigned n) {
+        for (size_t k = t; k < recs.size(); k += n)
+            if (!recs[k].parts.empty() && !pfa_copy_record(recs[k], buf + f->row_off[k])) non_ascii[t] = 1;
+    });
+    if (getenv("PFA_PARSE_TRACE"))
+        fprintf(stderr, "[pfa parse] %zu bytes in place: line scan %.1f ms, compaction %.1f ms\n", size, t1 - t0, now_ms() - t1);
+    for (char b : non_ascii)
+        if (b) {
+            pfa_fasta_free(f);
+            return PFA_ERR_NON_ASCII;
+        }
+    *out = f;
+    return PFA_OK;
+}
+
 int pfa_fasta_parse_file(const char* path, pfa_fasta** out) {
     if (!out || !path) return PFA_ERR_ARG;
     *out = nullptr;
+    struct stat st;
+    if (stat(path, &st) == 0 && S_ISREG(st.st_mode) && (size_t)st.st_size >= big_min() && st.st_size > 0) return parse_big_file(path, (size_t)st.st_size, out);
     static thread_local std::vector<unsigned char> buf;  // warm across the files one thread parses
     size_t n = 0;
     int rc = pfa_read_file(path, &buf, &n);

@@ -12,7 +12,8 @@ struct pfa_fasta {
     int64_t seqlen = -1;             // common row length or -1
     unsigned char* data = nullptr;   // rows back to back in first-seen order; a matrix [n][seqlen] when seqlen >= 0
     size_t data_bytes = 0;
-    std::vector<int64_t> row_off;    // n+1
+    std::vector<int64_t> row_off;    // n+1 (in_place: n offsets of the rows inside the file buffer, any stride)
+    bool in_place = false;           // large files: `data` is the file buffer itself, every row compacted where its lines were
     std::vector<int64_t> row_len;    // n
     std::string headers;             // concatenated header bytes
     std::vector<int64_t> header_off; // n+1

@@ -18,6 +18,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -84,6 +85,8 @@ constexpr int kSlots = 3;  // packed chunks in flight (pinned + device staging e
 struct Hybrid {
     pfa_aln* a;
     const uint8_t* text;  // first column of the shard
+    const int64_t* row_off = nullptr;  // optional: row r starts at text + row_off[r] (rows of any stride)
+    const uint8_t* row(int64_t r) const { return text + (row_off ? row_off[r] : r * ld); }
     int64_t ld, n, ns, chunk, nchunks, ldt, ldp;
     unsigned long long* d_count;
     int64_t cap;
@@ -99,7 +102,10 @@ struct Hybrid {
     int rc_packed = PFA_OK;
     std::string err_packed;
     int threads = 1;
-    bool raw_takes_chunks = true;     // false (PFA_INGEST_HYBRID=2, tests): the raw lane only gets the dirty chunks
+    bool raw_takes_chunks = true;     // false: the raw lane only gets the dirty chunks (pageable source, or PFA_INGEST_HYBRID=2)
+    bool bounce = false;              // the source is pageable: text chunks reach the copy engine through pinned bounce buffers
+    uint8_t* bounce_buf[2] = {nullptr, nullptr};
+    PackPool* pool = nullptr;
     std::atomic<bool> lane_up{false};  // the packed lane's pool is running
     double t_pack = 0, t_wait_slot = 0, t_wait_raw = 0, t_pool_start = 0, t0 = 0, t_lane_end = 0;  // PFA_INGEST_TRACE
 };
@@ -111,8 +117,24 @@ int raw_chunk(Hybrid& h, int64_t c, int& issued) {
     if (issued >= 2) PFA_CUDA(ctx, cudaEventSynchronize(ctx->ev_encoded[b]));  // throttle: the buffer is free again
     h.t_wait_raw += now_ms() - tw;
     const int64_t c0 = c * h.chunk, cols = std::min(h.chunk, h.ns - c0);
-    PFA_CUDA(ctx, cudaMemcpy2DAsync(h.stage_raw[b], (size_t)h.ldt, h.text + c0, (size_t)h.ld, (size_t)cols, (size_t)h.n,
-                                    cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (h.bounce) {
+        // pageable source: the pool copies the chunk's rows into a pinned buffer (the copy engine cannot read pageable
+        // memory asynchronously, and pinning the whole source in place costs more than the upload itself)
+        uint8_t* bb = h.bounce_buf[b];
+        std::atomic<int64_t> row_next(0);
+        h.pool->run([&] {
+            for (;;) {
+                const int64_t r0 = row_next.fetch_add(32);
+                if (r0 >= h.n) break;
+                const int64_t r1 = std::min(h.n, r0 + 32);
+                for (int64_t r = r0; r < r1; ++r) memcpy(bb + r * h.ldt, h.row(r) + c0, (size_t)cols);
+            }
+        });
+        PFA_CUDA(ctx, cudaMemcpyAsync(h.stage_raw[b], bb, (size_t)(h.n * h.ldt), cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        PFA_CUDA(ctx, cudaMemcpy2DAsync(h.stage_raw[b], (size_t)h.ldt, h.text + c0, (size_t)h.ld, (size_t)cols, (size_t)h.n,
+                                        cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
     PFA_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
     PFA_CUDA(ctx, cudaStreamWaitEvent(ctx->enc_stream, ctx->ev_copied[b], 0));
     int rc = pfa_encode_chunk(h.a, h.stage_raw[b], h.ldt, cols, c0, h.d_count, h.cap, h.d_inv, ctx->enc_stream);
@@ -135,9 +157,7 @@ void packed_lane(Hybrid* hp) {
     };
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail(e, "cudaSetDevice");
-    const double tp = now_ms();
-    PackPool pool(h.threads);
-    h.t_pool_start = now_ms() - tp;
+    PackPool& pool = *h.pool;
     h.lane_up = true;
     const size_t slot_bytes = (size_t)(h.n * h.ldp);
     bool used[kSlots] = {};
@@ -160,7 +180,7 @@ void packed_lane(Hybrid* hp) {
                 if (r0 >= h.n || is_dirty.load(std::memory_order_relaxed)) break;
                 const int64_t r1 = std::min(h.n, r0 + 16);
                 for (int64_t r = r0; r < r1; ++r)
-                    if (pfa_pack2_row(h.text + r * h.ld + c0, cols, dst + r * h.ldp)) is_dirty.store(1, std::memory_order_relaxed);
+                    if (pfa_pack2_row(h.row(r) + c0, cols, dst + r * h.ldp)) is_dirty.store(1, std::memory_order_relaxed);
             }
         });
         h.t_pack += now_ms() - tq;
@@ -202,13 +222,14 @@ int host_threads(const pfa_ctx* ctx) {
 }
 
 // all chunks of one attempt through the two lanes; the planes are complete when ctx->stream reaches the joins at the end
-int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, unsigned long long* d_count, int64_t cap, int* d_inv, int threads,
-                  bool raw_takes_chunks) {
+int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* row_off, unsigned long long* d_count, int64_t cap,
+                  int* d_inv, int threads, bool raw_takes_chunks, bool bounce) {
     pfa_ctx* ctx = a->ctx;
     Hybrid h;
     h.a = a;
     h.text = text;
     h.ld = ld;
+    h.row_off = row_off;
     h.n = a->n;
     h.ns = a->ns;
     int64_t chunk_mb = 64;
@@ -221,7 +242,8 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, unsigned long lon
     h.cap = cap;
     h.d_inv = d_inv;
     h.threads = threads;
-    h.raw_takes_chunks = raw_takes_chunks;
+    h.raw_takes_chunks = raw_takes_chunks && !bounce;
+    h.bounce = bounce;
     const size_t slot_bytes = (size_t)(h.n * h.ldp);
     if (ctx->pack_pinned_bytes < kSlots * slot_bytes) {
         if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
@@ -247,6 +269,9 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, unsigned long lon
         return pfa_fail(ctx, PFA_ERR_CUDA, "hybrid ingest setup failed: %s", cudaGetErrorString(e));
     }
     h.t0 = now_ms();
+    PackPool pool(threads);
+    h.pool = &pool;
+    h.t_pool_start = now_ms() - h.t0;
     std::thread lane(packed_lane, &h);
     int rc = PFA_OK, issued = 0;
     while (!h.lane_up.load()) std::this_thread::yield();  // ~0.2 ms: both lanes start taking chunks together
@@ -258,6 +283,20 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, unsigned long lon
     if (rc) h.give_up = true;
     lane.join();
     if (!rc && h.rc_packed) rc = pfa_fail(ctx, h.rc_packed, "packed lane: %s", h.err_packed.c_str());
+    if (!rc && h.bounce && (h.give_up.load() || !h.dirty.empty())) {
+        const size_t need = 2 * (size_t)(h.n * h.ldt);
+        if (ctx->raw_pinned_bytes < need) {
+            if (ctx->raw_pinned) cudaFreeHost(ctx->raw_pinned);
+            ctx->raw_pinned = nullptr;
+            ctx->raw_pinned_bytes = 0;
+            if ((e = cudaHostAlloc(&ctx->raw_pinned, need, cudaHostAllocDefault)) != cudaSuccess)
+                rc = pfa_fail(ctx, PFA_ERR_CUDA, "pinned bounce buffers: %s", cudaGetErrorString(e));
+            else
+                ctx->raw_pinned_bytes = need;
+        }
+        h.bounce_buf[0] = static_cast<uint8_t*>(ctx->raw_pinned);
+        h.bounce_buf[1] = h.bounce_buf[0] + (size_t)(h.n * h.ldt);
+    }
     if (!rc && h.give_up.load())  // the packed lane stopped early: chunks it never took are still on the counter
         for (;;) {
             const int64_t c = h.next.fetch_add(1);
@@ -295,10 +334,10 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, unsigned long lon
 }  // namespace
 
 int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
-                      int64_t col_end, pfa_aln** out) {
-    if (!ctx || !out) return PFA_ERR_ARG;
+                      int64_t col_end, pfa_aln** out, const int64_t* row_off) {
+    if (!ctx || !out || (dev && row_off)) return PFA_ERR_ARG;
     *out = nullptr;
-    if (n < 0 || L < 0 || col_begin < 0 || col_end < col_begin || col_end > L || (n > 0 && L > 0 && (!text || ld < L)))
+    if (n < 0 || L < 0 || col_begin < 0 || col_end < col_begin || col_end > L || (n > 0 && L > 0 && (!text || (ld < L && !row_off))))
         return pfa_fail(ctx, PFA_ERR_ARG, "bad alignment shape n=%lld L=%lld ld=%lld cols=[%lld,%lld)", (long long)n,
                         (long long)L, (long long)ld, (long long)col_begin, (long long)col_end);
     if (n >= (1ll << 24)) return pfa_fail(ctx, PFA_ERR_ARG, "more than 2^24-1 sequences are not supported");
@@ -335,31 +374,34 @@ int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, in
     if (ns > 0 && n > 0) {
         UP(pfa_dmalloc(ctx, &d_count, sizeof(unsigned long long)));
         UP(pfa_dmalloc(ctx, &d_inv, sizeof(int)));
-        // hybrid ingest for large host inputs (PFA_INGEST_HYBRID overrides the size test)
+        // hybrid ingest for large host inputs (PFA_INGEST_HYBRID overrides the size test: 0 plain, 1 hybrid, 2 hybrid with the
+        // raw lane restricted to dirty chunks)
         const int threads = host_threads(ctx);
-        bool hybrid = !dev && threads > 1 && n * ns >= (256ll << 20);
+        bool hybrid = !dev && ((threads > 1 && n * ns >= (64ll << 20)) || row_off);
         bool raw_takes_chunks = true;
-        if (const char* s = getenv("PFA_INGEST_HYBRID")) {  // 0 plain, 1 hybrid, 2 hybrid with the raw lane restricted to dirty chunks
-            hybrid = !dev && atoi(s) != 0;
+        if (const char* s = getenv("PFA_INGEST_HYBRID")) {
+            hybrid = !dev && (atoi(s) != 0 || row_off);  // rows of any stride exist only on the hybrid path
             raw_takes_chunks = atoi(s) != 2;
+        }
+        bool is_pinned = true;
+        if (!dev) {
+            cudaPointerAttributes attr;
+            is_pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+            cudaGetLastError();
         }
         // columns per chunk of the plain path: ~256 MB of text, a multiple of 256 columns
         int64_t chunk = ((256ll << 20) / n) & ~255ll;
         if (chunk < 256) chunk = 256;
         if (chunk > ns) chunk = ns;
         const int64_t ldt = pfa_round_up(chunk, 256);
-        if (!dev) {
-            if (!hybrid) {
-                const int nbuf = chunk < ns ? 2 : 1;
-                for (int i = 0; i < nbuf; ++i) UP(pfa_dmalloc(ctx, &stage[i], (size_t)(n * ldt)));
-                // the copy stream may touch the staging buffers only after their (stream-ordered) allocation
-                UP(cudaEventRecord(ctx->ev_ready, ctx->stream));
-                UP(cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
-            }
-            // pin large pageable inputs in place so that the 2-D copies run asynchronously at full PCIe rate
-            cudaPointerAttributes attr;
-            const bool is_pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-            cudaGetLastError();
+        if (!dev && !hybrid) {
+            const int nbuf = chunk < ns ? 2 : 1;
+            for (int i = 0; i < nbuf; ++i) UP(pfa_dmalloc(ctx, &stage[i], (size_t)(n * ldt)));
+            // the copy stream may touch the staging buffers only after their (stream-ordered) allocation
+            UP(cudaEventRecord(ctx->ev_ready, ctx->stream));
+            UP(cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
+            // pin mid-sized pageable inputs in place so that the 2-D copies run asynchronously (large ones take the hybrid
+            // path, whose packer reads pageable memory directly)
             const size_t span = (size_t)((n - 1) * ld + L);
             if (!is_pinned && span >= (32u << 20)) {
                 registered = cudaHostRegister(const_cast<uint8_t*>(text), span, cudaHostRegisterReadOnly) == cudaSuccess ||
@@ -375,7 +417,8 @@ int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, in
             UP(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
             UP(cudaMemsetAsync(d_inv, 0, sizeof(int), ctx->stream));
             if (hybrid) {
-                rc = upload_hybrid(a, text + col_begin, ld, d_count, cap, d_inv, std::max(1, threads), raw_takes_chunks);
+                rc = upload_hybrid(a, text + col_begin, ld, row_off, d_count, cap, d_inv, std::max(1, threads), raw_takes_chunks,
+                                   !is_pinned || row_off != nullptr);
                 if (rc) {
                     cleanup();
                     pfa_aln_free(a);

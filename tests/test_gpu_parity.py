@@ -401,8 +401,9 @@ def _planes(a):
     return [a.plane(i) for i in range(3)]
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("n,L,c0,c1", [(33, 70000, 0, None), (260, 40001, 0, None), (1000, 9000, 1200, 8190), (129, 30011, 3, 30011)])
-def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1):
+def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1, pinned):
     """large host inputs are split in column chunks between a raw lane (text over PCIe, K1) and a packed lane (host threads
     pack 4 bases per byte, pfa_encode_packed_kernel); chunks holding non-ACGT symbols fall back to the raw lane.  The planes,
     the exception list and every statistic must not depend on which lane a chunk took."""
@@ -413,12 +414,24 @@ def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1):
     gappy = _random_text(rng, n, L, p_junk=0.05)
     monkeypatch.setenv("PFA_INGEST_CHUNK_MB", "1")
     pops = [list(range(n)), list(range(0, n, 2))]
+    import torch
+
+    def upload(text):
+        # pageable numpy memory: packed lane first, dirty chunks through pinned bounce buffers; pinned memory: the two lanes
+        # race for the chunks and the raw lane copies straight from the source
+        if not pinned:
+            return pf.Alignment.from_rows(ctx, text, c0, c1)
+        t = torch.from_numpy(text).pin_memory()
+        a = pf.Alignment.from_host_ptr(ctx, t.data_ptr(), n, L, L, c0, L if c1 is None else c1)
+        ctx.sync()
+        return a
+
     for name, text in (("clean", clean), ("some", some), ("gappy", gappy)):
         monkeypatch.setenv("PFA_INGEST_HYBRID", "0")
         plain = pf.Alignment.from_rows(ctx, text, c0, c1)
         # mode 2: every chunk is offered to the packer first (deterministic); mode 1: the lanes race for the chunks
         monkeypatch.setenv("PFA_INGEST_HYBRID", "2")
-        hyb = pf.Alignment.from_rows(ctx, text, c0, c1)
+        hyb = upload(text)
         st = ctx.ingest_stats()
         assert st["raw_chunks"] + st["packed_chunks"] >= 2, st
         if name == "clean":
@@ -428,7 +441,7 @@ def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1):
         if name == "gappy":
             assert st["packed_chunks"] == 0 and st["dirty_chunks"] >= 1, st
         monkeypatch.setenv("PFA_INGEST_HYBRID", "1")
-        race = pf.Alignment.from_rows(ctx, text, c0, c1)
+        race = upload(text)
         for x, y, z in zip(_planes(plain), _planes(hyb), _planes(race)):
             assert np.array_equal(x, y) and np.array_equal(x, z), name
         assert race.num_escapes == plain.num_escapes
@@ -447,3 +460,49 @@ def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1):
             assert (b[1]["S"], b[1]["H"], b[1]["sfs"]) == (want["S"], want["H"], want["sfs"])
         plain.free()
         hyb.free()
+
+
+def test_large_file_rows_in_place(ctx, tmp_path, monkeypatch):
+    """files of 64 MB and more are parsed in place: the rows stay inside the file buffer at arbitrary offsets and the
+    uploader gathers them (packed lane, dirty chunks through pinned bounce buffers).  Forced here on a small file with
+    wrapped lines, headers of different lengths and a few non-ACGT symbols; column shards included."""
+    rng = np.random.default_rng(99)
+    n, L = 90, 20000
+    text = _random_text(rng, n, L, p_junk=0.0)
+    text[rng.integers(0, n, 25), rng.integers(L // 3, L, 25)] = np.frombuffer(b"-NRy?", dtype=np.uint8)[rng.integers(0, 5, 25)]
+    path = tmp_path / "big.fa"
+    with open(path, "wb") as f:
+        for i in range(n):
+            f.write((">pop%d_%d%s\n" % (i % 2, i, "x" * (i % 7))).encode())
+            row = text[i].tobytes()
+            w = 60 if i % 3 else 977
+            for o in range(0, L, w):
+                f.write(row[o:o + w] + b"\n")
+    monkeypatch.setenv("PFA_INGEST_CHUNK_MB", "1")
+    ref = pf.Fasta.from_file(str(path))
+    pops = [list(range(n)), [i for i, h in enumerate(ref.headers) if "pop1" in h]]
+    want = []
+    for c0, c1 in ((0, L), (0, 9999), (9999, L)):
+        a = pf.Alignment.from_fasta(ctx, ref, c0, c1)
+        a.set_pops(pops)
+        want.append((a.site_stats(), a.cds_stats(), [a.plane(i) for i in range(3)], a.num_escapes))
+        a.free()
+    monkeypatch.setenv("PFA_BIG_FILE_MIN", "1")
+    big = pf.Fasta.from_file(str(path))
+    assert big.headers == ref.headers and big.seqlen == L and [big.row(i) for i in (0, 1, n - 1)] == [ref.row(i) for i in (0, 1, n - 1)]
+    for (c0, c1), (ws, wc, wp, we) in zip(((0, L), (0, 9999), (9999, L)), want):
+        a = pf.Alignment.from_fasta(ctx, big, c0, c1)
+        st = ctx.ingest_stats()
+        assert st["packed_chunks"] + st["raw_chunks"] >= 1
+        a.set_pops(pops)
+        gs, gc = a.site_stats(), a.cds_stats()
+        for x, y in zip(wp, [a.plane(i) for i in range(3)]):
+            assert np.array_equal(x, y)
+        assert a.num_escapes == we
+        for q in range(2):
+            assert (gs[q]["S"], gs[q]["H"], gs[q]["sfs"]) == (ws[q]["S"], ws[q]["H"], ws[q]["sfs"])
+            assert np.array_equal(gc[q]["raw"], wc[q]["raw"])
+        a.free()
+    up = _upper(text)
+    o = co.site_stats(up, pops[1])
+    assert (want[0][0][1]["S"], want[0][0][1]["H"]) == (o["S"], o["H"])
