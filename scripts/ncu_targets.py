@@ -1,8 +1,11 @@
-"""Small fixed workloads for ncu captures of K4 (C3 shape) and K3.  usage: python scripts/ncu_targets.py k4|k3"""
+"""Small fixed workloads for ncu captures.  usage: python scripts/ncu_targets.py k4|k3|k1
+k4: codon scan on the C3 shape (2000 x 3 Mb, 2 populations);  k3: pairwise 2000 rows x 100 kb;
+k1: one hybrid upload of 10000 x 200 kb pinned text (raw K1 + packed K1 kernels)"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import polyfasta_b200 as pf
+from polyfasta_b200 import api
 from polyfasta_b200._lib import lib, check
 
 which = sys.argv[1]
@@ -15,6 +18,19 @@ if which == "k4":
         aln.cds_stats_device(out.data_ptr())
     ctx.sync()
     print("k4", out[:6].tolist())
+elif which == "k1":
+    n, cols = 10000, 200_000
+    d = torch.empty((n, cols), dtype=torch.uint8, device="cuda")
+    api.synth_text_device(ctx, d.data_ptr(), cols, n, 4, 50000, 10000, 0, cols)
+    ctx.sync()
+    h = torch.empty((n, cols), dtype=torch.uint8, pin_memory=True)
+    h.copy_(d)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        a = pf.Alignment.from_host_ptr(ctx, h.data_ptr(), n, cols, cols)
+        ctx.sync()
+        print("k1", ctx.ingest_stats())
+        a.free()
 else:
     a = pf.Alignment.synthetic(ctx, 2000, 100_000, 3)
     out = torch.zeros(1, dtype=torch.int64, device="cuda")
