@@ -143,7 +143,83 @@ def format_rows(ctx, file, seqlen, cds, jc, pops, site, cdsst):
     return lines
 
 
+class RankGroup:
+    """the ranks of a torchrun launch (one process per GPU): rendezvous and row gathering go through torch.distributed
+    (gloo, host plumbing only); the per-shard count vectors are summed inside the scan kernels over NVLink (api.Exchange)"""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.device = int(os.environ.get("LOCAL_RANK", str(self.rank)))
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("gloo", rank=self.rank, world_size=self.world)
+        self.xchg = None
+
+    def exchange(self, ctx, words):
+        """an exchange of at least `words` int64 (collective: every rank asks for the same size at the same point)"""
+        from . import parallel
+        if self.xchg is None or self.xchg.capacity < words:
+            if self.xchg is not None:
+                ctx.sync()
+                self.dist.barrier()
+                self.xchg.close()
+            self.xchg = parallel.connect_exchange(ctx, max(words, 1 << 14))
+        return self.xchg
+
+    def close(self, ctx):
+        if self.xchg is not None:
+            ctx.sync()
+            self.dist.barrier()
+            self.xchg.close()
+            self.xchg = None
+
+
+def sharded_alignment_rows(ctx, group, fasta, file, cds, jc, found):
+    """rows of one large alignment whose COLUMNS are split over the ranks: every rank uploads and scans its
+    codon-aligned range, the scan kernels sum the integer vectors over all ranks, rank 0 formats the rows"""
+    import numpy as np
+    import torch
+    from . import parallel
+    c0, c1 = parallel.shard_columns(fasta.seqlen, group.world, group.rank)
+    aln = api.Alignment.from_fasta(ctx, fasta, c0, c1)
+    try:
+        if found[0][1] is not None:
+            m = np.stack([mask for _, mask, _ in found])
+            api.check(api.lib().pfa_aln_set_pops(aln.handle, m.ctypes.data, len(found)), ctx.handle)
+        k = len(found)
+        ns, nc = aln.site_len(), api.PFA_CDS_LEN * k
+        x = group.exchange(ctx, max(ns, nc))
+        d_site = torch.zeros(ns, dtype=torch.int64, device="cuda:%d" % ctx.device)
+        d_cds = torch.zeros(nc, dtype=torch.int64, device="cuda:%d" % ctx.device)
+        torch.cuda.synchronize(ctx.device)
+        aln.site_stats_xchg(x, d_site.data_ptr())
+        if cds:
+            aln.cds_stats_xchg(x, d_cds.data_ptr())
+        ctx.sync()
+        if x.timed_out():
+            raise api.PolyFastaError(1, "a rank did not arrive at the exchange")
+        site = aln.unpack_site(d_site.cpu().numpy())
+        cdsst = None
+        if cds:
+            raw = d_cds.cpu().numpy().reshape(k, api.PFA_CDS_LEN)
+            ss = ctx.cds_ssites(raw)
+            cdsst = []
+            for q in range(k):
+                d = aln.unpack_cds(raw[q])
+                d["ssites"] = float(ss[q])
+                cdsst.append(d)
+    finally:
+        aln.free()
+    if group.rank != 0:
+        return [None] * len(found)
+    return format_rows(ctx, file, fasta.seqlen, cds, jc, [(label, rows) for label, _, rows in found], site, cdsst)
+
+
 BATCH_FILES = int(os.environ.get("POLYFASTA_BATCH_FILES", "512"))   # loci per batched GPU pass
+SHARD_MIN_BYTES = int(os.environ.get("POLYFASTA_SHARD_MIN_BYTES", str(64 << 20)))   # files this large are column-sharded over the ranks
 BATCH_BYTES = 1 << 30          # ... or this much text
 
 
@@ -173,7 +249,7 @@ def single_alignment_rows(ctx, fasta, file, cds, jc, found):
     return format_rows(ctx, file, fasta.seqlen, cds, jc, [(label, rows) for label, _, rows in found], site, cdsst)
 
 
-def process_chunk(ctx, batch, items, cds, jc, popkeys):
+def process_chunk(ctx, batch, items, cds, jc, popkeys, group=None):
     """items: [(path, Fasta | exception)] in output order -> ordered actions ('stdout' | 'note' | 'row', ...).
     Small non-CDS loci of the chunk share ONE batched GPU pass; everything else goes through the single-alignment path."""
     actions = []
@@ -197,7 +273,9 @@ def process_chunk(ctx, batch, items, cds, jc, popkeys):
         plan = plan_populations(fasta, popkeys)
         found = [p for p in plan if p[2] > 0]
         rows = iter(())
-        if found and (cds or not api.Batch.fits(fasta)):
+        if found and group is not None:
+            rows = iter(sharded_alignment_rows(ctx, group, fasta, file, cds, jc, found))
+        elif found and (cds or not api.Batch.fits(fasta)):
             rows = iter(single_alignment_rows(ctx, fasta, file, cds, jc, found))
         elif found:
             import numpy as np
@@ -209,7 +287,7 @@ def process_chunk(ctx, batch, items, cds, jc, popkeys):
         for label, mask, hits in plan:
             if hits == 0:
                 actions.append(("note", f"# Pop {label} string was not found in fasta headers."))   # :126-132
-            elif cds or not api.Batch.fits(fasta):
+            elif group is not None or cds or not api.Batch.fits(fasta):
                 actions.append(("row", next(rows), file, label))
             else:
                 pending.append((len(actions), locus, q, file, fasta.seqlen, label, hits))
@@ -365,6 +443,57 @@ def run_files(paths, cds, jc, popkeys, sink):
             pl.shutdown()
 
 
+def run_files_ranks(paths, cds, jc, popkeys, sink, group):
+    """the same loop under torchrun (one process per GPU).  Units in the reference's order: a file of at least
+    SHARD_MIN_BYTES is ONE alignment scanned by ALL ranks in column shards (exchange fused into the kernels); the other
+    files are grouped in chunks and chunk j goes to rank j mod world with no collective.  Rank 0 gathers the
+    finished rows and prints them in order."""
+    from . import parallel
+    ctx = api.Context(group.device)
+    batch = api.Batch(ctx)
+    threads = max(1, (os.cpu_count() or 1) // group.world)
+    ctx.set_host_threads(threads)
+    units, cur, cur_bytes = [], [], 0
+    for p in paths:
+        try:
+            sz = os.path.getsize(p)
+        except OSError:
+            sz = 0
+        if sz >= SHARD_MIN_BYTES:
+            if cur:
+                units.append(("chunk", cur))
+                cur, cur_bytes = [], 0
+            units.append(("all", [p]))
+            continue
+        if cur and (len(cur) >= BATCH_FILES or cur_bytes + sz > BATCH_BYTES):
+            units.append(("chunk", cur))
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += sz
+    if cur:
+        units.append(("chunk", cur))
+    mine, j = [], 0
+    for ui, (kind, ps) in enumerate(units):
+        if kind == "all":
+            fasta = api.parse_files(ps, threads=threads)[0]
+            acts = process_chunk(ctx, None, [(ps[0], fasta)], cds, jc, popkeys, group=group)
+            if group.rank == 0:
+                mine.append((ui, acts))
+            continue
+        if j % group.world == group.rank:
+            if not cds:
+                acts = process_chunk_native(ctx, batch, ps, jc, popkeys, threads)
+            else:
+                acts = process_chunk(ctx, batch, list(zip(ps, api.parse_files(ps, threads=threads))), cds, jc, popkeys)
+            mine.append((ui, acts))
+        j += 1
+    group.close(ctx)
+    gathered = parallel.gather_rows(mine)
+    if group.rank == 0:
+        for _, acts in gathered:
+            emit(acts, sink)
+
+
 def main(argv=None):
     parser = build_parser()
     args = parser.parse_args(argv)
@@ -380,7 +509,12 @@ def main(argv=None):
     elif len(args.file) == 0 and args.dir == "." and args.pipe:
         args.file = [args.name] if args.name else ["stdin"]
     sink = Sink(args.out, args.silent)
-    if not args.silent:
+    group = RankGroup() if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None   # torchrun: one process per GPU
+    if group is not None and group.rank != 0 and args.pipe:
+        return 0   # stdin belongs to rank 0
+    if group is not None and args.pipe:
+        group = None
+    if not args.silent and (group is None or group.rank == 0):
         sink.header(args.cds)
     popkeys = args.pops.split(",") if args.pops else None
     paths = sorted(args.file)
@@ -397,9 +531,11 @@ def main(argv=None):
                 fasta = e
             emit(process_chunk(ctx, batch, [(path, fasta)], args.cds, args.jc, popkeys), sink)
             data = b""
+    elif paths and group is not None:
+        run_files_ranks(paths, args.cds, args.jc, popkeys, sink, group)
     elif paths:
         run_files(paths, args.cds, args.jc, popkeys, sink)
-    if len(args.out) != 0 and not args.silent:
+    if len(args.out) != 0 and not args.silent and (group is None or group.rank == 0):
         print("")
     return 0
 

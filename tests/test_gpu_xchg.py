@@ -188,3 +188,60 @@ def test_two_processes_two_gpus():
         assert not bad
         for s, c in res:
             assert np.array_equal(s, want_s) and np.array_equal(c, want_c), rank
+
+
+def _cli_worker(rank, world, port, argv_list, shard_min, q):
+    import io
+    from contextlib import redirect_stdout
+    os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank), "MASTER_ADDR": "127.0.0.1",
+                       "MASTER_PORT": str(port)})
+    from polyfasta_b200 import cli
+    cli.SHARD_MIN_BYTES = shard_min
+    outs = []
+    for argv in argv_list:
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            cli.main(argv)
+        outs.append(buf.getvalue())
+    q.put((rank, outs))
+
+
+def test_cli_under_two_ranks(tmp_path):
+    """the drop-in CLI launched as one process per GPU: --dir loci round-robin over the ranks, a large file column-sharded
+    with the exchange fused into K2 / K4; rank 0 prints exactly what one process prints"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import io
+    import shutil
+    from contextlib import redirect_stdout
+    import torch.multiprocessing as mp
+    from conftest import GOLDEN
+    from polyfasta_b200 import cli
+    d = tmp_path / "loci"
+    shutil.copytree(os.path.join(GOLDEN, "example_theta_0.01"), d)
+    rng = np.random.default_rng(8)
+    n, L = 60, 30000
+    text = _random_text(rng, n, L, p_junk=0.002)
+    with open(d / "file5_big.fa", "wb") as f:      # sorts between file5.fa and file6.fa
+        for i in range(n):
+            f.write((">indiv%d\n" % i).encode() + text[i].tobytes() + b"\n")
+    argvs = [["-d", str(d), "-p", "indiv1,indiv2,nobody", "--jc"], ["-d", str(d), "--cds", "--jc"],
+             ["-f", str(d / "file5_big.fa"), "--cds", "-p", "indiv1,indiv3"]]
+    want = []
+    for argv in argvs:
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            cli.main(argv)
+        want.append(buf.getvalue())
+    assert "file5_big.fa" in want[0] and want[2].count("\n") == 3
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_cli_worker, args=(r, 2, port, argvs, 1_000_000, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert got[0] == want
+    assert all(o == "" for o in got[1])
