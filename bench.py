@@ -296,6 +296,9 @@ def main():
             raise SystemExit("PARITY FAILURE at full size: got S=%d H=%d, closed form S=%d H=%d" % (got[0], got[1], want["S"], want["H"]))
         parity = "S, H and the folded SFS of the %d x %d alignment equal the generator's closed form (S=%d)" % (n, L, want["S"])
     fin = ctx.finalize([(n, int(result[0]), int(result[1]), L, True)])[0]
+    # the read-only ceiling for exactly these bytes on this GPU (outside the timed region)
+    probe_ms = aln.read_probe(planes_read, 5)
+    read_only_gbs = aln.packed_bytes / 3 * planes_read / (probe_ms * 1e-3) / 1e9
     aln.free()
     ctx.trim()
 
@@ -376,7 +379,9 @@ def main():
                        "planes_read": planes_read, "seed": SEED, "p_seg_ppm": P_SEG_PPM, "tri_ppm": TRI_PPM},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                         "kernel": "pfa_site_scan_reg_kernel<16,5,HAS_V>" if n == N_SEQ else "pfa_site_scan_*", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes},
+                         "kernel": "pfa_site_scan_reg_kernel<16,5,HAS_V>" if n == N_SEQ else "pfa_site_scan_*", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "read_only_peak": read_only_gbs, "frac_of_read_only_peak": achieved / read_only_gbs,
+                         "read_only_peak_kind": "pfa_read_probe_kernel over the same planes (padded bytes), measured in this run"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "parity": parity,
             "result": {"S": int(result[0]), "H": int(result[1]), "pi_site_jc": fin[1], "theta_site": fin[2], "tajimasD": fin[3]},
         }

@@ -52,8 +52,9 @@ int pfa_ctx_set_stream(pfa_ctx* ctx, void* cuda_stream);
 int pfa_ctx_set_host_threads(pfa_ctx* ctx, int threads);
 /* the last upload of this ctx: out[0] column chunks shipped as text (K1), out[1] chunks packed 4 bases/byte on the host
  * (pfa_encode_packed_kernel), out[2] chunks the packer found dirty (non-ACGT) and handed back, out[3] host threads,
- * out[4] bytes copied host->device as text, out[5] bytes copied host->device packed */
-int pfa_ctx_ingest_stats(const pfa_ctx* ctx, int64_t out[6]);
+ * out[4] bytes copied host->device as text, out[5] bytes copied host->device packed, out[6] packed chunks that carried a
+ * validity bitmap (gaps / N / ?; needs AVX-512 VBMI on the host, else such chunks count as dirty), out[7] reserved */
+int pfa_ctx_ingest_stats(const pfa_ctx* ctx, int64_t out[8]);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t pfa_ctx_launch_count(const pfa_ctx* ctx);
 
@@ -77,6 +78,10 @@ int pfa_fasta_copy_row(const pfa_fasta* f, int64_t row, uint8_t* dst, int64_t ca
  * column chunks are uploaded as text and encoded by K1 instead), 0 when clean, < 0 on bad arguments / unsupported variant.
  * variant: 0 = best for this CPU, 1 = scalar, 2 = AVX2, 3 = AVX-512BW. */
 int pfa_host_pack2(const uint8_t* src, int64_t cols, uint8_t* dst, int variant);
+/* the packer with a validity bitmap (gaps, N and ? travel packed too): codes A0 C1 G2 T3 / '-'0 'N'1 '?'2 into
+ * codes[ceil(cols/4)], one validity bit per base into valid[ceil(cols/8)].  Returns bit 0 = the row holds '-', 'N' or '?',
+ * bit 1 = it holds any other byte (dirty); < 0 on bad arguments / unsupported variant (0 best, 1 scalar, 4 AVX-512 VBMI). */
+int pfa_host_pack3(const uint8_t* src, int64_t cols, uint8_t* codes, uint8_t* valid, int variant);
 /* a whole matrix text[row*ld + col] -> dst[row*ldp + col/4] with `threads` host threads (0 = all); returns the dirty rows */
 int64_t pfa_host_pack2_rows(const uint8_t* text, int64_t n, int64_t cols, int64_t ld, uint8_t* dst, int64_t ldp, int threads);
 
@@ -106,6 +111,9 @@ int64_t pfa_aln_packed_bytes(const pfa_aln* a);  /* bytes of the three planes */
 int pfa_aln_has_invalid(const pfa_aln* a);       /* any non-ACGT symbol in the shard */
 /* benchmarking: force the scans to read the validity plane even though the shard is pure ACGT (flag != 0) */
 int pfa_aln_force_validity(pfa_aln* a, int flag);
+/* measurement aid (bench.py): time `reps` passes of a kernel that only READS the first `planes` planes of this shard with the
+ * scans' streaming 128-bit loads: the read-only ceiling of this GPU for exactly these bytes */
+int pfa_aln_read_probe(pfa_aln* a, int planes, int reps, double* ms_per_pass);
 /* debugging / tests: copy plane p (0=b0,1=b1,2=v) to the host, nsites*Wq*16 bytes */
 int pfa_aln_copy_plane(pfa_aln* a, int plane, void* dst, size_t cap);
 

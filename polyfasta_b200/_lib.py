@@ -21,14 +21,14 @@ EXPORTS = [
     "pfa_fasta_row_len", "pfa_fasta_header", "pfa_fasta_copy_row",
     "pfa_aln_from_fasta", "pfa_aln_from_rows", "pfa_aln_from_device_rows", "pfa_aln_synthetic", "pfa_synth_text_device", "pfa_aln_force_validity", "pfa_aln_free",
     "pfa_aln_nseq", "pfa_aln_nsites", "pfa_aln_num_escapes", "pfa_aln_packed_bytes", "pfa_aln_has_invalid",
-    "pfa_aln_copy_plane", "pfa_aln_mask_words", "pfa_aln_set_pops", "pfa_aln_num_pops", "pfa_aln_pop_size",
+    "pfa_aln_copy_plane", "pfa_aln_read_probe", "pfa_aln_mask_words", "pfa_aln_set_pops", "pfa_aln_num_pops", "pfa_aln_pop_size",
     "pfa_site_len", "pfa_site_offset", "pfa_site_stats_device", "pfa_site_stats",
     "pfa_cds_stats_device", "pfa_cds_stats", "pfa_codon_pair_labels", "pfa_codon_set_labels", "pfa_codon_syn3",
     "pfa_codon_class", "pfa_pairwise_device", "pfa_pairwise", "pfa_finalize", "pfa_cds_ssites",
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
     "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
-    "pfa_host_pack2", "pfa_host_pack2_rows",
+    "pfa_host_pack2", "pfa_host_pack2_rows", "pfa_host_pack3",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
     "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce",
 ]
@@ -98,6 +98,7 @@ def lib():
         "pfa_aln_packed_bytes": (i64, [p]),
         "pfa_aln_has_invalid": (c.c_int, [p]),
         "pfa_aln_copy_plane": (c.c_int, [p, c.c_int, p, sz]),
+        "pfa_aln_read_probe": (c.c_int, [p, c.c_int, c.c_int, c.POINTER(c.c_double)]),
         "pfa_aln_mask_words": (i64, [p]),
         "pfa_aln_set_pops": (c.c_int, [p, p, c.c_int]),
         "pfa_aln_num_pops": (c.c_int, [p]),
@@ -133,6 +134,7 @@ def lib():
         "pfa_fasta_match_mask": (i64, [p, c.c_char_p, i64, p, i64]),
         "pfa_host_pack2": (c.c_int, [p, i64, p, c.c_int]),
         "pfa_host_pack2_rows": (i64, [p, i64, i64, i64, p, i64, c.c_int]),
+        "pfa_host_pack3": (c.c_int, [p, i64, p, p, c.c_int]),
         "pfa_xchg_create": (c.c_int, [p, i64, c.POINTER(p)]),
         "pfa_xchg_destroy": (c.c_int, [p]),
         "pfa_xchg_capacity": (i64, [p]),

@@ -53,10 +53,10 @@ class Context:
 
     def ingest_stats(self):
         """the last upload: dict(raw_chunks, packed_chunks, dirty_chunks, threads, h2d_text_bytes, h2d_packed_bytes)"""
-        out = (ctypes.c_int64 * 6)()
+        out = (ctypes.c_int64 * 8)()
         check(lib().pfa_ctx_ingest_stats(self.handle, out), self.handle)
         return {"raw_chunks": out[0], "packed_chunks": out[1], "dirty_chunks": out[2], "threads": out[3],
-                "h2d_text_bytes": out[4], "h2d_packed_bytes": out[5]}
+                "h2d_text_bytes": out[4], "h2d_packed_bytes": out[5], "packed_chunks_with_validity": out[6]}
 
     @property
     def launch_count(self):
@@ -301,6 +301,12 @@ class Alignment:
     @property
     def packed_bytes(self):
         return int(lib().pfa_aln_packed_bytes(self.handle))
+
+    def read_probe(self, planes=2, reps=5):
+        """ms per pass of a kernel that only reads the first `planes` planes (the read-only ceiling for these bytes)"""
+        ms = ctypes.c_double()
+        check(lib().pfa_aln_read_probe(self.handle, planes, reps, ctypes.byref(ms)), self.ctx.handle)
+        return ms.value
 
     def plane(self, which):
         """uint32 [nsites][4*Wq] copy of plane 0 (b0), 1 (b1) or 2 (v)"""

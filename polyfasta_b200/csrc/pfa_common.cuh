@@ -35,7 +35,7 @@ struct pfa_ctx {
     void* raw_pinned = nullptr;  // bounce buffers for text chunks of a pageable source
     size_t raw_pinned_bytes = 0;
     int host_threads = 0;  // host threads the ingest may use; 0 = PFA_HOST_THREADS or all hardware threads
-    int64_t ingest_stats[6] = {0, 0, 0, 0, 0, 0};  // last upload: chunks sent as text, chunks packed on the host, dirty chunks, threads, H2D bytes as text, H2D bytes packed
+    int64_t ingest_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // last upload: chunks sent as text, chunks packed on the host, dirty chunks, threads, H2D bytes as text, H2D bytes packed, packed chunks that carried a validity bitmap
 };
 
 struct pfa_aln {
@@ -111,7 +111,8 @@ int pfa_aln_default_pop(pfa_aln* a);
 // row_off (host sources only, optional): row r starts at text + row_off[r] instead of text + r * ld
 int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
                       int64_t col_end, pfa_aln** out, const int64_t* row_off = nullptr);
-int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, int64_t cols, int64_t site0, cudaStream_t st);
+int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, const uint8_t* d_valid, int64_t ldv, int direct,
+                            int64_t cols, int64_t site0, int* d_has_invalid, cudaStream_t st);
 
 // Device memory comes from the device's stream-ordered pool (release threshold = keep): allocating and freeing the planes
 // of one alignment after another (--dir mode, benchmark loops) reuses the same blocks without synchronising the device.

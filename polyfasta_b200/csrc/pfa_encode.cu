@@ -104,12 +104,15 @@ int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t col
     return PFA_OK;
 }
 
-// Same transposition for a chunk the HOST has packed (pfa_pack.cpp): 4 bases per byte, code t = A 0, C 1, T 2, G 3, all
-// rows clean.  One warp = 32 rows x 64 sites: lane j reads 16 bytes of row 32*w+j; b1 = t1, b0 = t0 ^ t1 turns the host
-// code into the planes' A 00, C 01, G 10, T 11; the validity word is the live-row mask.
-__global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* __restrict__ packed, int64_t ldp, int64_t n,
-                                                                int64_t cols, int64_t site0, uint32_t* __restrict__ b0,
-                                                                uint32_t* __restrict__ b1, uint32_t* __restrict__ v, int Wn) {
+// Same transposition for a chunk the HOST has packed (pfa_pack.cpp): 4 bases per byte, optionally one validity bit per base.
+// One warp = 32 rows x 64 sites: lane j reads 16 bytes of codes (and 8 bytes of validity) of row 32*w+j.
+//   direct = 0: codes t = A 0, C 1, T 2, G 3 of the ACGT-only packer (b1 = t1, b0 = t0 ^ t1), every base valid;
+//   direct = 1: codes already as the planes want them (A0 C1 G2 T3 / '-'0 'N'1 '?'2); valid == nullptr: every base valid.
+__global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* __restrict__ packed, int64_t ldp,
+                                                                const uint8_t* __restrict__ valid, int64_t ldv, int direct,
+                                                                int64_t n, int64_t cols, int64_t site0, uint32_t* __restrict__ b0,
+                                                                uint32_t* __restrict__ b1, uint32_t* __restrict__ v, int Wn,
+                                                                int* __restrict__ has_invalid) {
     const int lane = threadIdx.x & 31;
     const int64_t sg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // group of 64 sites
     const int64_t w = blockIdx.y;
@@ -118,36 +121,48 @@ __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* _
     const int64_t row = w * 32 + lane;
     const bool live = row < n;
     uint4 x = make_uint4(0, 0, 0, 0);
-    if (live) x = __ldg(reinterpret_cast<const uint4*>(packed + row * ldp + (c0 >> 2)));
-    const uint32_t wv = __ballot_sync(0xffffffffu, live);
+    uint2 vb = live ? make_uint2(0xffffffffu, 0xffffffffu) : make_uint2(0u, 0u);
+    if (live) {
+        x = __ldg(reinterpret_cast<const uint4*>(packed + row * ldp + (c0 >> 2)));
+        if (valid) vb = __ldg(reinterpret_cast<const uint2*>(valid + row * ldv + (c0 >> 3)));
+    }
+    const uint32_t wlive = __ballot_sync(0xffffffffu, live);
     const uint32_t words[4] = {x.x, x.y, x.z, x.w};
+    const uint32_t vwords[2] = {vb.x, vb.y};
+    bool any_invalid = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {  // sites c0 + 32h + s
-        uint32_t my0 = 0, my1 = 0;
+        uint32_t my0 = 0, my1 = 0, myv = 0;
 #pragma unroll
         for (int s = 0; s < 32; ++s) {
             const uint32_t t = (words[2 * h + (s >> 4)] >> (2 * (s & 15))) & 3u;
             const uint32_t w1 = __ballot_sync(0xffffffffu, t & 2u);
-            const uint32_t w0 = __ballot_sync(0xffffffffu, (t ^ (t >> 1)) & 1u);
-            if (lane == s) { my0 = w0; my1 = w1; }
+            const uint32_t w0 = __ballot_sync(0xffffffffu, (direct ? t : (t ^ (t >> 1))) & 1u);
+            uint32_t wv = wlive;
+            if (valid) wv = __ballot_sync(0xffffffffu, (vwords[h] >> s) & 1u);
+            if (lane == s) { my0 = w0; my1 = w1; myv = wv; }
         }
         const int64_t c = c0 + 32 * h + lane;
         if (c < cols) {
             const int64_t o = (site0 + c) * (int64_t)Wn + w;
-            b0[o] = my0; b1[o] = my1; v[o] = wv;
+            b0[o] = my0; b1[o] = my1; v[o] = myv;
+            if (myv != wlive) any_invalid = true;
         }
     }
+    if (valid && __any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(has_invalid, 1);
 }
 
-int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, int64_t cols, int64_t site0, cudaStream_t st) {
+int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, const uint8_t* d_valid, int64_t ldv, int direct,
+                            int64_t cols, int64_t site0, int* d_has_invalid, cudaStream_t st) {
     pfa_ctx* ctx = a->ctx;
     if (cols <= 0 || a->n <= 0) return PFA_OK;
-    if (ldp % 16 != 0 || reinterpret_cast<uintptr_t>(d_packed) % 16 != 0 || ldp * 4 < pfa_round_up(cols, 64))
+    if (ldp % 16 != 0 || reinterpret_cast<uintptr_t>(d_packed) % 16 != 0 || ldp * 4 < pfa_round_up(cols, 64) ||
+        (d_valid && (ldv % 8 != 0 || reinterpret_cast<uintptr_t>(d_valid) % 8 != 0 || ldv * 8 < pfa_round_up(cols, 64))))
         return pfa_fail(ctx, PFA_ERR_ARG, "packed chunk: rows must be 16-byte aligned and padded to 64 bases");
     const int64_t groups = (cols + 63) / 64;
     dim3 grid((unsigned)((groups + 7) / 8), (unsigned)((a->n + 31) / 32));
-    pfa_encode_packed_kernel<<<grid, 256, 0, st>>>(d_packed, ldp, a->n, cols, site0, (uint32_t*)a->b0, (uint32_t*)a->b1,
-                                                   (uint32_t*)a->v, a->Wq * 4);
+    pfa_encode_packed_kernel<<<grid, 256, 0, st>>>(d_packed, ldp, d_valid, ldv, direct, a->n, cols, site0, (uint32_t*)a->b0,
+                                                   (uint32_t*)a->b1, (uint32_t*)a->v, a->Wq * 4, d_has_invalid);
     PFA_LAUNCH_CHECK(ctx);
     return PFA_OK;
 }

@@ -44,3 +44,8 @@ int pfa_read_file(const char* path, std::vector<unsigned char>* buf, size_t* len
 // ---- host packer (pfa_pack.cpp): cols bases of one text row -> ceil(cols/4) bytes, 4 bases per byte, code (byte >> 1) & 3
 // (A 0, C 1, T 2, G 3, either case); returns 1 when the row holds any other byte (the chunk then travels as text)
 int pfa_pack2_row(const uint8_t* src, int64_t cols, uint8_t* dst);
+// the same with a validity bitmap (codes A0 C1 G2 T3 / '-'0 'N'1 '?'2, one validity bit per base): bit 0 of the result = the
+// row holds '-', 'N' or '?', bit 1 = it holds any other byte (dirty).  pfa_pack3_fast(): the CPU has AVX-512 VBMI (one
+// table-lookup instruction per 64 bases); without it the scalar version is slower than shipping the text.
+int pfa_pack3_row(const uint8_t* src, int64_t cols, uint8_t* codes, uint8_t* valid);
+bool pfa_pack3_fast();

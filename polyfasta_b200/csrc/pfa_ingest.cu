@@ -87,7 +87,7 @@ struct Hybrid {
     const uint8_t* text;  // first column of the shard
     const int64_t* row_off = nullptr;  // optional: row r starts at text + row_off[r] (rows of any stride)
     const uint8_t* row(int64_t r) const { return text + (row_off ? row_off[r] : r * ld); }
-    int64_t ld, n, ns, chunk, nchunks, ldt, ldp;
+    int64_t ld, n, ns, chunk, nchunks, ldt, ldp, ldv;
     unsigned long long* d_count;
     int64_t cap;
     int* d_inv;
@@ -98,7 +98,7 @@ struct Hybrid {
     std::atomic<bool> give_up{false};
     std::mutex m;
     std::vector<int64_t> dirty;
-    int64_t n_packed = 0, n_raw = 0, bytes_raw = 0, bytes_packed = 0;
+    int64_t n_packed = 0, n_gappy = 0, n_raw = 0, bytes_raw = 0, bytes_packed = 0;
     int rc_packed = PFA_OK;
     std::string err_packed;
     int threads = 1;
@@ -159,7 +159,8 @@ void packed_lane(Hybrid* hp) {
     if (e != cudaSuccess) return fail(e, "cudaSetDevice");
     PackPool& pool = *h.pool;
     h.lane_up = true;
-    const size_t slot_bytes = (size_t)(h.n * h.ldp);
+    const size_t code_bytes = (size_t)(h.n * h.ldp), slot_bytes = code_bytes + (size_t)(h.n * h.ldv);
+    const bool with_validity = pfa_pack3_fast();  // AVX-512 VBMI: gaps, N and ? are packed too (validity bitmap)
     bool used[kSlots] = {};
     int slot = 0;
     int64_t n_dirty = 0;
@@ -173,30 +174,38 @@ void packed_lane(Hybrid* hp) {
         h.t_wait_slot += tq - tw;
         uint8_t* dst = h.pinned + slot * slot_bytes;
         std::atomic<int64_t> row_next(0);
-        std::atomic<int> is_dirty(0);
+        std::atomic<int> flags(0);  // bit 0: the chunk holds '-', 'N' or '?'; bit 1: it holds any other symbol (dirty)
+        uint8_t* vdst = dst + code_bytes;
         pool.run([&] {
+            int mine = 0;
             for (;;) {
                 const int64_t r0 = row_next.fetch_add(16);
-                if (r0 >= h.n || is_dirty.load(std::memory_order_relaxed)) break;
+                if (r0 >= h.n || (flags.load(std::memory_order_relaxed) & 2)) break;
                 const int64_t r1 = std::min(h.n, r0 + 16);
                 for (int64_t r = r0; r < r1; ++r)
-                    if (pfa_pack2_row(h.row(r) + c0, cols, dst + r * h.ldp)) is_dirty.store(1, std::memory_order_relaxed);
+                    mine |= with_validity ? pfa_pack3_row(h.row(r) + c0, cols, dst + r * h.ldp, vdst + r * h.ldv)
+                                          : 2 * pfa_pack2_row(h.row(r) + c0, cols, dst + r * h.ldp);
+                if (mine) flags.fetch_or(mine, std::memory_order_relaxed);
             }
         });
         h.t_pack += now_ms() - tq;
-        if (is_dirty.load()) {
+        const int fl = flags.load();
+        if (fl & 2) {
             std::lock_guard<std::mutex> lk(h.m);
             h.dirty.push_back(c);
-            if (++n_dirty >= 2 && n_dirty > h.n_packed) h.give_up = true;  // gappy data: leave the rest to the raw lane
+            if (++n_dirty >= 2 && n_dirty > h.n_packed) h.give_up = true;  // symbols the packer does not know: leave the rest to the raw lane
             continue;
         }
         // the copy goes on the SAME stream as the raw lane's copies: on a stream of its own it is starved by the copy engine
         // until the raw lane has nothing left (measured); in one queue it waits for at most the two raw chunks in flight
-        if ((e = cudaMemcpyAsync(h.stage_packed[slot], dst, slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess)
+        const bool gappy = (fl & 1) != 0;
+        const size_t copy_bytes = gappy ? slot_bytes : code_bytes;
+        if ((e = cudaMemcpyAsync(h.stage_packed[slot], dst, copy_bytes, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess)
             return fail(e, "cudaMemcpyAsync");
         if ((e = cudaEventRecord(ctx->ev_slot_copied[slot], ctx->copy_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
         if ((e = cudaStreamWaitEvent(ctx->pack_stream, ctx->ev_slot_copied[slot], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
-        const int rc = pfa_encode_packed_chunk(h.a, h.stage_packed[slot], h.ldp, cols, c0, ctx->pack_stream);
+        const int rc = pfa_encode_packed_chunk(h.a, h.stage_packed[slot], h.ldp, gappy ? h.stage_packed[slot] + code_bytes : nullptr, h.ldv,
+                                               with_validity ? 1 : 0, cols, c0, h.d_inv, ctx->pack_stream);
         if (rc) {
             h.rc_packed = rc;
             h.err_packed = ctx->err;
@@ -206,7 +215,8 @@ void packed_lane(Hybrid* hp) {
         if ((e = cudaEventRecord(ctx->ev_slot[slot], ctx->pack_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
         used[slot] = true;
         ++h.n_packed;
-        h.bytes_packed += (int64_t)slot_bytes;
+        h.n_gappy += gappy ? 1 : 0;
+        h.bytes_packed += (int64_t)copy_bytes;
         slot = (slot + 1) % kSlots;
     }
     h.t_lane_end = now_ms();
@@ -238,13 +248,14 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
     h.nchunks = (h.ns + h.chunk - 1) / h.chunk;
     h.ldt = pfa_round_up(std::min(h.chunk, h.ns), 256);
     h.ldp = h.ldt / 4;
+    h.ldv = h.ldt / 8;
     h.d_count = d_count;
     h.cap = cap;
     h.d_inv = d_inv;
     h.threads = threads;
     h.raw_takes_chunks = raw_takes_chunks && !bounce;
     h.bounce = bounce;
-    const size_t slot_bytes = (size_t)(h.n * h.ldp);
+    const size_t slot_bytes = (size_t)(h.n * (h.ldp + h.ldv));
     if (ctx->pack_pinned_bytes < kSlots * slot_bytes) {
         if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
         ctx->pack_pinned = nullptr;
@@ -328,6 +339,7 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
     ctx->ingest_stats[3] = threads;
     ctx->ingest_stats[4] = h.bytes_raw;
     ctx->ingest_stats[5] = h.bytes_packed;
+    ctx->ingest_stats[6] = h.n_gappy;
     return rc;
 }
 
@@ -447,7 +459,7 @@ int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, in
                     }
                 }
                 ctx->ingest_stats[0] = ci;
-                ctx->ingest_stats[1] = ctx->ingest_stats[2] = ctx->ingest_stats[5] = 0;
+                ctx->ingest_stats[1] = ctx->ingest_stats[2] = ctx->ingest_stats[5] = ctx->ingest_stats[6] = 0;
                 ctx->ingest_stats[3] = 1;
                 ctx->ingest_stats[4] = dev ? 0 : n * ns;
             }
@@ -491,9 +503,9 @@ int pfa_ctx_set_host_threads(pfa_ctx* ctx, int threads) {
     return PFA_OK;
 }
 
-int pfa_ctx_ingest_stats(const pfa_ctx* ctx, int64_t out[6]) {
+int pfa_ctx_ingest_stats(const pfa_ctx* ctx, int64_t out[8]) {
     if (!ctx || !out) return PFA_ERR_ARG;
-    for (int i = 0; i < 6; ++i) out[i] = ctx->ingest_stats[i];
+    for (int i = 0; i < 8; ++i) out[i] = ctx->ingest_stats[i];
     return PFA_OK;
 }
 

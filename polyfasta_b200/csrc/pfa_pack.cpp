@@ -129,6 +129,73 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) int pack_avx512(const uint8
     return dirty;
 }
 
+// ---- packer with a validity bitmap: gaps, N and ? travel packed too -------------------------------------------------------
+// codes as the planes want them (A 0, C 1, G 2, T 3; '-' 0, 'N' 1, '?' 2 with validity 0), one validity BIT per base
+// (bit s%8 of byte s/8).  Return value: bit 0 = the row holds '-', 'N' or '?', bit 1 = it holds any other byte (the chunk
+// is dirty and travels as text: the exception list of K1 keeps the identity of such symbols).
+struct Lut7 {
+    alignas(64) uint8_t t[128];  // bits 0-1 code, bit 2 valid, bit 7 unknown symbol
+    Lut7() {
+        memset(t, 0x83, sizeof t);
+        const char* b = "ACGT";
+        for (int i = 0; i < 4; ++i) t[(uint8_t)b[i]] = t[(uint8_t)(b[i] | 0x20)] = (uint8_t)(4 | i);
+        t[(uint8_t)'-'] = 0;
+        t[(uint8_t)'N'] = t[(uint8_t)'n'] = 1;
+        t[(uint8_t)'?'] = 2;
+    }
+};
+const Lut7 g_lut7;
+
+int pack3_scalar(const uint8_t* src, int64_t cols, uint8_t* codes, uint8_t* valid) {
+    unsigned bad = 0, inval = 0;
+    for (int64_t i = 0; i < cols; i += 8) {
+        unsigned v = 0, c01 = 0, c23 = 0;
+        const int lim = (int)std::min<int64_t>(8, cols - i);
+        for (int j = 0; j < lim; ++j) {
+            const unsigned x = src[i + j];
+            const unsigned r = (x & 0x80) ? 0x83u : g_lut7.t[x];
+            bad |= r;
+            v |= ((r >> 2) & 1u) << j;
+            if (j < 4) c01 |= (r & 3u) << (2 * j);
+            else c23 |= (r & 3u) << (2 * (j - 4));
+        }
+        inval |= ~v & ((1u << lim) - 1u);
+        valid[i >> 3] = (uint8_t)v;
+        codes[i >> 2] = (uint8_t)c01;
+        if (lim > 4) codes[(i >> 2) + 1] = (uint8_t)c23;
+    }
+    return ((bad & 0x80) ? 2 : 0) | (inval ? 1 : 0);
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) int pack3_vbmi(const uint8_t* src, int64_t cols, uint8_t* codes,
+                                                                                uint8_t* valid) {
+    const __m512i lo = _mm512_load_si512(g_lut7.t), hi = _mm512_load_si512(g_lut7.t + 64);
+    const __m512i three = _mm512_set1_epi8(3), four = _mm512_set1_epi8(4);
+    const __m512i w14 = _mm512_set1_epi16(0x0401), w116 = _mm512_set1_epi32(0x00100001);
+    __mmask64 bad = 0, inval = 0;
+    int64_t i = 0;
+    for (; i + 64 <= cols; i += 64) {
+        const __m512i x = _mm512_loadu_si512(src + i);
+        const __m512i r = _mm512_permutex2var_epi8(lo, x, hi);  // 128-entry table: bits 0-6 of the byte select the entry
+        bad |= _mm512_movepi8_mask(r) | _mm512_movepi8_mask(x);  // unknown symbol, or a byte >= 0x80 (bit 7 is not looked up)
+        const __mmask64 v = _mm512_test_epi8_mask(r, four);
+        inval |= ~v;
+        memcpy(valid + (i >> 3), &v, 8);
+        const __m512i c = _mm512_and_si512(r, three);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(codes + (i >> 2)),
+                         _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(c, w14), w116)));
+    }
+    int flags = (bad ? 2 : 0) | (inval ? 1 : 0);
+    if (i < cols) flags |= pack3_scalar(src + i, cols - i, codes + (i >> 2), valid + (i >> 3));
+    return flags;
+}
+
+bool have_vbmi() {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+}
+const bool g_vbmi = have_vbmi();
+
 typedef int (*pack_fn)(const uint8_t*, int64_t, uint8_t*);
 
 pack_fn choose() {
@@ -142,6 +209,17 @@ const pack_fn g_pack = choose();
 }  // namespace
 
 int pfa_pack2_row(const uint8_t* src, int64_t cols, uint8_t* dst) { return g_pack(src, cols, dst); }
+bool pfa_pack3_fast() { return g_vbmi; }
+int pfa_pack3_row(const uint8_t* src, int64_t cols, uint8_t* codes, uint8_t* valid) {
+    return g_vbmi ? pack3_vbmi(src, cols, codes, valid) : pack3_scalar(src, cols, codes, valid);
+}
+
+extern "C" int pfa_host_pack3(const uint8_t* src, int64_t cols, uint8_t* codes, uint8_t* valid, int variant) {
+    if (!src || !codes || !valid || cols < 0) return -1;
+    if (variant == 1) return pack3_scalar(src, cols, codes, valid);
+    if (variant == 4) return g_vbmi ? pack3_vbmi(src, cols, codes, valid) : -2;
+    return pfa_pack3_row(src, cols, codes, valid);
+}
 
 extern "C" int pfa_host_pack2(const uint8_t* src, int64_t cols, uint8_t* dst, int variant) {
     if (!src || !dst || cols < 0) return -1;

@@ -327,6 +327,8 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         if (rc) return rc;
     }
     // lanes per site: the smallest power of two that leaves every lane at most 5 chunks
+    // (measured over n = 100 ... 10,000, scripts/probe_k2_shapes.py: fewer chunks per lane with more lanes per site, at
+    // higher occupancy, is never faster -- bytes in flight per lane win)
     int lps = 1;
     while (lps < 32 && (a->Wq + lps - 1) / lps > 5) lps *= 2;
     const int iter = (a->Wq + lps - 1) / lps;
@@ -365,5 +367,55 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
 #undef PFA_REG_CASE
     PFA_LAUNCH_CHECK(ctx);
     if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
+    return PFA_OK;
+}
+
+// ---- measurement aid: how fast can this GPU READ the planes at all? -------------------------------------------------------
+// The same streaming 128-bit loads as K2 over the same bytes, nothing else (XOR into a register, one store per thread that
+// never happens in practice).  bench.py reports K2 against this read-only ceiling next to the read+write copy peak.
+__global__ void __launch_bounds__(256) pfa_read_probe_kernel(const uint4* __restrict__ p, int64_t n16, unsigned int* __restrict__ sink) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (; i + 7 * stride < n16; i += 8 * stride) {
+        uint4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = pfa_ld_stream(p + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc.x ^= x[u].x; acc.y ^= x[u].y; acc.z ^= x[u].z; acc.w ^= x[u].w;
+        }
+    }
+    for (; i < n16; i += stride) {
+        const uint4 x = pfa_ld_stream(p + i);
+        acc.x ^= x.x; acc.y ^= x.y; acc.z ^= x.z; acc.w ^= x.w;
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u && acc.x == 0x7f4a7c15u) *sink = acc.x;
+}
+
+extern "C" int pfa_aln_read_probe(pfa_aln* a, int planes, int reps, double* ms_per_pass) {
+    if (!a || !ms_per_pass || planes < 1 || planes > 3 || reps < 1) return PFA_ERR_ARG;
+    pfa_ctx* ctx = a->ctx;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned int* sink = nullptr;
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &sink, sizeof(unsigned int)));
+    cudaEvent_t e0, e1;
+    PFA_CUDA(ctx, cudaEventCreate(&e0));
+    PFA_CUDA(ctx, cudaEventCreate(&e1));
+    const int64_t n16 = (int64_t)(a->plane_bytes / 16) * planes;  // b0 | b1 | v are one allocation
+    const unsigned grid = (unsigned)ctx->sm_count * 8;
+    pfa_read_probe_kernel<<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);  // warm-up
+    cudaEventRecord(e0, ctx->stream);
+    for (int r = 0; r < reps; ++r) pfa_read_probe_kernel<<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    pfa_dfree(ctx, sink);
+    ctx->launches += reps + 1;
+    if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "read probe: %s", cudaGetErrorString(e));
+    *ms_per_pass = ms / reps;
     return PFA_OK;
 }

@@ -31,3 +31,11 @@ for t in (16, 15, 12, 8):
 for mb in (16, 32, 128):
     run("hybrid 14 thr chunk %d MB" % mb, {"PFA_HOST_THREADS": "14", "PFA_INGEST_CHUNK_MB": str(mb)})
 run("plain again", {"PFA_INGEST_HYBRID": "0"})
+# the same alignment with 1 % gaps / N: packed with a validity bitmap on AVX-512 VBMI hosts, raw otherwise
+import numpy as np
+hv = h.numpy()
+rng = np.random.default_rng(0)
+idx_r = rng.integers(0, n, 6_000_000); idx_c = rng.integers(0, cols, 6_000_000)
+hv[idx_r, idx_c] = np.frombuffer(b"-N", dtype=np.uint8)[rng.integers(0, 2, 6_000_000)]
+run("gaps+N: plain", {"PFA_INGEST_HYBRID": "0"})
+run("gaps+N: hybrid", {})

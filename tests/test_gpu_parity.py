@@ -412,6 +412,7 @@ def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1, pinn
     some = clean.copy()
     some[rng.integers(0, n, 40), rng.integers(L // 2, L, 40)] = np.frombuffer(b"-NR?n", dtype=np.uint8)[rng.integers(0, 5, 40)]
     gappy = _random_text(rng, n, L, p_junk=0.05)
+    gaps_only = _random_text(rng, n, L, p_junk=0.03, junk=b"-Nn?")   # no escape symbols: packed with a validity bitmap (VBMI hosts)
     monkeypatch.setenv("PFA_INGEST_CHUNK_MB", "1")
     pops = [list(range(n)), list(range(0, n, 2))]
     import torch
@@ -426,7 +427,7 @@ def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1, pinn
         ctx.sync()
         return a
 
-    for name, text in (("clean", clean), ("some", some), ("gappy", gappy)):
+    for name, text in (("clean", clean), ("some", some), ("gappy", gappy), ("gaps_only", gaps_only)):
         monkeypatch.setenv("PFA_INGEST_HYBRID", "0")
         plain = pf.Alignment.from_rows(ctx, text, c0, c1)
         # mode 2: every chunk is offered to the packer first (deterministic); mode 1: the lanes race for the chunks
@@ -440,6 +441,8 @@ def test_hybrid_ingest_matches_plain_upload(ctx, monkeypatch, n, L, c0, c1, pinn
             assert st["packed_chunks"] > 0 and 0 < st["dirty_chunks"] <= st["raw_chunks"], st
         if name == "gappy":
             assert st["packed_chunks"] == 0 and st["dirty_chunks"] >= 1, st
+        if name == "gaps_only":   # hosts without AVX-512 VBMI treat these chunks as dirty
+            assert st["packed_chunks_with_validity"] == st["packed_chunks"] > 0 or st["packed_chunks"] == 0, st
         monkeypatch.setenv("PFA_INGEST_HYBRID", "1")
         race = upload(text)
         for x, y, z in zip(_planes(plain), _planes(hyb), _planes(race)):

@@ -226,3 +226,42 @@ def test_segmented_parse_equals_sequential(tmp_path, monkeypatch, segments):
         except pf.NotFasta:
             got = "not fasta"
         assert got == want, name
+
+
+def test_host_packer_with_validity_bitmap():
+    """gaps, N and ? are packed too (codes A0 C1 G2 T3 / '-'0 'N'1 '?'2 + one validity bit per base); any other byte marks
+    the row dirty.  Scalar and AVX-512 VBMI variants against a numpy restatement."""
+    L = _lib.lib()
+    rng = np.random.default_rng(12)
+    code = {65: 0, 67: 1, 71: 2, 84: 3, 97: 0, 99: 1, 103: 2, 116: 3, 45: 0, 78: 1, 110: 1, 63: 2}
+    ok = {65, 67, 71, 84, 97, 99, 103, 116}
+    alpha = np.frombuffer(b"ACGTacgtNn-?", dtype=np.uint8)
+    ran = 0
+    for variant in (0, 1, 4):
+        for cols in list(range(0, 150)) + [511, 512, 1000]:
+            for kind in range(3):
+                row = alpha[rng.integers(0, 8 if kind == 0 else 12, cols)].copy()
+                if kind == 2 and cols:
+                    row[rng.integers(0, cols)] = rng.choice([82, 0x80, 0xC1, 32, 42, 0])
+                c = np.array([code.get(int(x), 3) for x in row], np.uint8)
+                v = np.array([int(x) in ok for x in row], np.uint8)
+                flags = (0 if v.all() else 1) | (0 if all(int(x) in code for x in row) else 2)
+                cp = np.concatenate([c, np.zeros((-cols) % 4, np.uint8)]).reshape(-1, 4)
+                vp = np.concatenate([v, np.zeros((-cols) % 8, np.uint8)]).reshape(-1, 8)
+                wc = (cp[:, 0] | (cp[:, 1] << 2) | (cp[:, 2] << 4) | (cp[:, 3] << 6)).astype(np.uint8)
+                wv = np.packbits(vp, axis=1, bitorder="little").reshape(-1)
+                codes = np.full(cols // 4 + 2, 0xEE, np.uint8)
+                valid = np.full(cols // 8 + 2, 0xEE, np.uint8)
+                r = L.pfa_host_pack3(row.ctypes.data, cols, codes.ctypes.data, valid.ctypes.data, variant)
+                if r == -2:
+                    break
+                assert r == flags, (variant, cols, kind)
+                if not flags & 2:
+                    assert np.array_equal(codes[: (cols + 3) // 4], wc) and np.array_equal(valid[: (cols + 7) // 8], wv), (variant, cols)
+                assert codes[(cols + 3) // 4] == 0xEE and valid[(cols + 7) // 8] == 0xEE
+            else:
+                continue
+            break
+        else:
+            ran += 1
+    assert ran >= 2
