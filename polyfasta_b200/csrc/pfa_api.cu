@@ -103,7 +103,7 @@ int pfa_ctx_create(int device, pfa_ctx** out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_encoded[i], cudaEventDisableTiming | cudaEventBlockingSync);  // the ingest lanes sleep on these
     }
@@ -133,7 +133,7 @@ int pfa_ctx_destroy(pfa_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_encoded[i]) cudaEventDestroy(ctx->ev_encoded[i]);
     }

@@ -25,11 +25,11 @@ struct pfa_ctx {
     size_t scratch_bytes = 0;
     // upload pipeline: copy stream + events, created once per context
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_encoded[2] = {nullptr, nullptr}, ev_ready = nullptr;
+    cudaEvent_t ev_copied[3] = {}, ev_encoded[3] = {}, ev_ready = nullptr;
     // hybrid ingest (pfa_ingest.cu): encode stream of the raw lane, copy + encode stream of the packed lane, one event per
     // packed staging slot, pinned staging for the host-packed chunks (kept between uploads)
     cudaStream_t enc_stream = nullptr, pack_stream = nullptr;
-    cudaEvent_t ev_slot[3] = {nullptr, nullptr, nullptr}, ev_slot_copied[3] = {nullptr, nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_slot[6] = {}, ev_slot_copied[6] = {}, ev_join[2] = {nullptr, nullptr};
     void* pack_pinned = nullptr;
     size_t pack_pinned_bytes = 0;
     void* raw_pinned = nullptr;  // bounce buffers for text chunks of a pageable source

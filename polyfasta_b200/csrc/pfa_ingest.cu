@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -80,7 +81,9 @@ inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-constexpr int kSlots = 3;  // packed chunks in flight (pinned + device staging each)
+constexpr int kSlots = 3;     // packed chunks in flight per packed lane (pinned + device staging each)
+constexpr int kRawBufs = 2;   // text chunks in flight on the raw lane (device staging each); a third one only shifts chunks away from the packer (measured)
+constexpr int kMaxLanes = 2;  // packed lanes: while one waits at its end-of-chunk barrier the other keeps the cores busy
 
 struct Hybrid {
     pfa_aln* a;
@@ -91,8 +94,10 @@ struct Hybrid {
     unsigned long long* d_count;
     int64_t cap;
     int* d_inv;
-    uint8_t* stage_raw[2] = {nullptr, nullptr};
-    uint8_t* stage_packed[kSlots] = {};
+    uint8_t* stage_raw[kRawBufs] = {};
+    uint8_t* stage_packed[kSlots * kMaxLanes] = {};
+    int lanes = 1;
+    PackPool* pools[kMaxLanes] = {};
     uint8_t* pinned = nullptr;
     std::atomic<int64_t> next{0};
     std::atomic<bool> give_up{false};
@@ -104,17 +109,17 @@ struct Hybrid {
     int threads = 1;
     bool raw_takes_chunks = true;     // false: the raw lane only gets the dirty chunks (pageable source, or PFA_INGEST_HYBRID=2)
     bool bounce = false;              // the source is pageable: text chunks reach the copy engine through pinned bounce buffers
-    uint8_t* bounce_buf[2] = {nullptr, nullptr};
+    uint8_t* bounce_buf[kRawBufs] = {};
     PackPool* pool = nullptr;
-    std::atomic<bool> lane_up{false};  // the packed lane's pool is running
+    std::atomic<int> lanes_up{0};  // packed lanes that are running
     double t_pack = 0, t_wait_slot = 0, t_wait_raw = 0, t_pool_start = 0, t0 = 0, t_lane_end = 0;  // PFA_INGEST_TRACE
 };
 
 int raw_chunk(Hybrid& h, int64_t c, int& issued) {
     pfa_ctx* ctx = h.a->ctx;
-    const int b = issued & 1;
+    const int b = issued % kRawBufs;
     const double tw = now_ms();
-    if (issued >= 2) PFA_CUDA(ctx, cudaEventSynchronize(ctx->ev_encoded[b]));  // throttle: the buffer is free again
+    if (issued >= kRawBufs) PFA_CUDA(ctx, cudaEventSynchronize(ctx->ev_encoded[b]));  // throttle: the buffer is free again
     h.t_wait_raw += now_ms() - tw;
     const int64_t c0 = c * h.chunk, cols = std::min(h.chunk, h.ns - c0);
     if (h.bounce) {
@@ -146,19 +151,26 @@ int raw_chunk(Hybrid& h, int64_t c, int& issued) {
     return PFA_OK;
 }
 
-void packed_lane(Hybrid* hp) {
+void packed_lane(Hybrid* hp, int lane_id) {
     Hybrid& h = *hp;
     pfa_ctx* ctx = h.a->ctx;
+    bool counted_up = false;
     auto fail = [&](cudaError_t e, const char* what) {
-        h.lane_up = true;
+        if (!counted_up) ++h.lanes_up;
+        counted_up = true;
+        std::lock_guard<std::mutex> lk(h.m);
         h.rc_packed = PFA_ERR_CUDA;
         h.err_packed = std::string(what) + " failed: " + cudaGetErrorString(e);
         h.give_up = true;
     };
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail(e, "cudaSetDevice");
-    PackPool& pool = *h.pool;
-    h.lane_up = true;
+    PackPool& pool = *h.pools[lane_id];
+    ++h.lanes_up;
+    counted_up = true;
+    const int slot0 = lane_id * kSlots;
+    int64_t my_packed = 0, my_gappy = 0, my_bytes = 0;
+    double my_pack = 0, my_wait = 0;
     const size_t code_bytes = (size_t)(h.n * h.ldp), slot_bytes = code_bytes + (size_t)(h.n * h.ldv);
     const bool with_validity = pfa_pack3_fast();  // AVX-512 VBMI: gaps, N and ? are packed too (validity bitmap)
     bool used[kSlots] = {};
@@ -169,10 +181,10 @@ void packed_lane(Hybrid* hp) {
         if (c >= h.nchunks) break;
         const int64_t c0 = c * h.chunk, cols = std::min(h.chunk, h.ns - c0);
         const double tw = now_ms();
-        if (used[slot] && (e = cudaEventSynchronize(ctx->ev_slot[slot])) != cudaSuccess) return fail(e, "cudaEventSynchronize");
+        if (used[slot] && (e = cudaEventSynchronize(ctx->ev_slot[slot0 + slot])) != cudaSuccess) return fail(e, "cudaEventSynchronize");
         const double tq = now_ms();
-        h.t_wait_slot += tq - tw;
-        uint8_t* dst = h.pinned + slot * slot_bytes;
+        my_wait += tq - tw;
+        uint8_t* dst = h.pinned + (slot0 + slot) * slot_bytes;
         std::atomic<int64_t> row_next(0);
         std::atomic<int> flags(0);  // bit 0: the chunk holds '-', 'N' or '?'; bit 1: it holds any other symbol (dirty)
         uint8_t* vdst = dst + code_bytes;
@@ -188,38 +200,45 @@ void packed_lane(Hybrid* hp) {
                 if (mine) flags.fetch_or(mine, std::memory_order_relaxed);
             }
         });
-        h.t_pack += now_ms() - tq;
+        my_pack += now_ms() - tq;
         const int fl = flags.load();
         if (fl & 2) {
             std::lock_guard<std::mutex> lk(h.m);
             h.dirty.push_back(c);
-            if (++n_dirty >= 2 && n_dirty > h.n_packed) h.give_up = true;  // symbols the packer does not know: leave the rest to the raw lane
+            if (++n_dirty >= 2 && n_dirty > my_packed) h.give_up = true;  // symbols the packer does not know: leave the rest to the raw lane
             continue;
         }
         // the copy goes on the SAME stream as the raw lane's copies: on a stream of its own it is starved by the copy engine
         // until the raw lane has nothing left (measured); in one queue it waits for at most the two raw chunks in flight
         const bool gappy = (fl & 1) != 0;
         const size_t copy_bytes = gappy ? slot_bytes : code_bytes;
-        if ((e = cudaMemcpyAsync(h.stage_packed[slot], dst, copy_bytes, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess)
+        if ((e = cudaMemcpyAsync(h.stage_packed[slot0 + slot], dst, copy_bytes, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess)
             return fail(e, "cudaMemcpyAsync");
-        if ((e = cudaEventRecord(ctx->ev_slot_copied[slot], ctx->copy_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
-        if ((e = cudaStreamWaitEvent(ctx->pack_stream, ctx->ev_slot_copied[slot], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
-        const int rc = pfa_encode_packed_chunk(h.a, h.stage_packed[slot], h.ldp, gappy ? h.stage_packed[slot] + code_bytes : nullptr, h.ldv,
+        if ((e = cudaEventRecord(ctx->ev_slot_copied[slot0 + slot], ctx->copy_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
+        if ((e = cudaStreamWaitEvent(ctx->pack_stream, ctx->ev_slot_copied[slot0 + slot], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+        const int rc = pfa_encode_packed_chunk(h.a, h.stage_packed[slot0 + slot], h.ldp, gappy ? h.stage_packed[slot0 + slot] + code_bytes : nullptr, h.ldv,
                                                with_validity ? 1 : 0, cols, c0, h.d_inv, ctx->pack_stream);
         if (rc) {
+            std::lock_guard<std::mutex> lk(h.m);
             h.rc_packed = rc;
             h.err_packed = ctx->err;
             h.give_up = true;
             return;
         }
-        if ((e = cudaEventRecord(ctx->ev_slot[slot], ctx->pack_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
+        if ((e = cudaEventRecord(ctx->ev_slot[slot0 + slot], ctx->pack_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
         used[slot] = true;
-        ++h.n_packed;
-        h.n_gappy += gappy ? 1 : 0;
-        h.bytes_packed += (int64_t)copy_bytes;
+        ++my_packed;
+        my_gappy += gappy ? 1 : 0;
+        my_bytes += (int64_t)copy_bytes;
         slot = (slot + 1) % kSlots;
     }
-    h.t_lane_end = now_ms();
+    std::lock_guard<std::mutex> lk(h.m);
+    h.n_packed += my_packed;
+    h.n_gappy += my_gappy;
+    h.bytes_packed += my_bytes;
+    h.t_pack += my_pack;
+    h.t_wait_slot += my_wait;
+    h.t_lane_end = std::max(h.t_lane_end, now_ms());
 }
 
 int host_threads(const pfa_ctx* ctx) {
@@ -256,12 +275,15 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
     h.raw_takes_chunks = raw_takes_chunks && !bounce;
     h.bounce = bounce;
     const size_t slot_bytes = (size_t)(h.n * (h.ldp + h.ldv));
-    if (ctx->pack_pinned_bytes < kSlots * slot_bytes) {
+    h.lanes = threads >= 8 ? kMaxLanes : 1;
+    if (const char* s = getenv("PFA_PACK_LANES")) h.lanes = std::max(1, std::min(kMaxLanes, atoi(s)));
+    const size_t nslots = (size_t)kSlots * h.lanes;
+    if (ctx->pack_pinned_bytes < nslots * slot_bytes) {
         if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
         ctx->pack_pinned = nullptr;
         ctx->pack_pinned_bytes = 0;
-        PFA_CUDA(ctx, cudaHostAlloc(&ctx->pack_pinned, kSlots * slot_bytes, cudaHostAllocDefault));
-        ctx->pack_pinned_bytes = kSlots * slot_bytes;
+        PFA_CUDA(ctx, cudaHostAlloc(&ctx->pack_pinned, nslots * slot_bytes, cudaHostAllocDefault));
+        ctx->pack_pinned_bytes = nslots * slot_bytes;
     }
     h.pinned = static_cast<uint8_t*>(ctx->pack_pinned);
     auto release = [&]() {
@@ -269,8 +291,8 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
         for (auto& p : h.stage_packed) pfa_dfree(ctx, p);
     };
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = pfa_dmalloc(ctx, &h.stage_raw[i], (size_t)(h.n * h.ldt));
-    for (int i = 0; i < kSlots && e == cudaSuccess; ++i) e = pfa_dmalloc(ctx, &h.stage_packed[i], slot_bytes);
+    for (int i = 0; i < kRawBufs && e == cudaSuccess; ++i) e = pfa_dmalloc(ctx, &h.stage_raw[i], (size_t)(h.n * h.ldt));
+    for (size_t i = 0; i < nslots && e == cudaSuccess; ++i) e = pfa_dmalloc(ctx, &h.stage_packed[i], slot_bytes);
     // the lanes' streams may touch the planes / staging buffers only after ctx->stream has allocated and cleared them
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_ready, ctx->stream);
     for (cudaStream_t st : {ctx->copy_stream, ctx->enc_stream, ctx->pack_stream})
@@ -280,22 +302,27 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
         return pfa_fail(ctx, PFA_ERR_CUDA, "hybrid ingest setup failed: %s", cudaGetErrorString(e));
     }
     h.t0 = now_ms();
-    PackPool pool(threads);
-    h.pool = &pool;
+    std::vector<std::unique_ptr<PackPool>> pools;
+    for (int l = 0; l < h.lanes; ++l) {
+        pools.emplace_back(new PackPool(std::max(1, (threads + (h.lanes - 1 - l)) / h.lanes)));
+        h.pools[l] = pools.back().get();
+    }
+    h.pool = h.pools[0];  // after the lanes have finished: bounce copies of the raw lane
     h.t_pool_start = now_ms() - h.t0;
-    std::thread lane(packed_lane, &h);
+    std::vector<std::thread> lane;
+    for (int l = 0; l < h.lanes; ++l) lane.emplace_back(packed_lane, &h, l);
     int rc = PFA_OK, issued = 0;
-    while (!h.lane_up.load()) std::this_thread::yield();  // ~0.2 ms: both lanes start taking chunks together
+    while (h.lanes_up.load() < h.lanes) std::this_thread::yield();  // ~0.2 ms: all lanes start taking chunks together
     while (h.raw_takes_chunks) {
         const int64_t c = h.next.fetch_add(1);
         if (c >= h.nchunks) break;
         if ((rc = raw_chunk(h, c, issued)) != PFA_OK) break;
     }
     if (rc) h.give_up = true;
-    lane.join();
+    for (auto& t : lane) t.join();
     if (!rc && h.rc_packed) rc = pfa_fail(ctx, h.rc_packed, "packed lane: %s", h.err_packed.c_str());
     if (!rc && h.bounce && (h.give_up.load() || !h.dirty.empty())) {
-        const size_t need = 2 * (size_t)(h.n * h.ldt);
+        const size_t need = kRawBufs * (size_t)(h.n * h.ldt);
         if (ctx->raw_pinned_bytes < need) {
             if (ctx->raw_pinned) cudaFreeHost(ctx->raw_pinned);
             ctx->raw_pinned = nullptr;
@@ -305,8 +332,7 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
             else
                 ctx->raw_pinned_bytes = need;
         }
-        h.bounce_buf[0] = static_cast<uint8_t*>(ctx->raw_pinned);
-        h.bounce_buf[1] = h.bounce_buf[0] + (size_t)(h.n * h.ldt);
+        for (int i = 0; i < kRawBufs; ++i) h.bounce_buf[i] = static_cast<uint8_t*>(ctx->raw_pinned) + (size_t)i * (size_t)(h.n * h.ldt);
     }
     if (!rc && h.give_up.load())  // the packed lane stopped early: chunks it never took are still on the counter
         for (;;) {
