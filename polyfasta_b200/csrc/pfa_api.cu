@@ -1,6 +1,8 @@
 // C ABI of the library: contexts, alignment upload, populations, result wrappers.  See include/polyfasta_b200.h.
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -91,12 +93,16 @@ int pfa_ctx_create(int device, pfa_ctx** out) {
     pfa_ctx* ctx = new (std::nothrow) pfa_ctx();
     if (!ctx) return PFA_ERR_NOMEM;
     ctx->device = device;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_dev = 0, t_streams = 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         pfa_set_global_error("cannot initialise device %d: %s", device, cudaGetErrorString(e));
         delete ctx;
         return PFA_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    t_dev = since();
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long keep = ~0ull;
@@ -114,15 +120,13 @@ int pfa_ctx_create(int device, pfa_ctx** out) {
     for (auto& ev : ctx->ev_slot_copied) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : ctx->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaGetLastError();
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    int rc = pfa_upload_codon_tables(ctx);
-    if (rc) {
-        pfa_set_global_error("%s", ctx->err.c_str());
-        cudaStreamDestroy(ctx->own_stream);
-        delete ctx;
-        return rc;
-    }
+    t_streams = since();
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
+    if (getenv("PFA_TRACE_INIT"))
+        fprintf(stderr, "[pfa ctx] set device + first stream %.1f ms, pool / streams / events %.1f ms, attributes %.1f ms\n", t_dev,
+                t_streams - t_dev, since() - t_streams);
+    // the codon tables go to constant memory on the first codon scan (loading that module costs a cold start ~0.1 s)
     *out = ctx;
     return PFA_OK;
 }

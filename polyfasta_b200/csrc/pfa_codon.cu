@@ -620,6 +620,11 @@ static int launch_cds_escape(pfa_aln* a, const PfaCdsArgs& args) {
 
 int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg* x) {
     pfa_ctx* ctx = a->ctx;
+    if (!ctx->codon_tables_ready) {
+        int rc = pfa_upload_codon_tables(ctx);
+        if (rc) return rc;
+        ctx->codon_tables_ready = true;
+    }
     if (a->col_begin % 3 != 0) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: the shard must start on a codon boundary");
     const bool last = a->col_begin + a->ns == a->L_total;
     if (a->ns % 3 != 0 && !last) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: only the last shard may end inside a codon");

@@ -34,6 +34,7 @@ struct pfa_ctx {
     size_t pack_pinned_bytes = 0;
     void* raw_pinned = nullptr;  // bounce buffers for text chunks of a pageable source
     size_t raw_pinned_bytes = 0;
+    bool codon_tables_ready = false;  // constant-memory tables of K4 uploaded (first codon scan)
     int host_threads = 0;  // host threads the ingest may use; 0 = PFA_HOST_THREADS or all hardware threads
     int64_t ingest_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // last upload: chunks sent as text, chunks packed on the host, dirty chunks, threads, H2D bytes as text, H2D bytes packed, packed chunks that carried a validity bitmap
 };
