@@ -4,7 +4,10 @@
 // identity sum_{i<j} d_ij = H/2 ties it to the site scan.  Integer work on the INT pipe -- XOR / OR / POPC over
 // packed words -- not tensor cores.
 //
-//  1. pfa_rowmajor_kernel transposes the site-major planes into row-major bit-planes over SITES
+//  0. pfa_var_flags_kernel marks the sites at which at least two rows differ (one memory-bound pass over the planes); only
+//     those can contribute to any d_ij -- the reference, too, runs over the variable columns only (:469) -- and they are
+//     a few per cent of a real alignment, so the K dimension of step 2 shrinks by that factor.
+//  1. pfa_rowmajor_kernel transposes the marked sites of the site-major planes into row-major bit-planes over SITES
 //     ([plane][row][word], 32 sites per word) with warp ballots.
 //  2. pfa_pairwise_kernel: one 64x64 tile of row pairs per CTA, 4x4 pairs per thread; the K dimension (site words)
 //     is staged through shared memory in [plane][word][row] order so that a thread fetches its four rows with one
@@ -12,23 +15,62 @@
 //  3. rows that both show the escape class compare equal in the planes; pfa_pairwise_escape_kernel adds the pairs
 //     whose escape BYTES differ from the sorted exception list.
 //  4. pfa_pairwise_popsum_kernel reduces the upper triangle per population.
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
 #include "pfa_common.cuh"
 
 #define PW_TILE 64
 #define PW_KC 16
+#define PW_LD (PW_TILE + 4)  // row pitch of the staged tiles: the transposing stores hit 2 banks twice instead of 1 bank 16 times
 
-__global__ void __launch_bounds__(256) pfa_rowmajor_kernel(const uint32_t* __restrict__ b0, const uint32_t* __restrict__ b1,
-                                                           const uint32_t* __restrict__ v, int64_t ns, int Wn, int64_t npad,
-                                                           int64_t Wl, uint32_t* __restrict__ out) {
+// one warp per site: does any plane show both a 0 and a 1 among the n rows?  (rows beyond n are padding)
+__global__ void __launch_bounds__(256) pfa_var_flags_kernel(const uint4* __restrict__ b0, const uint4* __restrict__ b1,
+                                                            const uint4* __restrict__ v, int64_t ns, int Wq, int64_t n,
+                                                            uint8_t* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
-    const int64_t sw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // word over sites
+    const int64_t site = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (site >= ns) return;
+    uint32_t o[3] = {0, 0, 0}, z[3] = {0, 0, 0};
+    const uint4* planes[3] = {b0, b1, v};
+    for (int j = lane; j < Wq; j += 32) {
+        uint32_t m[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int64_t lo = ((int64_t)j * 4 + w) * 32;
+            m[w] = lo + 32 <= n ? 0xffffffffu : (lo >= n ? 0u : ((1u << (n - lo)) - 1u));
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint4 x = __ldg(planes[p] + site * Wq + j);
+            o[p] |= (x.x & m[0]) | (x.y & m[1]) | (x.z & m[2]) | (x.w & m[3]);
+            z[p] |= (~x.x & m[0]) | (~x.y & m[1]) | (~x.z & m[2]) | (~x.w & m[3]);
+        }
+    }
+    unsigned both = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const unsigned any_o = __any_sync(0xffffffffu, o[p] != 0), any_z = __any_sync(0xffffffffu, z[p] != 0);
+        both |= (any_o && any_z) ? 1u : 0u;
+    }
+    if (lane == 0) flags[site] = (uint8_t)both;
+}
+
+// sites[i]: the i-th marked site; word sw of the row-major planes holds marked sites 32*sw .. 32*sw+31
+__global__ void __launch_bounds__(256) pfa_rowmajor_kernel(const uint32_t* __restrict__ b0, const uint32_t* __restrict__ b1,
+                                                           const uint32_t* __restrict__ v, const int64_t* __restrict__ sites,
+                                                           int64_t nsel, int Wn, int64_t npad, int64_t Wl,
+                                                           uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t sw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // word over marked sites
     const int64_t w = blockIdx.y;                                                      // word over rows
-    if (sw * 32 >= ns) return;
-    const int64_t site = sw * 32 + lane;
+    if (sw * 32 >= nsel) return;
+    const int64_t idx = sw * 32 + lane;
+    const int64_t site = idx < nsel ? sites[idx] : -1;
     const uint32_t* planes[3] = {b0, b1, v};
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-        const uint32_t x = site < ns ? __ldg(planes[p] + site * Wn + w) : 0u;
+        const uint32_t x = site >= 0 ? __ldg(planes[p] + site * Wn + w) : 0u;
         uint32_t mine = 0;
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
@@ -47,8 +89,8 @@ __global__ void __launch_bounds__(256) pfa_pairwise_kernel(const uint32_t* __res
     int bi = 0, rem = blockIdx.x;
     while (rem >= nt - bi) { rem -= nt - bi; ++bi; }
     const int bj = bi + rem;
-    __shared__ __align__(16) uint32_t As[3][PW_KC][PW_TILE];
-    __shared__ __align__(16) uint32_t Bs[3][PW_KC][PW_TILE];
+    __shared__ __align__(16) uint32_t As[3][PW_KC][PW_LD];
+    __shared__ __align__(16) uint32_t Bs[3][PW_KC][PW_LD];
     const int tj = threadIdx.x & 15, ti = threadIdx.x >> 4;
     int acc[4][4];
 #pragma unroll
@@ -148,6 +190,7 @@ int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)a->k, ctx->stream));
     const int64_t n = a->n;
     if (n == 0) return PFA_OK;
+    if (a->ns > 0x7fffffffll) return pfa_fail(ctx, PFA_ERR_ARG, "pairwise: a shard of more than 2^31-1 sites is not supported");
     int32_t* D = d_matrix;
     bool own = false;
     if (!D) {
@@ -160,17 +203,44 @@ int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     cudaError_t e = cudaMemsetAsync(D, 0, sizeof(int32_t) * (size_t)(n * n), ctx->stream);
     if (e == cudaSuccess && a->ns > 0) {
         if (!a->rowmajor) {
-            a->Wl = pfa_round_up((a->ns + 31) / 32, 4);
-            e = pfa_dmalloc(ctx, &a->rowmajor, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl));
-            if (e == cudaSuccess) e = cudaMemsetAsync(a->rowmajor, 0, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl), ctx->stream);
+            // mark the sites at which two rows differ, list them, transpose only those
+            uint8_t* flags = nullptr;
+            int64_t *sites = nullptr, *d_num = nullptr;
+            void* tmp = nullptr;
+            size_t tmp_bytes = 0;
+            int64_t nsel = 0;
+            e = pfa_dmalloc(ctx, &flags, (size_t)a->ns);
+            if (e == cudaSuccess) e = pfa_dmalloc(ctx, &sites, sizeof(int64_t) * (size_t)a->ns);
+            if (e == cudaSuccess) e = pfa_dmalloc(ctx, &d_num, sizeof(int64_t));
             if (e == cudaSuccess) {
-                const int64_t sw = (a->ns + 31) / 32;
-                dim3 grid((unsigned)((sw + 7) / 8), (unsigned)Wn);
-                pfa_rowmajor_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t*)a->b0, (const uint32_t*)a->b1, (const uint32_t*)a->v,
-                                                                   a->ns, Wn, npad, a->Wl, a->rowmajor);
+                pfa_var_flags_kernel<<<(unsigned)((a->ns + 7) / 8), 256, 0, ctx->stream>>>(a->b0, a->b1, a->v, a->ns, a->Wq, n, flags);
                 ctx->launches++;
                 e = cudaGetLastError();
             }
+            cub::CountingInputIterator<int64_t> idx(0);
+            if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, flags, sites, d_num, (int)a->ns, ctx->stream);
+            if (e == cudaSuccess) e = pfa_dmalloc(ctx, &tmp, tmp_bytes);
+            if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, flags, sites, d_num, (int)a->ns, ctx->stream);
+            ctx->launches += 2;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&nsel, d_num, sizeof nsel, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess) {
+                a->Wl = pfa_round_up(std::max<int64_t>((nsel + 31) / 32, 1), 4);
+                e = pfa_dmalloc(ctx, &a->rowmajor, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl));
+            }
+            if (e == cudaSuccess) e = cudaMemsetAsync(a->rowmajor, 0, sizeof(uint32_t) * (size_t)(3 * npad * a->Wl), ctx->stream);
+            if (e == cudaSuccess && nsel > 0) {
+                const int64_t sw = (nsel + 31) / 32;
+                dim3 grid((unsigned)((sw + 7) / 8), (unsigned)Wn);
+                pfa_rowmajor_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t*)a->b0, (const uint32_t*)a->b1, (const uint32_t*)a->v,
+                                                                   sites, nsel, Wn, npad, a->Wl, a->rowmajor);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+            pfa_dfree(ctx, tmp);
+            pfa_dfree(ctx, flags);
+            pfa_dfree(ctx, sites);
+            pfa_dfree(ctx, d_num);
         }
         if (e == cudaSuccess) {
             const int64_t nt = npad / PW_TILE;
