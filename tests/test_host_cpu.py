@@ -265,3 +265,19 @@ def test_host_packer_with_validity_bitmap():
         else:
             ran += 1
     assert ran >= 2
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys;
+    tiny sizes here so that it runs in seconds"""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--n", "200", "--sites", "20000", "--cpu-sample-sites", "2000"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "bases/s" and d["higher_is_better"] is True and d["steps"] == 2
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert "workload" in d["config"]
