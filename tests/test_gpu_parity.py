@@ -509,3 +509,43 @@ def test_large_file_rows_in_place(ctx, tmp_path, monkeypatch):
     up = _upper(text)
     o = co.site_stats(up, pops[1])
     assert (want[0][0][1]["S"], want[0][0][1]["H"]) == (o["S"], o["H"])
+
+
+@pytest.mark.parametrize("n,L,force", [(129, 1500, True), (2049, 900, True), (21000, 240, False), (13000, 303, False)])
+def test_streaming_scan_kernels(ctx, monkeypatch, n, L, force):
+    """alignments with more rows than the register-resident kernels hold (K2: 20,480, K4: 12,288) go through the streaming
+    two-pass kernels; PFA_GENERIC_SCAN=1 forces them for smaller shapes.  Same checks as test_against_c_oracle, plus the
+    exchange epilogue (world = 1) on this path."""
+    if force:
+        monkeypatch.setenv("PFA_GENERIC_SCAN", "1")
+    rng = np.random.default_rng(n + 7 * L)
+    text = _random_text(rng, n, L, p_junk=0.01)
+    up = _upper(text)
+    pops = [list(range(n)), list(range(0, n, 3))]
+    aln = pf.Alignment.from_rows(ctx, text)
+    aln.set_pops(pops)
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    import torch
+    from polyfasta_b200 import parallel
+    x = parallel.connect_exchange(ctx, max(aln.site_len(), 71 * 2))
+    d_s = torch.zeros(aln.site_len(), dtype=torch.int64, device="cuda")
+    d_c = torch.zeros(71 * 2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    aln.site_stats_xchg(x, d_s.data_ptr())
+    aln.cds_stats_xchg(x, d_c.data_ptr())
+    ctx.sync()
+    fused_s, fused_c = d_s.cpu().numpy(), d_c.cpu().numpy().reshape(2, 71)
+    off = aln.site_offsets()
+    aln.free()
+    x.close()
+    for q, rows in enumerate(pops):
+        want = co.site_stats(up, rows, per_site=True)
+        assert (site[q]["S"], site[q]["H"], site[q]["sfs"]) == (want["S"], want["H"], want["sfs"]), (n, L, q)
+        assert np.array_equal(site[q]["isvar"], want["isvar"])
+        assert fused_s[off[q]: off[q + 1]].tolist() == [want["S"], want["H"]] + want["sfs"]
+        wc = co.cds_stats(up, rows, want_labels=True)
+        for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
+            assert cds[q][k] == wc[k], (n, L, q, k)
+        assert np.array_equal(cds[q]["labels"], wc["labels"])
+        assert np.array_equal(fused_c[q], cds[q]["raw"])
