@@ -309,45 +309,82 @@ int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out) {
     return parse_impl(static_cast<const unsigned char*>(buf), len, out);
 }
 
-// large files: no zero-filled vector, the slices of the file are read (and their pages touched) by several threads
+// Large files.  The file is mapped privately (copy-on-write): the page-cache pages are used as they are, no copy at all
+// for the common layout of one line per sequence; wrapped records are compacted in place, which copies only the pages
+// that are written.  PFA_PARSE_MMAP=0, or a file that cannot be mapped, takes the read path: a malloc'ed buffer filled
+// by several threads with pread.
 static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
     int fd = open(path, O_RDONLY);
     if (fd < 0) return PFA_ERR_IO;
-    unsigned char* buf = static_cast<unsigned char*>(malloc(size));
-    if (!buf) {
-        close(fd);
-        return PFA_ERR_NOMEM;
-    }
-#ifdef MADV_HUGEPAGE
-    madvise(buf, size, MADV_HUGEPAGE);
-#endif
     const unsigned nt = big_threads();
-    std::vector<char> bad(nt, 0);
-    parallel_run(nt, [&](unsigned t, unsigned n) {
-        size_t lo = size * t / n;
-        const size_t hi = size * (t + 1) / n;
-        while (lo < hi) {
-            const ssize_t r = pread(fd, buf + lo, hi - lo, (off_t)lo);
-            if (r <= 0) {
-                bad[t] = 1;
-                return;
+    unsigned char* buf = nullptr;
+    size_t mapped = 0;
+    const char* mm = getenv("PFA_PARSE_MMAP");
+    if (!mm || atoi(mm) != 0) {
+        void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            buf = static_cast<unsigned char*>(m);
+            mapped = size;
+            // sniff the first record: when its sequence is wrapped over several lines the compaction would write (copy on
+            // write, one fault per page: 1.1 s for 6 GB measured) nearly every page -- such files take the read path
+            const size_t look = std::min<size_t>(size, 4u << 20);
+            const unsigned char* h = static_cast<const unsigned char*>(memchr(buf, '>', look));
+            bool wrapped = false;
+            if (h) {
+                const unsigned char* l1 = static_cast<const unsigned char*>(memchr(h, '\n', look - (size_t)(h - buf)));
+                const unsigned char* l2 = l1 ? static_cast<const unsigned char*>(memchr(l1 + 1, '\n', look - (size_t)(l1 + 1 - buf))) : nullptr;
+                wrapped = l2 && (size_t)(l2 + 1 - buf) < size && l2[1] != '>';
             }
-            lo += (size_t)r;
+            if (wrapped) {
+                munmap(buf, size);
+                buf = nullptr;
+                mapped = 0;
+            } else {
+                madvise(buf, size, MADV_WILLNEED);
+            }
         }
-    });
+    }
+    if (!buf) {
+        buf = static_cast<unsigned char*>(malloc(size));
+        if (!buf) {
+            close(fd);
+            return PFA_ERR_NOMEM;
+        }
+#ifdef MADV_HUGEPAGE
+        madvise(buf, size, MADV_HUGEPAGE);
+#endif
+        std::vector<char> bad(nt, 0);
+        parallel_run(nt, [&](unsigned t, unsigned n) {
+            size_t lo = size * t / n;
+            const size_t hi = size * (t + 1) / n;
+            while (lo < hi) {
+                const ssize_t r = pread(fd, buf + lo, hi - lo, (off_t)lo);
+                if (r <= 0) {
+                    bad[t] = 1;
+                    return;
+                }
+                lo += (size_t)r;
+            }
+        });
+        for (char b : bad)
+            if (b) {
+                close(fd);
+                free(buf);
+                return PFA_ERR_IO;
+            }
+    }
     close(fd);
-    for (char b : bad)
-        if (b) {
-            free(buf);
-            return PFA_ERR_IO;
-        }
+    auto release = [&]() {
+        if (mapped) munmap(buf, mapped);
+        else free(buf);
+    };
     // no second copy: every record is compacted where its lines were (the lines of a record lie between its header and
     // the next one, so the records' spans are disjoint and the rows move independently, in parallel)
     const double t0 = now_ms();
     PfaParsed parsed;
     int rc = pfa_parse_lines(buf, size, &parsed);
     if (rc) {
-        free(buf);
+        release();
         return rc;
     }
     const double t1 = now_ms();
@@ -357,6 +394,7 @@ static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
     f->in_place = true;
     f->data = buf;
     f->data_bytes = size;
+    f->mapped_bytes = mapped;
     f->seqlen = parsed.seqlen;
     f->row_len.resize(recs.size());
     f->row_off.resize(recs.size() + 1);
@@ -374,7 +412,8 @@ static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
             if (!recs[k].parts.empty() && !pfa_copy_record(recs[k], buf + f->row_off[k])) non_ascii[t] = 1;
     });
     if (getenv("PFA_PARSE_TRACE"))
-        fprintf(stderr, "[pfa parse] %zu bytes in place: line scan %.1f ms, compaction %.1f ms\n", size, t1 - t0, now_ms() - t1);
+        fprintf(stderr, "[pfa parse] %zu bytes in place (%s): line scan %.1f ms, compaction %.1f ms\n", size, mapped ? "mapped" : "read",
+                t1 - t0, now_ms() - t1);
     for (char b : non_ascii)
         if (b) {
             pfa_fasta_free(f);
@@ -435,7 +474,8 @@ int64_t pfa_fasta_match_mask(const pfa_fasta* f, const char* key, int64_t key_le
 void pfa_fasta_free(pfa_fasta* f) {
     if (!f) return;
     if (f->unpin) f->unpin(f->data);
-    free(f->data);
+    if (f->mapped_bytes) munmap(f->data, f->mapped_bytes);
+    else free(f->data);
     delete f;
 }
 

@@ -18,6 +18,7 @@ struct pfa_fasta {
     std::string headers;             // concatenated header bytes
     std::vector<int64_t> header_off; // n+1
     bool pinned = false;             // data registered with cudaHostRegister by the uploader
+    size_t mapped_bytes = 0;         // > 0: `data` is a private file mapping of this size (munmap), not malloc memory
     void (*unpin)(void*) = nullptr;
 };
 

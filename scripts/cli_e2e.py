@@ -18,11 +18,15 @@ mat = d.cpu().numpy()
 del d
 path = "/tmp/c3_like.fa"
 t0 = time.perf_counter()
+wrap = int(os.environ.get("WRAP", "0"))   # 0: one line per sequence; else that many bases per line
 with open(path, "wb") as f:
     for i in range(n):
         f.write((">pop%d_indiv%d\n" % (1 if i < n // 2 else 2, i)).encode())
-        f.write(mat[i].tobytes())
-        f.write(b"\n")
+        if wrap and L % wrap == 0:
+            f.write(np.concatenate([mat[i].reshape(-1, wrap), np.full((L // wrap, 1), 10, np.uint8)], axis=1).tobytes())
+        else:
+            f.write(mat[i].tobytes())
+            f.write(b"\n")
 print("wrote %s (%.2f GB) in %.1f s" % (path, os.path.getsize(path) / 1e9, time.perf_counter() - t0))
 for rep in range(2):
     t0 = time.perf_counter(); fa = pf.Fasta.from_file(path); t1 = time.perf_counter()

@@ -221,11 +221,13 @@ def test_segmented_parse_equals_sequential(tmp_path, monkeypatch, segments):
         p = tmp_path / "case.fa"
         p.write_bytes(text.encode("utf-8", "surrogateescape") if isinstance(text, str) else text)
         monkeypatch.setenv("PFA_BIG_FILE_MIN", "1")
-        try:
-            got = _fasta_dump(pf.Fasta.from_file(str(p)))
-        except pf.NotFasta:
-            got = "not fasta"
-        assert got == want, name
+        for mapped in ("1", "0"):   # private file mapping (copy-on-write), or a buffer filled with pread
+            monkeypatch.setenv("PFA_PARSE_MMAP", mapped)
+            try:
+                got = _fasta_dump(pf.Fasta.from_file(str(p)))
+            except pf.NotFasta:
+                got = "not fasta"
+            assert got == want, (name, mapped)
 
 
 def test_host_packer_with_validity_bitmap():
