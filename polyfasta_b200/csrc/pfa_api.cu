@@ -213,7 +213,8 @@ int pfa_aln_from_fasta(pfa_ctx* ctx, const pfa_fasta* f, int64_t col_begin, int6
     if (!ctx || !f || !out) return PFA_ERR_ARG;
     if (f->seqlen < 0) return pfa_fail(ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
     return pfa_aln_from_text(ctx, f->data, false, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), col_begin, col_end, out,
-                             f->in_place ? f->row_off.data() : nullptr);
+                             f->in_place ? f->row_off.data() : nullptr, f->wrap_w.empty() ? nullptr : f->wrap_w.data(),
+                             f->wrap_gap.empty() ? nullptr : f->wrap_gap.data());
 }
 
 int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm, int64_t col_begin,

@@ -467,7 +467,13 @@ int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k
     if (f->seqlen < 0) return pfa_fail(b->ctx, PFA_ERR_RAGGED, "sequences do not have the same length");
     if (f->in_place) {  // a large file whose rows are slices of the file buffer: gather them into a matrix first (rare here)
         std::vector<uint8_t> mat((size_t)std::max<int64_t>(f->n * f->seqlen, 1));
-        for (int64_t r = 0; r < f->n; ++r) memcpy(mat.data() + r * f->seqlen, f->data + f->row_off[(size_t)r], (size_t)f->seqlen);
+        for (int64_t r = 0; r < f->n; ++r) {
+            const uint8_t* src = f->data + f->row_off[(size_t)r];
+            if (!f->wrap_w.empty() && f->wrap_w[(size_t)r] > 0)
+                pfa_gather_wrapped(src, f->wrap_w[(size_t)r], f->wrap_gap[(size_t)r], 0, f->seqlen, mat.data() + r * f->seqlen);
+            else
+                memcpy(mat.data() + r * f->seqlen, src, (size_t)f->seqlen);
+        }
         return pfa_batch_add_rows(b, mat.data(), f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), masks, k, index);
     }
     return pfa_batch_add_rows(b, f->data, f->n, f->seqlen, std::max<int64_t>(f->seqlen, 1), masks, k, index);

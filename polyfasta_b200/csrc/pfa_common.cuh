@@ -109,9 +109,11 @@ int pfa_upload_codon_tables(pfa_ctx* ctx);
 int pfa_aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out);
 int pfa_aln_default_pop(pfa_aln* a);
 // upload + encode of columns [col_begin, col_end) of a text matrix (pfa_ingest.cu); `dev`: the matrix is in device memory
-// row_off (host sources only, optional): row r starts at text + row_off[r] instead of text + r * ld
+// row_off (host sources only, optional): row r starts at text + row_off[r] instead of text + r * ld; wrap_w / wrap_gap
+// (optional, with row_off): row r is wrapped over lines of wrap_w[r] bytes every wrap_w[r] + wrap_gap[r] bytes (0: contiguous)
 int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
-                      int64_t col_end, pfa_aln** out, const int64_t* row_off = nullptr);
+                      int64_t col_end, pfa_aln** out, const int64_t* row_off = nullptr, const int32_t* wrap_w = nullptr,
+                      const int32_t* wrap_gap = nullptr);
 int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, const uint8_t* d_valid, int64_t ldv, int direct,
                             int64_t cols, int64_t site0, int* d_has_invalid, cudaStream_t st);
 

@@ -309,118 +309,150 @@ int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out) {
     return parse_impl(static_cast<const unsigned char*>(buf), len, out);
 }
 
-// Large files.  The file is mapped privately (copy-on-write): the page-cache pages are used as they are, no copy at all
-// for the common layout of one line per sequence; wrapped records are compacted in place, which copies only the pages
-// that are written.  PFA_PARSE_MMAP=0, or a file that cannot be mapped, takes the read path: a malloc'ed buffer filled
-// by several threads with pread.
+// Large files.  The file is mapped privately and NEVER written: rows that sit on one line are used where they lie, rows
+// wrapped over lines of one width are described by (first byte, line width, gap) and gathered by whoever reads them (the
+// ingest's packer, pfa_fasta_copy_row) -- no copy of the file at all.  Files whose wrapping is irregular (blank lines,
+// lines of different widths inside a record), files that cannot be mapped and PFA_PARSE_MMAP=0 take the read path: a
+// malloc'ed buffer filled by several threads with pread, every record compacted in place.
+static bool regular_wrap(const PfaRecord& r, int32_t* w, int32_t* gap) {
+    const std::vector<PfaSlice>& p = r.parts;
+    if (p.size() < 2) return false;
+    const int64_t W = (int64_t)p[0].len, stride = (int64_t)(p[1].p - p[0].p);
+    if (W <= 0 || stride <= W || W > 0x7fffffff || stride - W > 0x7fffffff) return false;
+    for (size_t i = 1; i < p.size(); ++i) {
+        if ((int64_t)(p[i].p - p[i - 1].p) != stride) return false;
+        if (i + 1 < p.size() ? (int64_t)p[i].len != W : ((int64_t)p[i].len > W || p[i].len == 0)) return false;
+    }
+    *w = (int32_t)W;
+    *gap = (int32_t)(stride - W);
+    return true;
+}
+
 static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) return PFA_ERR_IO;
     const unsigned nt = big_threads();
-    unsigned char* buf = nullptr;
-    size_t mapped = 0;
     const char* mm = getenv("PFA_PARSE_MMAP");
-    if (!mm || atoi(mm) != 0) {
-        void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
-        if (m != MAP_FAILED) {
+    for (int attempt = (!mm || atoi(mm) != 0) ? 0 : 1; attempt < 2; ++attempt) {
+        const bool want_map = attempt == 0;
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) return PFA_ERR_IO;
+        unsigned char* buf = nullptr;
+        size_t mapped = 0;
+        if (want_map) {
+            void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) {
+                close(fd);
+                continue;
+            }
             buf = static_cast<unsigned char*>(m);
             mapped = size;
-            // sniff the first record: when its sequence is wrapped over several lines the compaction would write (copy on
-            // write, one fault per page: 1.1 s for 6 GB measured) nearly every page -- such files take the read path
-            const size_t look = std::min<size_t>(size, 4u << 20);
-            const unsigned char* h = static_cast<const unsigned char*>(memchr(buf, '>', look));
-            bool wrapped = false;
-            if (h) {
-                const unsigned char* l1 = static_cast<const unsigned char*>(memchr(h, '\n', look - (size_t)(h - buf)));
-                const unsigned char* l2 = l1 ? static_cast<const unsigned char*>(memchr(l1 + 1, '\n', look - (size_t)(l1 + 1 - buf))) : nullptr;
-                wrapped = l2 && (size_t)(l2 + 1 - buf) < size && l2[1] != '>';
+            madvise(buf, size, MADV_WILLNEED);
+        } else {
+            buf = static_cast<unsigned char*>(malloc(size));
+            if (!buf) {
+                close(fd);
+                return PFA_ERR_NOMEM;
             }
-            if (wrapped) {
-                munmap(buf, size);
-                buf = nullptr;
-                mapped = 0;
-            } else {
-                madvise(buf, size, MADV_WILLNEED);
-            }
-        }
-    }
-    if (!buf) {
-        buf = static_cast<unsigned char*>(malloc(size));
-        if (!buf) {
-            close(fd);
-            return PFA_ERR_NOMEM;
-        }
 #ifdef MADV_HUGEPAGE
-        madvise(buf, size, MADV_HUGEPAGE);
+            madvise(buf, size, MADV_HUGEPAGE);
 #endif
-        std::vector<char> bad(nt, 0);
-        parallel_run(nt, [&](unsigned t, unsigned n) {
-            size_t lo = size * t / n;
-            const size_t hi = size * (t + 1) / n;
-            while (lo < hi) {
-                const ssize_t r = pread(fd, buf + lo, hi - lo, (off_t)lo);
-                if (r <= 0) {
-                    bad[t] = 1;
-                    return;
+            std::vector<char> bad(nt, 0);
+            parallel_run(nt, [&](unsigned t, unsigned n) {
+                size_t lo = size * t / n;
+                const size_t hi = size * (t + 1) / n;
+                while (lo < hi) {
+                    const ssize_t r = pread(fd, buf + lo, hi - lo, (off_t)lo);
+                    if (r <= 0) {
+                        bad[t] = 1;
+                        return;
+                    }
+                    lo += (size_t)r;
                 }
-                lo += (size_t)r;
+            });
+            for (char b : bad)
+                if (b) {
+                    close(fd);
+                    free(buf);
+                    return PFA_ERR_IO;
+                }
+        }
+        close(fd);
+        auto release = [&]() {
+            if (mapped) munmap(buf, mapped);
+            else free(buf);
+        };
+        const double t0 = now_ms();
+        PfaParsed parsed;
+        int rc = pfa_parse_lines(buf, size, &parsed);
+        if (rc) {
+            release();
+            return rc;
+        }
+        const double t1 = now_ms();
+        const std::vector<PfaRecord>& recs = parsed.recs;
+        // mapped: wrapped rows must be regular, or the file goes through the read path
+        std::vector<int32_t> ww, wg;
+        if (mapped) {
+            bool any_wrapped = false, irregular = false;
+            for (const PfaRecord& r : recs) any_wrapped |= r.parts.size() > 1;
+            if (any_wrapped) {
+                ww.assign(recs.size(), 0);
+                wg.assign(recs.size(), 0);
+                for (size_t k = 0; k < recs.size() && !irregular; ++k)
+                    if (recs[k].parts.size() > 1 && !regular_wrap(recs[k], &ww[k], &wg[k])) irregular = true;
+            }
+            if (irregular) {
+                release();
+                continue;
+            }
+        }
+        pfa_fasta* f = new pfa_fasta();
+        f->n = (int64_t)recs.size();
+        f->in_place = true;
+        f->data = buf;
+        f->data_bytes = size;
+        f->mapped_bytes = mapped;
+        f->seqlen = parsed.seqlen;
+        f->wrap_w = std::move(ww);
+        f->wrap_gap = std::move(wg);
+        f->row_len.resize(recs.size());
+        f->row_off.resize(recs.size() + 1);
+        for (size_t k = 0; k < recs.size(); ++k) {
+            f->row_len[k] = recs[k].len;
+            f->row_off[k] = recs[k].parts.empty() ? 0 : (int64_t)(recs[k].parts[0].p - buf);
+            f->header_off.push_back((int64_t)f->headers.size());
+            f->headers += recs[k].header;
+        }
+        f->row_off[recs.size()] = (int64_t)size;
+        f->header_off.push_back((int64_t)f->headers.size());
+        // bytes >= 0x80 in sequence lines are refused; read path: the same pass compacts every record where its lines were
+        // (the lines of a record lie between its header and the next one: disjoint spans, rows move independently)
+        std::vector<char> non_ascii(nt, 0);
+        parallel_run(nt, [&](unsigned t, unsigned n) {
+            for (size_t k = t; k < recs.size(); k += n) {
+                if (recs[k].parts.empty()) continue;
+                if (mapped) {
+                    // one pass over the record's whole span: the bytes between its lines are line ends and stripped blanks,
+                    // all below 0x80, so they cannot hide or fake a high bit
+                    const PfaSlice& first = recs[k].parts.front();
+                    const PfaSlice& last = recs[k].parts.back();
+                    if (or_bytes(first.p, (size_t)(last.p + last.len - first.p)) & 0x80) non_ascii[t] = 1;
+                } else if (!pfa_copy_record(recs[k], buf + f->row_off[k])) {
+                    non_ascii[t] = 1;
+                }
             }
         });
-        for (char b : bad)
+        if (getenv("PFA_PARSE_TRACE"))
+            fprintf(stderr, "[pfa parse] %zu bytes in place (%s%s): line scan %.1f ms, %s %.1f ms\n", size, mapped ? "mapped" : "read",
+                    f->wrap_w.empty() ? "" : ", wrapped rows gathered on access", t1 - t0, mapped ? "byte check" : "compaction", now_ms() - t1);
+        for (char b : non_ascii)
             if (b) {
-                close(fd);
-                free(buf);
-                return PFA_ERR_IO;
+                pfa_fasta_free(f);
+                return PFA_ERR_NON_ASCII;
             }
+        *out = f;
+        return PFA_OK;
     }
-    close(fd);
-    auto release = [&]() {
-        if (mapped) munmap(buf, mapped);
-        else free(buf);
-    };
-    // no second copy: every record is compacted where its lines were (the lines of a record lie between its header and
-    // the next one, so the records' spans are disjoint and the rows move independently, in parallel)
-    const double t0 = now_ms();
-    PfaParsed parsed;
-    int rc = pfa_parse_lines(buf, size, &parsed);
-    if (rc) {
-        release();
-        return rc;
-    }
-    const double t1 = now_ms();
-    const std::vector<PfaRecord>& recs = parsed.recs;
-    pfa_fasta* f = new pfa_fasta();
-    f->n = (int64_t)recs.size();
-    f->in_place = true;
-    f->data = buf;
-    f->data_bytes = size;
-    f->mapped_bytes = mapped;
-    f->seqlen = parsed.seqlen;
-    f->row_len.resize(recs.size());
-    f->row_off.resize(recs.size() + 1);
-    for (size_t k = 0; k < recs.size(); ++k) {
-        f->row_len[k] = recs[k].len;
-        f->row_off[k] = recs[k].parts.empty() ? 0 : (int64_t)(recs[k].parts[0].p - buf);
-        f->header_off.push_back((int64_t)f->headers.size());
-        f->headers += recs[k].header;
-    }
-    f->row_off[recs.size()] = (int64_t)size;
-    f->header_off.push_back((int64_t)f->headers.size());
-    std::vector<char> non_ascii(nt, 0);
-    parallel_run(nt, [&](unsigned t, unsigned n) {
-        for (size_t k = t; k < recs.size(); k += n)
-            if (!recs[k].parts.empty() && !pfa_copy_record(recs[k], buf + f->row_off[k])) non_ascii[t] = 1;
-    });
-    if (getenv("PFA_PARSE_TRACE"))
-        fprintf(stderr, "[pfa parse] %zu bytes in place (%s): line scan %.1f ms, compaction %.1f ms\n", size, mapped ? "mapped" : "read",
-                t1 - t0, now_ms() - t1);
-    for (char b : non_ascii)
-        if (b) {
-            pfa_fasta_free(f);
-            return PFA_ERR_NON_ASCII;
-        }
-    *out = f;
-    return PFA_OK;
+    return PFA_ERR_IO;
 }
 
 int pfa_fasta_parse_file(const char* path, pfa_fasta** out) {
@@ -492,7 +524,12 @@ const char* pfa_fasta_header(const pfa_fasta* f, int64_t row, int64_t* len) {
 int pfa_fasta_copy_row(const pfa_fasta* f, int64_t row, uint8_t* dst, int64_t cap) {
     if (!f || row < 0 || row >= f->n || !dst || cap < f->row_len[(size_t)row]) return PFA_ERR_ARG;
     const unsigned char* src = f->data + f->row_off[(size_t)row];
-    for (int64_t i = 0; i < f->row_len[(size_t)row]; ++i) {
+    const int64_t len = f->row_len[(size_t)row];
+    if (!f->wrap_w.empty() && f->wrap_w[(size_t)row] > 0) {
+        pfa_gather_wrapped(src, f->wrap_w[(size_t)row], f->wrap_gap[(size_t)row], 0, len, dst);
+        src = dst;
+    }
+    for (int64_t i = 0; i < len; ++i) {
         unsigned char c = src[i];
         dst[i] = (c >= 'a' && c <= 'z') ? (unsigned char)(c - 32) : c;  // str.upper() on ASCII
     }

@@ -1,6 +1,9 @@
 // Host-only part of the library (no CUDA headers): the parsed FASTA file.
 #pragma once
 #include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include <string>
 #include <vector>
@@ -19,6 +22,10 @@ struct pfa_fasta {
     std::vector<int64_t> header_off; // n+1
     bool pinned = false;             // data registered with cudaHostRegister by the uploader
     size_t mapped_bytes = 0;         // > 0: `data` is a private file mapping of this size (munmap), not malloc memory
+    // rows of a mapped file that are wrapped over lines stay as they are in the file (no write, no copy): row r is lines of
+    // wrap_w[r] bytes every wrap_w[r] + wrap_gap[r] bytes from row_off[r]; wrap_w[r] == 0: the row is contiguous.  Empty
+    // vectors: every row is contiguous.
+    std::vector<int32_t> wrap_w, wrap_gap;
     void (*unpin)(void*) = nullptr;
 };
 
@@ -50,3 +57,17 @@ int pfa_pack2_row(const uint8_t* src, int64_t cols, uint8_t* dst);
 // table-lookup instruction per 64 bases); without it the scalar version is slower than shipping the text.
 int pfa_pack3_row(const uint8_t* src, int64_t cols, uint8_t* codes, uint8_t* valid);
 bool pfa_pack3_fast();
+
+// columns [c0, c0 + cols) of a row stored as lines of w bytes every (w + gap) bytes from p, copied to dst
+static inline void pfa_gather_wrapped(const uint8_t* p, int32_t w, int32_t gap, int64_t c0, int64_t cols, uint8_t* dst) {
+    int64_t o = c0 % w;
+    const uint8_t* src = p + (c0 / w) * (int64_t)(w + gap) + o;
+    while (cols > 0) {
+        const int64_t take = std::min<int64_t>(w - o, cols);
+        memcpy(dst, src, (size_t)take);
+        dst += take;
+        cols -= take;
+        src += take + gap;  // only used again when `take` reached the end of the line
+        o = 0;
+    }
+}

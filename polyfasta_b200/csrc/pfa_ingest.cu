@@ -89,7 +89,16 @@ struct Hybrid {
     pfa_aln* a;
     const uint8_t* text;  // first column of the shard
     const int64_t* row_off = nullptr;  // optional: row r starts at text + row_off[r] (rows of any stride)
-    const uint8_t* row(int64_t r) const { return text + (row_off ? row_off[r] : r * ld); }
+    const int32_t *wrap_w = nullptr, *wrap_gap = nullptr;  // optional: rows wrapped over lines (mapped files)
+    int64_t col_begin = 0;  // first column of the shard (wrapped rows are addressed by column, not by pointer)
+    // columns [c0, c0 + cols) of the shard's row r: a pointer into the source, or tmp after gathering the line pieces
+    const uint8_t* span(int64_t r, int64_t c0, int64_t cols, uint8_t* tmp) const {
+        if (wrap_w && wrap_w[r] > 0) {
+            pfa_gather_wrapped(text - col_begin + row_off[r], wrap_w[r], wrap_gap[r], col_begin + c0, cols, tmp);
+            return tmp;
+        }
+        return text + (row_off ? row_off[r] : r * ld) + c0;
+    }
     int64_t ld, n, ns, chunk, nchunks, ldt, ldp, ldv;
     unsigned long long* d_count;
     int64_t cap;
@@ -132,7 +141,10 @@ int raw_chunk(Hybrid& h, int64_t c, int& issued) {
                 const int64_t r0 = row_next.fetch_add(32);
                 if (r0 >= h.n) break;
                 const int64_t r1 = std::min(h.n, r0 + 32);
-                for (int64_t r = r0; r < r1; ++r) memcpy(bb + r * h.ldt, h.row(r) + c0, (size_t)cols);
+                for (int64_t r = r0; r < r1; ++r) {
+                    const uint8_t* src = h.span(r, c0, cols, bb + r * h.ldt);
+                    if (src != bb + r * h.ldt) memcpy(bb + r * h.ldt, src, (size_t)cols);
+                }
             }
         });
         PFA_CUDA(ctx, cudaMemcpyAsync(h.stage_raw[b], bb, (size_t)(h.n * h.ldt), cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -190,13 +202,16 @@ void packed_lane(Hybrid* hp, int lane_id) {
         uint8_t* vdst = dst + code_bytes;
         pool.run([&] {
             int mine = 0;
+            std::vector<uint8_t> tmp(h.wrap_w ? (size_t)cols : 0);  // wrapped rows: the line pieces are gathered here first
             for (;;) {
                 const int64_t r0 = row_next.fetch_add(16);
                 if (r0 >= h.n || (flags.load(std::memory_order_relaxed) & 2)) break;
                 const int64_t r1 = std::min(h.n, r0 + 16);
-                for (int64_t r = r0; r < r1; ++r)
-                    mine |= with_validity ? pfa_pack3_row(h.row(r) + c0, cols, dst + r * h.ldp, vdst + r * h.ldv)
-                                          : 2 * pfa_pack2_row(h.row(r) + c0, cols, dst + r * h.ldp);
+                for (int64_t r = r0; r < r1; ++r) {
+                    const uint8_t* src = h.span(r, c0, cols, tmp.data());
+                    mine |= with_validity ? pfa_pack3_row(src, cols, dst + r * h.ldp, vdst + r * h.ldv)
+                                          : 2 * pfa_pack2_row(src, cols, dst + r * h.ldp);
+                }
                 if (mine) flags.fetch_or(mine, std::memory_order_relaxed);
             }
         });
@@ -251,14 +266,17 @@ int host_threads(const pfa_ctx* ctx) {
 }
 
 // all chunks of one attempt through the two lanes; the planes are complete when ctx->stream reaches the joins at the end
-int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* row_off, unsigned long long* d_count, int64_t cap,
-                  int* d_inv, int threads, bool raw_takes_chunks, bool bounce) {
+int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* row_off, const int32_t* wrap_w, const int32_t* wrap_gap,
+                  unsigned long long* d_count, int64_t cap, int* d_inv, int threads, bool raw_takes_chunks, bool bounce) {
     pfa_ctx* ctx = a->ctx;
     Hybrid h;
     h.a = a;
     h.text = text;
     h.ld = ld;
     h.row_off = row_off;
+    h.wrap_w = wrap_w;
+    h.wrap_gap = wrap_gap;
+    h.col_begin = a->col_begin;
     h.n = a->n;
     h.ns = a->ns;
     int64_t chunk_mb = 64;
@@ -372,8 +390,8 @@ int upload_hybrid(pfa_aln* a, const uint8_t* text, int64_t ld, const int64_t* ro
 }  // namespace
 
 int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, int64_t L, int64_t ld, int64_t col_begin,
-                      int64_t col_end, pfa_aln** out, const int64_t* row_off) {
-    if (!ctx || !out || (dev && row_off)) return PFA_ERR_ARG;
+                      int64_t col_end, pfa_aln** out, const int64_t* row_off, const int32_t* wrap_w, const int32_t* wrap_gap) {
+    if (!ctx || !out || (dev && row_off) || (wrap_w && (!row_off || !wrap_gap))) return PFA_ERR_ARG;
     *out = nullptr;
     if (n < 0 || L < 0 || col_begin < 0 || col_end < col_begin || col_end > L || (n > 0 && L > 0 && (!text || (ld < L && !row_off))))
         return pfa_fail(ctx, PFA_ERR_ARG, "bad alignment shape n=%lld L=%lld ld=%lld cols=[%lld,%lld)", (long long)n,
@@ -455,7 +473,7 @@ int pfa_aln_from_text(pfa_ctx* ctx, const uint8_t* text, bool dev, int64_t n, in
             UP(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
             UP(cudaMemsetAsync(d_inv, 0, sizeof(int), ctx->stream));
             if (hybrid) {
-                rc = upload_hybrid(a, text + col_begin, ld, row_off, d_count, cap, d_inv, std::max(1, threads), raw_takes_chunks,
+                rc = upload_hybrid(a, text + col_begin, ld, row_off, wrap_w, wrap_gap, d_count, cap, d_inv, std::max(1, threads), raw_takes_chunks,
                                    !is_pinned || row_off != nullptr);
                 if (rc) {
                     cleanup();

@@ -204,6 +204,10 @@ def test_segmented_parse_equals_sequential(tmp_path, monkeypatch, segments):
         if rng.random() < 0.2:
             text = text.replace("\n", "\r\n")
         cases["rand%d" % i] = text
+    # regularly wrapped records (what a mapped file keeps as (first byte, line width, gap) and gathers on access)
+    for i, (w, nl) in enumerate(((60, "\n"), (7, "\n"), (13, "\r\n"), (1, "\n"), (80, " \n"))):
+        rows = ["".join("ACGTN-acgt"[int(x)] for x in rng.integers(0, 10, 157 + 3 * r)) for r in range(5)]
+        cases["wrap%d" % i] = "".join(">r%d%s" % (r, nl) + "".join(row[o:o + w] + nl for o in range(0, len(row), w)) for r, row in enumerate(rows))
     for name, text in cases.items():
         monkeypatch.delenv("PFA_PARSE_SEGMENTS", raising=False)
         monkeypatch.delenv("PFA_BIG_FILE_MIN", raising=False)
@@ -283,3 +287,19 @@ def test_bench_reference_arm_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
     assert "workload" in d["config"]
+
+
+@pytest.mark.parametrize("mapped", ["1", "0"])
+def test_big_file_path_refuses_non_ascii_sequence_bytes(tmp_path, monkeypatch, mapped):
+    """bytes >= 0x80 in SEQUENCE lines are refused on every parse path (headers may hold them)"""
+    monkeypatch.setenv("PFA_BIG_FILE_MIN", "1")
+    monkeypatch.setenv("PFA_PARSE_MMAP", mapped)
+    ok = tmp_path / "ok.fa"
+    ok.write_bytes(b">caf\xc3\xa9\nACGT\nACGT\n>b\nACGT\nACGT\n")
+    f = pf.Fasta.from_file(str(ok))
+    assert f.nseq == 2 and f.seqlen == 8 and f.row(0) == "ACGTACGT"
+    for body in (b">a\nAC\xc3\xa9T\n>b\nACGGT\n", b">a\nACGT\nAC\xe9T\nAC\n>b\nACGT\nACGT\nAC\n"):
+        bad = tmp_path / "bad.fa"
+        bad.write_bytes(body)
+        with pytest.raises(ValueError):
+            pf.Fasta.from_file(str(bad))
