@@ -379,7 +379,7 @@ def main():
                        "planes_read": planes_read, "seed": SEED, "p_seg_ppm": P_SEG_PPM, "tri_ppm": TRI_PPM},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                         "kernel": "pfa_site_scan_reg_kernel<16,5,HAS_V>" if n == N_SEQ else "pfa_site_scan_*", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel": "pfa_site_scan_tma_kernel<16,5,HAS_V,512>" if n == N_SEQ else "pfa_site_scan_*", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "read_only_peak": read_only_gbs, "frac_of_read_only_peak": achieved / read_only_gbs,
                          "read_only_peak_kind": "pfa_read_probe_kernel over the same planes (padded bytes), measured in this run"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "parity": parity,

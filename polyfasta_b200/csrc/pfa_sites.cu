@@ -11,6 +11,7 @@
 // symbol classes per population with popcounts and group shuffles.  Sites holding "escape" symbols (IUPAC
 // codes etc., which are distinct alleles in the reference) are finished by pfa_escape_sites_kernel from the
 // sorted exception list.
+#include <cstdio>
 #include <cstdlib>
 
 #include "pfa_sites.cuh"
@@ -104,6 +105,85 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
     if (a.x.world) pfa_xchg_epilogue(a.x);
 }
 
+// passes 1 and 2 of one site whose record chunks are already in registers (x0, x1, xv: the lane's ITER chunks of each plane;
+// um: its slice of the union mask).  Shared by the register-resident kernel (chunks loaded from global memory) and the
+// TMA kernel (chunks read from the warp's shared-memory ring).
+template <int LPS, int ITER, bool HAS_V>
+__device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
+                                                 const uint4 (&xv)[ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
+                                                 bool one_pop, unsigned long long* sm_SH, unsigned int* sm_sfs) {
+    // ---- pass 1 on registers ----
+    uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const uint4 m = um[i];
+        o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
+        z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
+        o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
+        z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
+        ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
+        if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
+    }
+    unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+    f = pfa_group_or<LPS>(f, gmask);
+    const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
+    const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
+    if (mono && !all_escape) {
+        if (a.isvar && sub == 0)
+            for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
+        return;
+    }
+    // ---- pass 2 on registers ----
+    for (int q = 0; q < a.k; ++q) {
+        uint32_t c[PFA_NCLASS];
+#pragma unroll
+        for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+        const uint4* mq = a.masks + (int64_t)q * Wq;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int j = sub + LPS * i;
+            uint4 m4 = um[i];
+            if (!one_pop) m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+            const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
+                           w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w}, wv[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t vm = HAS_V ? (wv[w] & m[w]) : m[w];
+                const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
+                c[PFA_C_T] += __popc(hi & w0[w]);
+                c[PFA_C_G] += __popc(hi & ~w0[w]);
+                c[PFA_C_C] += __popc(lo & w0[w]);
+                c[PFA_C_A] += __popc(lo & ~w0[w]);
+                if (HAS_V) {
+                    const uint32_t im = ~wv[w] & m[w];
+                    const uint32_t ihi = im & w1[w];
+                    c[PFA_C_ESC] += __popc(ihi & w0[w]);
+                    c[PFA_C_Q] += __popc(ihi & ~w0[w]);
+                    c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
+                }
+            }
+        }
+        if (LPS > 1) {
+#pragma unroll
+            for (int i = 0; i < PFA_NCLASS; ++i)
+                if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
+        }
+        if (sub != 0) continue;
+        const int64_t nq = a.pop_n[q];
+        PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
+        if (r.has_escape) continue;
+        if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
+        if (r.isvar) {
+            atomicAdd(&sm_SH[2 * q], 1ull);
+            atomicAdd(&sm_SH[2 * q + 1], r.h);
+            if (r.sfs_bin >= 0) {
+                if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
+                else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
+            }
+        }
+    }
+}
+
 // Register-resident variant for Wq <= 5*32 chunks: every lane owns ITER fixed chunks of the site record, loads them
 // once (all loads of a site are issued back to back: 2-3 * ITER independent 128-bit requests per lane), keeps its slice
 // of the union mask in registers for the whole kernel, and both passes work on registers -- each byte of the planes
@@ -150,76 +230,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(
                 if (HAS_V) xv[i] = pfa_ld_stream(pv + j);
             }
         }
-        // ---- pass 1 on registers ----
-        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-            const uint4 m = um[i];
-            o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
-            z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
-            o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
-            z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
-            ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
-            if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
-        }
-        unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
-        f = pfa_group_or<LPS>(f, gmask);
-        const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
-        const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
-        if (mono && !all_escape) {
-            if (a.isvar && sub == 0)
-                for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
-            continue;
-        }
-        // ---- pass 2 on registers ----
-        for (int q = 0; q < a.k; ++q) {
-            uint32_t c[PFA_NCLASS];
-#pragma unroll
-            for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
-            const uint4* mq = a.masks + (int64_t)q * Wq;
-#pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const int j = sub + LPS * i;
-                uint4 m4 = um[i];
-                if (!one_pop) m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
-                const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
-                               w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w}, wv[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t vm = HAS_V ? (wv[w] & m[w]) : m[w];
-                    const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
-                    c[PFA_C_T] += __popc(hi & w0[w]);
-                    c[PFA_C_G] += __popc(hi & ~w0[w]);
-                    c[PFA_C_C] += __popc(lo & w0[w]);
-                    c[PFA_C_A] += __popc(lo & ~w0[w]);
-                    if (HAS_V) {
-                        const uint32_t im = ~wv[w] & m[w];
-                        const uint32_t ihi = im & w1[w];
-                        c[PFA_C_ESC] += __popc(ihi & w0[w]);
-                        c[PFA_C_Q] += __popc(ihi & ~w0[w]);
-                        c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
-                    }
-                }
-            }
-            if (LPS > 1) {
-#pragma unroll
-                for (int i = 0; i < PFA_NCLASS; ++i)
-                    if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
-            }
-            if (sub != 0) continue;
-            const int64_t nq = a.pop_n[q];
-            PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
-            if (r.has_escape) continue;
-            if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
-            if (r.isvar) {
-                atomicAdd(&sm_SH[2 * q], 1ull);
-                atomicAdd(&sm_SH[2 * q + 1], r.h);
-                if (r.sfs_bin >= 0) {
-                    if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
-                    else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
-                }
-            }
-        }
+        pfa_site_process<LPS, ITER, HAS_V>(a, s, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_SH, sm_sfs);
     }
     __syncthreads();
     for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
@@ -293,6 +304,106 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
     }
 }
 
+// TMA variant of the register-resident kernel: the bytes in flight are bounded by shared memory instead of registers.
+// Every WARP owns a private ring of STAGES shared-memory slots; a slot holds the records of the 32/LPS consecutive sites the
+// warp's groups handle in one iteration (contiguous in each plane), fetched with one cp.async.bulk per plane that completes
+// on the slot's mbarrier.  No block-wide synchronisation: a warp waits for its own slot, copies its chunks to registers,
+// refills the slot for the iteration STAGES ahead and then runs the same passes as the register kernel.
+template <int LPS, int ITER, bool HAS_V, int NT>
+__global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    constexpr int GW = 32 / LPS;      // sites per warp iteration
+    constexpr int NPL = HAS_V ? 3 : 2;  // planes read
+    constexpr int NWARP = NT / 32;
+    const int Wq = a.Wq;
+    const unsigned rec = (unsigned)Wq * 16u;            // bytes of one site record in one plane
+    const unsigned slot_bytes = (unsigned)NPL * GW * rec;  // [plane][site in warp][Wq] uint4
+    unsigned char* ring_base = dyn;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);  // [warp][stage]
+    unsigned long long* sm_SH = reinterpret_cast<unsigned long long*>(bars + NWARP * stages);
+    unsigned int* sm_sfs = reinterpret_cast<unsigned int*>(sm_SH + 2 * a.k);
+    if (a.x.world && blockIdx.x == 0 && threadIdx.x == 0) a.x.stamps[5] = pfa_globaltimer();
+    for (int i = threadIdx.x; i < 2 * a.k; i += blockDim.x) sm_SH[i] = 0ull;
+    if (a.sfs_in_smem)
+        for (int i = threadIdx.x; i < a.sfs_bins; i += blockDim.x) sm_sfs[i] = 0u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NWARP * stages; ++i) pfa_mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane & (LPS - 1), grp = lane / LPS;
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const bool one_pop = a.k == 1;
+    unsigned char* ring = ring_base + (size_t)wib * stages * slot_bytes;
+    uint64_t* bar = bars + wib * stages;
+    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib, nw = (int64_t)gridDim.x * NWARP;
+    const int64_t nblk = (a.ns + GW - 1) / GW;                       // blocks of GW consecutive sites
+    const int64_t mine = gw < nblk ? (nblk - gw + nw - 1) / nw : 0;  // this warp's blocks: gw, gw + nw, ...
+    const unsigned char* planes[3] = {reinterpret_cast<const unsigned char*>(a.b0), reinterpret_cast<const unsigned char*>(a.b1),
+                                      reinterpret_cast<const unsigned char*>(a.v)};
+
+    uint4 um[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int j = sub + LPS * i;
+        um[i] = j < Wq ? __ldg(a.umask + j) : make_uint4(0, 0, 0, 0);
+    }
+    auto issue = [&](int64_t k) {  // lane 0: fetch block k of this warp into slot k % stages
+        const int64_t s0 = (gw + k * nw) * GW;
+        const unsigned nsite = (unsigned)min((int64_t)GW, a.ns - s0);
+        const int st = (int)(k % stages);
+        pfa_mbar_expect_tx(&bar[st], NPL * nsite * rec);
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+            pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * GW * rec, planes[p] + (size_t)s0 * rec, nsite * rec, &bar[st]);
+    };
+    if (lane == 0)
+        for (int64_t k = 0; k < mine && k < stages; ++k) issue(k);
+
+    for (int64_t k = 0; k < mine; ++k) {
+        const int st = (int)(k % stages);
+        pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
+        const int64_t s = (gw + k * nw) * GW + grp;
+        const uint4* q0 = reinterpret_cast<const uint4*>(ring + (size_t)st * slot_bytes + (size_t)grp * rec);
+        const uint4* q1 = reinterpret_cast<const uint4*>(ring + (size_t)st * slot_bytes + (size_t)(GW + grp) * rec);
+        const uint4* qv = reinterpret_cast<const uint4*>(ring + (size_t)st * slot_bytes + (size_t)(2 * GW + grp) * rec);
+        uint4 x0[ITER], x1[ITER], xv[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int j = sub + LPS * i;
+            x0[i] = x1[i] = make_uint4(0, 0, 0, 0);
+            xv[i] = um[i];
+            if (j < Wq && s < a.ns) {
+                x0[i] = q0[j];
+                x1[i] = q1[j];
+                if (HAS_V) xv[i] = qv[j];
+            }
+        }
+        __syncwarp();  // every lane has its chunks in registers: the slot may be refilled
+        if (lane == 0 && k + stages < mine) issue(k + stages);
+        if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V>(a, s, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_SH, sm_sfs);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
+        if (sm_SH[2 * q]) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q]), sm_SH[2 * q]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 1), sm_SH[2 * q + 1]);
+        }
+    }
+    if (a.sfs_in_smem) {
+        for (int q = 0; q < a.k; ++q) {
+            const int nb = (int)(a.pop_n[q] / 2);
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+                const unsigned int cnt = sm_sfs[a.sfs_off[q] + i];
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + i), (unsigned long long)cnt);
+            }
+        }
+    }
+    if (a.x.world) pfa_xchg_epilogue(a.x);
+}
+
 template <int LPS>
 static void launch_scan(const PfaSiteArgs& args, bool has_v, dim3 grid, size_t smem, cudaStream_t st) {
     if (has_v) pfa_site_scan_kernel<LPS, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);
@@ -341,6 +452,42 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     if (blocks > max_blocks) blocks = max_blocks;
     dim3 grid((unsigned)blocks);
     cudaStream_t st = ctx->stream;
+    // Wide site records (16 or 32 lanes per site) go through the TMA variant: one CTA of 512 threads per SM, every warp
+    // fed by cp.async.bulk through its own shared-memory slot.  Measured 1-2 % above the register-resident kernel on
+    // n = 8,300 ... 20,000 (scripts/probe_k2_tma.py); ONE slot per warp is best -- deeper rings put more bytes in flight
+    // than the memory system likes (7.0 -> 6.5 TB/s at two slots).  PFA_SITE_TMA=<slots> (0 = off), PFA_SITE_TMA_THREADS.
+    int tma_stages = 1;
+    if (const char* e = getenv("PFA_SITE_TMA")) tma_stages = std::max(0, std::min(16, atoi(e)));
+    if (tma_stages > 0 && !generic && lps >= 16) {
+        int nt = 512;
+        if (const char* e = getenv("PFA_SITE_TMA_THREADS")) nt = atoi(e) == 256 ? 256 : 512;
+        const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
+        const size_t slot = (size_t)planes * gw * a->Wq * 16, ring = (size_t)nwarp * tma_stages * slot;
+        const size_t dyn = ring + sizeof(uint64_t) * nwarp * tma_stages + smem;
+        const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (a->ns + (int64_t)gw * nwarp - 1) / ((int64_t)gw * nwarp));
+        bool launched = false;
+#define PFA_TMA_LAUNCH(L_, I_, V_, N_)                                                                                  \
+        {                                                                                                                 \
+            cudaFuncSetAttribute(pfa_site_scan_tma_kernel<L_, I_, V_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
+            pfa_site_scan_tma_kernel<L_, I_, V_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages);                            \
+        }
+#define PFA_TMA_CASE(L_, I_)                                                                                            \
+        if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
+            if (hv && nt == 512) PFA_TMA_LAUNCH(L_, I_, true, 512)                                                        \
+            else if (hv) PFA_TMA_LAUNCH(L_, I_, true, 256)                                                                \
+            else if (nt == 512) PFA_TMA_LAUNCH(L_, I_, false, 512)                                                        \
+            else PFA_TMA_LAUNCH(L_, I_, false, 256)                                                                       \
+            launched = true;                                                                                              \
+        }
+        PFA_TMA_CASE(16, 3) PFA_TMA_CASE(16, 4) PFA_TMA_CASE(16, 5) PFA_TMA_CASE(32, 3) PFA_TMA_CASE(32, 4) PFA_TMA_CASE(32, 5)
+#undef PFA_TMA_CASE
+#undef PFA_TMA_LAUNCH
+        if (launched) {
+            PFA_LAUNCH_CHECK(ctx);
+            if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
+            return PFA_OK;
+        }
+    }
 #define PFA_REG_CASE(L_, I_)                                                                                          \
     if (lps == L_ && iter == I_) {                                                                                    \
         if (hv) pfa_site_scan_reg_kernel<L_, I_, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                    \
@@ -373,22 +520,62 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
 // ---- measurement aid: how fast can this GPU READ the planes at all? -------------------------------------------------------
 // The same streaming 128-bit loads as K2 over the same bytes, nothing else (XOR into a register, one store per thread that
 // never happens in practice).  bench.py reports K2 against this read-only ceiling next to the read+write copy peak.
+template <int UNROLL>
 __global__ void __launch_bounds__(256) pfa_read_probe_kernel(const uint4* __restrict__ p, int64_t n16, unsigned int* __restrict__ sink) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint4 acc = make_uint4(0, 0, 0, 0);
-    for (; i + 7 * stride < n16; i += 8 * stride) {
-        uint4 x[8];
+    for (; i + (UNROLL - 1) * stride < n16; i += UNROLL * stride) {
+        uint4 x[UNROLL];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = pfa_ld_stream(p + i + u * stride);
+        for (int u = 0; u < UNROLL; ++u) x[u] = pfa_ld_stream(p + i + u * stride);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
             acc.x ^= x[u].x; acc.y ^= x[u].y; acc.z ^= x[u].z; acc.w ^= x[u].w;
         }
     }
     for (; i < n16; i += stride) {
         const uint4 x = pfa_ld_stream(p + i);
         acc.x ^= x.x; acc.y ^= x.y; acc.z ^= x.z; acc.w ^= x.w;
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u && acc.x == 0x7f4a7c15u) *sink = acc.x;
+}
+
+// the same bytes through the bulk-copy engine (TMA, cp.async.bulk) into a ring of shared-memory stages, one CTA per SM:
+// bytes in flight are bounded by shared memory (stages x stage size), not by registers
+__global__ void __launch_bounds__(256, 1) pfa_read_probe_tma_kernel(const unsigned char* __restrict__ p, int64_t bytes, int stages,
+                                                                    int stage_bytes, unsigned int* __restrict__ sink) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ uint64_t full[16];
+    const int64_t nblk = (bytes + stage_bytes - 1) / stage_bytes;
+    const int64_t mine = blockIdx.x < nblk ? (nblk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) pfa_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t k) {
+        const int64_t off = ((int64_t)blockIdx.x + k * gridDim.x) * stage_bytes;
+        const unsigned len = (unsigned)min((int64_t)stage_bytes, bytes - off);
+        const int s = (int)(k % stages);
+        pfa_mbar_expect_tx(&full[s], len);
+        pfa_bulk_load(ring + (size_t)s * stage_bytes, p + off, len, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < mine && k < stages; ++k) issue(k);
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = (int)(k % stages);
+        pfa_mbar_wait(&full[s], (unsigned)((k / stages) & 1));
+        const int64_t off = ((int64_t)blockIdx.x + k * gridDim.x) * stage_bytes;
+        const int n16 = (int)(min((int64_t)stage_bytes, bytes - off) / 16);
+        const uint4* q = reinterpret_cast<const uint4*>(ring + (size_t)s * stage_bytes);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+            const uint4 x = q[i];
+            acc.x ^= x.x; acc.y ^= x.y; acc.z ^= x.z; acc.w ^= x.w;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && k + stages < mine) issue(k + stages);
     }
     if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u && acc.x == 0x7f4a7c15u) *sink = acc.x;
 }
@@ -403,10 +590,29 @@ extern "C" int pfa_aln_read_probe(pfa_aln* a, int planes, int reps, double* ms_p
     PFA_CUDA(ctx, cudaEventCreate(&e0));
     PFA_CUDA(ctx, cudaEventCreate(&e1));
     const int64_t n16 = (int64_t)(a->plane_bytes / 16) * planes;  // b0 | b1 | v are one allocation
-    const unsigned grid = (unsigned)ctx->sm_count * 8;
-    pfa_read_probe_kernel<<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);  // warm-up
+    // PFA_PROBE="<blocks per SM>,<loads in flight per thread>" (experiments); default 8 CTAs x 8 loads of 16 bytes
+    int bps = 8, unroll = 8;
+    if (const char* e = getenv("PFA_PROBE")) sscanf(e, "%d,%d", &bps, &unroll);
+    const unsigned grid = (unsigned)ctx->sm_count * (unsigned)std::max(1, bps);
+    int tma_stages = 0, tma_kb = 0;
+    if (const char* e = getenv("PFA_PROBE_TMA")) sscanf(e, "%d,%d", &tma_stages, &tma_kb);  // "<stages>,<KB per stage>"
+    if (tma_stages > 0) {
+        tma_stages = std::min(tma_stages, 16);
+        const size_t smem = (size_t)tma_stages * tma_kb * 1024;
+        cudaError_t ea = cudaFuncSetAttribute(pfa_read_probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "read probe: %s", cudaGetErrorString(ea));
+    }
+    auto launch = [&]() {
+        if (tma_stages > 0)
+            pfa_read_probe_tma_kernel<<<(unsigned)ctx->sm_count, 256, (size_t)tma_stages * tma_kb * 1024, ctx->stream>>>(
+                reinterpret_cast<const unsigned char*>(a->planes), n16 * 16, tma_stages, tma_kb * 1024, sink);
+        else if (unroll >= 16) pfa_read_probe_kernel<16><<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);
+        else if (unroll <= 4) pfa_read_probe_kernel<4><<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);
+        else pfa_read_probe_kernel<8><<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);
+    };
+    launch();  // warm-up
     cudaEventRecord(e0, ctx->stream);
-    for (int r = 0; r < reps; ++r) pfa_read_probe_kernel<<<grid, 256, 0, ctx->stream>>>(a->planes, n16, sink);
+    for (int r = 0; r < reps; ++r) launch();
     cudaEventRecord(e1, ctx->stream);
     cudaError_t e = cudaEventSynchronize(e1);
     float ms = 0.f;

@@ -137,4 +137,32 @@ __device__ __forceinline__ PfaSiteResult pfa_site_result(const uint32_t c[PFA_NC
     return r;
 }
 
+// ---- bulk copies (TMA) into shared memory completing on an mbarrier ------------------------------------------------------
+__device__ __forceinline__ uint32_t pfa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pfa_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pfa_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pfa_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pfa_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pfa_bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pfa_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(pfa_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(pfa_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args);
