@@ -310,14 +310,15 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
 // on the slot's mbarrier.  No block-wide synchronisation: a warp waits for its own slot, copies its chunks to registers,
 // refills the slot for the iteration STAGES ahead and then runs the same passes as the register kernel.
 template <int LPS, int ITER, bool HAS_V, int NT>
-__global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages) {
+__global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages, int m) {
     extern __shared__ __align__(128) unsigned char dyn[];
-    constexpr int GW = 32 / LPS;      // sites per warp iteration
+    constexpr int GW = 32 / LPS;        // sites per warp pass
     constexpr int NPL = HAS_V ? 3 : 2;  // planes read
     constexpr int NWARP = NT / 32;
     const int Wq = a.Wq;
-    const unsigned rec = (unsigned)Wq * 16u;            // bytes of one site record in one plane
-    const unsigned slot_bytes = (unsigned)NPL * GW * rec;  // [plane][site in warp][Wq] uint4
+    const unsigned rec = (unsigned)Wq * 16u;  // bytes of one site record in one plane
+    const int SPS = GW * m;                   // sites per slot: m passes of the warp (narrow records: keeps a copy >= ~2 KB)
+    const unsigned slot_bytes = (unsigned)NPL * SPS * rec;  // [plane][site in slot][Wq] uint4
     unsigned char* ring_base = dyn;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);  // [warp][stage]
     unsigned long long* sm_SH = reinterpret_cast<unsigned long long*>(bars + NWARP * stages);
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteA
     unsigned char* ring = ring_base + (size_t)wib * stages * slot_bytes;
     uint64_t* bar = bars + wib * stages;
     const int64_t gw = (int64_t)blockIdx.x * NWARP + wib, nw = (int64_t)gridDim.x * NWARP;
-    const int64_t nblk = (a.ns + GW - 1) / GW;                       // blocks of GW consecutive sites
+    const int64_t nblk = (a.ns + SPS - 1) / SPS;                     // blocks of SPS consecutive sites
     const int64_t mine = gw < nblk ? (nblk - gw + nw - 1) / nw : 0;  // this warp's blocks: gw, gw + nw, ...
     const unsigned char* planes[3] = {reinterpret_cast<const unsigned char*>(a.b0), reinterpret_cast<const unsigned char*>(a.b1),
                                       reinterpret_cast<const unsigned char*>(a.v)};
@@ -351,13 +352,13 @@ __global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteA
         um[i] = j < Wq ? __ldg(a.umask + j) : make_uint4(0, 0, 0, 0);
     }
     auto issue = [&](int64_t k) {  // lane 0: fetch block k of this warp into slot k % stages
-        const int64_t s0 = (gw + k * nw) * GW;
-        const unsigned nsite = (unsigned)min((int64_t)GW, a.ns - s0);
+        const int64_t s0 = (gw + k * nw) * SPS;
+        const unsigned nsite = (unsigned)min((int64_t)SPS, a.ns - s0);
         const int st = (int)(k % stages);
         pfa_mbar_expect_tx(&bar[st], NPL * nsite * rec);
 #pragma unroll
         for (int p = 0; p < NPL; ++p)
-            pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * GW * rec, planes[p] + (size_t)s0 * rec, nsite * rec, &bar[st]);
+            pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * SPS * rec, planes[p] + (size_t)s0 * rec, nsite * rec, &bar[st]);
     };
     if (lane == 0)
         for (int64_t k = 0; k < mine && k < stages; ++k) issue(k);
@@ -365,25 +366,31 @@ __global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteA
     for (int64_t k = 0; k < mine; ++k) {
         const int st = (int)(k % stages);
         pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
-        const int64_t s = (gw + k * nw) * GW + grp;
-        const uint4* q0 = reinterpret_cast<const uint4*>(ring + (size_t)st * slot_bytes + (size_t)grp * rec);
-        const uint4* q1 = reinterpret_cast<const uint4*>(ring + (size_t)st * slot_bytes + (size_t)(GW + grp) * rec);
-        const uint4* qv = reinterpret_cast<const uint4*>(ring + (size_t)st * slot_bytes + (size_t)(2 * GW + grp) * rec);
-        uint4 x0[ITER], x1[ITER], xv[ITER];
+        const unsigned char* slot = ring + (size_t)st * slot_bytes;
+        for (int t = 0; t < m; ++t) {
+            const int idx = t * GW + grp;  // site of this group inside the slot
+            const int64_t s = (gw + k * nw) * SPS + idx;
+            const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
+            const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
+            const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
+            uint4 x0[ITER], x1[ITER], xv[ITER];
 #pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-            const int j = sub + LPS * i;
-            x0[i] = x1[i] = make_uint4(0, 0, 0, 0);
-            xv[i] = um[i];
-            if (j < Wq && s < a.ns) {
-                x0[i] = q0[j];
-                x1[i] = q1[j];
-                if (HAS_V) xv[i] = qv[j];
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                x0[i] = x1[i] = make_uint4(0, 0, 0, 0);
+                xv[i] = um[i];
+                if (j < Wq && s < a.ns) {
+                    x0[i] = q0[j];
+                    x1[i] = q1[j];
+                    if (HAS_V) xv[i] = qv[j];
+                }
             }
+            if (t == m - 1) {
+                __syncwarp();  // every lane has the slot's last chunks in registers: the slot may be refilled
+                if (lane == 0 && k + stages < mine) issue(k + stages);
+            }
+            if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V>(a, s, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_SH, sm_sfs);
         }
-        __syncwarp();  // every lane has its chunks in registers: the slot may be refilled
-        if (lane == 0 && k + stages < mine) issue(k + stages);
-        if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V>(a, s, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_SH, sm_sfs);
     }
     __syncthreads();
     for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
@@ -452,24 +459,34 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     if (blocks > max_blocks) blocks = max_blocks;
     dim3 grid((unsigned)blocks);
     cudaStream_t st = ctx->stream;
-    // Wide site records (16 or 32 lanes per site) go through the TMA variant: one CTA of 512 threads per SM, every warp
-    // fed by cp.async.bulk through its own shared-memory slot.  Measured 1-2 % above the register-resident kernel on
-    // n = 8,300 ... 20,000 (scripts/probe_k2_tma.py); ONE slot per warp is best -- deeper rings put more bytes in flight
-    // than the memory system likes (7.0 -> 6.5 TB/s at two slots).  PFA_SITE_TMA=<slots> (0 = off), PFA_SITE_TMA_THREADS.
+    // The TMA variant: one CTA of 512 threads per SM, every warp fed by cp.async.bulk through its own shared-memory slot of
+    // about 5 KB per plane (several passes of the warp for narrow records).  Measured against the register-resident kernel
+    // over n = 100 ... 20,000 (scripts/probe_k2_shapes.py): 1-2 % faster at n = 10,000, 6-20 % at n = 2,000 ... 6,000 and
+    // 16,000, ~10 % for n <= 384; slower only for records of 4 ... 10 chunks handled by 1-2 lanes (n = 385 ... 1,280), which
+    // stay on the register kernel.  ONE slot per warp: a second one puts more bytes in flight than the memory system likes
+    // (7.0 -> 6.5 TB/s).  PFA_SITE_TMA=<slots> (0 = off), PFA_SITE_TMA_THREADS, PFA_SITE_TMA_M (passes per slot).
     int tma_stages = 1;
     if (const char* e = getenv("PFA_SITE_TMA")) tma_stages = std::max(0, std::min(16, atoi(e)));
-    if (tma_stages > 0 && !generic && lps >= 16) {
+    bool use_tma = lps >= 4 || a->Wq <= 3;
+    if (const char* e = getenv("PFA_SITE_TMA_MIN_LPS")) use_tma = lps >= std::max(1, atoi(e));
+    if (tma_stages > 0 && !generic && use_tma) {
         int nt = 512;
         if (const char* e = getenv("PFA_SITE_TMA_THREADS")) nt = atoi(e) == 256 ? 256 : 512;
         const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
-        const size_t slot = (size_t)planes * gw * a->Wq * 16, ring = (size_t)nwarp * tma_stages * slot;
-        const size_t dyn = ring + sizeof(uint64_t) * nwarp * tma_stages + smem;
-        const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (a->ns + (int64_t)gw * nwarp - 1) / ((int64_t)gw * nwarp));
+        int m = (int)std::max<int64_t>(1, 5000 / ((int64_t)gw * a->Wq * 16));
+        if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
+        auto dyn_for = [&](int mm) {
+            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * a->Wq * 16) + sizeof(uint64_t) * nwarp * tma_stages + smem;
+        };
+        while (m > 1 && dyn_for(m) > 220 * 1024) --m;
+        const size_t dyn = dyn_for(m);
+        const int64_t per_cta = (int64_t)gw * m * nwarp;
+        const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (a->ns + per_cta - 1) / per_cta);
         bool launched = false;
 #define PFA_TMA_LAUNCH(L_, I_, V_, N_)                                                                                  \
         {                                                                                                                 \
             cudaFuncSetAttribute(pfa_site_scan_tma_kernel<L_, I_, V_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
-            pfa_site_scan_tma_kernel<L_, I_, V_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages);                            \
+            pfa_site_scan_tma_kernel<L_, I_, V_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                         \
         }
 #define PFA_TMA_CASE(L_, I_)                                                                                            \
         if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
@@ -480,6 +497,9 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
             launched = true;                                                                                              \
         }
         PFA_TMA_CASE(16, 3) PFA_TMA_CASE(16, 4) PFA_TMA_CASE(16, 5) PFA_TMA_CASE(32, 3) PFA_TMA_CASE(32, 4) PFA_TMA_CASE(32, 5)
+        PFA_TMA_CASE(1, 1) PFA_TMA_CASE(1, 2) PFA_TMA_CASE(1, 3) PFA_TMA_CASE(1, 4) PFA_TMA_CASE(1, 5)
+        PFA_TMA_CASE(2, 3) PFA_TMA_CASE(2, 4) PFA_TMA_CASE(2, 5) PFA_TMA_CASE(4, 3) PFA_TMA_CASE(4, 4) PFA_TMA_CASE(4, 5)
+        PFA_TMA_CASE(8, 3) PFA_TMA_CASE(8, 4) PFA_TMA_CASE(8, 5)
 #undef PFA_TMA_CASE
 #undef PFA_TMA_LAUNCH
         if (launched) {
