@@ -282,9 +282,203 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const Pf
     if (a.s.x.world) pfa_xchg_epilogue(a.s.x);
 }
 
+__device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 0 ? x.x : w == 1 ? x.y : w == 2 ? x.z : x.w; }
+
+// passes 1 and 2 of one codon column whose three site records are already in registers; shared by the register-resident
+// kernel (chunks loaded from global memory) and the TMA kernel (chunks read from the warp's shared-memory slot)
+template <int LPS, int ITER, bool HAS_V>
+__device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t site0, const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER],
+                                                const uint4 (&xv)[3][ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
+                                                bool one_pop, unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing,
+                                                unsigned& u_sum3) {
+    // ---- pass 1 ----
+    unsigned f = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const uint4 m = um[i];
+            o0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
+            z0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
+            o1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
+            z1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
+            ov |= (xv[t][i].x & m.x) | (xv[t][i].y & m.y) | (xv[t][i].z & m.z) | (xv[t][i].w & m.w);
+            if (HAS_V) zv |= (~xv[t][i].x & m.x) | (~xv[t][i].y & m.y) | (~xv[t][i].z & m.z) | (~xv[t][i].w & m.w);
+        }
+        f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
+    }
+    f = pfa_group_or<LPS>(f, gmask);
+    bool uniform = true, clean = true;
+    int codon = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const unsigned ft = (f >> (6 * t)) & 63u;
+        const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
+        const bool all_escape = (ft & 1u) && (ft & 4u) && !(ft & 16u);
+        uniform = uniform && mono && !all_escape;
+        clean = clean && (ft & 16u) && !(ft & 32u);
+        codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+    }
+    if (uniform) {
+        if (sub == 0) {
+            if (clean) {
+                u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
+                u_sum3 += c_syn3[codon];
+            } else {
+                u_missing += 3;
+            }
+        }
+        return;
+    }
+    // ---- pass 2, common case: exactly ONE of the three sites varies and the other two show one valid base.  Then the
+    // clean codons of a population are that fixed pair combined with the bases present at the variable site, so the
+    // presence mask follows from the four base counts of ONE column (no codon peeling, a third of the popcounts); only
+    // the variable position can carry a label (a label needs codons that differ there). ----
+    int nvar = 0, tv = 0, fixed = 0;
+    bool fixed_valid = true;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const unsigned ft = (f >> (6 * t)) & 63u;
+        const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
+        if (!mono) {
+            ++nvar;
+            tv = t;
+        } else {
+            fixed_valid = fixed_valid && (ft & 16u) && !(ft & 32u);
+            fixed |= (((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0)) << (2 * (2 - t));
+        }
+    }
+    if (nvar == 1 && fixed_valid) {
+        for (int q = 0; q < a.s.k; ++q) {
+            const uint4* mq = a.s.masks + (int64_t)q * Wq;
+            uint32_t c[PFA_NCLASS];
+#pragma unroll
+            for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                uint4 m4 = um[i];
+                if (!one_pop) m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+                const uint4 s0 = tv == 0 ? x0[0][i] : tv == 1 ? x0[1][i] : x0[2][i];
+                const uint4 s1 = tv == 0 ? x1[0][i] : tv == 1 ? x1[1][i] : x1[2][i];
+                const uint4 sv = tv == 0 ? xv[0][i] : tv == 1 ? xv[1][i] : xv[2][i];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t m = pfa_u4(m4, w), w0 = pfa_u4(s0, w), w1 = pfa_u4(s1, w), wv = pfa_u4(sv, w);
+                    const uint32_t vm = HAS_V ? (wv & m) : m;
+                    const uint32_t hi = vm & w1, lo = vm & ~w1;
+                    c[PFA_C_T] += __popc(hi & w0);
+                    c[PFA_C_G] += __popc(hi & ~w0);
+                    c[PFA_C_C] += __popc(lo & w0);
+                    c[PFA_C_A] += __popc(lo & ~w0);
+                    if (HAS_V) {
+                        const uint32_t im = ~wv & m;
+                        const uint32_t ihi = im & w1;
+                        c[PFA_C_ESC] += __popc(ihi & w0);
+                        c[PFA_C_Q] += __popc(ihi & ~w0);
+                        c[PFA_C_N] += __popc(im & ~w1 & w0);
+                    }
+                }
+            }
+            if (LPS > 1) {
+#pragma unroll
+                for (int i = 0; i < PFA_NCLASS; ++i)
+                    if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
+            }
+            if (c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
+            if (sub != 0) continue;
+            const int shift = 2 * (2 - tv);
+            unsigned long long P = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (c[b]) P |= 1ull << (fixed | (b << shift));
+            unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
+                                                    : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
+            pfa_cds_contribute_one(P, c, tv, a.s.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+        }
+        return;
+    }
+    // ---- pass 2, general case ----
+    for (int q = 0; q < a.s.k; ++q) {
+        const uint4* mq = a.s.masks + (int64_t)q * Wq;
+        uint4 m4[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int j = sub + LPS * i;
+            m4[i] = um[i];
+            if (!one_pop) m4[i] = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t cnt[3][PFA_NCLASS];
+        unsigned long long P = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int c = 0; c < PFA_NCLASS; ++c) cnt[t][c] = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t m = pfa_u4(m4[i], w);
+                uint32_t live = m;
+                uint32_t x[6];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t w0 = pfa_u4(x0[t][i], w), w1 = pfa_u4(x1[t][i], w), wv = pfa_u4(xv[t][i], w);
+                    const uint32_t vm = HAS_V ? (wv & m) : m;
+                    const uint32_t hi = vm & w1, lo = vm & ~w1;
+                    cnt[t][PFA_C_T] += __popc(hi & w0);
+                    cnt[t][PFA_C_G] += __popc(hi & ~w0);
+                    cnt[t][PFA_C_C] += __popc(lo & w0);
+                    cnt[t][PFA_C_A] += __popc(lo & ~w0);
+                    if (HAS_V) {
+                        const uint32_t im = ~wv & m;
+                        const uint32_t ihi = im & w1;
+                        cnt[t][PFA_C_ESC] += __popc(ihi & w0);
+                        cnt[t][PFA_C_Q] += __popc(ihi & ~w0);
+                        cnt[t][PFA_C_N] += __popc(im & ~w1 & w0);
+                        live &= wv;
+                    }
+                    x[2 * t] = w1;
+                    x[2 * t + 1] = w0;
+                }
+                while (live) {  // peel one distinct codon per iteration
+                    const int r = __ffs(live) - 1;
+                    uint32_t match = live;
+                    int c = 0;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        const uint32_t bit = (x[t] >> r) & 1u;
+                        c = (c << 1) | (int)bit;
+                        match &= x[t] ^ (bit - 1u);
+                    }
+                    P |= 1ull << c;
+                    live &= ~match;
+                }
+            }
+        if (LPS > 1) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int c = 0; c < PFA_NCLASS; ++c)
+                    if (HAS_V || c < 4) cnt[t][c] = pfa_group_add<LPS>(cnt[t][c], gmask);
+            uint32_t lo = (uint32_t)P, hi = (uint32_t)(P >> 32);
+            lo = pfa_group_or<LPS>(lo, gmask);
+            hi = pfa_group_or<LPS>(hi, gmask);
+            P = ((unsigned long long)hi << 32) | lo;
+        }
+        if (cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
+        if (sub != 0) continue;
+        const uint32_t escd[3] = {0, 0, 0};
+        const unsigned long long escsq[3] = {0, 0, 0};
+        unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
+                                                : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
+        pfa_cds_contribute(P, cnt, a.s.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+    }
+}
+
 // Register-resident variant (Wq <= 3*32 chunks): the three site records of a codon column are loaded once -- all
 // loads back to back -- and pass 1, the class counts and the codon peeling of pass 2 all work on registers.
-__device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 0 ? x.x : w == 1 ? x.y : w == 2 ? x.z : x.w; }
 
 template <int LPS, int ITER, bool HAS_V>
 __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds_scan_reg_kernel(const PfaCdsArgs a) {
@@ -326,189 +520,115 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
                     if (HAS_V) xv[t][i] = pfa_ld_stream(a.s.v + (site0 + t) * Wq + j);
                 }
             }
-        // ---- pass 1 ----
-        unsigned f = 0;
+        pfa_cds_process<LPS, ITER, HAS_V>(a, site0, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_acc, u_nstops, u_missing, u_sum3);
+    }
+    if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
+    for (int off = 16; off; off >>= 1) {
+        u_nstops += __shfl_xor_sync(0xffffffffu, u_nstops, off);
+        u_missing += __shfl_xor_sync(0xffffffffu, u_missing, off);
+        u_sum3 += __shfl_xor_sync(0xffffffffu, u_sum3, off);
+    }
+    if (lane == 0) {
+        if (u_nstops) atomicAdd(&smem[0], (unsigned long long)u_nstops);
+        if (u_missing) atomicAdd(&smem[1], (unsigned long long)u_missing);
+        if (u_sum3) atomicAdd(&smem[2], (unsigned long long)u_sum3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.s.k * PFA_CDS_LEN; i += blockDim.x) {
+        const int e = i % PFA_CDS_LEN;
+        unsigned long long x = a.acc_in_smem ? sm_acc[i] : 0ull;
+        if (e == PFA_CDS_NSTOPS) x += smem[0];
+        if (e == PFA_CDS_MISSING) x += smem[1];
+        if (e == PFA_CDS_SUM3 + 1) x += smem[2];
+        if (x) atomicAdd(reinterpret_cast<unsigned long long*>(a.out) + i, x);
+    }
+    if (a.s.x.world) pfa_xchg_epilogue(a.s.x);
+}
+
+// TMA variant (see pfa_site_scan_tma_kernel): every warp owns one shared-memory slot holding the site records of the codon
+// columns of one or several of its passes (3 * 32/LPS consecutive sites per pass), fed by one cp.async.bulk per plane.
+template <int LPS, int ITER, bool HAS_V, int NT>
+__global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArgs a, int stages, int m) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    constexpr int GW = 32 / LPS;        // codon columns per warp pass
+    constexpr int NPL = HAS_V ? 3 : 2;  // planes read
+    constexpr int NWARP = NT / 32;
+    const int Wq = a.s.Wq;
+    const unsigned rec = (unsigned)Wq * 16u;  // one site record in one plane
+    const int CPS = GW * m;                   // codon columns per slot
+    const unsigned slot_bytes = (unsigned)NPL * CPS * 3u * rec;  // [plane][site in slot][Wq] uint4
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);
+    unsigned long long* smem = reinterpret_cast<unsigned long long*>(bars + NWARP * stages);  // [3] uniform + accumulators
+    const int nacc = 3 + (a.acc_in_smem ? a.s.k * PFA_CDS_LEN : 0);
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) smem[i] = 0ull;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NWARP * stages; ++i) pfa_mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned long long* sm_acc = smem + 3;
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane & (LPS - 1), grp = lane / LPS;
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const bool one_pop = a.s.k == 1;
+    unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;
+    unsigned char* ring = dyn + (size_t)wib * stages * slot_bytes;
+    uint64_t* bar = bars + wib * stages;
+    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib, nw = (int64_t)gridDim.x * NWARP;
+    const int64_t nblk = (a.ncf + CPS - 1) / CPS;                    // blocks of CPS consecutive codon columns
+    const int64_t mine = gw < nblk ? (nblk - gw + nw - 1) / nw : 0;
+    const unsigned char* planes[3] = {reinterpret_cast<const unsigned char*>(a.s.b0), reinterpret_cast<const unsigned char*>(a.s.b1),
+                                      reinterpret_cast<const unsigned char*>(a.s.v)};
+    uint4 um[ITER];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+    for (int i = 0; i < ITER; ++i) {
+        const int j = sub + LPS * i;
+        um[i] = j < Wq ? __ldg(a.s.umask + j) : make_uint4(0, 0, 0, 0);
+    }
+    auto issue = [&](int64_t k) {
+        const int64_t c0 = (gw + k * nw) * CPS;
+        const unsigned ncol = (unsigned)min((int64_t)CPS, a.ncf - c0);
+        const int st = (int)(k % stages);
+        pfa_mbar_expect_tx(&bar[st], NPL * ncol * 3u * rec);
 #pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const uint4 m = um[i];
-                o0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
-                z0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
-                o1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
-                z1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
-                ov |= (xv[t][i].x & m.x) | (xv[t][i].y & m.y) | (xv[t][i].z & m.z) | (xv[t][i].w & m.w);
-                if (HAS_V) zv |= (~xv[t][i].x & m.x) | (~xv[t][i].y & m.y) | (~xv[t][i].z & m.z) | (~xv[t][i].w & m.w);
-            }
-            f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
-        }
-        f = pfa_group_or<LPS>(f, gmask);
-        bool uniform = true, clean = true;
-        int codon = 0;
+        for (int p = 0; p < NPL; ++p)
+            pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * CPS * 3u * rec, planes[p] + (size_t)c0 * 3u * rec, ncol * 3u * rec, &bar[st]);
+    };
+    if (lane == 0)
+        for (int64_t k = 0; k < mine && k < stages; ++k) issue(k);
+
+    for (int64_t k = 0; k < mine; ++k) {
+        const int st = (int)(k % stages);
+        pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
+        const unsigned char* slot = ring + (size_t)st * slot_bytes;
+        for (int t0 = 0; t0 < m; ++t0) {
+            const int idx = t0 * GW + grp;  // codon column of this group inside the slot
+            const int64_t cc = (gw + k * nw) * CPS + idx;
+            uint4 x0[3][ITER], x1[3][ITER], xv[3][ITER];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const unsigned ft = (f >> (6 * t)) & 63u;
-            const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
-            const bool all_escape = (ft & 1u) && (ft & 4u) && !(ft & 16u);
-            uniform = uniform && mono && !all_escape;
-            clean = clean && (ft & 16u) && !(ft & 32u);
-            codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
-        }
-        if (uniform) {
-            if (sub == 0) {
-                if (clean) {
-                    u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
-                    u_sum3 += c_syn3[codon];
-                } else {
-                    u_missing += 3;
-                }
-            }
-            continue;
-        }
-        // ---- pass 2, common case: exactly ONE of the three sites varies and the other two show one valid base.  Then the
-        // clean codons of a population are that fixed pair combined with the bases present at the variable site, so the
-        // presence mask follows from the four base counts of ONE column (no codon peeling, a third of the popcounts); only
-        // the variable position can carry a label (a label needs codons that differ there). ----
-        int nvar = 0, tv = 0, fixed = 0;
-        bool fixed_valid = true;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const unsigned ft = (f >> (6 * t)) & 63u;
-            const bool mono = ((ft & 3u) != 3u) && ((ft & 12u) != 12u) && ((ft & 48u) != 48u);
-            if (!mono) {
-                ++nvar;
-                tv = t;
-            } else {
-                fixed_valid = fixed_valid && (ft & 16u) && !(ft & 32u);
-                fixed |= (((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0)) << (2 * (2 - t));
-            }
-        }
-        if (nvar == 1 && fixed_valid) {
-            for (int q = 0; q < a.s.k; ++q) {
-                const uint4* mq = a.s.masks + (int64_t)q * Wq;
-                uint32_t c[PFA_NCLASS];
-#pragma unroll
-                for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+            for (int t = 0; t < 3; ++t) {
+                const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)(idx * 3 + t) * rec);
+                const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(CPS * 3 + idx * 3 + t) * rec);
+                const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * CPS * 3 + idx * 3 + t) * rec);
 #pragma unroll
                 for (int i = 0; i < ITER; ++i) {
                     const int j = sub + LPS * i;
-                    uint4 m4 = um[i];
-                    if (!one_pop) m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
-                    const uint4 s0 = tv == 0 ? x0[0][i] : tv == 1 ? x0[1][i] : x0[2][i];
-                    const uint4 s1 = tv == 0 ? x1[0][i] : tv == 1 ? x1[1][i] : x1[2][i];
-                    const uint4 sv = tv == 0 ? xv[0][i] : tv == 1 ? xv[1][i] : xv[2][i];
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const uint32_t m = pfa_u4(m4, w), w0 = pfa_u4(s0, w), w1 = pfa_u4(s1, w), wv = pfa_u4(sv, w);
-                        const uint32_t vm = HAS_V ? (wv & m) : m;
-                        const uint32_t hi = vm & w1, lo = vm & ~w1;
-                        c[PFA_C_T] += __popc(hi & w0);
-                        c[PFA_C_G] += __popc(hi & ~w0);
-                        c[PFA_C_C] += __popc(lo & w0);
-                        c[PFA_C_A] += __popc(lo & ~w0);
-                        if (HAS_V) {
-                            const uint32_t im = ~wv & m;
-                            const uint32_t ihi = im & w1;
-                            c[PFA_C_ESC] += __popc(ihi & w0);
-                            c[PFA_C_Q] += __popc(ihi & ~w0);
-                            c[PFA_C_N] += __popc(im & ~w1 & w0);
-                        }
+                    x0[t][i] = x1[t][i] = make_uint4(0, 0, 0, 0);
+                    xv[t][i] = um[i];
+                    if (j < Wq && cc < a.ncf) {
+                        x0[t][i] = q0[j];
+                        x1[t][i] = q1[j];
+                        if (HAS_V) xv[t][i] = qv[j];
                     }
                 }
-                if (LPS > 1) {
-#pragma unroll
-                    for (int i = 0; i < PFA_NCLASS; ++i)
-                        if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
-                }
-                if (c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
-                if (sub != 0) continue;
-                const int shift = 2 * (2 - tv);
-                unsigned long long P = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (c[b]) P |= 1ull << (fixed | (b << shift));
-                unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
-                                                        : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
-                pfa_cds_contribute_one(P, c, tv, a.s.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
             }
-            continue;
-        }
-        // ---- pass 2, general case ----
-        for (int q = 0; q < a.s.k; ++q) {
-            const uint4* mq = a.s.masks + (int64_t)q * Wq;
-            uint4 m4[ITER];
-#pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const int j = sub + LPS * i;
-                m4[i] = um[i];
-                if (!one_pop) m4[i] = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+            if (t0 == m - 1) {
+                __syncwarp();
+                if (lane == 0 && k + stages < mine) issue(k + stages);
             }
-            uint32_t cnt[3][PFA_NCLASS];
-            unsigned long long P = 0;
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-#pragma unroll
-                for (int c = 0; c < PFA_NCLASS; ++c) cnt[t][c] = 0;
-#pragma unroll
-            for (int i = 0; i < ITER; ++i)
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t m = pfa_u4(m4[i], w);
-                    uint32_t live = m;
-                    uint32_t x[6];
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const uint32_t w0 = pfa_u4(x0[t][i], w), w1 = pfa_u4(x1[t][i], w), wv = pfa_u4(xv[t][i], w);
-                        const uint32_t vm = HAS_V ? (wv & m) : m;
-                        const uint32_t hi = vm & w1, lo = vm & ~w1;
-                        cnt[t][PFA_C_T] += __popc(hi & w0);
-                        cnt[t][PFA_C_G] += __popc(hi & ~w0);
-                        cnt[t][PFA_C_C] += __popc(lo & w0);
-                        cnt[t][PFA_C_A] += __popc(lo & ~w0);
-                        if (HAS_V) {
-                            const uint32_t im = ~wv & m;
-                            const uint32_t ihi = im & w1;
-                            cnt[t][PFA_C_ESC] += __popc(ihi & w0);
-                            cnt[t][PFA_C_Q] += __popc(ihi & ~w0);
-                            cnt[t][PFA_C_N] += __popc(im & ~w1 & w0);
-                            live &= wv;
-                        }
-                        x[2 * t] = w1;
-                        x[2 * t + 1] = w0;
-                    }
-                    while (live) {  // peel one distinct codon per iteration
-                        const int r = __ffs(live) - 1;
-                        uint32_t match = live;
-                        int c = 0;
-#pragma unroll
-                        for (int t = 0; t < 6; ++t) {
-                            const uint32_t bit = (x[t] >> r) & 1u;
-                            c = (c << 1) | (int)bit;
-                            match &= x[t] ^ (bit - 1u);
-                        }
-                        P |= 1ull << c;
-                        live &= ~match;
-                    }
-                }
-            if (LPS > 1) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t)
-#pragma unroll
-                    for (int c = 0; c < PFA_NCLASS; ++c)
-                        if (HAS_V || c < 4) cnt[t][c] = pfa_group_add<LPS>(cnt[t][c], gmask);
-                uint32_t lo = (uint32_t)P, hi = (uint32_t)(P >> 32);
-                lo = pfa_group_or<LPS>(lo, gmask);
-                hi = pfa_group_or<LPS>(hi, gmask);
-                P = ((unsigned long long)hi << 32) | lo;
-            }
-            if (cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
-            if (sub != 0) continue;
-            const uint32_t escd[3] = {0, 0, 0};
-            const unsigned long long escsq[3] = {0, 0, 0};
-            unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
-                                                    : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
-            pfa_cds_contribute(P, cnt, a.s.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+            if (cc < a.ncf)
+                pfa_cds_process<LPS, ITER, HAS_V>(a, cc * 3, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_acc, u_nstops, u_missing, u_sum3);
         }
     }
     if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
@@ -663,6 +783,43 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     if (blocks > max_blocks) blocks = max_blocks;
     dim3 grid((unsigned)blocks);
     cudaStream_t st = ctx->stream;
+    // TMA variant: per-warp shared-memory slots of ~5 KB per plane fed by cp.async.bulk (PFA_CDS_TMA=0 turns it off)
+    int tma_stages = 1;
+    if (const char* e = getenv("PFA_CDS_TMA")) tma_stages = std::max(0, std::min(8, atoi(e)));
+    if (tma_stages > 0 && !generic && a->ns >= 3) {
+        const int nt = iter >= 3 ? 256 : 512;
+        const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
+        int m = (int)std::max<int64_t>(1, 10000 / ((int64_t)gw * 3 * a->Wq * 16));
+        if (const char* e = getenv("PFA_CDS_TMA_M")) m = std::max(1, atoi(e));
+        auto dyn_for = [&](int mm) {
+            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16) + sizeof(uint64_t) * nwarp * tma_stages + smem;
+        };
+        while (m > 1 && dyn_for(m) > 220 * 1024) --m;
+        const size_t dyn = dyn_for(m);
+        const int64_t per_cta = (int64_t)gw * m * nwarp;
+        const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (std::max<int64_t>(args.ncf, 1) + per_cta - 1) / per_cta);
+        bool launched = false;
+#define PFA_CDS_TMA_LAUNCH(L_, I_, V_, N_)                                                                              \
+        {                                                                                                                 \
+            cudaFuncSetAttribute(pfa_cds_scan_tma_kernel<L_, I_, V_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
+            pfa_cds_scan_tma_kernel<L_, I_, V_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                          \
+        }
+#define PFA_CDS_TMA_CASE(L_, I_, N_)                                                                                    \
+        if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
+            if (hv) PFA_CDS_TMA_LAUNCH(L_, I_, true, N_)                                                                  \
+            else PFA_CDS_TMA_LAUNCH(L_, I_, false, N_)                                                                    \
+            launched = true;                                                                                              \
+        }
+        PFA_CDS_TMA_CASE(1, 1, 512) PFA_CDS_TMA_CASE(1, 2, 512) PFA_CDS_TMA_CASE(2, 2, 512) PFA_CDS_TMA_CASE(4, 2, 512)
+        PFA_CDS_TMA_CASE(8, 2, 512) PFA_CDS_TMA_CASE(16, 2, 512) PFA_CDS_TMA_CASE(32, 2, 512) PFA_CDS_TMA_CASE(32, 3, 256)
+#undef PFA_CDS_TMA_CASE
+#undef PFA_CDS_TMA_LAUNCH
+        if (launched) {
+            PFA_LAUNCH_CHECK(ctx);
+            if (!x && a->n_exc_sites > 0) return launch_cds_escape(a, args);
+            return PFA_OK;
+        }
+    }
 #define PFA_CDS_CASE(L_, I_)                                                                                          \
     if (lps == L_ && iter == I_) {                                                                                    \
         if (hv) pfa_cds_scan_reg_kernel<L_, I_, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                     \
