@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
 // passes 1 and 2 of one site whose record chunks are already in registers (x0, x1, xv: the lane's ITER chunks of each plane;
 // um: its slice of the union mask).  Shared by the register-resident kernel (chunks loaded from global memory) and the
 // TMA kernel (chunks read from the warp's shared-memory ring).
-template <int LPS, int ITER, bool HAS_V>
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
                                                  const uint4 (&xv)[ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
-                                                 bool one_pop, unsigned long long* sm_SH, unsigned int* sm_sfs) {
+                                                 unsigned long long* sm_SH, unsigned int* sm_sfs) {
+    constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask, lane 0 finishes the site at once
     // ---- pass 1 on registers ----
     uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
 #pragma unroll
@@ -134,6 +135,26 @@ __device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s
         return;
     }
     // ---- pass 2 on registers ----
+    // The popcounts of a population run on all lanes of the group and every lane ends up with the group's sums; what
+    // follows per population (distinct symbols, H, SFS bin, accumulator updates) is scalar work.  Lane q of the group
+    // keeps population q's sums and the scalar parts of all populations run side by side after the loop instead of one
+    // after the other on lane 0 (with more populations than lanes a lane finishes its previous one first).
+    uint32_t mine[PFA_NCLASS];
+    int myq = -1;
+    auto finish = [&](int q, const uint32_t (&c)[PFA_NCLASS]) {
+        const int64_t nq = a.pop_n[q];
+        PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
+        if (r.has_escape) return;
+        if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
+        if (r.isvar) {
+            atomicAdd(&sm_SH[2 * q], 1ull);
+            atomicAdd(&sm_SH[2 * q + 1], r.h);
+            if (r.sfs_bin >= 0) {
+                if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
+                else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
+            }
+        }
+    };
     for (int q = 0; q < a.k; ++q) {
         uint32_t c[PFA_NCLASS];
 #pragma unroll
@@ -168,27 +189,25 @@ __device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s
             for (int i = 0; i < PFA_NCLASS; ++i)
                 if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
         }
-        if (sub != 0) continue;
-        const int64_t nq = a.pop_n[q];
-        PfaSiteResult r = pfa_site_result(c, nq, 0u, 0ull);
-        if (r.has_escape) continue;
-        if (a.isvar) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
-        if (r.isvar) {
-            atomicAdd(&sm_SH[2 * q], 1ull);
-            atomicAdd(&sm_SH[2 * q + 1], r.h);
-            if (r.sfs_bin >= 0) {
-                if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
-                else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
-            }
+        if (one_pop) {  // the common single-population case keeps its short path: lane 0 finishes at once
+            if (sub == 0) finish(0, c);
+            return;
+        }
+        if (sub == (q & (LPS - 1))) {
+            if (myq >= 0) finish(myq, mine);
+#pragma unroll
+            for (int i = 0; i < PFA_NCLASS; ++i) mine[i] = c[i];
+            myq = q;
         }
     }
+    if (myq >= 0) finish(myq, mine);
 }
 
 // Register-resident variant for Wq <= 5*32 chunks: every lane owns ITER fixed chunks of the site record, loads them
 // once (all loads of a site are issued back to back: 2-3 * ITER independent 128-bit requests per lane), keeps its slice
 // of the union mask in registers for the whole kernel, and both passes work on registers -- each byte of the planes
 // crosses L2 exactly once.
-template <int LPS, int ITER, bool HAS_V>
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
 __global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(const PfaSiteArgs a) {
     extern __shared__ unsigned long long smem[];
     if (a.x.world && blockIdx.x == 0 && threadIdx.x == 0) a.x.stamps[5] = pfa_globaltimer();
@@ -205,7 +224,6 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPS;
     const int Wq = a.Wq;
-    const bool one_pop = a.k == 1;
 
     uint4 um[ITER];
 #pragma unroll
@@ -230,7 +248,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, 2) pfa_site_scan_reg_kernel(
                 if (HAS_V) xv[i] = pfa_ld_stream(pv + j);
             }
         }
-        pfa_site_process<LPS, ITER, HAS_V>(a, s, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_SH, sm_sfs);
+        pfa_site_process<LPS, ITER, HAS_V, MULTI>(a, s, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
     }
     __syncthreads();
     for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
@@ -309,8 +327,9 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
 // warp's groups handle in one iteration (contiguous in each plane), fetched with one cp.async.bulk per plane that completes
 // on the slot's mbarrier.  No block-wide synchronisation: a warp waits for its own slot, copies its chunks to registers,
 // refills the slot for the iteration STAGES ahead and then runs the same passes as the register kernel.
-template <int LPS, int ITER, bool HAS_V, int NT>
-__global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages, int m) {
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
+__global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages, int m) {
+    constexpr int NT = 512;
     extern __shared__ __align__(128) unsigned char dyn[];
     constexpr int GW = 32 / LPS;        // sites per warp pass
     constexpr int NPL = HAS_V ? 3 : 2;  // planes read
@@ -336,7 +355,6 @@ __global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteA
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane & (LPS - 1), grp = lane / LPS;
     const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
-    const bool one_pop = a.k == 1;
     unsigned char* ring = ring_base + (size_t)wib * stages * slot_bytes;
     uint64_t* bar = bars + wib * stages;
     const int64_t gw = (int64_t)blockIdx.x * NWARP + wib, nw = (int64_t)gridDim.x * NWARP;
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_site_scan_tma_kernel(const PfaSiteA
                 __syncwarp();  // every lane has the slot's last chunks in registers: the slot may be refilled
                 if (lane == 0 && k + stages < mine) issue(k + stages);
             }
-            if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V>(a, s, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_SH, sm_sfs);
+            if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V, MULTI>(a, s, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
         }
     }
     __syncthreads();
@@ -453,7 +471,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     const size_t smem = sizeof(unsigned long long) * 2 * (size_t)a->k + (args.sfs_in_smem ? sizeof(unsigned int) * (size_t)args.sfs_bins : 0);
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;
     int64_t blocks = (a->ns + groups_per_block - 1) / groups_per_block;
-    const bool hv = a->has_invalid != 0;
+    const bool hv = a->has_invalid != 0, multi = a->k > 1;
     const bool generic = iter > 5 || getenv("PFA_GENERIC_SCAN") != nullptr;
     const int64_t max_blocks = (int64_t)ctx->sm_count * (generic ? 4 : 2);
     if (blocks > max_blocks) blocks = max_blocks;
@@ -464,14 +482,13 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     // over n = 100 ... 20,000 (scripts/probe_k2_shapes.py): 1-2 % faster at n = 10,000, 6-20 % at n = 2,000 ... 6,000 and
     // 16,000, ~10 % for n <= 384; slower only for records of 4 ... 10 chunks handled by 1-2 lanes (n = 385 ... 1,280), which
     // stay on the register kernel.  ONE slot per warp: a second one puts more bytes in flight than the memory system likes
-    // (7.0 -> 6.5 TB/s).  PFA_SITE_TMA=<slots> (0 = off), PFA_SITE_TMA_THREADS, PFA_SITE_TMA_M (passes per slot).
+    // (7.0 -> 6.5 TB/s).  PFA_SITE_TMA=<slots> (0 = off), PFA_SITE_TMA_M (passes per slot).
     int tma_stages = 1;
     if (const char* e = getenv("PFA_SITE_TMA")) tma_stages = std::max(0, std::min(16, atoi(e)));
     bool use_tma = lps >= 4 || a->Wq <= 3;
     if (const char* e = getenv("PFA_SITE_TMA_MIN_LPS")) use_tma = lps >= std::max(1, atoi(e));
     if (tma_stages > 0 && !generic && use_tma) {
-        int nt = 512;
-        if (const char* e = getenv("PFA_SITE_TMA_THREADS")) nt = atoi(e) == 256 ? 256 : 512;
+        const int nt = 512;
         const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
         int m = (int)std::max<int64_t>(1, 5000 / ((int64_t)gw * a->Wq * 16));
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
@@ -483,17 +500,17 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         const int64_t per_cta = (int64_t)gw * m * nwarp;
         const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (a->ns + per_cta - 1) / per_cta);
         bool launched = false;
-#define PFA_TMA_LAUNCH(L_, I_, V_, N_)                                                                                  \
+#define PFA_TMA_LAUNCH(L_, I_, V_, M_)                                                                                  \
         {                                                                                                                 \
-            cudaFuncSetAttribute(pfa_site_scan_tma_kernel<L_, I_, V_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
-            pfa_site_scan_tma_kernel<L_, I_, V_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                         \
+            cudaFuncSetAttribute(pfa_site_scan_tma_kernel<L_, I_, V_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
+            pfa_site_scan_tma_kernel<L_, I_, V_, M_><<<tgrid, nt, dyn, st>>>(args, tma_stages, m);                         \
         }
 #define PFA_TMA_CASE(L_, I_)                                                                                            \
         if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
-            if (hv && nt == 512) PFA_TMA_LAUNCH(L_, I_, true, 512)                                                        \
-            else if (hv) PFA_TMA_LAUNCH(L_, I_, true, 256)                                                                \
-            else if (nt == 512) PFA_TMA_LAUNCH(L_, I_, false, 512)                                                        \
-            else PFA_TMA_LAUNCH(L_, I_, false, 256)                                                                       \
+            if (hv && multi) PFA_TMA_LAUNCH(L_, I_, true, true)                                                           \
+            else if (hv) PFA_TMA_LAUNCH(L_, I_, true, false)                                                              \
+            else if (multi) PFA_TMA_LAUNCH(L_, I_, false, true)                                                           \
+            else PFA_TMA_LAUNCH(L_, I_, false, false)                                                                     \
             launched = true;                                                                                              \
         }
         PFA_TMA_CASE(16, 3) PFA_TMA_CASE(16, 4) PFA_TMA_CASE(16, 5) PFA_TMA_CASE(32, 3) PFA_TMA_CASE(32, 4) PFA_TMA_CASE(32, 5)
@@ -510,8 +527,10 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     }
 #define PFA_REG_CASE(L_, I_)                                                                                          \
     if (lps == L_ && iter == I_) {                                                                                    \
-        if (hv) pfa_site_scan_reg_kernel<L_, I_, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                    \
-        else pfa_site_scan_reg_kernel<L_, I_, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                      \
+        if (hv && multi) pfa_site_scan_reg_kernel<L_, I_, true, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);      \
+        else if (hv) pfa_site_scan_reg_kernel<L_, I_, true, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);         \
+        else if (multi) pfa_site_scan_reg_kernel<L_, I_, false, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);      \
+        else pfa_site_scan_reg_kernel<L_, I_, false, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                \
     } else
     if (generic) {
         switch (lps) {

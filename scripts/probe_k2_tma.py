@@ -21,8 +21,8 @@ with torch.cuda.stream(stream):
                 aln.set_pops(pops)
                 out = torch.zeros(aln.site_len(), dtype=torch.int64, device="cuda")
                 res = []
-                for label, env in (("reg", {"PFA_SITE_TMA": "0"}), ("tma 512x1", {"PFA_SITE_TMA": "1", "PFA_SITE_TMA_THREADS": "512"}),
-                                   ("tma 256x2", {"PFA_SITE_TMA": "2", "PFA_SITE_TMA_THREADS": "256"})):
+                for label, env in (("reg", {"PFA_SITE_TMA": "0"}), ("tma", {"PFA_SITE_TMA": "1"}),
+                                   ("tma 2 slots", {"PFA_SITE_TMA": "2"})):
                     os.environ.update(env)
                     ms = min(timed(lambda: aln.site_stats_device(out.data_ptr())) for _ in range(2))
                     ref = out.cpu().clone() if label == "reg" else ref
