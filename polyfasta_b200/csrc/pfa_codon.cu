@@ -286,11 +286,11 @@ __device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 
 
 // passes 1 and 2 of one codon column whose three site records are already in registers; shared by the register-resident
 // kernel (chunks loaded from global memory) and the TMA kernel (chunks read from the warp's shared-memory slot)
-template <int LPS, int ITER, bool HAS_V>
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t site0, const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER],
                                                 const uint4 (&xv)[3][ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
-                                                bool one_pop, unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing,
-                                                unsigned& u_sum3) {
+                                                unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing, unsigned& u_sum3) {
+    constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask
     // ---- pass 1 ----
     unsigned f = 0;
 #pragma unroll
@@ -350,6 +350,18 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t sit
         }
     }
     if (nvar == 1 && fixed_valid) {
+        uint32_t mine[PFA_NCLASS];
+        int myq = -1;
+        auto finish_one = [&](int q, const uint32_t (&c)[PFA_NCLASS]) {
+            const int shift = 2 * (2 - tv);
+            unsigned long long P = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (c[b]) P |= 1ull << (fixed | (b << shift));
+            unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
+                                                    : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
+            pfa_cds_contribute_one(P, c, tv, a.s.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+        };
         for (int q = 0; q < a.s.k; ++q) {
             const uint4* mq = a.s.masks + (int64_t)q * Wq;
             uint32_t c[PFA_NCLASS];
@@ -386,17 +398,20 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t sit
                 for (int i = 0; i < PFA_NCLASS; ++i)
                     if (HAS_V || i < 4) c[i] = pfa_group_add<LPS>(c[i], gmask);
             }
-            if (c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
-            if (sub != 0) continue;
-            const int shift = 2 * (2 - tv);
-            unsigned long long P = 0;
+            if (c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel (group-uniform: every lane holds the sums)
+            if (one_pop) {
+                if (sub == 0) finish_one(0, c);
+                return;
+            }
+            // several populations: lane q of the group keeps population q's counts, the scalar parts run side by side
+            if (sub == (q & (LPS - 1))) {
+                if (myq >= 0) finish_one(myq, mine);
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (c[b]) P |= 1ull << (fixed | (b << shift));
-            unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
-                                                    : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
-            pfa_cds_contribute_one(P, c, tv, a.s.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+                for (int i = 0; i < PFA_NCLASS; ++i) mine[i] = c[i];
+                myq = q;
+            }
         }
+        if (myq >= 0) finish_one(myq, mine);
         return;
     }
     // ---- pass 2, general case ----
@@ -480,7 +495,7 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t sit
 // Register-resident variant (Wq <= 3*32 chunks): the three site records of a codon column are loaded once -- all
 // loads back to back -- and pass 1, the class counts and the codon peeling of pass 2 all work on registers.
 
-template <int LPS, int ITER, bool HAS_V>
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
 __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds_scan_reg_kernel(const PfaCdsArgs a) {
     extern __shared__ unsigned long long smem[];
     const int nacc = 3 + (a.acc_in_smem ? a.s.k * PFA_CDS_LEN : 0);
@@ -494,7 +509,6 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPS;
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPS;
     const int Wq = a.s.Wq;
-    const bool one_pop = a.s.k == 1;
     unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;
 
     uint4 um[ITER];
@@ -520,7 +534,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
                     if (HAS_V) xv[t][i] = pfa_ld_stream(a.s.v + (site0 + t) * Wq + j);
                 }
             }
-        pfa_cds_process<LPS, ITER, HAS_V>(a, site0, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_acc, u_nstops, u_missing, u_sum3);
+        pfa_cds_process<LPS, ITER, HAS_V, MULTI>(a, site0, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
     }
     if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
     for (int off = 16; off; off >>= 1) {
@@ -547,7 +561,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
 
 // TMA variant (see pfa_site_scan_tma_kernel): every warp owns one shared-memory slot holding the site records of the codon
 // columns of one or several of its passes (3 * 32/LPS consecutive sites per pass), fed by one cp.async.bulk per plane.
-template <int LPS, int ITER, bool HAS_V, int NT>
+template <int LPS, int ITER, bool HAS_V, bool MULTI, int NT>
 __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArgs a, int stages, int m) {
     extern __shared__ __align__(128) unsigned char dyn[];
     constexpr int GW = 32 / LPS;        // codon columns per warp pass
@@ -571,7 +585,6 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane & (LPS - 1), grp = lane / LPS;
     const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
-    const bool one_pop = a.s.k == 1;
     unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;
     unsigned char* ring = dyn + (size_t)wib * stages * slot_bytes;
     uint64_t* bar = bars + wib * stages;
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 if (lane == 0 && k + stages < mine) issue(k + stages);
             }
             if (cc < a.ncf)
-                pfa_cds_process<LPS, ITER, HAS_V>(a, cc * 3, x0, x1, xv, um, sub, gmask, Wq, one_pop, sm_acc, u_nstops, u_missing, u_sum3);
+                pfa_cds_process<LPS, ITER, HAS_V, MULTI>(a, cc * 3, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
         }
     }
     if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
@@ -763,7 +776,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     int lps = 1;
     while (lps < 32 && (a->Wq + lps - 1) / lps > 2) lps *= 2;
     int iter = (a->Wq + lps - 1) / lps;
-    const bool hv = a->has_invalid != 0;
+    const bool hv = a->has_invalid != 0, multi = a->k > 1;
     const bool generic = iter > 3 || getenv("PFA_GENERIC_SCAN") != nullptr;
     if (generic) {
         lps = 1;
@@ -799,15 +812,17 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         const int64_t per_cta = (int64_t)gw * m * nwarp;
         const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (std::max<int64_t>(args.ncf, 1) + per_cta - 1) / per_cta);
         bool launched = false;
-#define PFA_CDS_TMA_LAUNCH(L_, I_, V_, N_)                                                                              \
+#define PFA_CDS_TMA_LAUNCH(L_, I_, V_, M_, N_)                                                                          \
         {                                                                                                                 \
-            cudaFuncSetAttribute(pfa_cds_scan_tma_kernel<L_, I_, V_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
-            pfa_cds_scan_tma_kernel<L_, I_, V_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                          \
+            cudaFuncSetAttribute(pfa_cds_scan_tma_kernel<L_, I_, V_, M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
+            pfa_cds_scan_tma_kernel<L_, I_, V_, M_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                      \
         }
 #define PFA_CDS_TMA_CASE(L_, I_, N_)                                                                                    \
         if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
-            if (hv) PFA_CDS_TMA_LAUNCH(L_, I_, true, N_)                                                                  \
-            else PFA_CDS_TMA_LAUNCH(L_, I_, false, N_)                                                                    \
+            if (hv && multi) PFA_CDS_TMA_LAUNCH(L_, I_, true, true, N_)                                                   \
+            else if (hv) PFA_CDS_TMA_LAUNCH(L_, I_, true, false, N_)                                                      \
+            else if (multi) PFA_CDS_TMA_LAUNCH(L_, I_, false, true, N_)                                                   \
+            else PFA_CDS_TMA_LAUNCH(L_, I_, false, false, N_)                                                             \
             launched = true;                                                                                              \
         }
         PFA_CDS_TMA_CASE(1, 1, 512) PFA_CDS_TMA_CASE(1, 2, 512) PFA_CDS_TMA_CASE(2, 2, 512) PFA_CDS_TMA_CASE(4, 2, 512)
@@ -822,8 +837,10 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     }
 #define PFA_CDS_CASE(L_, I_)                                                                                          \
     if (lps == L_ && iter == I_) {                                                                                    \
-        if (hv) pfa_cds_scan_reg_kernel<L_, I_, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                     \
-        else pfa_cds_scan_reg_kernel<L_, I_, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                       \
+        if (hv && multi) pfa_cds_scan_reg_kernel<L_, I_, true, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);       \
+        else if (hv) pfa_cds_scan_reg_kernel<L_, I_, true, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);          \
+        else if (multi) pfa_cds_scan_reg_kernel<L_, I_, false, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);       \
+        else pfa_cds_scan_reg_kernel<L_, I_, false, false><<<grid, PFA_SITE_THREADS, smem, st>>>(args);                 \
     } else
     if (generic) {
         switch (lps) {
