@@ -108,8 +108,9 @@ int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t col
 // One warp = 32 rows x 64 sites: lane j reads 16 bytes of codes (and 8 bytes of validity) of row 32*w+j.
 //   direct = 0: codes t = A 0, C 1, T 2, G 3 of the ACGT-only packer (b1 = t1, b0 = t0 ^ t1), every base valid;
 //   direct = 1: codes already as the planes want them (A0 C1 G2 T3 / '-'0 'N'1 '?'2); valid == nullptr: every base valid.
+template <bool HAS_VALID, bool DIRECT>
 __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* __restrict__ packed, int64_t ldp,
-                                                                const uint8_t* __restrict__ valid, int64_t ldv, int direct,
+                                                                const uint8_t* __restrict__ valid, int64_t ldv,
                                                                 int64_t n, int64_t cols, int64_t site0, uint32_t* __restrict__ b0,
                                                                 uint32_t* __restrict__ b1, uint32_t* __restrict__ v, int Wn,
                                                                 int* __restrict__ has_invalid) {
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* _
     uint2 vb = live ? make_uint2(0xffffffffu, 0xffffffffu) : make_uint2(0u, 0u);
     if (live) {
         x = __ldg(reinterpret_cast<const uint4*>(packed + row * ldp + (c0 >> 2)));
-        if (valid) vb = __ldg(reinterpret_cast<const uint2*>(valid + row * ldv + (c0 >> 3)));
+        if (HAS_VALID) vb = __ldg(reinterpret_cast<const uint2*>(valid + row * ldv + (c0 >> 3)));
     }
     const uint32_t wlive = __ballot_sync(0xffffffffu, live);
     const uint32_t words[4] = {x.x, x.y, x.z, x.w};
@@ -137,9 +138,9 @@ __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* _
         for (int s = 0; s < 32; ++s) {
             const uint32_t t = (words[2 * h + (s >> 4)] >> (2 * (s & 15))) & 3u;
             const uint32_t w1 = __ballot_sync(0xffffffffu, t & 2u);
-            const uint32_t w0 = __ballot_sync(0xffffffffu, (direct ? t : (t ^ (t >> 1))) & 1u);
+            const uint32_t w0 = __ballot_sync(0xffffffffu, (DIRECT ? t : (t ^ (t >> 1))) & 1u);
             uint32_t wv = wlive;
-            if (valid) wv = __ballot_sync(0xffffffffu, (vwords[h] >> s) & 1u);
+            if (HAS_VALID) wv = __ballot_sync(0xffffffffu, (vwords[h] >> s) & 1u);
             if (lane == s) { my0 = w0; my1 = w1; myv = wv; }
         }
         const int64_t c = c0 + 32 * h + lane;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* _
             if (myv != wlive) any_invalid = true;
         }
     }
-    if (valid && __any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(has_invalid, 1);
+    if (HAS_VALID && __any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(has_invalid, 1);
 }
 
 int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, const uint8_t* d_valid, int64_t ldv, int direct,
@@ -161,8 +162,14 @@ int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, co
         return pfa_fail(ctx, PFA_ERR_ARG, "packed chunk: rows must be 16-byte aligned and padded to 64 bases");
     const int64_t groups = (cols + 63) / 64;
     dim3 grid((unsigned)((groups + 7) / 8), (unsigned)((a->n + 31) / 32));
-    pfa_encode_packed_kernel<<<grid, 256, 0, st>>>(d_packed, ldp, d_valid, ldv, direct, a->n, cols, site0, (uint32_t*)a->b0,
-                                                   (uint32_t*)a->b1, (uint32_t*)a->v, a->Wq * 4, d_has_invalid);
+#define PFA_PACKED_LAUNCH(V_, D_)                                                                                     \
+    pfa_encode_packed_kernel<V_, D_><<<grid, 256, 0, st>>>(d_packed, ldp, d_valid, ldv, a->n, cols, site0, (uint32_t*)a->b0,    \
+                                                           (uint32_t*)a->b1, (uint32_t*)a->v, a->Wq * 4, d_has_invalid)
+    if (d_valid && direct) PFA_PACKED_LAUNCH(true, true);
+    else if (d_valid) PFA_PACKED_LAUNCH(true, false);
+    else if (direct) PFA_PACKED_LAUNCH(false, true);
+    else PFA_PACKED_LAUNCH(false, false);
+#undef PFA_PACKED_LAUNCH
     PFA_LAUNCH_CHECK(ctx);
     return PFA_OK;
 }
