@@ -86,8 +86,7 @@ static inline void line_end(const unsigned char* buf, size_t len, size_t i, bool
 // one segment of the buffer scanned on its own: the sequence lines in front of its first header (they continue the last
 // record of the previous segment) and its records in file order, not yet merged by header
 struct PfaSegment {
-    std::vector<PfaSlice> lead;
-    int64_t lead_len = 0;
+    PfaLines lead;
     std::vector<PfaRecord> recs;
 };
 
@@ -100,17 +99,13 @@ static void scan_segment(const unsigned char* buf, size_t len, size_t lo, size_t
         size_t r = e;
         while (r > i && py_space(buf[r - 1])) --r;
         if (e > i && buf[i] == '>') {
-            seg->recs.push_back(PfaRecord{std::string(reinterpret_cast<const char*>(buf + i + 1), r > i + 1 ? r - (i + 1) : 0), {}, 0});
+            seg->recs.emplace_back();
+            seg->recs.back().header.assign(reinterpret_cast<const char*>(buf + i + 1), r > i + 1 ? r - (i + 1) : 0);
             in_rec = true;
             keep = !seg->recs.back().header.empty();
         } else if (r > i) {
-            if (!in_rec) {
-                seg->lead.push_back(PfaSlice{buf + i, r - i});
-                seg->lead_len += (int64_t)(r - i);
-            } else if (keep) {
-                seg->recs.back().parts.push_back(PfaSlice{buf + i, r - i});
-                seg->recs.back().len += (int64_t)(r - i);
-            }
+            if (!in_rec) seg->lead.add_line(buf + i, r - i);
+            else if (keep) seg->recs.back().lines.add_line(buf + i, r - i);
         }
         i = next;
     }
@@ -145,10 +140,7 @@ int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out) {
     bool seen_header = false, head_nonempty = false;
     size_t cur = 0;
     for (PfaSegment& seg : segs) {
-        if (seen_header && head_nonempty && !seg.lead.empty()) {
-            recs[cur].parts.insert(recs[cur].parts.end(), seg.lead.begin(), seg.lead.end());
-            recs[cur].len += seg.lead_len;
-        }
+        if (seen_header && head_nonempty && seg.lead.nlines) recs[cur].lines.append(seg.lead);
         for (PfaRecord& r : seg.recs) {
             seen_header = true;
             head_nonempty = !r.header.empty();
@@ -159,14 +151,14 @@ int pfa_parse_lines(const unsigned char* buf, size_t len, PfaParsed* out) {
                 recs.push_back(std::move(r));
             } else {
                 cur = it->second;
-                recs[cur].parts = std::move(r.parts);
-                recs[cur].len = r.len;
+                recs[cur].lines = std::move(r.lines);
             }
         }
     }
     if (!seen_header || !head_nonempty) return PFA_ERR_NOT_FASTA;
     out->total = 0;
     out->same = true;
+    for (PfaRecord& rec : recs) rec.len = rec.lines.len;
     for (const PfaRecord& rec : recs) {
         out->total += rec.len;
         if (rec.len != recs[0].len) out->same = false;
@@ -200,10 +192,14 @@ static inline unsigned char or_bytes(const unsigned char* p, size_t n) {
 // returns false when a byte >= 0x80 was seen
 bool pfa_copy_record(const PfaRecord& rec, unsigned char* dst) {
     unsigned char acc = 0;
-    for (const PfaSlice& s : rec.parts) {
-        acc |= or_bytes(s.p, s.len);
-        if (dst != s.p) memmove(dst, s.p, s.len);
-        dst += s.len;
+    for (const PfaRun& r : rec.lines.runs) {
+        // the bytes between the lines of a run are line ends and stripped blanks, all below 0x80: one pass over the span
+        acc |= or_bytes(r.p, (size_t)(r.end() - r.p));
+        for (int64_t i = 0; i < r.count; ++i) {
+            const unsigned char* src = r.p + i * r.stride;
+            if (dst != src) memmove(dst, src, r.w);
+            dst += r.w;
+        }
     }
     return !(acc & 0x80);
 }
@@ -314,14 +310,21 @@ int pfa_fasta_parse_buffer(const void* buf, size_t len, pfa_fasta** out) {
 // ingest's packer, pfa_fasta_copy_row) -- no copy of the file at all.  Files whose wrapping is irregular (blank lines,
 // lines of different widths inside a record), files that cannot be mapped and PFA_PARSE_MMAP=0 take the read path: a
 // malloc'ed buffer filled by several threads with pread, every record compacted in place.
-static bool regular_wrap(const PfaRecord& r, int32_t* w, int32_t* gap) {
-    const std::vector<PfaSlice>& p = r.parts;
-    if (p.size() < 2) return false;
-    const int64_t W = (int64_t)p[0].len, stride = (int64_t)(p[1].p - p[0].p);
+static bool regular_wrap(const PfaRecord& rec, int32_t* w, int32_t* gap) {
+    // every line but the last has one width W, the first bytes of consecutive lines are one stride apart
+    const std::vector<PfaRun>& runs = rec.lines.runs;
+    if (rec.lines.nlines < 2) return false;
+    const int64_t W = (int64_t)runs[0].w;
+    const int64_t stride = runs[0].count > 1 ? runs[0].stride : (int64_t)(runs[1].p - runs[0].p);
     if (W <= 0 || stride <= W || W > 0x7fffffff || stride - W > 0x7fffffff) return false;
-    for (size_t i = 1; i < p.size(); ++i) {
-        if ((int64_t)(p[i].p - p[i - 1].p) != stride) return false;
-        if (i + 1 < p.size() ? (int64_t)p[i].len != W : ((int64_t)p[i].len > W || p[i].len == 0)) return false;
+    int64_t before = 0;
+    for (size_t i = 0; i < runs.size(); ++i) {
+        const PfaRun& r = runs[i];
+        if (r.p != runs[0].p + before * stride) return false;
+        if (r.count > 1 && r.stride != stride) return false;
+        const bool last_line = i + 1 == runs.size() && r.count == 1;
+        if ((int64_t)r.w != W && !(last_line && (int64_t)r.w < W && r.w > 0)) return false;
+        before += r.count;
     }
     *w = (int32_t)W;
     *gap = (int32_t)(stride - W);
@@ -393,12 +396,12 @@ static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
         std::vector<int32_t> ww, wg;
         if (mapped) {
             bool any_wrapped = false, irregular = false;
-            for (const PfaRecord& r : recs) any_wrapped |= r.parts.size() > 1;
+            for (const PfaRecord& r : recs) any_wrapped |= r.lines.nlines > 1;
             if (any_wrapped) {
                 ww.assign(recs.size(), 0);
                 wg.assign(recs.size(), 0);
                 for (size_t k = 0; k < recs.size() && !irregular; ++k)
-                    if (recs[k].parts.size() > 1 && !regular_wrap(recs[k], &ww[k], &wg[k])) irregular = true;
+                    if (recs[k].lines.nlines > 1 && !regular_wrap(recs[k], &ww[k], &wg[k])) irregular = true;
             }
             if (irregular) {
                 release();
@@ -418,7 +421,7 @@ static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
         f->row_off.resize(recs.size() + 1);
         for (size_t k = 0; k < recs.size(); ++k) {
             f->row_len[k] = recs[k].len;
-            f->row_off[k] = recs[k].parts.empty() ? 0 : (int64_t)(recs[k].parts[0].p - buf);
+            f->row_off[k] = recs[k].lines.runs.empty() ? 0 : (int64_t)(recs[k].lines.runs[0].p - buf);
             f->header_off.push_back((int64_t)f->headers.size());
             f->headers += recs[k].header;
         }
@@ -429,13 +432,12 @@ static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
         std::vector<char> non_ascii(nt, 0);
         parallel_run(nt, [&](unsigned t, unsigned n) {
             for (size_t k = t; k < recs.size(); k += n) {
-                if (recs[k].parts.empty()) continue;
+                if (recs[k].lines.runs.empty()) continue;
                 if (mapped) {
                     // one pass over the record's whole span: the bytes between its lines are line ends and stripped blanks,
                     // all below 0x80, so they cannot hide or fake a high bit
-                    const PfaSlice& first = recs[k].parts.front();
-                    const PfaSlice& last = recs[k].parts.back();
-                    if (or_bytes(first.p, (size_t)(last.p + last.len - first.p)) & 0x80) non_ascii[t] = 1;
+                    const unsigned char* first = recs[k].lines.runs.front().p;
+                    if (or_bytes(first, (size_t)(recs[k].lines.runs.back().end() - first)) & 0x80) non_ascii[t] = 1;
                 } else if (!pfa_copy_record(recs[k], buf + f->row_off[k])) {
                     non_ascii[t] = 1;
                 }

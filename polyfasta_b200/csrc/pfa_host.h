@@ -30,14 +30,66 @@ struct pfa_fasta {
 };
 
 // ---- parser internals shared with the batched path --------------------------------------------------------------------
-struct PfaSlice {
+// The sequence lines of a record as RUNS: `count` lines of `w` bytes whose first bytes are `stride` apart.  A sequence
+// on one line is one run of one line; a sequence wrapped at a fixed width is one run (plus one for a shorter last line),
+// whatever its length -- 10^8 lines of a 6 GB file take a few dozen bytes, not 16 bytes each.
+struct PfaRun {
     const unsigned char* p;
-    size_t len;
+    size_t w;
+    int64_t stride;
+    int64_t count;
+    const unsigned char* end() const { return p + (count - 1) * stride + w; }  // one past the last byte of the last line
+};
+struct PfaLines {
+    std::vector<PfaRun> runs;
+    int64_t len = 0;     // bytes of all lines
+    int64_t nlines = 0;
+    void add_line(const unsigned char* p, size_t n) {
+        len += (int64_t)n;
+        ++nlines;
+        if (!runs.empty()) {
+            PfaRun& r = runs.back();
+            if (n == r.w) {
+                if (r.count == 1) {
+                    r.stride = (int64_t)(p - r.p);
+                    r.count = 2;
+                    return;
+                }
+                if (p == r.p + r.count * r.stride) {
+                    ++r.count;
+                    return;
+                }
+            }
+        }
+        runs.push_back(PfaRun{p, n, 0, 1});
+    }
+    void append(const PfaLines& o) {  // the lines of `o` follow these (next segment of the buffer)
+        for (const PfaRun& r : o.runs) {
+            add_line(r.p, r.w);
+            if (r.count == 1) continue;
+            const int64_t rest = r.count - 1;
+            PfaRun& l = runs.back();
+            const bool first_is_tail = l.w == r.w && l.p + (l.count - 1) * l.stride == r.p;
+            if (first_is_tail && l.count >= 2 && l.stride == r.stride) l.count += rest;  // the run goes on
+            else if (first_is_tail && l.count == 1) {                                     // it was pushed as a single line
+                l.stride = r.stride;
+                l.count = r.count;
+            } else {
+                runs.push_back(PfaRun{r.p + r.stride, r.w, r.stride, rest});
+            }
+            len += (int64_t)r.w * rest;
+            nlines += rest;
+        }
+    }
+    void clear() {
+        runs.clear();
+        len = nlines = 0;
+    }
 };
 struct PfaRecord {
     std::string header;
-    std::vector<PfaSlice> parts;
-    int64_t len = 0;
+    PfaLines lines;
+    int64_t len = 0;  // == lines.len (kept for the callers that only need the length)
 };
 struct PfaParsed {
     std::vector<PfaRecord> recs;
