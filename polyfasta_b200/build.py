@@ -11,7 +11,7 @@ SO = os.path.join(HERE, "libpolyfasta_b200.so")
 CU = ["pfa_api.cu", "pfa_encode.cu", "pfa_sites.cu", "pfa_codon.cu", "pfa_pairwise.cu", "pfa_finalize.cu", "pfa_batch.cu", "pfa_xchg.cu", "pfa_ingest.cu"]
 CPP = ["pfa_fasta.cpp", "pfa_codon_rules.cpp", "pfa_pack.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
-              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-deprecated-declarations", "-diag-suppress", "128", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-deprecated-declarations", "-diag-suppress", "128", "-Xptxas", "-v", "--split-compile=0"]
 
 
 def _newer(target, sources):
@@ -29,13 +29,23 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(os.path.dirname(HERE), "include", "polyfasta_b200.h"))
     objs = []
     logs = []
+    todo = []
     for src in CU + CPP:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src + ".o")
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
-            p = subprocess.run(cmd, capture_output=True, text=True)
+            todo.append((src, [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]))
+
+    def compile_one(item):
+        src, cmd = item
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        return src, cmd, p
+
+    # the translation units are independent: compile them side by side (the template-heavy scan kernels dominate)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+        for src, cmd, p in ex.map(compile_one, todo):
             logs.append("$ " + " ".join(cmd) + "\n" + p.stdout + p.stderr)
             if p.returncode != 0:
                 sys.stderr.write(logs[-1])
