@@ -171,7 +171,9 @@ int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix /* host, optional */)
  * (CUDA IPC over NVLink / NVSwitch peer access) and the LAST block of K2 / K4 adds the shard's vector into every
  * rank's buffer with system-scope 64-bit reductions, signals, waits for the other ranks and writes the total to d_out:
  * one launch per scan, no collective library on the data path.  All ranks must issue the same sequence of exchanges
- * (same lengths); a rank that never arrives makes the others time out after 4 s (pfa_xchg_status), not hang.
+ * (same lengths); a rank that never arrives makes the others time out (pfa_xchg_status) instead of hanging: after 4 s
+ * by default, PFA_XCHG_TIMEOUT_MS or pfa_xchg_set_timeout_ms change it.  Ranks should meet on the host (a barrier after
+ * their uploads) before they launch an exchange, so that the wait only has to cover launch skew.
  * Usage: create on every rank -> export -> all-gather the handles on the host -> connect -> host barrier -> scans. */
 typedef struct pfa_xchg pfa_xchg;
 #define PFA_XCHG_HANDLE_BYTES 64
@@ -183,7 +185,8 @@ int pfa_xchg_connect(pfa_xchg* x, int rank, int world, const void* handles /* wo
 /* same with the buffers already addressable (several ranks in ONE process: tests) */
 void* pfa_xchg_base(const pfa_xchg* x);
 int pfa_xchg_connect_ptrs(pfa_xchg* x, int rank, int world, void* const* bases);
-int pfa_xchg_status(pfa_xchg* x, int* timed_out); /* synchronises the ctx stream */
+int pfa_xchg_status(pfa_xchg* x, int* timed_out); /* synchronises the ctx stream; a reported timeout is cleared */
+int pfa_xchg_set_timeout_ms(pfa_xchg* x, int64_t ms);
 /* profiling: %globaltimer (ns) of the last exchange on this rank: [0] last block entered, [1] vector pushed to all ranks,
  * [2] pushes acknowledged (fence), [3] all ranks have signalled, [4] total copied to d_out, [5] block 0 of K2 started */
 int pfa_xchg_stamps(pfa_xchg* x, uint64_t out[8]);

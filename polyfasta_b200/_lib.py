@@ -30,7 +30,7 @@ EXPORTS = [
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
     "pfa_host_pack2", "pfa_host_pack2_rows", "pfa_host_pack3",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
-    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce",
+    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_set_timeout_ms", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce",
 ]
 
 
@@ -143,6 +143,7 @@ def lib():
         "pfa_xchg_base": (p, [p]),
         "pfa_xchg_connect_ptrs": (c.c_int, [p, c.c_int, c.c_int, c.POINTER(p)]),
         "pfa_xchg_status": (c.c_int, [p, c.POINTER(c.c_int)]),
+        "pfa_xchg_set_timeout_ms": (c.c_int, [p, i64]),
         "pfa_xchg_stamps": (c.c_int, [p, c.POINTER(c.c_uint64)]),
         "pfa_site_stats_xchg": (c.c_int, [p, p, p, p]),
         "pfa_cds_stats_xchg": (c.c_int, [p, p, p, p]),

@@ -463,6 +463,10 @@ class Exchange:
         check(lib().pfa_xchg_status(self.handle, ctypes.byref(st)), self.ctx.handle)
         return bool(st.value)
 
+    def set_timeout_ms(self, ms):
+        """how long an exchange waits for a missing rank before it reports a timeout (default 4 s / PFA_XCHG_TIMEOUT_MS)"""
+        check(lib().pfa_xchg_set_timeout_ms(self.handle, int(ms)), self.ctx.handle)
+
     def stamps(self):
         """ns between the stages of the last exchange on this rank: dict(scan, push, fence, wait, copy); scan = first block's start to the last block's arrival (K2 only)"""
         t = (ctypes.c_uint64 * 8)()

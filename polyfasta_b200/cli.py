@@ -157,6 +157,12 @@ class RankGroup:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("gloo", rank=self.rank, world_size=self.world)
         self.xchg = None
+        # the in-kernel exchange maps every rank's buffer with CUDA IPC: one host, at most 16 ranks.  Anything else (several
+        # nodes, more ranks) sums the small count vectors on the host through the rendezvous backend instead.
+        import socket
+        hosts = [None] * self.world
+        dist.all_gather_object(hosts, socket.gethostname())
+        self.fused = self.world <= 16 and len(set(hosts)) == 1 and os.environ.get("POLYFASTA_HOST_ALLREDUCE", "0") != "1"
 
     def exchange(self, ctx, words):
         """an exchange of at least `words` int64 (collective: every rank asks for the same size at the same point)"""
@@ -191,20 +197,35 @@ def sharded_alignment_rows(ctx, group, fasta, file, cds, jc, found):
             api.check(api.lib().pfa_aln_set_pops(aln.handle, m.ctypes.data, len(found)), ctx.handle)
         k = len(found)
         ns, nc = aln.site_len(), api.PFA_CDS_LEN * k
-        x = group.exchange(ctx, max(ns, nc))
         d_site = torch.zeros(ns, dtype=torch.int64, device="cuda:%d" % ctx.device)
         d_cds = torch.zeros(nc, dtype=torch.int64, device="cuda:%d" % ctx.device)
         torch.cuda.synchronize(ctx.device)
-        aln.site_stats_xchg(x, d_site.data_ptr())
-        if cds:
-            aln.cds_stats_xchg(x, d_cds.data_ptr())
-        ctx.sync()
-        if x.timed_out():
-            raise api.PolyFastaError(1, "a rank did not arrive at the exchange")
-        site = aln.unpack_site(d_site.cpu().numpy())
+        if group.fused:
+            x = group.exchange(ctx, max(ns, nc))
+            # the ranks meet on the host AFTER their uploads (parse + ingest times differ by seconds on cold files), so the
+            # wait inside the kernels only has to cover launch skew
+            ctx.sync()
+            group.dist.barrier()
+            aln.site_stats_xchg(x, d_site.data_ptr())
+            if cds:
+                aln.cds_stats_xchg(x, d_cds.data_ptr())
+            ctx.sync()
+            if x.timed_out():
+                raise api.PolyFastaError(1, "a rank did not arrive at the exchange")
+            h_site, h_cds = d_site.cpu(), d_cds.cpu()
+        else:
+            aln.site_stats_device(d_site.data_ptr())
+            if cds:
+                aln.cds_stats_device(d_cds.data_ptr())
+            ctx.sync()
+            h_site, h_cds = d_site.cpu(), d_cds.cpu()
+            group.dist.all_reduce(h_site)
+            if cds:
+                group.dist.all_reduce(h_cds)
+        site = aln.unpack_site(h_site.numpy())
         cdsst = None
         if cds:
-            raw = d_cds.cpu().numpy().reshape(k, api.PFA_CDS_LEN)
+            raw = h_cds.numpy().reshape(k, api.PFA_CDS_LEN)
             ss = ctx.cds_ssites(raw)
             cdsst = []
             for q in range(k):
@@ -390,6 +411,13 @@ def emit(actions, sink):
             raise a[1]
 
 
+def _file_size(p):
+    try:
+        return os.path.getsize(p)
+    except OSError:
+        return 0
+
+
 def devices_from_env():
     """POLYFASTA_DEVICES=0,1,... (or POLYFASTA_DEVICE=0): the GPUs the --dir loci are spread over, round-robin by chunk"""
     spec = os.environ.get("POLYFASTA_DEVICES") or os.environ.get("POLYFASTA_DEVICE") or "0"
@@ -400,26 +428,15 @@ def run_files(paths, cds, jc, popkeys, sink):
     """the per-file loop of PolyFastA.py:104-140 over sorted paths, in chunks; chunk i runs on device i mod G and the
     rows are emitted in the reference's order"""
     from concurrent.futures import ThreadPoolExecutor
+    from . import parallel
     devs = devices_from_env()
-    chunks, cur, cur_bytes = [], [], 0
-    for p in paths:
-        try:
-            sz = os.path.getsize(p)
-        except OSError:
-            sz = 0
-        if cur and (len(cur) >= BATCH_FILES or cur_bytes + sz > BATCH_BYTES):
-            chunks.append(cur)
-            cur, cur_bytes = [], 0
-        cur.append(p)
-        cur_bytes += sz
-    if cur:
-        chunks.append(cur)
+    chunks = [ps for _, ps in parallel.plan_units(paths, [_file_size(p) for p in paths], None, BATCH_FILES, BATCH_BYTES)]
     if len(chunks) > 1 and os.environ.get("POLYFASTA_DOUBLE_BUFFER", "1") != "0":
         devs = [d for d in devs for _ in (0, 1)]   # two slots per GPU: host staging of chunk i+1 overlaps the GPU pass of chunk i
     state = {}
 
     def work(ci):
-        slot = ci % len(devs)   # one context + batch per listed device slot (a context is not re-entrant)
+        slot = parallel.chunk_owner(ci, len(devs))   # one context + batch per listed device slot (a context is not re-entrant)
         if slot not in state:
             ctx = api.Context(devs[slot])
             state[slot] = (ctx, api.Batch(ctx))
@@ -436,7 +453,7 @@ def run_files(paths, cds, jc, popkeys, sink):
     else:
         # one worker thread per device (a context is not re-entrant); ctypes releases the GIL during library calls
         pools = [ThreadPoolExecutor(max_workers=1) for _ in devs]
-        futs = [pools[ci % len(devs)].submit(work, ci) for ci in range(len(chunks))]
+        futs = [pools[parallel.chunk_owner(ci, len(devs))].submit(work, ci) for ci in range(len(chunks))]
         for f in futs:
             emit(f.result(), sink)
         for pl in pools:
@@ -453,25 +470,7 @@ def run_files_ranks(paths, cds, jc, popkeys, sink, group):
     batch = api.Batch(ctx)
     threads = max(1, (os.cpu_count() or 1) // group.world)
     ctx.set_host_threads(threads)
-    units, cur, cur_bytes = [], [], 0
-    for p in paths:
-        try:
-            sz = os.path.getsize(p)
-        except OSError:
-            sz = 0
-        if sz >= SHARD_MIN_BYTES:
-            if cur:
-                units.append(("chunk", cur))
-                cur, cur_bytes = [], 0
-            units.append(("all", [p]))
-            continue
-        if cur and (len(cur) >= BATCH_FILES or cur_bytes + sz > BATCH_BYTES):
-            units.append(("chunk", cur))
-            cur, cur_bytes = [], 0
-        cur.append(p)
-        cur_bytes += sz
-    if cur:
-        units.append(("chunk", cur))
+    units = parallel.plan_units(paths, [_file_size(p) for p in paths], SHARD_MIN_BYTES, BATCH_FILES, BATCH_BYTES)
     mine, j = [], 0
     for ui, (kind, ps) in enumerate(units):
         if kind == "all":
@@ -480,7 +479,7 @@ def run_files_ranks(paths, cds, jc, popkeys, sink, group):
             if group.rank == 0:
                 mine.append((ui, acts))
             continue
-        if j % group.world == group.rank:
+        if parallel.chunk_owner(j, group.world) == group.rank:
             if not cds:
                 acts = process_chunk_native(ctx, batch, ps, jc, popkeys, threads)
             else:

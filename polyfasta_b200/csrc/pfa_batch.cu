@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -506,10 +507,16 @@ int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const
     std::atomic<size_t> cursor((size_t)pfa_round_up((int64_t)b->h_text_used, 256));
     std::vector<size_t> klen((size_t)nkeys);
     for (int j = 0; j < nkeys; ++j) klen[(size_t)j] = strlen(keys[j]);
+    // files whose padded rows did not fit the estimate (many short rows: every row is padded to 32 bytes) are staged in a
+    // second round, after the blob has grown by their exact need
+    std::vector<int> todo((size_t)count), deferred;
+    for (int i = 0; i < count; ++i) todo[(size_t)i] = i;
+    std::vector<char> overflow((size_t)count, 0);
     auto work = [&](int t) {
         std::vector<unsigned char> buf;
         PfaParsed parsed;
-        for (int i = t; i < count; i += threads) {
+        for (size_t ii = (size_t)t; ii < todo.size(); ii += (size_t)threads) {
+            const int i = todo[ii];
             locus[i] = -1;
             shape[2 * i] = shape[2 * i + 1] = 0;
             for (int j = 0; j < nk; ++j) hits[(size_t)i * nk + j] = 0;
@@ -552,7 +559,11 @@ int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const
             }
             const size_t need = (size_t)pfa_round_up((int64_t)((size_t)n * e.ld), 256);
             const size_t off = cursor.fetch_add(need);
-            if (off + need > b->h_text_cap) { status[i] = PFA_BATCH_TOO_BIG; continue; }
+            if (off + need > b->h_text_cap) {
+                status[i] = PFA_BATCH_TOO_BIG;
+                overflow[(size_t)i] = 1;
+                continue;
+            }
             bool ascii = true;
             for (int64_t r = 0; r < n; ++r) ascii &= pfa_copy_record(parsed.recs[(size_t)r], b->h_text + off + (size_t)r * e.ld);
             if (!ascii) { status[i] = PFA_ERR_NON_ASCII; continue; }
@@ -562,12 +573,44 @@ int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const
             status[i] = PFA_OK;
         }
     };
-    if (threads == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
-        for (auto& x : th) x.join();
+    auto run_round = [&]() {
+        const int nt = (int)std::min<size_t>((size_t)threads, todo.size());
+        if (nt <= 1) {
+            const int keep = threads;
+            threads = 1;
+            work(0);
+            threads = keep;
+        } else {
+            const int keep = threads;
+            threads = nt;
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+            threads = keep;
+        }
+    };
+    run_round();
+    size_t extra = 0;
+    for (int i = 0; i < count; ++i)
+        if (overflow[(size_t)i]) {
+            deferred.push_back(i);
+            extra += (size_t)pfa_round_up(shape[2 * i] * pfa_round_up(std::max<int64_t>(shape[2 * i + 1], 1), 32), 256);
+        }
+    if (!deferred.empty()) {
+        // the first round's cursor may have run past the capacity: restart it at the end of what was really written
+        size_t used = (size_t)pfa_round_up((int64_t)b->h_text_used, 256);
+        for (int i = 0; i < count; ++i)
+            if (locus[i] == 0) {
+                const PfaBatchEntry& e = slots[(size_t)i];
+                used = std::max(used, (size_t)e.text_off + (size_t)pfa_round_up((int64_t)((size_t)e.n * e.ld), 256));
+            }
+        b->h_text_used = used;  // grow_text copies this much
+        rc = grow_text(b, used + extra);
+        if (rc) return rc;
+        cursor.store(used);
+        todo = deferred;
+        std::fill(overflow.begin(), overflow.end(), 0);
+        run_round();
     }
     b->h_text_used = std::min(cursor.load(), b->h_text_cap);
     for (int i = 0; i < count; ++i)
@@ -611,6 +654,7 @@ int pfa_batch_run(pfa_batch* b, int jc) {
     int64_t* heads = nullptr;
     const size_t plane_bytes = (size_t)pfa_round_up(std::max<long long>(b->plane_u4, 1) * 16, 256);
     long long cap = std::max<long long>(1 << 16, (long long)(b->h_text_used / 64));
+    if (const char* ev = getenv("PFA_BATCH_EXC_CAP")) cap = std::max<long long>(1, atoll(ev));  // tests: force the retry
     int rc = PFA_OK;
     cudaError_t e = cudaSuccess;
 #define BR(call)                                                                       \
@@ -665,8 +709,26 @@ int pfa_batch_run(pfa_batch* b, int jc) {
         unsigned long long count = 0;
         BR(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, st));
         BR(cudaStreamSynchronize(st));
+        if (e == cudaSuccess && !rc && (long long)count > cap) {
+            // more symbols outside ACGT-N? than the list was sized for (dense IUPAC codes, '.', '*' ...: every character is an
+            // allele in the reference, PolyFastA.py:256-258): encode once more with a list of the exact size.  The planes and
+            // the site scan do not depend on the list, so only K1b runs again.
+            pfa_dfree(ctx, d_keys);
+            d_keys = nullptr;
+            cap = (long long)count;
+            BR(pfa_dmalloc(ctx, &d_keys, sizeof(unsigned long long) * (size_t)cap));
+            BR(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+            if (e == cudaSuccess) {
+                pfa_batch_encode_kernel<<<(unsigned)((b->n_tiles + 7) / 8), 256, 0, st>>>(d_text, d_desc, d_tile_base, nloci, b->n_tiles, (uint32_t*)p0,
+                                                                                        (uint32_t*)p1, (uint32_t*)pv, d_keys, d_count, cap, d_inv);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+            BR(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, st));
+            BR(cudaStreamSynchronize(st));
+            if (e == cudaSuccess && (long long)count != cap) rc = pfa_fail(ctx, PFA_ERR_CUDA, "batched path: the exception list changed between two encodes");
+        }
         if (e == cudaSuccess && !rc && count > 0) {
-            if ((long long)count > cap) rc = pfa_fail(ctx, PFA_ERR_ARG, "batched path: too many non-ACGT/-/N/? symbols (%llu); use the single-alignment path", count);
             int64_t n_heads = 0;
             if (!rc) rc = pfa_sort_exceptions(ctx, &d_keys, (int64_t)count, &heads, &n_heads);
             if (!rc && n_heads > 0) {

@@ -831,6 +831,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
 #undef PFA_CDS_TMA_LAUNCH
         if (launched) {
             PFA_LAUNCH_CHECK(ctx);
+            if (x) pfa_xchg_commit(x);
             if (!x && a->n_exc_sites > 0) return launch_cds_escape(a, args);
             return PFA_OK;
         }
@@ -858,6 +859,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     }
 #undef PFA_CDS_CASE
     PFA_LAUNCH_CHECK(ctx);
+    if (x) pfa_xchg_commit(x);
     if (!x && a->n_exc_sites > 0) return launch_cds_escape(a, args);
     return PFA_OK;
 }

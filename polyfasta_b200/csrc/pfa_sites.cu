@@ -521,6 +521,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
 #undef PFA_TMA_LAUNCH
         if (launched) {
             PFA_LAUNCH_CHECK(ctx);
+            if (x) pfa_xchg_commit(x);
             if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
             return PFA_OK;
         }
@@ -552,6 +553,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     }
 #undef PFA_REG_CASE
     PFA_LAUNCH_CHECK(ctx);
+    if (x) pfa_xchg_commit(x);
     if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
     return PFA_OK;
 }

@@ -2,6 +2,7 @@
 // scan entry points that fuse K2 / K4 with the sum over column shards.  One process per GPU; the handles travel
 // between the processes through whatever the host uses for plumbing (torch.distributed all_gather in
 // polyfasta_b200/parallel.py).
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -16,8 +17,9 @@ struct pfa_xchg {
     unsigned long long* partial = nullptr;  // [cap]
     unsigned int* ticket = nullptr;       // ticket, status
     int rank = 0, world = 0;
-    unsigned int epoch = 0;
+    unsigned int epoch = 0;  // exchanges LAUNCHED so far (pfa_xchg_commit): a call that fails before its launch leaves it alone
     int high_water = 0;
+    unsigned long long timeout_ns = PFA_XCHG_TIMEOUT_NS;
     char* peer[PFA_XCHG_MAX_RANKS] = {};
     bool opened[PFA_XCHG_MAX_RANKS] = {};  // mapped with cudaIpcOpenMemHandle (to be closed)
 };
@@ -37,10 +39,11 @@ int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev) {
     if ((int)len > x->high_water) x->high_water = (int)len;
     dev->world = x->world;
     dev->rank = x->rank;
-    dev->epoch = x->epoch++;
+    dev->epoch = x->epoch;
     dev->len = (int)len;
     dev->zero_len = x->high_water;
     dev->cap = x->cap;
+    dev->timeout_ns = x->timeout_ns;
     dev->partial = x->partial;
     dev->ticket = x->ticket;
     dev->status = x->ticket + 1;
@@ -52,12 +55,17 @@ int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev) {
 
 unsigned long long* pfa_xchg_partial(pfa_xchg* x) { return x->partial; }
 
+// the kernel that carries exchange number x->epoch is in the stream: the next launch uses the other slot.  Called only
+// after a successful launch, so that an argument or launch error leaves this rank in step with its peers.
+void pfa_xchg_commit(pfa_xchg* x) { x->epoch++; }
+
 int pfa_xchg_launch_only(pfa_xchg* x, const int64_t* d_src, int64_t len, int64_t* d_out) {
     PfaXchgDev dev;
     int rc = pfa_xchg_fill(x, len, d_out, &dev);
     if (rc) return rc;
     pfa_xchg_only_kernel<<<1, 256, 0, x->ctx->stream>>>(dev, d_src);
     PFA_LAUNCH_CHECK(x->ctx);
+    pfa_xchg_commit(x);
     return PFA_OK;
 }
 
@@ -70,6 +78,10 @@ int pfa_xchg_create(pfa_ctx* ctx, int64_t cap_words, pfa_xchg** out) {
     pfa_xchg* x = new (std::nothrow) pfa_xchg();
     if (!x) return pfa_fail(ctx, PFA_ERR_NOMEM, "out of host memory");
     x->ctx = ctx;
+    if (const char* e = getenv("PFA_XCHG_TIMEOUT_MS")) {
+        const long long ms = atoll(e);
+        if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
     x->cap = pfa_round_up(cap_words, 32);
     x->bytes = PFA_XCHG_FLAG_BYTES + sizeof(int64_t) * 2 * (size_t)x->cap;
     // plain cudaMalloc: pool (cudaMallocAsync) memory cannot be exported with cudaIpcGetMemHandle
@@ -166,6 +178,16 @@ int pfa_xchg_status(pfa_xchg* x, int* timed_out) {
     PFA_CUDA(ctx, cudaMemcpyAsync(&st, x->ticket + 1, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
     PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *timed_out = (int)st;
+    if (st) {  // reported once: the next exchange starts from a clean status word
+        PFA_CUDA(ctx, cudaMemsetAsync(x->ticket + 1, 0, sizeof(unsigned int), ctx->stream));
+        PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PFA_OK;
+}
+
+int pfa_xchg_set_timeout_ms(pfa_xchg* x, int64_t ms) {
+    if (!x || ms <= 0) return PFA_ERR_ARG;
+    x->timeout_ns = (unsigned long long)ms * 1000000ull;
     return PFA_OK;
 }
 

@@ -14,7 +14,7 @@
 
 #define PFA_XCHG_MAX_RANKS 16
 #define PFA_XCHG_FLAG_BYTES 256  // two 128-byte flag slots in front of the accumulators
-#define PFA_XCHG_TIMEOUT_NS 4000000000ull
+#define PFA_XCHG_TIMEOUT_NS 4000000000ull  // default; PFA_XCHG_TIMEOUT_MS / pfa_xchg_set_timeout_ms override it per exchange
 
 struct PfaXchgDev {
     int world;  // 0: no exchange (single-GPU launches)
@@ -23,6 +23,7 @@ struct PfaXchgDev {
     int len;             // int64 words exchanged by this launch (<= cap)
     int zero_len;        // longest vector exchanged so far (>= len): that much of the idle slot is cleared
     int64_t cap;
+    unsigned long long timeout_ns;  // how long the last block waits for the other ranks' flags before it gives up
     unsigned long long* partial;  // this rank's vector: the blocks add into it; zero at entry, zeroed again at exit
     unsigned int* ticket;         // block counter, zero at entry and at exit
     unsigned int* status;         // set to 1 when the wait timed out (a rank is missing)
@@ -92,7 +93,7 @@ __device__ __forceinline__ void pfa_xchg_epilogue(const PfaXchgDev& x) {
         const unsigned int* mine = pfa_xchg_flag(x.base[x.rank], slot);
         const unsigned long long t0 = pfa_globaltimer();
         while ((int)(pfa_ld_acquire_sys(mine) - want) < 0) {
-            if (pfa_globaltimer() - t0 > PFA_XCHG_TIMEOUT_NS) {
+            if (pfa_globaltimer() - t0 > x.timeout_ns) {
                 *x.status = 1u;
                 break;
             }

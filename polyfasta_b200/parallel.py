@@ -18,17 +18,32 @@ def shard_columns(total, world, rank, multiple=3):
     return begin, end
 
 
-def round_robin(items, world, rank):
-    """the loci of this rank: sorted() order, item i -> rank i mod world"""
-    return [(i, x) for i, x in enumerate(sorted(items)) if i % world == rank]
+def plan_units(paths, sizes, shard_min_bytes, batch_files, batch_bytes):
+    """the work units of a multi-rank run over `paths` (already in the reference's sorted() order, PolyFastA.py:104):
+    ("all", [path]) for a file of at least shard_min_bytes -- ONE alignment whose columns are split over all ranks -- and
+    ("chunk", [paths...]) for runs of smaller files (at most batch_files files / batch_bytes bytes each), which go to
+    single ranks round-robin (chunk_owner).  Units keep the order of `paths`."""
+    units, cur, cur_bytes = [], [], 0
+    for p, sz in zip(paths, sizes):
+        if shard_min_bytes is not None and sz >= shard_min_bytes:
+            if cur:
+                units.append(("chunk", cur))
+                cur, cur_bytes = [], 0
+            units.append(("all", [p]))
+            continue
+        if cur and (len(cur) >= batch_files or cur_bytes + sz > batch_bytes):
+            units.append(("chunk", cur))
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += sz
+    if cur:
+        units.append(("chunk", cur))
+    return units
 
 
-def allreduce_sum(tensor):
-    """in-place sum over ranks of an int64 count vector (NCCL on GPU tensors, gloo on CPU tensors); no-op when not distributed"""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
-    return tensor
+def chunk_owner(j, world):
+    """the rank (or device slot) that processes the j-th chunk: round-robin, no collective"""
+    return j % world
 
 
 def connect_exchange(ctx, cap_words, group=None):

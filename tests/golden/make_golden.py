@@ -156,14 +156,39 @@ cli.append(run_cli(["--pipe", "--name", "locusX"], stdin=file1_text, cwd=HERE))
 cli.append(run_cli(["--pipe", "--cds", "--jc", "-n", "geneY"], stdin=file1_text, cwd=HERE))
 cli.append(run_cli(["-f", "example_theta_0.01/file1.fa", "-d", "example_theta_0.01"], cwd=HERE))
 cli.append(run_cli(["-f", "example_theta_0.01/file1.fa", "-p"], cwd=HERE))
+# data problems are rows, not exceptions (PolyFastA.py:135-140, :246-248, :160, :105-106): small fixtures written here
+edge = os.path.join(HERE, "edge")
+os.makedirs(edge, exist_ok=True)
+edge_files = {
+    "ragged.fa": ">a\nACGTACGT\n>b\nACGTACG\n>c\nACGTACGT\n",
+    "notfasta.txt": "this is not\na fasta file\n",
+    "novar_cds.fa": ">a\nATGGCTAAATTT\n>b\nATGGCTAAATTT\n>c\nATGGCTAAATTT\n",
+    "novar_cds_partial.fa": ">a\nATGGCTAAATT\n>b\nATGGCTAAATT\n",
+    "empty_header_last.fa": ">a\nACGT\n>\nTTTT\n",
+}
+for fn, text in edge_files.items():
+    with open(os.path.join(edge, fn), "w", newline="") as f:
+        f.write(text)
+cli.append(run_cli(["-f", "edge/ragged.fa"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/ragged.fa", "--cds", "--jc"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/notfasta.txt"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/empty_header_last.fa", "-s"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/novar_cds.fa", "--cds"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/novar_cds.fa", "--cds", "--jc", "-s"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/novar_cds_partial.fa", "--cds"], cwd=HERE))
+cli.append(run_cli(["-f", "edge/novar_cds.fa"], cwd=HERE))
+cli.append(run_cli(["-f", "example_theta_0.01/file1.fa", "--pipe"], stdin=file1_text, cwd=HERE))
+cli.append(run_cli(["-f", "edge/ragged.fa", "edge/notfasta.txt", "example_theta_0.01/file2.fa", "edge/novar_cds.fa"], cwd=HERE))
+cli.append(run_cli(["-d", "edge", "-s"], cwd=HERE))
 # --out behaviour: capture both the screen text and the file that was written
-for extra in ([], ["-s"], ["--cds"]):
+for src_args, extra in ((["-d", "example_theta_0.01"], []), (["-d", "example_theta_0.01"], ["-s"]), (["-d", "example_theta_0.01"], ["--cds"]),
+                        (["-d", "edge"], []), (["-d", "edge"], ["--cds"])):
     with tempfile.TemporaryDirectory() as td:
         outp = os.path.join(td, "out.csv")
         with open(outp, "w") as f:
             f.write("PRE-EXISTING LINE\n")
-        r = run_cli(["-d", "example_theta_0.01", "--out", outp] + extra, cwd=HERE)
-        r["args"] = ["-d", "example_theta_0.01", "--out", "@OUT@"] + extra
+        r = run_cli(src_args + ["--out", outp] + extra, cwd=HERE)
+        r["args"] = src_args + ["--out", "@OUT@"] + extra
         r["stdout"] = r["stdout"].replace(outp, "@OUT@")
         with open(outp) as f:
             r["outfile"] = f.read()
@@ -250,7 +275,7 @@ for _ in range(6000):
     if rng.random() < 0.5:
         # clustered sets (few variable positions) are what real data produce
         base = rng.choice(codons)
-        cs = list({base[:i] + x + base[i + 1:] for i in rng.sample(range(3), rng.choice([1, 2])) for x in bases} | {base})
+        cs = sorted({base[:i] + x + base[i + 1:] for i in rng.sample(range(3), rng.choice([1, 2])) for x in bases} | {base})
         rng.shuffle(cs)
         cs = cs[: max(3, rng.randint(3, len(cs)))]
     S, N = ref.get_syn_nonsyn_cod_sites([list(cs), 0])

@@ -174,16 +174,20 @@ def _upper(mat):
     return np.where((mat >= 97) & (mat <= 122), mat - 32, mat).astype(np.uint8)
 
 
+@pytest.mark.parametrize("p_junk", [0.0, 0.01])
 @pytest.mark.parametrize("n,L", [(1, 50), (2, 333), (31, 1000), (32, 999), (33, 1001), (127, 700), (128, 701), (129, 650),
                                  (300, 5000), (1000, 6001), (2049, 3000), (5000, 1500), (10001, 600)])
-def test_against_c_oracle(ctx, n, L):
-    """seeded alignments of many shapes (word / chunk boundary cases for n), three overlapping populations"""
+def test_against_c_oracle(ctx, n, L, p_junk):
+    """seeded alignments of many shapes (word / chunk boundary cases for n), three overlapping populations.
+    p_junk = 0: pure ACGT, i.e. the two-plane (HAS_V = false) instantiations every throughput figure is quoted on;
+    p_junk = 0.01: gaps / N / ? / IUPAC codes, the three-plane instantiations plus the escape kernels"""
     rng = np.random.default_rng(n * 1000003 + L)
-    text = _random_text(rng, n, L)
+    text = _random_text(rng, n, L, p_junk=p_junk)
     up = _upper(text)
     pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n))]
     pops = [p for p in pops if p]
     aln = pf.Alignment.from_rows(ctx, text)
+    assert aln.has_invalid == bool((~np.isin(up, np.frombuffer(b"ACGT", dtype=np.uint8))).any())
     aln.set_pops(pops)
     site = aln.site_stats(want_isvar=True)
     cds = aln.cds_stats(want_labels=True)
@@ -511,15 +515,16 @@ def test_large_file_rows_in_place(ctx, tmp_path, monkeypatch):
     assert (want[0][0][1]["S"], want[0][0][1]["H"]) == (o["S"], o["H"])
 
 
+@pytest.mark.parametrize("p_junk", [0.0, 0.01])
 @pytest.mark.parametrize("n,L,force", [(129, 1500, True), (2049, 900, True), (21000, 240, False), (13000, 303, False)])
-def test_streaming_scan_kernels(ctx, monkeypatch, n, L, force):
+def test_streaming_scan_kernels(ctx, monkeypatch, n, L, force, p_junk):
     """alignments with more rows than the register-resident kernels hold (K2: 20,480, K4: 12,288) go through the streaming
     two-pass kernels; PFA_GENERIC_SCAN=1 forces them for smaller shapes.  Same checks as test_against_c_oracle, plus the
     exchange epilogue (world = 1) on this path."""
     if force:
         monkeypatch.setenv("PFA_GENERIC_SCAN", "1")
     rng = np.random.default_rng(n + 7 * L)
-    text = _random_text(rng, n, L, p_junk=0.01)
+    text = _random_text(rng, n, L, p_junk=p_junk)
     up = _upper(text)
     pops = [list(range(n)), list(range(0, n, 3))]
     aln = pf.Alignment.from_rows(ctx, text)
@@ -549,3 +554,168 @@ def test_streaming_scan_kernels(ctx, monkeypatch, n, L, force):
             assert cds[q][k] == wc[k], (n, L, q, k)
         assert np.array_equal(cds[q]["labels"], wc["labels"])
         assert np.array_equal(fused_c[q], cds[q]["raw"])
+
+
+def _check_site_cds(site, cds, up, pops, what):
+    for q, rows in enumerate(pops):
+        want = co.site_stats(up, rows, per_site=True)
+        assert (site[q]["S"], site[q]["H"], site[q]["sfs"]) == (want["S"], want["H"], want["sfs"]), (what, q)
+        if "isvar" in site[q]:
+            assert np.array_equal(site[q]["isvar"], want["isvar"]), (what, q)
+        wc = co.cds_stats(up, rows, want_labels=True)
+        for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
+            assert cds[q][k] == wc[k], (what, q, k)
+        if "labels" in cds[q]:
+            assert np.array_equal(cds[q]["labels"], wc["labels"]), (what, q)
+        assert math.isclose(cds[q]["ssites"], wc["ssites"], rel_tol=1e-12), (what, q)
+
+
+@pytest.mark.parametrize("pops_kind", ["halves", "one"])
+def test_c3_shape_pure_acgt(ctx, pops_kind):
+    """C3's shape (2,000 rows, in-frame CDS, two populations = the two halves) at 300 kb, pure ACGT from the synthetic
+    generator: the instantiations C3's figures are quoted on -- pfa_cds_scan_tma_kernel<8,2,HAS_V=false,MULTI,512> and
+    pfa_site_scan_tma_kernel<4,4,false,MULTI> -- against the C oracle, bit-exact (PolyFastA.py:252-261, 284-315)"""
+    n, L, seed = 2000, 300_000, 3
+    text = co.synth_text(seed, n, L)
+    pops = [list(range(n // 2)), list(range(n // 2, n))] if pops_kind == "halves" else [list(range(n))]
+    aln = pf.Alignment.from_rows(ctx, text)
+    assert not aln.has_invalid and aln.num_escapes == 0
+    aln.set_pops(pops)
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    aln.free()
+    _check_site_cds(site, cds, text, pops, "c3")
+    assert sum(c["S_s"] + c["S_n"] for c in cds) > 1000   # the case does exercise the variable-column paths
+
+
+@pytest.mark.parametrize("n,L,k", [(200, 30_000, 2), (640, 9_000, 3), (2000, 6_000, 2), (5000, 1_500, 1), (100, 60_000, 2)])
+def test_pure_acgt_multi_population_shapes(ctx, n, L, k):
+    """pure-ACGT (two-plane) register / TMA kernels over the lanes-per-site and chunks-per-lane cases the launcher picks
+    between (Wq = 2 ... 40), with 1-3 populations of unequal size that do not cover all rows"""
+    rng = np.random.default_rng(n * 31 + L)
+    text = _random_text(rng, n, L, p_var=0.08, p_junk=0.0, lower=0.05)
+    up = _upper(text)
+    pops = [list(range(0, n // 2)), list(range(n // 2 + 3, n)), list(range(1, n, 3))][:k]
+    aln = pf.Alignment.from_rows(ctx, text)
+    assert not aln.has_invalid
+    aln.set_pops(pops)
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    aln.free()
+    _check_site_cds(site, cds, up, pops, (n, L, k))
+
+
+def _brute_pairwise(up):
+    """d_ij by one-hot matrix products over the variable columns: an independent numpy restatement of the pairwise loop
+    of nucleotide_diversity3 (PolyFastA.py:469-479)"""
+    var = (up != up[0:1, :]).any(axis=0)
+    sub = up[:, var]
+    same = np.zeros((up.shape[0], up.shape[0]), dtype=np.float64)
+    for sym in np.unique(sub):
+        x = (sub == sym).astype(np.float32)
+        same += x @ x.T
+    return (int(var.sum()) - np.rint(same)).astype(np.int32)
+
+
+@pytest.mark.parametrize("n,L,p_junk", [(2000, 20_000, 0.0), (2000, 20_000, 0.002), (333, 5_000, 0.02), (64, 100_000, 0.0)])
+def test_pairwise_matrix(ctx, n, L, p_junk):
+    """K3: the n x n matrix of pairwise differences against a numpy brute force and the C oracle (matrix and sums per
+    population), at the profiled shape (2,000 rows) with the variable-site compaction at a large L
+    (PolyFastA.py:468-480)"""
+    rng = np.random.default_rng(n + L)
+    text = _random_text(rng, n, L, p_var=0.05, p_junk=p_junk, lower=0.1)
+    up = _upper(text)
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 4, n // 2))]
+    aln = pf.Alignment.from_rows(ctx, text)
+    aln.set_pops(pops)
+    sums, mat = aln.pairwise(want_matrix=True)
+    only_sums = aln.pairwise()
+    site = aln.site_stats()
+    aln.free()
+    brute = _brute_pairwise(up)
+    assert np.array_equal(mat, brute)
+    tot, omat = co.pairwise_sum(up, None, want_matrix=True)
+    assert np.array_equal(mat, omat)
+    assert only_sums == sums
+    for q, rows in enumerate(pops):
+        r = np.asarray(rows)
+        assert sums[q] == int(np.triu(brute[np.ix_(r, r)], 1).sum(dtype=np.int64)), q
+        assert 2 * sums[q] == site[q]["H"], q
+    assert sums[0] == tot
+
+
+def test_integration_stub_runs_as_printed(ctx):
+    """the reference-side ctypes stub of INTEGRATION.md (Option B), executed as printed, against the reference's rows"""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        md = f.read()
+    a = md.index("```python\n# --- PolyFastA.py, after the imports") + len("```python\n")
+    code = md[a: md.index("```", a)].replace('"libpolyfasta_b200.so"', repr(pf._lib.SO_PATH))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    assert isinstance(ns["_pfa"].pfa_global_error(), bytes)
+    kat = load_golden("kat_examples.json")
+    for fn in ("file1.fa", "file7.fa"):
+        d = pf.readfasta(os.path.join(GOLDEN, "example_theta_0.01", fn), False)
+        rec = kat[fn]["pops"]["NA"]
+        for jc in (False, True):
+            check_poly(ns["polymorphism_gpu"](d, 1000, jc), rec["poly_jc%d" % jc], 20, rec["S"], rec["H"])
+    assert ns["polymorphism_gpu"]({"a": "ACGT", "b": "ACGT"}, 4, False) == (0, 0, 0, "NA")
+
+
+def test_batch_exception_list_overflow_retries(ctx, tmp_path):
+    """loci holding far more symbols outside ACGT-N? than the batched path sizes its exception list for ('.', '*', dense
+    IUPAC codes: all alleles in the reference, PolyFastA.py:256-258): K1b is re-run with a list of the exact size instead
+    of failing the chunk; through the API and through --dir"""
+    rng = np.random.default_rng(31)
+    batch = pf.api.Batch(ctx)
+    loci = []
+    for n, L in [(200, 2000), (64, 3000), (300, 700)]:
+        text = _random_text(rng, n, L, p_var=0.2, p_junk=0.35, junk=b"RYKMSW.*BDHV")
+        loci.append((text, batch.add_rows(text, [list(range(n)), list(range(0, n, 2))])))
+    assert sum(int((~np.isin(_upper(t), np.frombuffer(b"ACGT-N?", dtype=np.uint8))).sum()) for t, _ in loci) > (1 << 16)
+    batch.run(jc=False)
+    for text, idx in loci:
+        up = _upper(text)
+        for q, rows in enumerate([list(range(text.shape[0])), list(range(0, text.shape[0], 2))]):
+            got, want = batch.result(idx, q, want_sfs=True), co.site_stats(up, rows)
+            assert (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"])
+    batch.close()
+    d = tmp_path / "dense"
+    d.mkdir()
+    want = {}
+    for i in range(3):
+        n, L = 250, 600
+        text = _upper(_random_text(rng, n, L, p_junk=0.5, junk=b"RYKMSW.*", lower=0.0))
+        rows = [text[r].tobytes().decode() for r in range(n)]
+        with open(d / ("l%d.fa" % i), "w") as f:
+            f.write("".join(">s%d\n%s\n" % (r, s) for r, s in enumerate(rows)))
+        want["l%d.fa" % i] = orc.noncds_row("l%d.fa" % i, L, "NA", rows, False)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "PolyFastA.py"), "-d", str(d), "-s"], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    for ln in p.stdout.strip().split("\n"):
+        _rows_close(ln, want[ln.split(",")[0]])
+
+
+def test_batch_many_short_rows(ctx, tmp_path):
+    """files with many short rows need more staging space than their size (every row is padded to 32 bytes): they are staged
+    in a second round instead of silently leaving the batched path"""
+    rng = np.random.default_rng(32)
+    d = tmp_path / "short"
+    d.mkdir()
+    paths, texts = [], []
+    for i in range(6):
+        n, L = (1500, 6) if i % 2 == 0 else (40, 300)
+        text = _upper(_random_text(rng, n, L, p_var=0.5, lower=0.0))
+        with open(d / ("s%d.fa" % i), "w") as f:
+            f.write("".join(">%d\n%s\n" % (r, text[r].tobytes().decode()) for r in range(n)))
+        paths.append(str(d / ("s%d.fa" % i)))
+        texts.append(text)
+    batch = pf.api.Batch(ctx)
+    info = batch.add_files(paths)
+    assert [fi["status"] for fi in info] == [0] * 6 and sorted(fi["locus"] for fi in info) == list(range(6))
+    batch.run(jc=False)
+    for fi, text in zip(info, texts):
+        got, want = batch.result(fi["locus"], 0, want_sfs=True), co.site_stats(text)
+        assert (fi["n"], fi["L"]) == text.shape and (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"])
+    batch.close()

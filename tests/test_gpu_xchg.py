@@ -54,12 +54,13 @@ def test_single_rank_exchange_equals_plain_scan():
     ctx.close()
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_ranks_in_one_process(world):
+@pytest.mark.parametrize("world,L", [(2, 4099), (3, 4099), (8, 4099), (2, 5), (4, 10), (8, 20)])
+def test_ranks_in_one_process(world, L):
     """`world` ranks on one device, each with its own context / stream / buffer, column shards of one alignment:
-    every rank must end up with the whole alignment's vector"""
+    every rank must end up with the whole alignment's vector.  L = 4099: --cds with a trailing partial codon on the last
+    shard; L < 3 * world: all ranks but the last hold EMPTY shards (the exchange-only launch)"""
     rng = np.random.default_rng(100 + world)
-    n, L = 260, 4099
+    n = 260
     text = _random_text(rng, n, L, p_junk=0.02)
     up = _upper(text)
     pops = [list(range(n)), list(range(1, n, 3))]
@@ -68,6 +69,10 @@ def test_ranks_in_one_process(world):
     oracle = co.site_stats(up, pops[1])
     off1 = 2 + n // 2
     assert (int(want_s[off1]), int(want_s[off1 + 1])) == (oracle["S"], oracle["H"])
+    wc = co.cds_stats(up, pops[1])
+    assert [int(x) for x in want_c[api.PFA_CDS_LEN: api.PFA_CDS_LEN + 6]] == [wc[k] for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n")]
+    if L < 3 * world:
+        assert parallel.shard_columns(L, world, 0) == (0, 0)
     xs = [api.Exchange(c, 1024) for c in ctxs]
     api.Exchange.connect_local(xs)
     shards = []
@@ -116,8 +121,10 @@ def test_missing_rank_times_out_instead_of_hanging():
     api.Exchange.connect_local(xs)
     buf = torch.ones(4, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
+    xs[0].set_timeout_ms(300)
     xs[0].allreduce(buf.data_ptr(), 4)   # rank 1 never calls
     assert xs[0].timed_out()
+    assert not xs[0].timed_out()   # reported once, then cleared
     for x in xs:
         x.close()
     ctx.close()

@@ -37,10 +37,13 @@ def _worker(rank, world, port, n, L, q):
             st = co.site_stats(mat, rows)
             vec += [st["S"], st["H"]] + st["sfs"]
         t = torch.tensor(vec, dtype=torch.int64)
-        parallel.allreduce_sum(t)
-        loci = ["file%d.fa" % i for i in range(1, 12)]
-        mine = parallel.round_robin(loci, world, rank)
-        rows = parallel.gather_rows([(i, "row for " + name) for i, name in mine])
+        dist.all_reduce(t)   # what cli.sharded_alignment_rows does when the fused NVLink exchange is not available
+        # the CLI's own planning: sorted paths -> units -> owner ranks -> gathered rows
+        loci = sorted("file%d.fa" % i for i in range(1, 12))
+        units = parallel.plan_units(loci, [100] * len(loci), 1 << 20, 2, 1 << 30)
+        mine = [(ui, ["row for " + name for name in ps]) for ui, (kind, ps) in enumerate(units)
+                if parallel.chunk_owner(ui, world) == rank]
+        rows = parallel.gather_rows(mine)
         if rank == 0:
             q.put((t.tolist(), rows))
     finally:
@@ -68,7 +71,17 @@ def test_column_shards_allreduce_gloo(world):
         want += [st["S"], st["H"]] + st["sfs"]
     assert got == want
     loci = sorted("file%d.fa" % i for i in range(1, 12))
-    assert rows == [(i, "row for " + name) for i, name in enumerate(loci)]
+    assert [r for _, part in rows for r in part] == ["row for " + name for name in loci]
+    assert [i for i, _ in rows] == list(range(6))
+
+
+def test_plan_units():
+    paths = ["a", "b", "BIG", "c", "d", "e"]
+    sizes = [10, 10, 5000, 10, 10, 10]
+    assert parallel.plan_units(paths, sizes, 1000, 2, 1 << 30) == [("chunk", ["a", "b"]), ("all", ["BIG"]), ("chunk", ["c", "d"]), ("chunk", ["e"])]
+    assert parallel.plan_units(paths, sizes, None, 512, 25) == [("chunk", ["a", "b"]), ("chunk", ["BIG"]), ("chunk", ["c", "d"]), ("chunk", ["e"])]
+    assert parallel.plan_units([], [], 1000, 2, 100) == []
+    assert [parallel.chunk_owner(j, 3) for j in range(5)] == [0, 1, 2, 0, 1]
 
 
 def test_shard_columns_properties():
