@@ -57,6 +57,8 @@ int pfa_ctx_set_host_threads(pfa_ctx* ctx, int threads);
 int pfa_ctx_ingest_stats(const pfa_ctx* ctx, int64_t out[8]);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t pfa_ctx_launch_count(const pfa_ctx* ctx);
+/* the site / codon scan kernel of the last K2 / K4 launch on this context as it was instantiated and launched (benchmarks) */
+const char* pfa_ctx_last_kernel(const pfa_ctx* ctx);
 
 /* ---- ingest: replaces readfasta (PolyFastA.py:227-250) -------------------------------------------- */
 /* Parsing semantics of the reference: a line whose first byte is '>' starts a record, header = rest of
@@ -199,8 +201,9 @@ int pfa_xchg_allreduce(pfa_xchg* x, int64_t* d_buf, int64_t len);
 
 /* ---- batched path for many small loci: replaces the per-file loop of --dir mode (PolyFastA.py:93-94,104) ------------- */
 /* A batch is filled on the host (rows are copied into one pinned blob), then pfa_batch_run does ONE upload, three segmented
- * launches (K1b encode, K2b site scan, K5b finalise; + the escape kernel when needed) and ONE synchronisation.  Non-CDS
- * statistics only; loci with more than 16,384 sequences go through pfa_aln_*. */
+ * launches (K1b encode, K2b site scan, K5b finalise; + the escape kernel when needed) and ONE synchronisation;
+ * pfa_batch_run_cds adds the segmented codon scan K4b (getvarCDSsites per file, PolyFastA.py:104,165) and its K5 entries.
+ * Loci with more than 16,384 sequences (codon scan: 12,288) go through pfa_aln_*. */
 typedef struct pfa_batch pfa_batch;
 int64_t pfa_mask_words_for(int64_t n); /* words of one population mask for an alignment of n rows */
 int pfa_batch_create(pfa_ctx* ctx, pfa_batch** out);
@@ -212,6 +215,10 @@ int64_t pfa_batch_text_bytes(const pfa_batch* b);
 int pfa_batch_add(pfa_batch* b, const pfa_fasta* f, const uint32_t* masks, int k, int64_t* index);
 int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k,
                        int64_t* index);
+/* a locus of the synthetic generator (the alignment pfa_aln_synthetic makes for these parameters): its text is written on the
+ * device when the batch is staged -- benchmarks hold 100,000 loci resident without host text.  Add host loci first. */
+int pfa_batch_add_synthetic(pfa_batch* b, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm, const uint32_t* masks,
+                            int k, int64_t* index);
 /* --dir in one native call: read + parse (reference semantics) + header-substring split + append of `count` files with
  * `threads` host threads, rows copied straight into the pinned blob.  status[i]: PFA_OK, PFA_ERR_NOT_FASTA, PFA_ERR_RAGGED,
  * PFA_ERR_IO, PFA_ERR_NON_ASCII or PFA_BATCH_TOO_BIG (not added: use pfa_aln_*); shape[2i], shape[2i+1] = n, L;
@@ -221,9 +228,18 @@ int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, 
 int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const char* const* keys, int nkeys, int threads,
                         int* status, int64_t* shape, int64_t* locus, int64_t* hits);
 int pfa_batch_run(pfa_batch* b, int jc);
+int pfa_batch_run_cds(pfa_batch* b, int jc);
+/* the two halves of a run, for callers that scan the same resident batch more than once (benchmarks): stage = upload +
+ * K1b (the planes of every locus stay in HBM), scan = K2b [+ K4b] + K5b + result copy, release frees the device side */
+int pfa_batch_stage(pfa_batch* b);
+int pfa_batch_scan(pfa_batch* b, int jc, int cds);
+int pfa_batch_release(pfa_batch* b);
 int pfa_batch_num_pops(const pfa_batch* b, int64_t locus);
 /* counts = {n, S, H}; sfs (optional) n/2 bins; fin (optional) the K5 output of that (locus, population) */
 int pfa_batch_result(const pfa_batch* b, int64_t locus, int pop, int64_t counts[3], int64_t* sfs, void* fin /* pfa_final_out* */);
+/* codon scan of (locus, population): cds = int64[PFA_CDS_LEN] (layout PFA_CDS_*), ssites, fin2 = pfa_final_out[2] for the
+ * synonymous and the nonsynonymous class (polymorphism(var_s, ssites), polymorphism(var_n, nsites), PolyFastA.py:172-173) */
+int pfa_batch_result_cds(const pfa_batch* b, int64_t locus, int pop, int64_t* cds, double* ssites, void* fin2 /* pfa_final_out[2] */);
 /* ingest helpers for --dir: parse many files with `threads` host threads (status[i] = PFA_OK / PFA_ERR_NOT_FASTA / ...), and
  * build the row mask of the headers containing `key` (PolyFastA.py:125); returns the number of matching rows */
 int pfa_fasta_parse_files(const char* const* paths, int count, int threads, pfa_fasta** out, int* status);

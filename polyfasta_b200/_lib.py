@@ -16,7 +16,7 @@ PFA_BATCH_TOO_BIG = 100
 EXPORTS = [
     "pfa_version", "pfa_device_count", "pfa_global_error",
     "pfa_ctx_create", "pfa_ctx_destroy", "pfa_last_error", "pfa_ctx_sync", "pfa_ctx_trim", "pfa_ctx_set_stream", "pfa_ctx_launch_count",
-    "pfa_ctx_set_host_threads", "pfa_ctx_ingest_stats",
+    "pfa_ctx_set_host_threads", "pfa_ctx_ingest_stats", "pfa_ctx_last_kernel",
     "pfa_fasta_parse_file", "pfa_fasta_parse_buffer", "pfa_fasta_free", "pfa_fasta_nseq", "pfa_fasta_seqlen",
     "pfa_fasta_row_len", "pfa_fasta_header", "pfa_fasta_copy_row",
     "pfa_aln_from_fasta", "pfa_aln_from_rows", "pfa_aln_from_device_rows", "pfa_aln_synthetic", "pfa_synth_text_device", "pfa_aln_force_validity", "pfa_aln_free",
@@ -26,7 +26,8 @@ EXPORTS = [
     "pfa_cds_stats_device", "pfa_cds_stats", "pfa_codon_pair_labels", "pfa_codon_set_labels", "pfa_codon_syn3",
     "pfa_codon_class", "pfa_pairwise_device", "pfa_pairwise", "pfa_finalize", "pfa_cds_ssites",
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
-    "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_num_pops", "pfa_batch_result",
+    "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_synthetic", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_run_cds", "pfa_batch_stage", "pfa_batch_scan",
+    "pfa_batch_release", "pfa_batch_num_pops", "pfa_batch_result", "pfa_batch_result_cds",
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
     "pfa_host_pack2", "pfa_host_pack2_rows", "pfa_host_pack3",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
@@ -125,9 +126,16 @@ def lib():
         "pfa_batch_text_bytes": (i64, [p]),
         "pfa_batch_add": (c.c_int, [p, p, p, c.c_int, c.POINTER(i64)]),
         "pfa_batch_add_rows": (c.c_int, [p, p, i64, i64, i64, p, c.c_int, c.POINTER(i64)]),
+        "pfa_batch_add_synthetic": (c.c_int, [p, i64, i64, c.c_uint64, c.c_uint32, c.c_uint32, p, c.c_int, c.POINTER(i64)]),
         "pfa_batch_add_files": (c.c_int, [p, c.POINTER(c.c_char_p), c.c_int, c.POINTER(c.c_char_p), c.c_int, c.c_int,
                                           c.POINTER(c.c_int), c.POINTER(i64), c.POINTER(i64), c.POINTER(i64)]),
+        "pfa_ctx_last_kernel": (c.c_char_p, [p]),
         "pfa_batch_run": (c.c_int, [p, c.c_int]),
+        "pfa_batch_run_cds": (c.c_int, [p, c.c_int]),
+        "pfa_batch_stage": (c.c_int, [p]),
+        "pfa_batch_scan": (c.c_int, [p, c.c_int, c.c_int]),
+        "pfa_batch_release": (c.c_int, [p]),
+        "pfa_batch_result_cds": (c.c_int, [p, i64, c.c_int, p, c.POINTER(c.c_double), p]),
         "pfa_batch_num_pops": (c.c_int, [p, i64]),
         "pfa_batch_result": (c.c_int, [p, i64, c.c_int, c.POINTER(i64), p, c.POINTER(FinalOut)]),
         "pfa_fasta_parse_files": (c.c_int, [c.POINTER(c.c_char_p), c.c_int, c.c_int, c.POINTER(p), c.POINTER(c.c_int)]),

@@ -59,6 +59,11 @@ class Context:
                 "h2d_text_bytes": out[4], "h2d_packed_bytes": out[5], "packed_chunks_with_validity": out[6]}
 
     @property
+    def last_kernel(self):
+        """the scan kernel of the last K2 / K4 launch as instantiated, e.g. 'pfa_site_scan_tma_kernel<LPS=16,ITER=5,...> grid=148 ...'"""
+        return lib().pfa_ctx_last_kernel(self.handle).decode()
+
+    @property
     def launch_count(self):
         return int(lib().pfa_ctx_launch_count(self.handle))
 
@@ -524,7 +529,8 @@ def match_mask(fasta, key):
 
 
 class Batch:
-    """many small loci, one upload + three segmented launches + one synchronisation (pfa_batch); non-CDS statistics"""
+    """many small loci, one upload + a few segmented launches + one synchronisation (pfa_batch): the site scan and, with
+    cds=True, the codon scan of every locus"""
 
     MAX_ROWS = 16384          # Wq <= 128: the batched site kernel keeps a site record in registers
     MAX_LOCUS_BYTES = 64 << 20
@@ -581,6 +587,17 @@ class Batch:
             check(lib().pfa_batch_add_rows(self._h, mat.ctypes.data, n, L, max(L, 1), None, 0, ctypes.byref(idx)), self.ctx.handle)
         return idx.value
 
+    def add_synthetic(self, n, L, seed, p_seg_ppm=50000, tri_ppm=10000, row_lists=None):
+        """a locus of the synthetic generator, produced on the device when the batch is staged (benchmarks)"""
+        idx = ctypes.c_int64()
+        if row_lists:
+            m = rows_to_masks(int(lib().pfa_mask_words_for(n)), row_lists)
+            check(lib().pfa_batch_add_synthetic(self._h, n, L, seed, p_seg_ppm, tri_ppm, m.ctypes.data, len(row_lists), ctypes.byref(idx)),
+                  self.ctx.handle)
+        else:
+            check(lib().pfa_batch_add_synthetic(self._h, n, L, seed, p_seg_ppm, tri_ppm, None, 0, ctypes.byref(idx)), self.ctx.handle)
+        return idx.value
+
     def add_files(self, paths, keys=(), threads=0):
         """read + parse + population split + append of many files in one native call (host threads).
         -> list of dict(status, n, L, locus, hits[list per key, or [n] without keys])"""
@@ -598,8 +615,36 @@ class Batch:
         return [{"status": status[i], "n": shape[2 * i], "L": shape[2 * i + 1], "locus": locus[i],
                  "hits": [hits[i * nk + j] for j in range(nk)]} for i in range(n)]
 
-    def run(self, jc=False):
-        check(lib().pfa_batch_run(self._h, int(bool(jc))), self.ctx.handle)
+    def run(self, jc=False, cds=False):
+        if cds:
+            check(lib().pfa_batch_run_cds(self._h, int(bool(jc))), self.ctx.handle)
+        else:
+            check(lib().pfa_batch_run(self._h, int(bool(jc))), self.ctx.handle)
+
+    def stage(self):
+        """upload + encode: the planes of every locus stay resident until release() / clear()"""
+        check(lib().pfa_batch_stage(self._h), self.ctx.handle)
+
+    def scan(self, jc=False, cds=False):
+        """the segmented scans over the staged batch (may be repeated)"""
+        check(lib().pfa_batch_scan(self._h, int(bool(jc)), int(bool(cds))), self.ctx.handle)
+
+    def release(self):
+        check(lib().pfa_batch_release(self._h), self.ctx.handle)
+
+    def result_cds(self, locus, pop=0):
+        """dict(nstops, missing, S_s, H_s, S_n, H_n, sum3_by_len, ssites, raw, poly_s, poly_n) of the codon scan"""
+        raw = np.zeros(PFA_CDS_LEN, dtype=np.int64)
+        ss = ctypes.c_double()
+        fin = (FinalOut * 2)()
+        check(lib().pfa_batch_result_cds(self._h, locus, pop, raw.ctypes.data, ctypes.byref(ss), fin), self.ctx.handle)
+        d = Alignment.unpack_cds(raw)
+        d["ssites"], d["raw"] = ss.value, raw
+
+        def poly(S, o):
+            return (0, 0, 0, "NA") if o.no_var else (int(S), o.pi_site, o.theta_site, "NA" if o.D_is_NA else o.D)
+        d["poly_s"], d["poly_n"] = poly(d["S_s"], fin[0]), poly(d["S_n"], fin[1])
+        return d
 
     def result(self, locus, pop=0, want_sfs=False):
         """dict(n, S, H[, sfs], poly) with poly = the tuple polymorphism returns"""

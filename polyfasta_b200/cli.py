@@ -339,9 +339,20 @@ def noncds_line(file, seqlen, label, n, r):
     return f"{file},{seqlen},{label},{n},{p[0]},{p[1]},{p[2]},{p[3]}"                          # :196/:198
 
 
-def process_chunk_native(ctx, batch, paths, jc, popkeys, threads):
-    """non-CDS --dir chunk: ONE native call reads, parses, splits and stages every file (host threads), ONE batched GPU pass
-    computes every (locus, population), then the rows are formatted in order"""
+def cds_line(file, seqlen, label, n, site, c):
+    """the --cds row of print_result.no_header (PolyFastA.py:160-180) from the batched results of one (locus, population)"""
+    ssites = c["ssites"]
+    nsites = (seqlen - c["missing"]) - ssites
+    head = f"{file},{round(ssites, 2)},{round(nsites, 2)},{label},{n}"
+    if site["S"] == 0:
+        return head + ",0,0,0,NA,0,0,0,NA,0"                                                   # :160/:162
+    s, m = c["poly_s"], c["poly_n"]
+    return head + f",{s[0]},{m[0]},{s[1]},{m[1]},{s[2]},{m[2]},{s[3]},{m[3]},{c['nstops']}"     # :178/:180
+
+
+def process_chunk_native(ctx, batch, paths, jc, popkeys, threads, cds=False):
+    """--dir chunk: ONE native call reads, parses, splits and stages every file (host threads), ONE batched GPU pass computes
+    every (locus, population) -- the site scan and, with --cds, the codon scan -- then the rows are formatted in order"""
     from ._lib import PFA_BATCH_TOO_BIG, PFA_ERR_IO, PFA_ERR_NON_ASCII, PFA_ERR_NOT_FASTA, PFA_ERR_RAGGED, PFA_OK
     import time
     t0 = time.perf_counter()
@@ -372,8 +383,10 @@ def process_chunk_native(ctx, batch, paths, jc, popkeys, threads):
         elif st == PFA_ERR_RAGGED:
             actions.append(("note", f"# Sequences do not have the same length: {file}"))
         elif st == PFA_BATCH_TOO_BIG:
-            actions.extend(process_chunk(ctx, None, [(path, api.parse_files([path], threads=threads)[0])], False, jc, popkeys))
+            actions.extend(process_chunk(ctx, None, [(path, api.parse_files([path], threads=threads)[0])], cds, jc, popkeys))
         elif st == PFA_OK:
+            if cds and fi["L"] % 3 != 0:
+                actions.append(("note", f"# CDS sequence length is not a multiple of 3: {file}"))   # :114-119
             q = 0
             for label, hits in zip(labels, fi["hits"]):
                 if hits == 0:
@@ -387,10 +400,14 @@ def process_chunk_native(ctx, batch, paths, jc, popkeys, threads):
             break
     t2 = time.perf_counter()
     if pending:
-        batch.run(jc)
+        batch.run(jc, cds)
         t3 = time.perf_counter()
         for pos, locus, q, file, seqlen, label, n in pending:
-            actions[pos] = ("row", noncds_line(file, seqlen, label, n, batch.result(locus, q)), file, label)
+            if cds:
+                line = cds_line(file, seqlen, label, n, batch.result(locus, q), batch.result_cds(locus, q))
+            else:
+                line = noncds_line(file, seqlen, label, n, batch.result(locus, q))
+            actions[pos] = ("row", line, file, label)
     else:
         t3 = t2
     if os.environ.get("POLYFASTA_TIMING"):
@@ -442,10 +459,7 @@ def run_files(paths, cds, jc, popkeys, sink):
             state[slot] = (ctx, api.Batch(ctx))
         ctx, batch = state[slot]
         threads = max(1, (os.cpu_count() or 1) // len(devs))
-        if not cds:
-            return process_chunk_native(ctx, batch, chunks[ci], jc, popkeys, threads)
-        fastas = api.parse_files(chunks[ci], threads=threads)
-        return process_chunk(ctx, batch, list(zip(chunks[ci], fastas)), cds, jc, popkeys)
+        return process_chunk_native(ctx, batch, chunks[ci], jc, popkeys, threads, cds)
 
     if len(devs) == 1 or len(chunks) == 1:
         for ci in range(len(chunks)):
@@ -480,11 +494,7 @@ def run_files_ranks(paths, cds, jc, popkeys, sink, group):
                 mine.append((ui, acts))
             continue
         if parallel.chunk_owner(j, group.world) == group.rank:
-            if not cds:
-                acts = process_chunk_native(ctx, batch, ps, jc, popkeys, threads)
-            else:
-                acts = process_chunk(ctx, batch, list(zip(ps, api.parse_files(ps, threads=threads))), cds, jc, popkeys)
-            mine.append((ui, acts))
+            mine.append((ui, process_chunk_native(ctx, batch, ps, jc, popkeys, threads, cds)))
         j += 1
     group.close(ctx)
     gathered = parallel.gather_rows(mine)

@@ -33,6 +33,15 @@ int pfa_fail(pfa_ctx* ctx, int code, const char* fmt, ...) {
 }
 
 
+void pfa_note_kernel(pfa_ctx* ctx, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    ctx->last_kernel = buf;
+}
+
 // run a *_device entry point into temporary device buffers and copy the results to the host
 template <typename F>
 static int run_to_host(pfa_aln* a, size_t out_bytes, void* out, size_t aux_bytes, void* aux, F launch) {
@@ -137,6 +146,7 @@ int pfa_ctx_destroy(pfa_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     for (int i = 0; i < 3; ++i) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_encoded[i]) cudaEventDestroy(ctx->ev_encoded[i]);
@@ -166,6 +176,7 @@ int pfa_ctx_trim(pfa_ctx* ctx) {
 }
 
 const char* pfa_last_error(const pfa_ctx* ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+const char* pfa_ctx_last_kernel(const pfa_ctx* ctx) { return ctx ? ctx->last_kernel.c_str() : ""; }
 
 int pfa_ctx_sync(pfa_ctx* ctx) {
     if (!ctx) return PFA_ERR_ARG;
@@ -409,8 +420,18 @@ int pfa_aln_default_pop(pfa_aln* a) {
     return pfa_aln_set_pops(a, all.data(), 1);
 }
 
+int pfa_ctx_work(pfa_ctx* ctx, unsigned int** out) {
+    if (!ctx->d_work) {
+        PFA_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_work), 256));
+        PFA_CUDA(ctx, cudaMemset(ctx->d_work, 0, 256));
+    }
+    *out = ctx->d_work;
+    return PFA_OK;
+}
+
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args) {
     memset(&args->x, 0, sizeof args->x);
+    args->work = a->ctx->d_work;
     args->b0 = a->b0;
     args->b1 = a->b1;
     args->v = a->v;

@@ -12,30 +12,17 @@
 #include <new>
 #include <thread>
 
+#include "pfa_batch.cuh"
 #include "pfa_host.h"
 #include "pfa_sites.cuh"
-
-struct PfaLocusDesc {
-    long long text_off;   // byte offset of the locus' text matrix in the blob
-    long long plane_off;  // uint4 offset of its first site record in each plane
-    long long mask_off;   // uint4 offset of its masks ([k][Wq], then the union [Wq])
-    long long site_base;  // global index of its first site (exception keys, group prefix)
-    long long tile_base;  // first K1b tile
-    long long pop_base;   // first (locus, population) slot
-    int n, L, ld, Wq, k, pad;
-};
-
-struct PfaPopSlot {
-    long long n;        // rows in the population
-    long long out_off;  // offset of [S, H, sfs...] in the batch result vector
-    long long locus;
-    double seqlen;
-};
 
 // one locus as added on the host; the device layout (PfaLocusDesc / PfaPopSlot) is derived from these in pfa_batch_run
 struct PfaBatchEntry {
     long long text_off = 0;
     int n = 0, L = 0, ld = 0, Wq = 0, k = 0;
+    bool synthetic = false;  // the text is written on the device by the synthetic generator (benchmarks): nothing to upload
+    uint64_t seed = 0;
+    uint32_t p_seg_ppm = 0, tri_ppm = 0;
     std::vector<uint32_t> masks;    // [k][4*Wq]
     std::vector<long long> pop_n;   // [k]
 };
@@ -48,12 +35,36 @@ struct pfa_batch {
     std::vector<uint32_t> masks;  // per locus: k masks then the union, each 4*Wq words
     unsigned char* h_text = nullptr;  // pinned
     size_t h_text_cap = 0, h_text_used = 0;
+    size_t synth_bytes = 0;  // device-only text of synthetic loci, laid out after the host text (host loci must be added first)
     long long n_sites = 0, n_tiles = 0, plane_u4 = 0, mask_u4 = 0, out_len = 0;
     int max_Wq = 0;
+    long long n_ctiles = 0;
     // results (host)
     std::vector<int64_t> out;
     std::vector<pfa_final_out> fin;
-    bool ran = false;
+    std::vector<int64_t> cds_out;         // [pops][PFA_CDS_LEN] (codon scan)
+    std::vector<double> cds_ssites;       // [pops]
+    std::vector<pfa_final_out> cds_fin;   // [pops][2]: synonymous, nonsynonymous
+    bool ran = false, ran_cds = false;
+    // device state between pfa_batch_stage and pfa_batch_release: the encoded planes of the whole batch and everything the
+    // segmented kernels read
+    struct Dev {
+        uint8_t* text = nullptr;
+        PfaLocusDesc* desc = nullptr;
+        PfaPopSlot* pops = nullptr;
+        long long *site_base = nullptr, *tile_base = nullptr, *ctile_base = nullptr, *out = nullptr, *cds_out = nullptr, *popn = nullptr;
+        uint4 *planes = nullptr, *masks = nullptr;
+        int* inv = nullptr;
+        unsigned long long *count = nullptr, *keys = nullptr;
+        pfa_final_in* fin_in = nullptr;
+        pfa_final_out* fin_out = nullptr;
+        double* ssites = nullptr;
+        int64_t* heads = nullptr;
+        int64_t n_heads = 0;
+        unsigned long long n_exc = 0;
+        size_t plane_bytes = 0;
+        bool staged = false;
+    } dev;
 };
 
 static int grow_text(pfa_batch* b, size_t need) {
@@ -78,17 +89,6 @@ static inline int wq_of(int64_t n) {
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ int pfa_find_locus(const long long* __restrict__ base, int nloci, long long x) {
-    // largest i with base[i] <= x ; base has nloci + 1 entries
-    int lo = 0, hi = nloci;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (base[mid] <= x) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
 
 __device__ __forceinline__ unsigned pfa_classify_byte(unsigned c) {
     if (c >= 'a' && c <= 'z') c -= 32;
@@ -167,20 +167,6 @@ __global__ void __launch_bounds__(256) pfa_batch_encode_kernel(const uint8_t* __
         b0[o] = my0; b1[o] = my1; v[o] = myv;
     }
 }
-
-struct PfaBatchArgs {
-    const uint4* b0;
-    const uint4* b1;
-    const uint4* v;
-    const uint4* masks;
-    const PfaLocusDesc* desc;
-    const PfaPopSlot* pops;
-    const long long* site_base;  // nloci + 1
-    const int* locus_invalid;
-    long long* out;
-    long long n_sites;
-    int nloci;
-};
 
 // K2b: a group of LPS lanes owns one site of one locus; same two passes as pfa_site_scan_reg_kernel, accumulators in global
 // memory (only variable columns touch them)
@@ -359,12 +345,17 @@ int pfa_batch_clear(pfa_batch* b) {
     if (!b) return PFA_ERR_ARG;
     b->entries.clear();
     b->h_text_used = 0;
-    b->ran = false;
+    b->synth_bytes = 0;
+    b->ran = b->ran_cds = false;
+    pfa_batch_release(b);
     return PFA_OK;
 }
 
+int pfa_batch_release(pfa_batch* b);
+
 int pfa_batch_destroy(pfa_batch* b) {
     if (!b) return PFA_OK;
+    pfa_batch_release(b);
     if (b->h_text) cudaFreeHost(b->h_text);
     delete b;
     return PFA_OK;
@@ -402,7 +393,7 @@ static void build_layout(pfa_batch* b) {
     b->desc.clear();
     b->pops.clear();
     b->masks.clear();
-    b->n_sites = b->n_tiles = b->plane_u4 = b->mask_u4 = b->out_len = 0;
+    b->n_sites = b->n_tiles = b->plane_u4 = b->mask_u4 = b->out_len = b->n_ctiles = 0;
     b->max_Wq = 0;
     for (size_t i = 0; i < b->entries.size(); ++i) {
         const PfaBatchEntry& e = b->entries[i];
@@ -445,6 +436,7 @@ extern "C" {
 int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, int64_t ld, const uint32_t* masks, int k, int64_t* index) {
     if (!b || n <= 0 || L < 0 || (L > 0 && (!text || ld < L)) || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
     if (L >= (1ll << 31) || wq_of(n) > PFA_BATCH_MAX_WQ) return pfa_fail(b->ctx, PFA_ERR_ARG, "locus too large for the batched path");
+    if (b->synth_bytes) return pfa_fail(b->ctx, PFA_ERR_ARG, "host loci must be added before synthetic ones");
     PfaBatchEntry e;
     e.n = (int)n;
     e.L = (int)L;
@@ -457,6 +449,31 @@ int pfa_batch_add_rows(pfa_batch* b, const uint8_t* text, int64_t n, int64_t L, 
     if (rc) return rc;
     for (int64_t r = 0; r < n; ++r) memcpy(b->h_text + e.text_off + r * e.ld, text + r * ld, (size_t)L);
     b->h_text_used = need;
+    if (index) *index = (int64_t)b->entries.size();
+    b->entries.push_back(std::move(e));
+    b->ran = false;
+    return PFA_OK;
+}
+
+/* a locus of the synthetic generator (pfa_aln_synthetic's alignment, all columns): its text is produced on the device when the
+ * batch is staged, so that benchmarks can hold many loci resident without 1 byte per base of host memory */
+int pfa_batch_add_synthetic(pfa_batch* b, int64_t n, int64_t L, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_ppm, const uint32_t* masks, int k,
+                            int64_t* index) {
+    if (!b || n <= 0 || L < 0 || k < 0 || (k > 0 && !masks)) return PFA_ERR_ARG;
+    if (L >= (1ll << 31) || wq_of(n) > PFA_BATCH_MAX_WQ) return pfa_fail(b->ctx, PFA_ERR_ARG, "locus too large for the batched path");
+    PfaBatchEntry e;
+    e.n = (int)n;
+    e.L = (int)L;
+    e.ld = (int)pfa_round_up(std::max<int64_t>(L, 1), 32);
+    e.Wq = wq_of(n);
+    e.synthetic = true;
+    e.seed = seed;
+    e.p_seg_ppm = p_seg_ppm;
+    e.tri_ppm = tri_ppm;
+    if (!entry_set_masks(&e, masks, k)) return pfa_fail(b->ctx, PFA_ERR_ARG, "empty population in batch");
+    // synthetic loci occupy the device blob only: their offsets continue after the host text
+    e.text_off = (long long)pfa_round_up((int64_t)(b->h_text_used + b->synth_bytes), 256);
+    b->synth_bytes = (size_t)e.text_off + (size_t)n * e.ld - b->h_text_used;
     if (index) *index = (int64_t)b->entries.size();
     b->entries.push_back(std::move(e));
     b->ran = false;
@@ -490,6 +507,7 @@ int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const
     if (!b || count < 0 || nkeys < 0 || (count > 0 && (!paths || !status || !shape || !locus || !hits)) || (nkeys > 0 && !keys))
         return PFA_ERR_ARG;
     if (count == 0) return PFA_OK;
+    if (b->synth_bytes) return pfa_fail(b->ctx, PFA_ERR_ARG, "host loci must be added before synthetic ones");
     // size the blob once: the rows of a file never need more than its size plus the padding of every row to 32 bytes
     std::vector<size_t> fsize((size_t)count, 0);
     size_t bound = (size_t)pfa_round_up((int64_t)b->h_text_used, 256);
@@ -622,38 +640,58 @@ int pfa_batch_add_files(pfa_batch* b, const char* const* paths, int count, const
     return PFA_OK;
 }
 
-int pfa_batch_run(pfa_batch* b, int jc) {
+static void batch_free_dev(pfa_batch* b) {
+    pfa_ctx* ctx = b->ctx;
+    pfa_batch::Dev& d = b->dev;
+    pfa_dfree(ctx, d.text); pfa_dfree(ctx, d.desc); pfa_dfree(ctx, d.pops); pfa_dfree(ctx, d.site_base); pfa_dfree(ctx, d.tile_base);
+    pfa_dfree(ctx, d.ctile_base); pfa_dfree(ctx, d.out); pfa_dfree(ctx, d.cds_out); pfa_dfree(ctx, d.popn); pfa_dfree(ctx, d.planes);
+    pfa_dfree(ctx, d.masks); pfa_dfree(ctx, d.inv); pfa_dfree(ctx, d.count); pfa_dfree(ctx, d.keys); pfa_dfree(ctx, d.fin_in);
+    pfa_dfree(ctx, d.fin_out); pfa_dfree(ctx, d.ssites); pfa_dfree(ctx, d.heads);
+    d = pfa_batch::Dev();
+}
+
+int pfa_batch_release(pfa_batch* b) {
+    if (!b) return PFA_ERR_ARG;
+    if (b->dev.staged) {
+        cudaSetDevice(b->ctx->device);
+        batch_free_dev(b);
+    }
+    return PFA_OK;
+}
+
+// ONE upload of the pinned blob + K1b: afterwards the planes of every locus of the batch are resident in HBM
+int pfa_batch_stage(pfa_batch* b) {
     if (!b) return PFA_ERR_ARG;
     pfa_ctx* ctx = b->ctx;
+    if (b->dev.staged) batch_free_dev(b);
     build_layout(b);
     const int nloci = (int)b->desc.size();
     const long long npops = (long long)b->pops.size();
-    b->out.assign((size_t)b->out_len, 0);
-    b->fin.assign((size_t)npops, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
-    b->ran = true;
+    b->ran = b->ran_cds = false;
+    b->dev.staged = true;
     if (nloci == 0) return PFA_OK;
     PFA_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    std::vector<long long> site_base((size_t)nloci + 1), tile_base((size_t)nloci + 1);
+    std::vector<long long> site_base((size_t)nloci + 1), tile_base((size_t)nloci + 1), ctile_base((size_t)nloci + 1), popn((size_t)npops);
+    long long ct = 0;
     for (int i = 0; i < nloci; ++i) {
-        site_base[(size_t)i] = b->desc[(size_t)i].site_base;
-        tile_base[(size_t)i] = b->desc[(size_t)i].tile_base;
+        const PfaLocusDesc& dd = b->desc[(size_t)i];
+        site_base[(size_t)i] = dd.site_base;
+        tile_base[(size_t)i] = dd.tile_base;
+        ctile_base[(size_t)i] = ct;
+        // at least one tile per non-empty locus: it also books the trailing partial codon column
+        if (dd.L > 0) ct += std::max<long long>(1, ((long long)(dd.L / 3) + PFA_BATCH_CTILE - 1) / PFA_BATCH_CTILE);
     }
     site_base[(size_t)nloci] = b->n_sites;
     tile_base[(size_t)nloci] = b->n_tiles;
+    ctile_base[(size_t)nloci] = ct;
+    b->n_ctiles = ct;
+    for (long long i = 0; i < npops; ++i) popn[(size_t)i] = b->pops[(size_t)i].n;
 
-    uint8_t* d_text = nullptr;
-    PfaLocusDesc* d_desc = nullptr;
-    PfaPopSlot* d_pops = nullptr;
-    long long *d_site_base = nullptr, *d_tile_base = nullptr, *d_out = nullptr;
-    uint4 *d_planes = nullptr, *d_masks = nullptr;
-    int* d_inv = nullptr;
-    unsigned long long *d_count = nullptr, *d_keys = nullptr;
-    pfa_final_in* d_fin_in = nullptr;
-    pfa_final_out* d_fin_out = nullptr;
-    int64_t* heads = nullptr;
-    const size_t plane_bytes = (size_t)pfa_round_up(std::max<long long>(b->plane_u4, 1) * 16, 256);
-    long long cap = std::max<long long>(1 << 16, (long long)(b->h_text_used / 64));
+    pfa_batch::Dev& d = b->dev;
+    d.plane_bytes = (size_t)pfa_round_up(std::max<long long>(b->plane_u4, 1) * 16, 256);
+    long long cap = std::max<long long>(1 << 16, (long long)((b->h_text_used + b->synth_bytes) / 64));
+    if (b->h_text_used == 0) cap = 1 << 10;  // synthetic loci are pure ACGT
     if (const char* ev = getenv("PFA_BATCH_EXC_CAP")) cap = std::max<long long>(1, atoll(ev));  // tests: force the retry
     int rc = PFA_OK;
     cudaError_t e = cudaSuccess;
@@ -661,37 +699,133 @@ int pfa_batch_run(pfa_batch* b, int jc) {
     do {                                                                               \
         if (e == cudaSuccess) e = (call);                                              \
     } while (0)
-    BR(pfa_dmalloc(ctx, &d_text, b->h_text_used));
-    BR(pfa_dmalloc(ctx, &d_desc, sizeof(PfaLocusDesc) * (size_t)nloci));
-    BR(pfa_dmalloc(ctx, &d_pops, sizeof(PfaPopSlot) * (size_t)npops));
-    BR(pfa_dmalloc(ctx, &d_site_base, sizeof(long long) * ((size_t)nloci + 1)));
-    BR(pfa_dmalloc(ctx, &d_tile_base, sizeof(long long) * ((size_t)nloci + 1)));
-    BR(pfa_dmalloc(ctx, &d_out, sizeof(long long) * (size_t)std::max<long long>(b->out_len, 1)));
-    BR(pfa_dmalloc(ctx, &d_planes, 3 * plane_bytes));
-    BR(pfa_dmalloc(ctx, &d_masks, sizeof(uint32_t) * std::max<size_t>(b->masks.size(), 4)));
-    BR(pfa_dmalloc(ctx, &d_inv, sizeof(int) * (size_t)nloci));
-    BR(pfa_dmalloc(ctx, &d_count, sizeof(unsigned long long)));
-    BR(pfa_dmalloc(ctx, &d_keys, sizeof(unsigned long long) * (size_t)cap));
-    BR(pfa_dmalloc(ctx, &d_fin_in, sizeof(pfa_final_in) * (size_t)npops));
-    BR(pfa_dmalloc(ctx, &d_fin_out, sizeof(pfa_final_out) * (size_t)npops));
-    BR(cudaMemcpyAsync(d_text, b->h_text, b->h_text_used, cudaMemcpyHostToDevice, st));
-    BR(cudaMemcpyAsync(d_desc, b->desc.data(), sizeof(PfaLocusDesc) * (size_t)nloci, cudaMemcpyHostToDevice, st));
-    BR(cudaMemcpyAsync(d_pops, b->pops.data(), sizeof(PfaPopSlot) * (size_t)npops, cudaMemcpyHostToDevice, st));
-    BR(cudaMemcpyAsync(d_site_base, site_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
-    BR(cudaMemcpyAsync(d_tile_base, tile_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
-    BR(cudaMemcpyAsync(d_masks, b->masks.data(), sizeof(uint32_t) * b->masks.size(), cudaMemcpyHostToDevice, st));
-    BR(cudaMemsetAsync(d_out, 0, sizeof(long long) * (size_t)std::max<long long>(b->out_len, 1), st));
-    BR(cudaMemsetAsync(d_planes, 0, 3 * plane_bytes, st));
-    BR(cudaMemsetAsync(d_inv, 0, sizeof(int) * (size_t)nloci, st));
-    BR(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    const size_t text_bytes = b->h_text_used + b->synth_bytes;
+    BR(pfa_dmalloc(ctx, &d.text, text_bytes));
+    BR(pfa_dmalloc(ctx, &d.desc, sizeof(PfaLocusDesc) * (size_t)nloci));
+    BR(pfa_dmalloc(ctx, &d.pops, sizeof(PfaPopSlot) * (size_t)npops));
+    BR(pfa_dmalloc(ctx, &d.site_base, sizeof(long long) * ((size_t)nloci + 1)));
+    BR(pfa_dmalloc(ctx, &d.tile_base, sizeof(long long) * ((size_t)nloci + 1)));
+    BR(pfa_dmalloc(ctx, &d.ctile_base, sizeof(long long) * ((size_t)nloci + 1)));
+    BR(pfa_dmalloc(ctx, &d.popn, sizeof(long long) * (size_t)npops));
+    BR(pfa_dmalloc(ctx, &d.out, sizeof(long long) * (size_t)std::max<long long>(b->out_len, 1)));
+    BR(pfa_dmalloc(ctx, &d.planes, 3 * d.plane_bytes));
+    BR(pfa_dmalloc(ctx, &d.masks, sizeof(uint32_t) * std::max<size_t>(b->masks.size(), 4)));
+    BR(pfa_dmalloc(ctx, &d.inv, sizeof(int) * (size_t)nloci));
+    BR(pfa_dmalloc(ctx, &d.count, sizeof(unsigned long long)));
+    BR(pfa_dmalloc(ctx, &d.keys, sizeof(unsigned long long) * (size_t)cap));
+    BR(pfa_dmalloc(ctx, &d.fin_in, sizeof(pfa_final_in) * 2 * (size_t)npops));
+    BR(pfa_dmalloc(ctx, &d.fin_out, sizeof(pfa_final_out) * 2 * (size_t)npops));
+    BR(cudaMemcpyAsync(d.text, b->h_text, b->h_text_used, cudaMemcpyHostToDevice, st));
+    if (e == cudaSuccess && b->synth_bytes)
+        for (size_t i = 0; i < b->entries.size() && !rc; ++i) {
+            const PfaBatchEntry& en = b->entries[i];
+            if (en.synthetic && en.L > 0)
+                rc = pfa_synth_text_device(ctx, d.text + en.text_off, en.ld, en.n, en.seed, en.p_seg_ppm, en.tri_ppm, 0, en.L);
+        }
+    BR(cudaMemcpyAsync(d.desc, b->desc.data(), sizeof(PfaLocusDesc) * (size_t)nloci, cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d.pops, b->pops.data(), sizeof(PfaPopSlot) * (size_t)npops, cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d.site_base, site_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d.tile_base, tile_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d.ctile_base, ctile_base.data(), sizeof(long long) * ((size_t)nloci + 1), cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d.popn, popn.data(), sizeof(long long) * (size_t)npops, cudaMemcpyHostToDevice, st));
+    BR(cudaMemcpyAsync(d.masks, b->masks.data(), sizeof(uint32_t) * b->masks.size(), cudaMemcpyHostToDevice, st));
+    BR(cudaMemsetAsync(d.planes, 0, 3 * d.plane_bytes, st));
+    BR(cudaMemsetAsync(d.inv, 0, sizeof(int) * (size_t)nloci, st));
+    BR(cudaMemsetAsync(d.count, 0, sizeof(unsigned long long), st));
     if (e == cudaSuccess && b->n_tiles > 0) {
-        uint4* p0 = d_planes;
-        uint4* p1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d_planes) + plane_bytes);
-        uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d_planes) + 2 * plane_bytes);
-        pfa_batch_encode_kernel<<<(unsigned)((b->n_tiles + 7) / 8), 256, 0, st>>>(d_text, d_desc, d_tile_base, nloci, b->n_tiles, (uint32_t*)p0,
-                                                                                (uint32_t*)p1, (uint32_t*)pv, d_keys, d_count, cap, d_inv);
-        ctx->launches++;
-        PfaBatchArgs args{p0, p1, pv, d_masks, d_desc, d_pops, d_site_base, d_inv, d_out, b->n_sites, nloci};
+        uint32_t* p0 = reinterpret_cast<uint32_t*>(d.planes);
+        uint32_t* p1 = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d.planes) + d.plane_bytes);
+        uint32_t* pv = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d.planes) + 2 * d.plane_bytes);
+        for (int attempt = 0; attempt < 2 && e == cudaSuccess && !rc; ++attempt) {
+            pfa_batch_encode_kernel<<<(unsigned)((b->n_tiles + 7) / 8), 256, 0, st>>>(d.text, d.desc, d.tile_base, nloci, b->n_tiles, p0, p1, pv, d.keys,
+                                                                                    d.count, cap, d.inv);
+            ctx->launches++;
+            e = cudaGetLastError();
+            // exception list: one small synchronisation per batch
+            unsigned long long count = 0;
+            BR(cudaMemcpyAsync(&count, d.count, sizeof(count), cudaMemcpyDeviceToHost, st));
+            BR(cudaStreamSynchronize(st));
+            if (e != cudaSuccess) break;
+            d.n_exc = count;
+            if ((long long)count <= cap) break;
+            // more symbols outside ACGT-N? than the list was sized for (dense IUPAC codes, '.', '*' ...: every character is an
+            // allele in the reference, PolyFastA.py:256-258): encode once more with a list of the exact size
+            if (attempt == 1) {
+                rc = pfa_fail(ctx, PFA_ERR_CUDA, "batched path: the exception list changed between two encodes");
+                break;
+            }
+            pfa_dfree(ctx, d.keys);
+            d.keys = nullptr;
+            cap = (long long)count;
+            BR(pfa_dmalloc(ctx, &d.keys, sizeof(unsigned long long) * (size_t)cap));
+            BR(cudaMemsetAsync(d.count, 0, sizeof(unsigned long long), st));
+        }
+        if (e == cudaSuccess && !rc && d.n_exc > 0) rc = pfa_sort_exceptions(ctx, &d.keys, (int64_t)d.n_exc, &d.heads, &d.n_heads);
+    }
+    // the text has done its duty
+    pfa_dfree(ctx, d.text);
+    d.text = nullptr;
+#undef BR
+    if (!rc && e != cudaSuccess) rc = pfa_fail(ctx, PFA_ERR_CUDA, "batched staging failed: %s", cudaGetErrorString(e));
+    if (rc) batch_free_dev(b);
+    return rc;
+}
+
+// per population of the batch: ssites, nsites and the two K5 inputs of the codon scan (PolyFastA.py:167,172-173)
+__global__ void pfa_batch_final_in_cds_kernel(const PfaPopSlot* __restrict__ pops, const long long* __restrict__ cds, int jc, long long n_pops,
+                                              pfa_final_in* __restrict__ fin_in, double* __restrict__ ssites) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pops) return;
+    const PfaPopSlot p = pops[i];
+    const long long* row = cds + i * PFA_CDS_LEN;
+    double s = 0.0;
+    for (int l = 1; l <= 64; ++l)
+        if (row[PFA_CDS_SUM3 + l]) s = __dadd_rn(s, __ddiv_rn((double)row[PFA_CDS_SUM3 + l], __dmul_rn(3.0, (double)l)));
+    ssites[i] = s;
+    const double nsites = __dsub_rn(__dsub_rn(p.seqlen, (double)row[PFA_CDS_MISSING]), s);
+    pfa_final_in f;
+    f.n = p.n; f.S = row[PFA_CDS_SS]; f.H = row[PFA_CDS_HS]; f.seqlen = s; f.jc = jc; f.pad = 0;
+    fin_in[2 * i] = f;
+    f.S = row[PFA_CDS_SN]; f.H = row[PFA_CDS_HN]; f.seqlen = nsites;
+    fin_in[2 * i + 1] = f;
+}
+
+// the segmented scans over the staged planes: K2b (+ escape sites), optionally K4b, K5b, ONE synchronisation
+int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
+    if (!b || !b->dev.staged) return PFA_ERR_ARG;
+    pfa_ctx* ctx = b->ctx;
+    pfa_batch::Dev& d = b->dev;
+    const int nloci = (int)b->desc.size();
+    const long long npops = (long long)b->pops.size();
+    b->out.assign((size_t)b->out_len, 0);
+    b->fin.assign((size_t)npops, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
+    b->ran = true;
+    b->ran_cds = cds != 0;
+    if (cds) {
+        b->cds_out.assign((size_t)npops * PFA_CDS_LEN, 0);
+        b->cds_ssites.assign((size_t)npops, 0.0);
+        b->cds_fin.assign((size_t)npops * 2, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
+    }
+    if (nloci == 0) return PFA_OK;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc = PFA_OK;
+    cudaError_t e = cudaSuccess;
+#define BR(call)                                                                       \
+    do {                                                                               \
+        if (e == cudaSuccess) e = (call);                                              \
+    } while (0)
+    if (cds && !d.cds_out) {
+        BR(pfa_dmalloc(ctx, &d.cds_out, sizeof(long long) * (size_t)npops * PFA_CDS_LEN));
+        BR(pfa_dmalloc(ctx, &d.ssites, sizeof(double) * (size_t)npops));
+    }
+    BR(cudaMemsetAsync(d.out, 0, sizeof(long long) * (size_t)std::max<long long>(b->out_len, 1), st));
+    if (cds) BR(cudaMemsetAsync(d.cds_out, 0, sizeof(long long) * (size_t)npops * PFA_CDS_LEN, st));
+    uint4* p0 = d.planes;
+    uint4* p1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d.planes) + d.plane_bytes);
+    uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d.planes) + 2 * d.plane_bytes);
+    PfaBatchArgs args{p0, p1, pv, d.masks, d.desc, d.pops, d.site_base, d.inv, d.out, b->n_sites, nloci, d.ctile_base, b->n_ctiles, d.cds_out, d.popn};
+    if (e == cudaSuccess && b->n_sites > 0) {
         int lps = 1;
         while (lps < 32 && (b->max_Wq + lps - 1) / lps > 4) lps *= 2;
         const int iter = (b->max_Wq + lps - 1) / lps;
@@ -705,56 +839,69 @@ int pfa_batch_run(pfa_batch* b, int jc) {
 #undef PFA_B_CASE
         ctx->launches++;
         e = cudaGetLastError();
-        // exception list: one small synchronisation per batch
-        unsigned long long count = 0;
-        BR(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, st));
-        BR(cudaStreamSynchronize(st));
-        if (e == cudaSuccess && !rc && (long long)count > cap) {
-            // more symbols outside ACGT-N? than the list was sized for (dense IUPAC codes, '.', '*' ...: every character is an
-            // allele in the reference, PolyFastA.py:256-258): encode once more with a list of the exact size.  The planes and
-            // the site scan do not depend on the list, so only K1b runs again.
-            pfa_dfree(ctx, d_keys);
-            d_keys = nullptr;
-            cap = (long long)count;
-            BR(pfa_dmalloc(ctx, &d_keys, sizeof(unsigned long long) * (size_t)cap));
-            BR(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-            if (e == cudaSuccess) {
-                pfa_batch_encode_kernel<<<(unsigned)((b->n_tiles + 7) / 8), 256, 0, st>>>(d_text, d_desc, d_tile_base, nloci, b->n_tiles, (uint32_t*)p0,
-                                                                                        (uint32_t*)p1, (uint32_t*)pv, d_keys, d_count, cap, d_inv);
-                ctx->launches++;
-                e = cudaGetLastError();
-            }
-            BR(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, st));
-            BR(cudaStreamSynchronize(st));
-            if (e == cudaSuccess && (long long)count != cap) rc = pfa_fail(ctx, PFA_ERR_CUDA, "batched path: the exception list changed between two encodes");
-        }
-        if (e == cudaSuccess && !rc && count > 0) {
-            int64_t n_heads = 0;
-            if (!rc) rc = pfa_sort_exceptions(ctx, &d_keys, (int64_t)count, &heads, &n_heads);
-            if (!rc && n_heads > 0) {
-                long long eb = std::min<long long>((n_heads + 7) / 8, (long long)ctx->sm_count * 8);
-                pfa_batch_escape_kernel<<<(unsigned)eb, 256, 0, st>>>(args, d_keys, (long long)count, (const long long*)heads, n_heads);
-                ctx->launches++;
-                e = cudaGetLastError();
-            }
+        if (e == cudaSuccess && !rc && d.n_heads > 0) {
+            long long eb = std::min<long long>((d.n_heads + 7) / 8, (long long)ctx->sm_count * 8);
+            pfa_batch_escape_kernel<<<(unsigned)eb, 256, 0, st>>>(args, d.keys, (long long)d.n_exc, (const long long*)d.heads, d.n_heads);
+            ctx->launches++;
+            e = cudaGetLastError();
         }
     }
+    if (e == cudaSuccess && !rc && cds)
+        rc = pfa_launch_batch_cds(ctx, args, b->max_Wq, d.keys, (long long)d.n_exc, (const long long*)d.heads, d.n_heads);
     if (e == cudaSuccess && !rc) {
-        pfa_batch_final_in_kernel<<<(unsigned)((npops + 127) / 128), 128, 0, st>>>(d_pops, d_out, jc, npops, d_fin_in);
+        pfa_batch_final_in_kernel<<<(unsigned)((npops + 127) / 128), 128, 0, st>>>(d.pops, d.out, jc, npops, d.fin_in);
         ctx->launches++;
         e = cudaGetLastError();
-        if (e == cudaSuccess) rc = pfa_launch_finalize(ctx, d_fin_in, d_fin_out, (int)npops);
+        if (e == cudaSuccess) rc = pfa_launch_finalize(ctx, d.fin_in, d.fin_out, (int)npops);
         if (rc) e = cudaErrorUnknown;
-        BR(cudaMemcpyAsync(b->out.data(), d_out, sizeof(long long) * (size_t)b->out_len, cudaMemcpyDeviceToHost, st));
-        BR(cudaMemcpyAsync(b->fin.data(), d_fin_out, sizeof(pfa_final_out) * (size_t)npops, cudaMemcpyDeviceToHost, st));
+        BR(cudaMemcpyAsync(b->out.data(), d.out, sizeof(long long) * (size_t)b->out_len, cudaMemcpyDeviceToHost, st));
+        BR(cudaMemcpyAsync(b->fin.data(), d.fin_out, sizeof(pfa_final_out) * (size_t)npops, cudaMemcpyDeviceToHost, st));
+        if (cds && e == cudaSuccess) {
+            // the K5 outputs of the site scan are on their way to the host; the same buffers take the codon scan's entries next
+            // (stream order keeps the copies ahead of the kernels)
+            pfa_batch_final_in_cds_kernel<<<(unsigned)((npops + 127) / 128), 128, 0, st>>>(d.pops, d.cds_out, jc, npops, d.fin_in, d.ssites);
+            ctx->launches++;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) rc = pfa_launch_finalize(ctx, d.fin_in, d.fin_out, (int)(2 * npops));
+            if (rc) e = cudaErrorUnknown;
+            BR(cudaMemcpyAsync(b->cds_out.data(), d.cds_out, sizeof(long long) * (size_t)npops * PFA_CDS_LEN, cudaMemcpyDeviceToHost, st));
+            BR(cudaMemcpyAsync(b->cds_ssites.data(), d.ssites, sizeof(double) * (size_t)npops, cudaMemcpyDeviceToHost, st));
+            BR(cudaMemcpyAsync(b->cds_fin.data(), d.fin_out, sizeof(pfa_final_out) * 2 * (size_t)npops, cudaMemcpyDeviceToHost, st));
+        }
         BR(cudaStreamSynchronize(st));
     }
 #undef BR
-    pfa_dfree(ctx, d_text); pfa_dfree(ctx, d_desc); pfa_dfree(ctx, d_pops); pfa_dfree(ctx, d_site_base); pfa_dfree(ctx, d_tile_base);
-    pfa_dfree(ctx, d_out); pfa_dfree(ctx, d_planes); pfa_dfree(ctx, d_masks); pfa_dfree(ctx, d_inv); pfa_dfree(ctx, d_count);
-    pfa_dfree(ctx, d_keys); pfa_dfree(ctx, d_fin_in); pfa_dfree(ctx, d_fin_out); pfa_dfree(ctx, heads);
     if (rc) return rc;
     if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "batched run failed: %s", cudaGetErrorString(e));
+    return PFA_OK;
+}
+
+int pfa_batch_run(pfa_batch* b, int jc) {
+    if (!b) return PFA_ERR_ARG;
+    int rc = pfa_batch_stage(b);
+    if (!rc) rc = pfa_batch_scan(b, jc, 0);
+    pfa_batch_release(b);
+    return rc;
+}
+
+int pfa_batch_run_cds(pfa_batch* b, int jc) {
+    if (!b) return PFA_ERR_ARG;
+    int rc = pfa_batch_stage(b);
+    if (!rc) rc = pfa_batch_scan(b, jc, 1);
+    pfa_batch_release(b);
+    return rc;
+}
+
+/* codon-scan result of (locus, pop) after pfa_batch_run_cds / pfa_batch_scan(cds = 1): cds = int64[PFA_CDS_LEN], fin2 = the two K5
+ * outputs (synonymous, nonsynonymous) */
+int pfa_batch_result_cds(const pfa_batch* b, int64_t locus, int pop, int64_t* cds, double* ssites, void* fin2) {
+    if (!b || !b->ran_cds || locus < 0 || locus >= (int64_t)b->desc.size()) return PFA_ERR_ARG;
+    const PfaLocusDesc& d = b->desc[(size_t)locus];
+    if (pop < 0 || pop >= d.k) return PFA_ERR_ARG;
+    const size_t i = (size_t)(d.pop_base + pop);
+    if (cds) memcpy(cds, b->cds_out.data() + i * PFA_CDS_LEN, sizeof(int64_t) * PFA_CDS_LEN);
+    if (ssites) *ssites = b->cds_ssites[i];
+    if (fin2) memcpy(fin2, b->cds_fin.data() + 2 * i, 2 * sizeof(pfa_final_out));
     return PFA_OK;
 }
 

@@ -15,6 +15,7 @@
 // population by peeling distinct codons off each 32-row word, and counts the three columns with popcounts.
 #include <cstdlib>
 
+#include "pfa_batch.cuh"
 #include "pfa_codon_rules.h"
 #include "pfa_sites.cuh"
 
@@ -22,7 +23,9 @@ __constant__ uint8_t c_syn3[64];
 __constant__ uint8_t c_pair[64 * 64];
 __constant__ unsigned long long c_class_mask[24];
 __constant__ unsigned long long c_stop_mask;
+__constant__ unsigned long long c_syn3_bits[3];  // bit b of 3*syncodfreq(c) at bit c of word b: sums over a codon set are three popcounts
 __constant__ int c_num_classes;
+__device__ uint8_t g_pair[64 * 64];  // the pair table once more in global memory: lane-divergent lookups (pfa_cds_flush) go through L1
 
 int pfa_upload_codon_tables(pfa_ctx* ctx) {
     const PfaCodonTables& t = pfa_codon_tables();
@@ -31,8 +34,14 @@ int pfa_upload_codon_tables(pfa_ctx* ctx) {
     const unsigned long long sm = t.stop_mask;
     PFA_CUDA(ctx, cudaMemcpyToSymbol(c_syn3, t.syn3, 64));
     PFA_CUDA(ctx, cudaMemcpyToSymbol(c_pair, t.pair, 64 * 64));
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(g_pair, t.pair, 64 * 64));
     PFA_CUDA(ctx, cudaMemcpyToSymbol(c_class_mask, cm, sizeof cm));
     PFA_CUDA(ctx, cudaMemcpyToSymbol(c_stop_mask, &sm, sizeof sm));
+    unsigned long long sb[3] = {0ull, 0ull, 0ull};
+    for (int c = 0; c < 64; ++c)
+        for (int b = 0; b < 3; ++b)
+            if ((t.syn3[c] >> b) & 1) sb[b] |= 1ull << c;
+    PFA_CUDA(ctx, cudaMemcpyToSymbol(c_syn3_bits, sb, sizeof sb));
     PFA_CUDA(ctx, cudaMemcpyToSymbol(c_num_classes, &t.num_classes, sizeof(int)));
     return PFA_OK;
 }
@@ -46,11 +55,29 @@ struct PfaCdsArgs {
     int acc_in_smem;
 };
 
+// what the per-column code needs to know about the alignment (or, on the batched path, about one locus of the batch)
+struct PfaCdsView {
+    const uint4* masks;     // [k][Wq]
+    const int64_t* pop_n;   // [k]
+    int64_t* out;           // [k][PFA_CDS_LEN] in global memory
+    uint8_t* labels;        // optional [k][ns]
+    int64_t ns;
+    int k;
+    int acc_in_smem;        // accumulate into sm_acc[k][PFA_CDS_LEN] instead of out
+};
+__device__ __forceinline__ PfaCdsView pfa_cds_view(const PfaCdsArgs& a) {
+    return PfaCdsView{a.s.masks, a.s.pop_n, a.out, a.labels, a.s.ns, a.s.k, a.acc_in_smem};
+}
+
 // labels of the three codon positions from the set of sense codons of a column (PolyFastA.py:331-432)
-__device__ int pfa_labels_from_set(unsigned long long g) {
+template <bool DIVERGENT = false>
+__device__ __forceinline__ int pfa_labels_from_set(unsigned long long g) {
     const int n = __popcll(g);
     if (n < 2) return 0;
-    if (n == 2) return c_pair[(__ffsll((long long)g) - 1) * 64 + (63 - __clzll((long long)g))];
+    if (n == 2) {
+        const int i = (__ffsll((long long)g) - 1) * 64 + (63 - __clzll((long long)g));
+        return DIVERGENT ? (int)__ldg(&g_pair[i]) : (int)c_pair[i];
+    }
     unsigned seen0 = 0, seen1 = 0, seen2 = 0;
     for (unsigned long long t = g; t; t &= t - 1) {
         const int c = __ffsll((long long)t) - 1;
@@ -287,7 +314,7 @@ __device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 
 // passes 1 and 2 of one codon column whose three site records are already in registers; shared by the register-resident
 // kernel (chunks loaded from global memory) and the TMA kernel (chunks read from the warp's shared-memory slot)
 template <int LPS, int ITER, bool HAS_V, bool MULTI>
-__device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t site0, const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER],
+__device__ __forceinline__ void pfa_cds_process(const PfaCdsView& a, int64_t site0, const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER],
                                                 const uint4 (&xv)[3][ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
                                                 unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing, unsigned& u_sum3) {
     constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask
@@ -360,10 +387,10 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t sit
                 if (c[b]) P |= 1ull << (fixed | (b << shift));
             unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
                                                     : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
-            pfa_cds_contribute_one(P, c, tv, a.s.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+            pfa_cds_contribute_one(P, c, tv, a.pop_n[q], dst, a.labels ? a.labels + (int64_t)q * a.ns : nullptr, site0);
         };
-        for (int q = 0; q < a.s.k; ++q) {
-            const uint4* mq = a.s.masks + (int64_t)q * Wq;
+        for (int q = 0; q < a.k; ++q) {
+            const uint4* mq = a.masks + (int64_t)q * Wq;
             uint32_t c[PFA_NCLASS];
 #pragma unroll
             for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
@@ -415,8 +442,8 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t sit
         return;
     }
     // ---- pass 2, general case ----
-    for (int q = 0; q < a.s.k; ++q) {
-        const uint4* mq = a.s.masks + (int64_t)q * Wq;
+    for (int q = 0; q < a.k; ++q) {
+        const uint4* mq = a.masks + (int64_t)q * Wq;
         uint4 m4[ITER];
 #pragma unroll
         for (int i = 0; i < ITER; ++i) {
@@ -488,7 +515,7 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsArgs& a, int64_t sit
         const unsigned long long escsq[3] = {0, 0, 0};
         unsigned long long* dst = a.acc_in_smem ? sm_acc + q * PFA_CDS_LEN
                                                 : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
-        pfa_cds_contribute(P, cnt, a.s.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.s.ns : nullptr, site0);
+        pfa_cds_contribute(P, cnt, a.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.ns : nullptr, site0);
     }
 }
 
@@ -534,7 +561,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
                     if (HAS_V) xv[t][i] = pfa_ld_stream(a.s.v + (site0 + t) * Wq + j);
                 }
             }
-        pfa_cds_process<LPS, ITER, HAS_V, MULTI>(a, site0, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
+        pfa_cds_process<LPS, ITER, HAS_V, MULTI>(pfa_cds_view(a), site0, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
     }
     if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
     for (int off = 16; off; off >>= 1) {
@@ -559,11 +586,223 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (ITER >= 3) ? 1 : 2) pfa_cds
     if (a.s.x.world) pfa_xchg_epilogue(a.s.x);
 }
 
-// TMA variant (see pfa_site_scan_tma_kernel): every warp owns one shared-memory slot holding the site records of the codon
-// columns of one or several of its passes (3 * 32/LPS consecutive sites per pass), fed by one cp.async.bulk per plane.
+// ---- deferred bookkeeping of the variable codon columns ---------------------------------------------------------------------
+// What a (variable codon column, population) contributes is a chain of dependent scalar steps -- stop test, number of clean
+// codons, syn-site sum, S/N labels (table lookups), five or six accumulator updates.  Run right after the counts it costs
+// the warp ~2,000 cycles per entry with nothing else to overlap (measured: the second population of C3 cost K4 0.06 ms).
+// Instead the warp appends (presence mask, H of the three columns, population, site) to a queue of 32 entries in shared
+// memory and, when the queue is full (and once at the end), finishes all 32 side by side, one lane each; lanes of the same
+// population then combine their terms (match.any + redux) so that one lane per population touches the accumulators.
+#define PFA_CDS_QFIELDS 7  // P lo, P hi, h0, h1, h2, population, first site of the column
+
+__device__ __forceinline__ void pfa_cds_enqueue(uint32_t* qbuf, int& count, int lane, unsigned long long P, uint32_t h0, uint32_t h1,
+                                                uint32_t h2, int q, uint32_t site0) {
+    if (lane < PFA_CDS_QFIELDS) {
+        const uint32_t val = lane == 0 ? (uint32_t)P : lane == 1 ? (uint32_t)(P >> 32) : lane == 2 ? h0 : lane == 3 ? h1 : lane == 4 ? h2
+                             : lane == 5 ? (uint32_t)q : site0;
+        qbuf[lane * 32 + count] = val;
+    }
+    ++count;
+}
+
+// acc: the accumulators [k][PFA_CDS_LEN] (shared or global memory); labels_base: optional [k][ns]
+__device__ __noinline__ void pfa_cds_flush(const uint32_t* qbuf, int count, int lane, unsigned long long* acc, uint8_t* labels_base, int64_t ns) {
+    __syncwarp();
+    const unsigned act = __ballot_sync(0xffffffffu, lane < count);
+    if (lane >= count) return;
+    const unsigned long long P = ((unsigned long long)qbuf[32 + lane] << 32) | qbuf[lane];
+    const uint32_t h[3] = {qbuf[64 + lane], qbuf[96 + lane], qbuf[128 + lane]};
+    const int q = (int)qbuf[160 + lane];
+    const int64_t site0 = (int64_t)qbuf[192 + lane];
+    unsigned long long* dst = acc + (int64_t)q * PFA_CDS_LEN;
+    const unsigned stop = (P & c_stop_mask) ? 1u : 0u;
+    const int len = __popcll(P);
+    unsigned miss = 0, ss = 0, sn = 0, tot3 = 0;
+    unsigned long long hs = 0ull, hn = 0ull;
+    if (len == 0) {
+        miss = 3;
+    } else {
+        tot3 = (unsigned)__popcll(P & c_syn3_bits[0]) + 2u * (unsigned)__popcll(P & c_syn3_bits[1]) + 4u * (unsigned)__popcll(P & c_syn3_bits[2]);
+        if (len >= 2) {
+            const int lab = pfa_labels_from_set<true>(P & ~c_stop_mask);
+            uint8_t* labels = labels_base ? labels_base + (int64_t)q * ns : nullptr;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int li = (lab >> (2 * i)) & 3;
+                if (li == 1) { ss += 1; hs += h[i]; }
+                if (li == 2) { sn += 1; hn += h[i]; }
+                if (li && labels) labels[site0 + i] = (uint8_t)li;
+            }
+        }
+    }
+    // lanes of the same population add up their terms; H in two halves (32 x 3 x n^2 does not fit 32 bits)
+    const unsigned peers = __match_any_sync(act, q);
+    const unsigned stop_s = __reduce_add_sync(peers, stop), miss_s = __reduce_add_sync(peers, miss);
+    const unsigned ss_s = __reduce_add_sync(peers, ss), sn_s = __reduce_add_sync(peers, sn);
+    const unsigned long long hs_s = ((unsigned long long)__reduce_add_sync(peers, (unsigned)(hs >> 16)) << 16) + __reduce_add_sync(peers, (unsigned)(hs & 0xffffu));
+    const unsigned long long hn_s = ((unsigned long long)__reduce_add_sync(peers, (unsigned)(hn >> 16)) << 16) + __reduce_add_sync(peers, (unsigned)(hn & 0xffffu));
+    if (lane == __ffs(peers) - 1) {
+        if (stop_s) atomicAdd(&dst[PFA_CDS_NSTOPS], (unsigned long long)stop_s);
+        if (miss_s) atomicAdd(&dst[PFA_CDS_MISSING], (unsigned long long)miss_s);
+        if (ss_s) { atomicAdd(&dst[PFA_CDS_SS], (unsigned long long)ss_s); atomicAdd(&dst[PFA_CDS_HS], hs_s); }
+        if (sn_s) { atomicAdd(&dst[PFA_CDS_SN], (unsigned long long)sn_s); atomicAdd(&dst[PFA_CDS_HN], hn_s); }
+    }
+    // sum3_by_len: lanes of the same (population, number of clean codons)
+    const unsigned peers2 = __match_any_sync(act, (q << 7) | len);
+    const unsigned t3 = __reduce_add_sync(peers2, tot3);
+    if (t3 && lane == __ffs(peers2) - 1) atomicAdd(&dst[PFA_CDS_SUM3 + len], (unsigned long long)t3);
+}
+
+// n^2 - sum_a c_a^2 of one column in 32-bit arithmetic (n < 65536), 0 when the rows show one symbol
+__device__ __forceinline__ uint32_t pfa_site_h32(const uint32_t c[PFA_NCLASS], uint32_t nq) {
+    uint32_t sum = 0, sq = 0, top = 0;
+#pragma unroll
+    for (int i = 0; i < PFA_NCLASS; ++i) {
+        if (i == PFA_C_ESC) continue;  // columns with escape symbols never come here
+        sum += c[i];
+        sq += c[i] * c[i];
+        top = max(top, c[i]);
+    }
+    const uint32_t gap = nq - sum;
+    sq += gap * gap;
+    top = max(top, gap);
+    return top == nq ? 0u : nq * nq - sq;
+}
+
+// second pass of ONE variable codon column by the whole warp (pfa_sites.cuh): r0 / r1 / rv point to the record of the
+// column's first site in the warp's shared-memory slot (32-bit words; the next site follows Wn words later); f = the 18
+// flag bits of pass 1 (6 per site)
+template <bool HAS_V, bool MULTI>
+__device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0, unsigned f, const uint32_t* r0, const uint32_t* r1,
+                                             const uint32_t* rv, int Wn, int lane, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount) {
+    int nvar = 0, tv = 0, fixed = 0;
+    bool fixed_valid = true;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const unsigned ft = (f >> (6 * t)) & 63u;
+        if (!pfa_flags_mono(ft)) {
+            ++nvar;
+            tv = t;
+        } else {
+            fixed_valid = fixed_valid && (ft & 16u) && !(ft & 32u);
+            fixed |= (((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0)) << (2 * (2 - t));
+        }
+    }
+    const int k = MULTI ? a.s.k : 1;
+    for (int q = 0; q < k; ++q) {
+        const uint32_t* mq = reinterpret_cast<const uint32_t*>(MULTI ? a.s.masks + (int64_t)q * a.s.Wq : a.s.umask);
+        const uint32_t nq = (uint32_t)a.s.pop_n[q];
+        unsigned long long P = 0ull;
+        uint32_t h[3] = {0u, 0u, 0u};
+        if (nvar == 1 && fixed_valid) {
+            // exactly one site varies, the other two show one valid base: the clean codons are that fixed pair combined with
+            // the bases present at the variable site, and only that position can carry a label
+            uint32_t c[PFA_NCLASS];
+            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, rv + tv * Wn, mq, Wn, lane, c);
+            if (HAS_V && c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
+            const int shift = 2 * (2 - tv);
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (c[b]) P |= 1ull << (fixed | (b << shift));
+            const uint32_t hv = pfa_site_h32(c, nq);
+            h[0] = tv == 0 ? hv : 0u;
+            h[1] = tv == 1 ? hv : 0u;
+            h[2] = tv == 2 ? hv : 0u;
+        } else {
+            // general case: class counts of the three columns and the presence mask by peeling distinct codons off each word
+            uint32_t cnt[3][PFA_NCLASS];
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int c = 0; c < PFA_NCLASS; ++c) cnt[t][c] = 0;
+            for (int w = lane; w < Wn; w += 32) {
+                const uint32_t m = __ldg(mq + w);
+                uint32_t live = m;
+                uint32_t x[6];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t w0 = r0[t * Wn + w], w1 = r1[t * Wn + w], wv = HAS_V ? rv[t * Wn + w] : m;
+                    const uint32_t vm = HAS_V ? (wv & m) : m;
+                    const uint32_t hi = vm & w1, lo = vm & ~w1;
+                    cnt[t][PFA_C_T] += __popc(hi & w0);
+                    cnt[t][PFA_C_G] += __popc(hi & ~w0);
+                    cnt[t][PFA_C_C] += __popc(lo & w0);
+                    cnt[t][PFA_C_A] += __popc(lo & ~w0);
+                    if (HAS_V) {
+                        const uint32_t im = ~wv & m;
+                        const uint32_t ihi = im & w1;
+                        cnt[t][PFA_C_ESC] += __popc(ihi & w0);
+                        cnt[t][PFA_C_Q] += __popc(ihi & ~w0);
+                        cnt[t][PFA_C_N] += __popc(im & ~w1 & w0);
+                        live &= wv;
+                    }
+                    x[2 * t] = w1;
+                    x[2 * t + 1] = w0;
+                }
+                while (live) {  // peel one distinct codon per iteration
+                    const int r = __ffs(live) - 1;
+                    uint32_t match = live;
+                    int c = 0;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        const uint32_t bit = (x[t] >> r) & 1u;
+                        c = (c << 1) | (int)bit;
+                        match &= x[t] ^ (bit - 1u);
+                    }
+                    P |= 1ull << c;
+                    live &= ~match;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int c = 0; c < PFA_NCLASS; ++c)
+                    if (HAS_V || c < 4) cnt[t][c] = __reduce_add_sync(0xffffffffu, cnt[t][c]);
+            P = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(P >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)P);
+            if (HAS_V && (cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC])) continue;  // pfa_cds_escape_kernel
+#pragma unroll
+            for (int t = 0; t < 3; ++t) h[t] = pfa_site_h32(cnt[t], nq);
+        }
+        pfa_cds_enqueue(qbuf, qcount, lane, P, h[0], h[1], h[2], q, (uint32_t)site0);
+        if (qcount == 32) {
+            pfa_cds_flush(qbuf, 32, lane, a.acc_in_smem ? sm_acc : reinterpret_cast<unsigned long long*>(a.out), a.labels, a.s.ns);
+            qcount = 0;
+            __syncwarp();
+        }
+    }
+}
+
+// pass 1 of one codon column whose three site records are in registers: 18 flag bits (6 per site), OR-reduced over the group
+template <int LPS, int ITER, bool HAS_V>
+__device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER],
+                                                  const uint4 (&um)[ITER], unsigned gmask) {
+    unsigned f = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const uint4 m = um[i];
+            o0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
+            z0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
+            o1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
+            z1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
+            ov |= (xv[t][i].x & m.x) | (xv[t][i].y & m.y) | (xv[t][i].z & m.z) | (xv[t][i].w & m.w);
+            if (HAS_V) zv |= (~xv[t][i].x & m.x) | (~xv[t][i].y & m.y) | (~xv[t][i].z & m.z) | (~xv[t][i].w & m.w);
+        }
+        f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
+    }
+    return pfa_group_or<LPS>(f, gmask);
+}
+
+// TMA variant (see pfa_site_scan_tma_kernel): every warp owns shared-memory slots holding the site records of the codon
+// columns of m of its passes (3 * 32/LPS consecutive sites per pass), fed by one cp.async.bulk per plane.  Pass 1 runs per
+// group on registers; variable columns (LPS >= 4) are finished by the whole warp one at a time from the slot (pfa_cds_coop).
 template <int LPS, int ITER, bool HAS_V, bool MULTI, int NT>
 __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArgs a, int stages, int m) {
     extern __shared__ __align__(128) unsigned char dyn[];
+    constexpr bool COOP = LPS >= 4;
     constexpr int GW = 32 / LPS;        // codon columns per warp pass
     constexpr int NPL = HAS_V ? 3 : 2;  // planes read
     constexpr int NWARP = NT / 32;
@@ -586,11 +825,12 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
     const int sub = lane & (LPS - 1), grp = lane / LPS;
     const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
     unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;
+    uint32_t* qbuf = reinterpret_cast<uint32_t*>(smem + nacc) + wib * (PFA_CDS_QFIELDS * 32);  // this warp's queue (COOP)
+    int qcount = 0;
     unsigned char* ring = dyn + (size_t)wib * stages * slot_bytes;
     uint64_t* bar = bars + wib * stages;
-    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib, nw = (int64_t)gridDim.x * NWARP;
+    const int64_t nw = (int64_t)gridDim.x * NWARP;
     const int64_t nblk = (a.ncf + CPS - 1) / CPS;                    // blocks of CPS consecutive codon columns
-    const int64_t mine = gw < nblk ? (nblk - gw + nw - 1) / nw : 0;
     const unsigned char* planes[3] = {reinterpret_cast<const unsigned char*>(a.s.b0), reinterpret_cast<const unsigned char*>(a.s.b1),
                                       reinterpret_cast<const unsigned char*>(a.s.v)};
     uint4 um[ITER];
@@ -599,25 +839,45 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         const int j = sub + LPS * i;
         um[i] = j < Wq ? __ldg(a.s.umask + j) : make_uint4(0, 0, 0, 0);
     }
-    auto issue = [&](int64_t k) {
-        const int64_t c0 = (gw + k * nw) * CPS;
+    auto issue = [&](int64_t blk, int st) {  // lane 0: fetch block blk into slot st (or mark the slot empty)
+        if (blk < 0) return;
+        const int64_t c0 = blk * CPS;
         const unsigned ncol = (unsigned)min((int64_t)CPS, a.ncf - c0);
-        const int st = (int)(k % stages);
         pfa_mbar_expect_tx(&bar[st], NPL * ncol * 3u * rec);
 #pragma unroll
         for (int p = 0; p < NPL; ++p)
             pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * CPS * 3u * rec, planes[p] + (size_t)c0 * 3u * rec, ncol * 3u * rec, &bar[st]);
     };
-    if (lane == 0)
-        for (int64_t k = 0; k < mine && k < stages; ++k) issue(k);
+    // blocks are claimed in chunks from a device-wide counter (PfaClaimer)
+    PfaClaimer claim;
+    PfaBlockFifo inflight{-1, -1, -1, -1};
+    if (lane == 0) claim.init(a.s.work, nblk, nw);
+    for (int j = 0; j < stages; ++j) {
+        const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);
+        if (lane == 0) issue(nb, j);
+        if (j == 0) inflight.f0 = nb;
+        else if (j == 1) inflight.f1 = nb;
+        else if (j == 2) inflight.f2 = nb;
+        else inflight.f3 = nb;
+    }
 
-    for (int64_t k = 0; k < mine; ++k) {
+    for (int64_t k = 0;; ++k) {
         const int st = (int)(k % stages);
+        const int64_t blk = inflight.pop();
+        if (blk < 0) break;
         pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
         const unsigned char* slot = ring + (size_t)st * slot_bytes;
+        auto refill = [&]() {  // see pfa_site_scan_tma_kernel
+            const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);  // the shuffle also brings the warp together
+            if (lane == 0) {
+                pfa_fence_proxy_async();
+                issue(nb, st);
+            }
+            inflight.push(nb, stages);
+        };
         for (int t0 = 0; t0 < m; ++t0) {
             const int idx = t0 * GW + grp;  // codon column of this group inside the slot
-            const int64_t cc = (gw + k * nw) * CPS + idx;
+            const int64_t cc = blk * CPS + idx;
             uint4 x0[3][ITER], x1[3][ITER], xv[3][ITER];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -636,14 +896,44 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                     }
                 }
             }
-            if (t0 == m - 1) {
-                __syncwarp();
-                if (lane == 0 && k + stages < mine) issue(k + stages);
+            if (COOP) {
+                const unsigned f = pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
+                bool uniform = true, clean = true;
+                int codon = 0;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const unsigned ft = (f >> (6 * t)) & 63u;
+                    uniform = uniform && pfa_flags_mono(ft) && !pfa_flags_all_escape(ft);
+                    clean = clean && (ft & 16u) && !(ft & 32u);
+                    codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+                }
+                if (uniform && sub == 0 && cc < a.ncf) {  // the same single codon for every population
+                    if (clean) {
+                        u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
+                        u_sum3 += c_syn3[codon];
+                    } else {
+                        u_missing += 3;
+                    }
+                }
+                const unsigned vm = __ballot_sync(0xffffffffu, !uniform && sub == 0 && cc < a.ncf);
+                if (t0 == m - 1 && !vm) refill();
+                for (unsigned rest = vm; rest; rest &= rest - 1) {
+                    const int leader = __ffs(rest) - 1;
+                    const int vidx = t0 * GW + leader / LPS;
+                    const unsigned fv = __shfl_sync(0xffffffffu, f, leader);
+                    pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, reinterpret_cast<const uint32_t*>(slot + (size_t)(vidx * 3) * rec),
+                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(CPS * 3 + vidx * 3) * rec),
+                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount);
+                }
+                if (t0 == m - 1 && vm) refill();
+            } else {
+                if (cc < a.ncf)
+                    pfa_cds_process<LPS, ITER, HAS_V, MULTI>(pfa_cds_view(a), cc * 3, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
+                if (t0 == m - 1) refill();
             }
-            if (cc < a.ncf)
-                pfa_cds_process<LPS, ITER, HAS_V, MULTI>(a, cc * 3, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
         }
     }
+    if (COOP && qcount) pfa_cds_flush(qbuf, qcount, lane, a.acc_in_smem ? sm_acc : reinterpret_cast<unsigned long long*>(a.out), a.labels, a.s.ns);
     if (a.has_partial && blockIdx.x == 0 && threadIdx.x == 0) u_missing += 3;
     for (int off = 16; off; off >>= 1) {
         u_nstops += __shfl_xor_sync(0xffffffffu, u_nstops, off);
@@ -656,6 +946,10 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         if (u_sum3) atomicAdd(&smem[2], (unsigned long long)u_sum3);
     }
     __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.s.work + 1, 1u) == gridDim.x - 1) {  // every CTA has made its last claim
+        a.s.work[0] = 0u;
+        a.s.work[1] = 0u;
+    }
     for (int i = threadIdx.x; i < a.s.k * PFA_CDS_LEN; i += blockDim.x) {
         const int e = i % PFA_CDS_LEN;
         unsigned long long x = a.acc_in_smem ? sm_acc[i] : 0ull;
@@ -766,6 +1060,8 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     if (d_labels && a->ns) PFA_CUDA(ctx, cudaMemsetAsync(d_labels, 0, (size_t)(a->k * a->ns), ctx->stream));
     if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, out_len, d_out) : PFA_OK;
     PfaCdsArgs args;
+    unsigned int* work = nullptr;
+    if (int rc = pfa_ctx_work(ctx, &work)) return rc;
     pfa_fill_site_args(a, nullptr, nullptr, &args.s);
     args.out = x ? reinterpret_cast<int64_t*>(pfa_xchg_partial(x)) : d_out;
     args.labels = d_labels;
@@ -805,7 +1101,8 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         int m = (int)std::max<int64_t>(1, 10000 / ((int64_t)gw * 3 * a->Wq * 16));
         if (const char* e = getenv("PFA_CDS_TMA_M")) m = std::max(1, atoi(e));
         auto dyn_for = [&](int mm) {
-            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16) + sizeof(uint64_t) * nwarp * tma_stages + smem;
+            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16) + sizeof(uint64_t) * nwarp * tma_stages + smem +
+                   (lps >= 4 ? (size_t)nwarp * PFA_CDS_QFIELDS * 32 * sizeof(uint32_t) : 0);
         };
         while (m > 1 && dyn_for(m) > 220 * 1024) --m;
         const size_t dyn = dyn_for(m);
@@ -816,6 +1113,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         {                                                                                                                 \
             cudaFuncSetAttribute(pfa_cds_scan_tma_kernel<L_, I_, V_, M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
             pfa_cds_scan_tma_kernel<L_, I_, V_, M_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                      \
+            pfa_note_kernel(ctx, "pfa_cds_scan_tma_kernel<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d,NT=%d> grid=%u slots=%d passes_per_slot=%d", L_, I_, (int)V_, (int)M_, N_, tgrid, tma_stages, m); \
         }
 #define PFA_CDS_TMA_CASE(L_, I_, N_)                                                                                    \
         if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
@@ -858,8 +1156,157 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: no kernel for lps=%d iter=%d", lps, iter);
     }
 #undef PFA_CDS_CASE
+    pfa_note_kernel(ctx, "%s<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d> grid=%u block=%d", generic ? "pfa_cds_scan_kernel" : "pfa_cds_scan_reg_kernel", lps, iter,
+                    (int)hv, (int)multi, grid.x, PFA_SITE_THREADS);
     PFA_LAUNCH_CHECK(ctx);
     if (x) pfa_xchg_commit(x);
     if (!x && a->n_exc_sites > 0) return launch_cds_escape(a, args);
+    return PFA_OK;
+}
+
+
+// ---- K4b: the codon scan over a batch of small loci (--dir --cds; PolyFastA.py:104 calling :165, :284-315) ----------------
+// One warp per tile of PFA_BATCH_CTILE consecutive codon columns of ONE locus (the tile finds its locus by binary search);
+// a group of LPS lanes owns a codon column, as in pfa_cds_scan_reg_kernel, and runs the same per-column code
+// (pfa_cds_process) on a view of the locus.  Contributions that are the same for every population of the locus -- the
+// monomorphic columns -- stay in registers until the end of the tile.
+template <int LPS, int ITER>
+__global__ void __launch_bounds__(256) pfa_batch_cds_kernel(const PfaBatchArgs a) {
+    constexpr int GW = 32 / LPS;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPS - 1);
+    const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
+    const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= a.n_ctiles) return;
+    const int li = pfa_find_locus(a.ctile_base, a.nloci, tile);
+    const PfaLocusDesc d = a.desc[li];
+    const int Wq = d.Wq;
+    const long long ncf = d.L / 3;
+    const long long c_lo = (tile - a.ctile_base[li]) * PFA_BATCH_CTILE, c_hi = min(ncf, c_lo + PFA_BATCH_CTILE);
+    const bool hv = a.locus_invalid[li] != 0;
+    const uint4* umask = a.masks + d.mask_off + (long long)d.k * Wq;
+    PfaCdsView view;
+    view.masks = a.masks + d.mask_off;
+    view.pop_n = reinterpret_cast<const int64_t*>(a.popn + d.pop_base);
+    view.out = reinterpret_cast<int64_t*>(a.cds_out + d.pop_base * PFA_CDS_LEN);
+    view.labels = nullptr;
+    view.ns = d.L;
+    view.k = d.k;
+    view.acc_in_smem = 0;
+    uint4 um[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int j = sub + LPS * i;
+        um[i] = j < Wq ? __ldg(umask + j) : make_uint4(0, 0, 0, 0);
+    }
+    unsigned u_nstops = 0, u_missing = 0, u_sum3 = 0;
+    for (long long cc = c_lo + lane / LPS; cc < c_hi; cc += GW) {
+        const long long site0 = cc * 3;
+        uint4 x0[3][ITER], x1[3][ITER], xv[3][ITER];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const int j = sub + LPS * i;
+                x0[t][i] = x1[t][i] = make_uint4(0, 0, 0, 0);
+                xv[t][i] = um[i];
+                if (j < Wq) {
+                    const long long o = d.plane_off + (site0 + t) * Wq + j;
+                    x0[t][i] = pfa_ld_stream(a.b0 + o);
+                    x1[t][i] = pfa_ld_stream(a.b1 + o);
+                    if (hv) xv[t][i] = pfa_ld_stream(a.v + o);
+                }
+            }
+        pfa_cds_process<LPS, ITER, true, true>(view, site0, x0, x1, xv, um, sub, gmask, Wq, nullptr, u_nstops, u_missing, u_sum3);
+    }
+    __syncwarp();
+    if (c_lo == 0 && lane == 0 && d.L % 3 != 0) u_missing += 3;  // the trailing partial column (:305), once per locus
+    for (int off = 16; off; off >>= 1) {
+        u_nstops += __shfl_xor_sync(0xffffffffu, u_nstops, off);
+        u_missing += __shfl_xor_sync(0xffffffffu, u_missing, off);
+        u_sum3 += __shfl_xor_sync(0xffffffffu, u_sum3, off);
+    }
+    for (int q = lane; q < d.k; q += 32) {
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(a.cds_out + (d.pop_base + q) * PFA_CDS_LEN);
+        if (u_nstops) atomicAdd(&o[PFA_CDS_NSTOPS], (unsigned long long)u_nstops);
+        if (u_missing) atomicAdd(&o[PFA_CDS_MISSING], (unsigned long long)u_missing);
+        if (u_sum3) atomicAdd(&o[PFA_CDS_SUM3 + 1], (unsigned long long)u_sum3);
+    }
+}
+
+// codon columns of the batch that hold escape symbols: one warp per column, owned by its first exception site (see
+// pfa_cds_escape_kernel); keys carry GLOBAL site indices of the batch
+__global__ void __launch_bounds__(256) pfa_batch_cds_escape_kernel(const PfaBatchArgs a, const unsigned long long* __restrict__ keys, long long n_exc,
+                                                                   const long long* __restrict__ heads, long long n_heads) {
+    __shared__ unsigned int hist[8][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long h = wid; h < n_heads; h += nwarps) {
+        const long long g = (long long)(keys[heads[h]] >> 32);
+        const int li = pfa_find_locus(a.site_base, a.nloci, g);
+        const PfaLocusDesc d = a.desc[li];
+        const long long s = g - d.site_base, cc = s / 3;
+        if (cc >= d.L / 3) continue;  // trailing partial column
+        if (h > 0) {                  // not the first exception site of this codon column?
+            const long long gp = (long long)(keys[heads[h - 1]] >> 32);
+            if (gp >= d.site_base && (gp - d.site_base) / 3 == cc) continue;
+        }
+        long long seg0[3] = {0, 0, 0}, seg1[3] = {0, 0, 0};
+        for (long long hh = h; hh < n_heads && hh < h + 3; ++hh) {
+            const long long g2 = (long long)(keys[heads[hh]] >> 32) - d.site_base;
+            if (g2 < 0 || g2 >= d.L || g2 / 3 != cc) break;
+            seg0[g2 % 3] = heads[hh];
+            seg1[g2 % 3] = (hh + 1 < n_heads) ? heads[hh + 1] : n_exc;
+        }
+        const int Wq = d.Wq;
+        const long long site0 = cc * 3;
+        const uint4 *p0 = a.b0 + d.plane_off, *p1 = a.b1 + d.plane_off, *pv = a.v + d.plane_off;
+        for (int q = 0; q < d.k; ++q) {
+            const uint4* mq = a.masks + d.mask_off + (long long)q * Wq;
+            uint32_t cnt[3][PFA_NCLASS];
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                pfa_class_counts<32, true>(p0 + (site0 + t) * Wq, p1 + (site0 + t) * Wq, pv + (site0 + t) * Wq, mq, Wq, lane, 0xffffffffu, cnt[t]);
+            if (!(cnt[0][PFA_C_ESC] | cnt[1][PFA_C_ESC] | cnt[2][PFA_C_ESC])) continue;  // the main kernel counted it
+            uint32_t escd[3] = {0, 0, 0};
+            unsigned long long escsq[3] = {0, 0, 0};
+            for (int t = 0; t < 3; ++t)
+                if (cnt[t][PFA_C_ESC])
+                    pfa_escape_stats(keys, seg0[t], seg1[t], reinterpret_cast<const uint32_t*>(mq), hist[wib], lane, &escd[t], &escsq[t]);
+            const unsigned long long P = pfa_codon_presence<32, true>(p0, p1, pv, site0, Wq, mq, lane, 0xffffffffu);
+            if (lane != 0) continue;
+            pfa_cds_contribute(P, cnt, a.popn[d.pop_base + q], escd, escsq, reinterpret_cast<unsigned long long*>(a.cds_out + (d.pop_base + q) * PFA_CDS_LEN),
+                               nullptr, site0);
+        }
+    }
+}
+
+int pfa_launch_batch_cds(pfa_ctx* ctx, const PfaBatchArgs& args, int max_Wq, const unsigned long long* keys, long long n_exc,
+                         const long long* heads, long long n_heads) {
+    if (!ctx->codon_tables_ready) {
+        int rc = pfa_upload_codon_tables(ctx);
+        if (rc) return rc;
+        ctx->codon_tables_ready = true;
+    }
+    if (args.n_ctiles > 0) {
+        int lps = 1;
+        while (lps < 32 && (max_Wq + lps - 1) / lps > 2) lps *= 2;
+        const int iter = (max_Wq + lps - 1) / lps;
+        const unsigned grid = (unsigned)((args.n_ctiles + 7) / 8);
+        cudaStream_t st = ctx->stream;
+#define PFA_BC_CASE(L_, I_) \
+    if (lps == L_ && iter == I_) pfa_batch_cds_kernel<L_, I_><<<grid, 256, 0, st>>>(args); else
+        PFA_BC_CASE(1, 1) PFA_BC_CASE(1, 2) PFA_BC_CASE(2, 2) PFA_BC_CASE(4, 2) PFA_BC_CASE(8, 2) PFA_BC_CASE(16, 2) PFA_BC_CASE(32, 2)
+        PFA_BC_CASE(32, 3) PFA_BC_CASE(32, 4)
+        return pfa_fail(ctx, PFA_ERR_ARG, "batched codon scan: a locus has too many sequences (Wq=%d); use the single-alignment path", max_Wq);
+#undef PFA_BC_CASE
+        PFA_LAUNCH_CHECK(ctx);
+    }
+    if (n_heads > 0) {
+        const long long eb = std::min<long long>((n_heads + 7) / 8, (long long)ctx->sm_count * 8);
+        pfa_batch_cds_escape_kernel<<<(unsigned)eb, 256, 0, ctx->stream>>>(args, keys, n_exc, heads, n_heads);
+        PFA_LAUNCH_CHECK(ctx);
+    }
     return PFA_OK;
 }

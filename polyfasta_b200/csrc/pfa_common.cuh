@@ -18,6 +18,7 @@ struct pfa_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // own_stream or a caller-owned stream
     std::string err;
+    std::string last_kernel;  // the scan kernel of the last K2 / K4 launch, as instantiated (pfa_ctx_last_kernel)
     std::atomic<int64_t> launches{0};  // kernels launched (the packed ingest lane launches from its own thread)
     // small pinned + device scratch for finalisation and synchronous result copies
     void* h_scratch = nullptr;
@@ -34,6 +35,7 @@ struct pfa_ctx {
     size_t pack_pinned_bytes = 0;
     void* raw_pinned = nullptr;  // bounce buffers for text chunks of a pageable source
     size_t raw_pinned_bytes = 0;
+    unsigned int* d_work = nullptr;  // block-claim counters of the TMA scan kernels (zero between launches)
     bool codon_tables_ready = false;  // constant-memory tables of K4 uploaded (first codon scan)
     int host_threads = 0;  // host threads the ingest may use; 0 = PFA_HOST_THREADS or all hardware threads
     int64_t ingest_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // last upload: chunks sent as text, chunks packed on the host, dirty chunks, threads, H2D bytes as text, H2D bytes packed, packed chunks that carried a validity bitmap
@@ -71,6 +73,7 @@ struct pfa_aln {
 // ---- error plumbing ----------------------------------------------------------------------------------
 int pfa_fail(pfa_ctx* ctx, int code, const char* fmt, ...);
 void pfa_set_global_error(const char* fmt, ...);
+void pfa_note_kernel(pfa_ctx* ctx, const char* fmt, ...);
 
 #define PFA_CUDA(ctx, call)                                                                       \
     do {                                                                                          \
@@ -107,6 +110,7 @@ void pfa_xchg_commit(pfa_xchg* x);
 int pfa_xchg_launch_only(pfa_xchg* x, const int64_t* d_src, int64_t len, int64_t* d_out);
 int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_upload_codon_tables(pfa_ctx* ctx);
+int pfa_ctx_work(pfa_ctx* ctx, unsigned int** out);
 int pfa_aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t col_end, pfa_aln** out);
 int pfa_aln_default_pop(pfa_aln* a);
 // upload + encode of columns [col_begin, col_end) of a text matrix (pfa_ingest.cu); `dev`: the matrix is in device memory

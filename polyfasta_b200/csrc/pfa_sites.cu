@@ -322,14 +322,69 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
     }
 }
 
+// pass 1 of one site whose chunks are in registers: the six presence flags, OR-reduced over the group
+template <int LPS, int ITER, bool HAS_V>
+__device__ __forceinline__ unsigned pfa_site_pass1(const uint4 (&x0)[ITER], const uint4 (&x1)[ITER], const uint4 (&xv)[ITER],
+                                                   const uint4 (&um)[ITER], unsigned gmask) {
+    uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const uint4 m = um[i];
+        o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
+        z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
+        o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
+        z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
+        ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
+        if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
+    }
+    const unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+    return pfa_group_or<LPS>(f, gmask);
+}
+
+// second pass of ONE variable site by the whole warp (see pfa_sites.cuh): w0 / w1 / wv are the site's records in the warp's
+// shared-memory slot.  S and H of population q < 32 accumulate in the registers of lane q.
+template <bool HAS_V, bool MULTI>
+__device__ __forceinline__ void pfa_site_coop(const PfaSiteArgs& a, int64_t s, const uint32_t* w0, const uint32_t* w1, const uint32_t* wv,
+                                              int Wn, int lane, unsigned long long* sm_SH, unsigned int* sm_sfs, uint32_t& S_mine,
+                                              unsigned long long& H_mine) {
+    const int k = MULTI ? a.k : 1;
+    for (int q = 0; q < k; ++q) {
+        const uint32_t* mq = reinterpret_cast<const uint32_t*>(MULTI ? a.masks + (int64_t)q * a.Wq : a.umask);
+        uint32_t c[PFA_NCLASS];
+        pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c);
+        const PfaSiteResult r = pfa_site_result(c, a.pop_n[q], 0u, 0ull);
+        if (r.has_escape) continue;  // finished by pfa_escape_sites_kernel
+        if (a.isvar && lane == 0) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
+        if (!r.isvar) continue;
+        if (q < 32) {
+            if (lane == q) {
+                S_mine += 1u;
+                H_mine += r.h;
+            }
+        } else if (lane == 0) {
+            atomicAdd(&sm_SH[2 * q], 1ull);
+            atomicAdd(&sm_SH[2 * q + 1], r.h);
+        }
+        if (r.sfs_bin >= 0 && lane == 0) {
+            if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
+            else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
+        }
+    }
+}
+
 // TMA variant of the register-resident kernel: the bytes in flight are bounded by shared memory instead of registers.
-// Every WARP owns a private ring of STAGES shared-memory slots; a slot holds the records of the 32/LPS consecutive sites the
-// warp's groups handle in one iteration (contiguous in each plane), fetched with one cp.async.bulk per plane that completes
-// on the slot's mbarrier.  No block-wide synchronisation: a warp waits for its own slot, copies its chunks to registers,
-// refills the slot for the iteration STAGES ahead and then runs the same passes as the register kernel.
+// Every WARP owns a private ring of STAGES shared-memory slots; a slot holds the records of the consecutive sites of m of the
+// warp's passes (contiguous in each plane), fetched with one cp.async.bulk per plane that completes on the slot's mbarrier.
+// No block-wide synchronisation: a warp waits for its own slot and runs pass 1 of every site on registers (a group of LPS
+// lanes per site).  Variable sites (LPS >= 4): the whole warp takes them one at a time, reading the record back from the slot
+// (pfa_site_coop); narrow records handled by 1-2 lanes keep the per-group second pass (every lane has its own site there).
+// The slot is refilled once its last pass no longer needs it: right after pass 1 when that pass found no variable site,
+// else after their second pass -- every shared-memory read of the slot has then been consumed (its value was used), and a
+// proxy fence orders those generic-proxy reads before the bulk copy's async-proxy writes.
 template <int LPS, int ITER, bool HAS_V, bool MULTI>
 __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages, int m) {
     constexpr int NT = 512;
+    constexpr bool COOP = LPS >= 4;
     extern __shared__ __align__(128) unsigned char dyn[];
     constexpr int GW = 32 / LPS;        // sites per warp pass
     constexpr int NPL = HAS_V ? 3 : 2;  // planes read
@@ -357,11 +412,12 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
     const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
     unsigned char* ring = ring_base + (size_t)wib * stages * slot_bytes;
     uint64_t* bar = bars + wib * stages;
-    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib, nw = (int64_t)gridDim.x * NWARP;
+    const int64_t nw = (int64_t)gridDim.x * NWARP;
     const int64_t nblk = (a.ns + SPS - 1) / SPS;                     // blocks of SPS consecutive sites
-    const int64_t mine = gw < nblk ? (nblk - gw + nw - 1) / nw : 0;  // this warp's blocks: gw, gw + nw, ...
     const unsigned char* planes[3] = {reinterpret_cast<const unsigned char*>(a.b0), reinterpret_cast<const unsigned char*>(a.b1),
                                       reinterpret_cast<const unsigned char*>(a.v)};
+    uint32_t S_mine = 0;               // COOP: S and H of population `lane`
+    unsigned long long H_mine = 0ull;
 
     uint4 um[ITER];
 #pragma unroll
@@ -369,25 +425,45 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
         const int j = sub + LPS * i;
         um[i] = j < Wq ? __ldg(a.umask + j) : make_uint4(0, 0, 0, 0);
     }
-    auto issue = [&](int64_t k) {  // lane 0: fetch block k of this warp into slot k % stages
-        const int64_t s0 = (gw + k * nw) * SPS;
+    auto issue = [&](int64_t blk, int st) {  // lane 0: fetch block blk into slot st (or mark the slot empty)
+        if (blk < 0) return;
+        const int64_t s0 = blk * SPS;
         const unsigned nsite = (unsigned)min((int64_t)SPS, a.ns - s0);
-        const int st = (int)(k % stages);
         pfa_mbar_expect_tx(&bar[st], NPL * nsite * rec);
 #pragma unroll
         for (int p = 0; p < NPL; ++p)
             pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * SPS * rec, planes[p] + (size_t)s0 * rec, nsite * rec, &bar[st]);
     };
-    if (lane == 0)
-        for (int64_t k = 0; k < mine && k < stages; ++k) issue(k);
+    // blocks are claimed in chunks from a device-wide counter (PfaClaimer): warps that meet few variable sites take more
+    PfaClaimer claim;
+    PfaBlockFifo inflight{-1, -1, -1, -1};
+    if (lane == 0) claim.init(a.work, nblk, nw);
+    for (int j = 0; j < stages; ++j) {
+        const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);
+        if (lane == 0) issue(nb, j);
+        if (j == 0) inflight.f0 = nb;
+        else if (j == 1) inflight.f1 = nb;
+        else if (j == 2) inflight.f2 = nb;
+        else inflight.f3 = nb;
+    }
 
-    for (int64_t k = 0; k < mine; ++k) {
+    for (int64_t k = 0;; ++k) {
         const int st = (int)(k % stages);
+        const int64_t blk = inflight.pop();
+        if (blk < 0) break;
         pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
         const unsigned char* slot = ring + (size_t)st * slot_bytes;
+        auto refill = [&]() {
+            const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);  // the shuffle also brings the warp together
+            if (lane == 0) {
+                pfa_fence_proxy_async();
+                issue(nb, st);
+            }
+            inflight.push(nb, stages);
+        };
         for (int t = 0; t < m; ++t) {
             const int idx = t * GW + grp;  // site of this group inside the slot
-            const int64_t s = (gw + k * nw) * SPS + idx;
+            const int64_t s = blk * SPS + idx;
             const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
             const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
             const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
@@ -403,14 +479,36 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                     if (HAS_V) xv[i] = qv[j];
                 }
             }
-            if (t == m - 1) {
-                __syncwarp();  // every lane has the slot's last chunks in registers: the slot may be refilled
-                if (lane == 0 && k + stages < mine) issue(k + stages);
+            if (COOP) {
+                const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
+                const bool var = s < a.ns && !(pfa_flags_mono(f) && !pfa_flags_all_escape(f));
+                if (a.isvar && sub == 0 && s < a.ns && !var)
+                    for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
+                const unsigned vm = __ballot_sync(0xffffffffu, var && sub == 0);
+                if (t == m - 1 && !vm) refill();
+                for (unsigned rest = vm; rest; rest &= rest - 1) {
+                    const int vidx = t * GW + (__ffs(rest) - 1) / LPS;
+                    pfa_site_coop<HAS_V, MULTI>(a, blk * SPS + vidx, reinterpret_cast<const uint32_t*>(slot + (size_t)vidx * rec),
+                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec),
+                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec), Wq * 4, lane, sm_SH,
+                                                sm_sfs, S_mine, H_mine);
+                }
+                if (t == m - 1 && vm) refill();
+            } else {
+                if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V, MULTI>(a, s, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
+                if (t == m - 1) refill();
             }
-            if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V, MULTI>(a, s, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
         }
     }
+    if (COOP && lane < a.k && S_mine) {
+        atomicAdd(&sm_SH[2 * lane], (unsigned long long)S_mine);
+        atomicAdd(&sm_SH[2 * lane + 1], H_mine);
+    }
     __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {  // every CTA has made its last claim: reset for the next launch
+        a.work[0] = 0u;
+        a.work[1] = 0u;
+    }
     for (int q = threadIdx.x; q < a.k; q += blockDim.x) {
         if (sm_SH[2 * q]) {
             atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q]), sm_SH[2 * q]);
@@ -450,6 +548,8 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     if (!x) PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
     if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, out_len, d_out) : PFA_OK;
     PfaSiteArgs args;
+    unsigned int* work = nullptr;
+    if (int rc = pfa_ctx_work(ctx, &work)) return rc;
     pfa_fill_site_args(a, d_out, d_isvar, &args);
     if (x) {
         // the blocks add into the exchange's partial vector (zero between launches); the escape kernel goes FIRST so that
@@ -504,6 +604,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         {                                                                                                                 \
             cudaFuncSetAttribute(pfa_site_scan_tma_kernel<L_, I_, V_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
             pfa_site_scan_tma_kernel<L_, I_, V_, M_><<<tgrid, nt, dyn, st>>>(args, tma_stages, m);                         \
+            pfa_note_kernel(ctx, "pfa_site_scan_tma_kernel<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d> grid=%u block=%d slots=%d passes_per_slot=%d", L_, I_, (int)V_, (int)M_, tgrid, nt, tma_stages, m); \
         }
 #define PFA_TMA_CASE(L_, I_)                                                                                            \
         if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
@@ -552,6 +653,8 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         return pfa_fail(ctx, PFA_ERR_ARG, "site scan: no kernel for lps=%d iter=%d", lps, iter);
     }
 #undef PFA_REG_CASE
+    pfa_note_kernel(ctx, "%s<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d> grid=%u block=%d", generic ? "pfa_site_scan_kernel" : "pfa_site_scan_reg_kernel", lps, iter,
+                    (int)hv, (int)multi, grid.x, PFA_SITE_THREADS);
     PFA_LAUNCH_CHECK(ctx);
     if (x) pfa_xchg_commit(x);
     if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);

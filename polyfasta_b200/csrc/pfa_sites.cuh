@@ -30,6 +30,7 @@ struct PfaSiteArgs {
     int k;
     int sfs_in_smem;
     int sfs_bins;  // total bins over all populations
+    unsigned int* work;  // [2], zero between launches: next block to claim / CTAs done (TMA kernels, pfa_ctx_work)
     PfaXchgDev x;  // x.world > 0: the last block sums `out` over the column shards of all GPUs (pfa_xchg.cuh)
 };
 
@@ -137,6 +138,120 @@ __device__ __forceinline__ PfaSiteResult pfa_site_result(const uint32_t c[PFA_NC
     return r;
 }
 
+// ---- warp-cooperative second pass ----------------------------------------------------------------------------------------
+// The first pass of the scan kernels gives a site (or codon column) to a GROUP of LPS lanes; the few variable ones then need
+// popcounts per population and scalar bookkeeping.  Done by the owning group alone that work runs with LPS of the 32 lanes
+// active (ncu, round 1: 17 active threads per warp in K4, 75 % of all issued instructions).  Here the WHOLE warp takes one
+// variable site at a time: lane l counts words l, l + 32, ... of the record (read back from the warp's shared-memory slot),
+// REDUX sums the counts, every lane holds the totals and the scalar part runs uniformly (one issue slot per instruction
+// whatever the number of active lanes), with the accumulators of population q in the registers of lane q.
+
+// class counts of one population at one site: w0 / w1 / wv point to the site's record in each plane (32-bit words, Wn of
+// them), mq to the population's row mask
+template <bool HAS_V>
+__device__ __forceinline__ void pfa_coop_counts(const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
+                                                const uint32_t* __restrict__ wv, const uint32_t* __restrict__ mq, int Wn, int lane,
+                                                uint32_t c[PFA_NCLASS]) {
+#pragma unroll
+    for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+    for (int w = lane; w < Wn; w += 32) {
+        const uint32_t m = __ldg(mq + w), x0 = w0[w], x1 = w1[w];
+        const uint32_t vm = HAS_V ? (wv[w] & m) : m;
+        const uint32_t hi = vm & x1, lo = vm & ~x1;
+        c[PFA_C_T] += __popc(hi & x0);
+        c[PFA_C_G] += __popc(hi & ~x0);
+        c[PFA_C_C] += __popc(lo & x0);
+        c[PFA_C_A] += __popc(lo & ~x0);
+        if (HAS_V) {
+            const uint32_t im = ~wv[w] & m;
+            const uint32_t ihi = im & x1;
+            c[PFA_C_ESC] += __popc(ihi & x0);
+            c[PFA_C_Q] += __popc(ihi & ~x0);
+            c[PFA_C_N] += __popc(im & ~x1 & x0);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PFA_NCLASS; ++i)
+        if (HAS_V || i < 4) c[i] = __reduce_add_sync(0xffffffffu, c[i]);
+}
+
+// flags of pass 1 (bit 0/1: plane b0 shows a one / a zero among the rows of the union mask, 2/3: b1, 4/5: v)
+__device__ __forceinline__ bool pfa_flags_mono(unsigned f) { return ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u); }
+__device__ __forceinline__ bool pfa_flags_all_escape(unsigned f) { return (f & 1u) && (f & 4u) && !(f & 16u); }
+
+// ---- dynamic distribution of the blocks of a scan over the warps of the grid ------------------------------------------------
+// A static split (block b to warp b mod W) left ~7 % of the warp time idle at the end of K4: warps that meet more variable
+// columns finish later.  Claiming every block from one counter does not scale either (same-address atomics serialise in L2:
+// 5e6 claims took 10 ms on C4).  So warps claim CHUNKS of blocks whose size halves from phase to phase (guided
+// self-scheduling): with W warps, phase p hands out P = 4 W chunks of c = C0 >> p blocks each, C0 = blocks / (8 W); the last
+// blocks go out one by one.  ~4 W log2(C0) claims per launch, each prefetched one chunk ahead.  The chunks of a phase are
+// INTERLEAVED -- claim j of a phase takes blocks start + j, start + j + P, ... -- so that the warps of the grid keep reading one
+// contiguous window of the planes as they did under the static split.  Used by lane 0 of a warp.
+struct PfaClaimer {
+    unsigned int* ctr;
+    long long nblk, P, C0, cur, remaining;
+    unsigned int pending;
+    __device__ __forceinline__ void init(unsigned int* counter, long long blocks, long long warps) {
+        ctr = counter;
+        nblk = blocks;
+        P = 4 * warps;
+        C0 = blocks / (8 * warps);
+        if (C0 < 1) C0 = 1;
+        cur = remaining = 0;
+        pending = atomicAdd(ctr, 1u);
+    }
+    __device__ __forceinline__ long long next() {  // the next block of this warp, -1 when none is left
+        for (;;) {
+            if (remaining > 0) {
+                const long long b = cur;
+                cur += P;
+                --remaining;
+                if (b < nblk) return b;
+                remaining = 0;  // the rest of this chunk lies beyond the end
+            }
+            if (pending == 0xffffffffu) return -1;
+            long long start = 0, c = C0, j = pending;
+            while (c > 1 && j >= P) {
+                start += P * c;
+                j -= P;
+                c >>= 1;
+            }
+            if (c == 1) {
+                start += (j / P) * P;
+                j %= P;
+            }
+            if (start >= nblk) {
+                pending = 0xffffffffu;
+                return -1;
+            }
+            cur = start + j;
+            remaining = c;
+            pending = atomicAdd(ctr, 1u);  // needed only when this chunk is used up
+        }
+    }
+};
+
+// the blocks in flight of one warp, oldest first (one per slot of its ring, at most 4), kept identically in every lane
+struct PfaBlockFifo {
+    long long f0, f1, f2, f3;
+    __device__ __forceinline__ long long pop() {
+        const long long b = f0;
+        f0 = f1; f1 = f2; f2 = f3; f3 = -1;
+        return b;
+    }
+    __device__ __forceinline__ void push(long long b, int stages) {  // after a pop: stages - 1 blocks are in flight
+        if (stages == 1) f0 = b;
+        else if (stages == 2) f1 = b;
+        else if (stages == 3) f2 = b;
+        else f3 = b;
+    }
+};
+__device__ __forceinline__ long long pfa_bcast0(long long x) {
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(unsigned long long)x, 0);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)((unsigned long long)x >> 32), 0);
+    return (long long)(((unsigned long long)hi << 32) | lo);
+}
+
 // ---- bulk copies (TMA) into shared memory completing on an mbarrier ------------------------------------------------------
 __device__ __forceinline__ uint32_t pfa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pfa_mbar_init(uint64_t* bar, unsigned count) {
@@ -150,6 +265,8 @@ __device__ __forceinline__ void pfa_bulk_load(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(pfa_smem_u32(bar))
                  : "memory");
 }
+// orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void pfa_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n"

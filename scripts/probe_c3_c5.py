@@ -34,6 +34,8 @@ with torch.cuda.stream(stream):
         print("C3 %s: K2 %.3f ms (%.0f GB/s)  K4 %.3f ms (%.0f GB/s)  -> %.2e bases/s for K2+K4" %
               (label, ms2, gb / ms2 * 1e3, ms4, gb / ms4 * 1e3, n * L / ((ms2 + ms4) * 1e-3)))
     aln.free()
+    if "--c3-only" in sys.argv:
+        sys.exit(0)
     # K3 on a 2000 x 100 kb slice
     a = pf.Alignment.synthetic(ctx, 2000, 100_000, 3)
     out_p = torch.zeros(1, dtype=torch.int64, device="cuda")

@@ -719,3 +719,39 @@ def test_batch_many_short_rows(ctx, tmp_path):
         got, want = batch.result(fi["locus"], 0, want_sfs=True), co.site_stats(text)
         assert (fi["n"], fi["L"]) == text.shape and (got["S"], got["H"], got["sfs"]) == (want["S"], want["H"], want["sfs"])
     batch.close()
+
+
+def test_batch_codon_scan(ctx):
+    """K4b: the segmented codon scan of the batched --dir --cds path == the single-alignment K4 == the C oracle, for loci of
+    mixed shapes (lengths not divisible by 3, shorter than a codon, more rows than one tile column handles), populations and
+    symbol content (escape symbols inside codon columns) in one batch; repeated scans of one staged batch agree"""
+    rng = np.random.default_rng(321)
+    shapes = [(20, 1000), (100, 5000), (3, 7), (1, 40), (33, 65), (128, 300), (129, 301), (700, 902), (2100, 257), (16, 0), (50, 31), (9, 2),
+              (40, 3), (300, 1535)]
+    batch = pf.api.Batch(ctx)
+    loci = []
+    for i, (n, L) in enumerate(shapes):
+        junk = 0.0 if i % 3 == 0 else 0.02
+        text = _random_text(rng, n, L, p_var=0.1, p_junk=junk) if L else np.zeros((n, 0), dtype=np.uint8)
+        pops = None if i % 2 == 0 else [p for p in (list(range(0, n, 2)), list(range(n // 2, n)), list(range(n))) if p]
+        loci.append((text, pops, batch.add_rows(text, pops)))
+    batch.stage()
+    for rep in range(2):
+        batch.scan(jc=True, cds=True)
+        for text, pops, idx in loci:
+            n, L = text.shape
+            up = _upper(text)
+            for q, rows in enumerate(pops or [list(range(n))]):
+                got = batch.result_cds(idx, q)
+                want = co.cds_stats(up, rows) if L else {"nstops": 0, "missing": 0, "S_s": 0, "H_s": 0, "S_n": 0, "H_n": 0, "sum3_by_len": {}, "ssites": 0.0}
+                for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
+                    assert got[k] == want[k], (n, L, q, k, rep)
+                assert math.isclose(got["ssites"], want["ssites"], rel_tol=1e-12) or got["ssites"] == want["ssites"]
+                site = batch.result(idx, q)
+                ws = co.site_stats(up, rows) if L else {"S": 0, "H": 0}
+                assert (site["S"], site["H"]) == (ws["S"], ws["H"])
+                nsites = (L - got["missing"]) - got["ssites"]
+                ref = ctx.finalize([(len(rows), got["S_s"], got["H_s"], got["ssites"], True), (len(rows), got["S_n"], got["H_n"], nsites, True)])
+                assert [got["poly_s"], got["poly_n"]] == ref, (n, L, q)
+    batch.release()
+    batch.close()
