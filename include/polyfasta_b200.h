@@ -103,6 +103,9 @@ int pfa_aln_synthetic(pfa_ctx* ctx, int64_t n, int64_t L, uint64_t seed, uint32_
                       int64_t col_begin, int64_t col_end, pfa_aln** out);
 /* the same synthetic alignment as upper-case text d_text[row*ld + (col-col_begin)] in DEVICE memory (benchmark input
  * for the end-to-end leg: copied to pinned host memory, then uploaded like any other alignment) */
+/* benchmarks / tests: turn gap_ppm cells per million of a resident alignment into '-' (deterministic in seed, site, row;
+ * polyfasta_b200.synth.poke_gaps is the numpy twin).  gap_ppm <= 31250. */
+int pfa_aln_poke_gaps(pfa_aln* a, uint64_t seed, uint32_t gap_ppm);
 int pfa_synth_text_device(pfa_ctx* ctx, uint8_t* d_text, int64_t ld, int64_t n, uint64_t seed, uint32_t p_seg_ppm,
                           uint32_t tri_ppm, int64_t col_begin, int64_t col_end);
 int pfa_aln_free(pfa_aln* a);

@@ -299,6 +299,10 @@ class Alignment:
     def has_invalid(self):
         return bool(lib().pfa_aln_has_invalid(self.handle))
 
+    def poke_gaps(self, seed, gap_ppm):
+        """turn gap_ppm cells per million into '-' (synth.poke_gaps is the numpy twin)"""
+        check(lib().pfa_aln_poke_gaps(self.handle, int(seed), int(gap_ppm)), self.ctx.handle)
+
     def force_validity(self, flag=True):
         """benchmarking: make the scans read the validity plane even for a pure-ACGT shard"""
         check(lib().pfa_aln_force_validity(self.handle, int(bool(flag))), self.ctx.handle)

@@ -200,6 +200,7 @@ int pfa_aln_free(pfa_aln* a) {
     pfa_ctx* ctx = a->ctx;
     cudaSetDevice(ctx->device);
     pfa_dfree(ctx, a->planes);
+    pfa_dfree(ctx, a->vflag);
     pfa_dfree(ctx, a->exc_keys);
     pfa_dfree(ctx, a->exc_heads);
     pfa_dfree(ctx, a->d_masks);
@@ -403,8 +404,12 @@ int pfa_aln_alloc(pfa_ctx* ctx, int64_t n, int64_t L, int64_t col_begin, int64_t
     a->b0 = a->planes;
     a->b1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a->planes) + a->plane_bytes);
     a->v = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a->planes) + 2 * a->plane_bytes);
+    a->gc = std::max(1, (a->Wq + 31) / 32);
+    const size_t vf_bytes = sizeof(uint32_t) * (size_t)(a->ns + 64);
+    if (e == cudaSuccess) e = pfa_dmalloc(ctx, &a->vflag, vf_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->vflag, 0, vf_bytes, ctx->stream);
     // rows beyond n (padding up to a multiple of 128) must read as zero in every plane
-    e = cudaMemsetAsync(a->planes, 0, 3 * a->plane_bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->planes, 0, 3 * a->plane_bytes, ctx->stream);
     if (e != cudaSuccess) {
         pfa_aln_free(a);
         return pfa_fail(ctx, PFA_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
@@ -443,6 +448,8 @@ void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaS
     args->out = d_out;
     args->isvar = d_isvar;
     args->ns = a->ns;
+    args->vflag = nullptr;  // the launchers switch the sparse validity fetch on
+    args->gc = a->gc;
     args->Wq = a->Wq;
     args->k = a->k;
     int64_t bins = 0;

@@ -674,7 +674,8 @@ __device__ __forceinline__ uint32_t pfa_site_h32(const uint32_t c[PFA_NCLASS], u
 // flag bits of pass 1 (6 per site)
 template <bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0, unsigned f, const uint32_t* r0, const uint32_t* r1,
-                                             const uint32_t* rv, int Wn, int lane, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount) {
+                                             const uint32_t* rv, int Wn, int lane, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount,
+                                             const uint32_t (&fw)[3], int gcw) {
     int nvar = 0, tv = 0, fixed = 0;
     bool fixed_valid = true;
 #pragma unroll
@@ -698,7 +699,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
             // exactly one site varies, the other two show one valid base: the clean codons are that fixed pair combined with
             // the bases present at the variable site, and only that position can carry a label
             uint32_t c[PFA_NCLASS];
-            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, rv + tv * Wn, mq, Wn, lane, c);
+            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, rv + tv * Wn, mq, Wn, lane, c, tv == 0 ? fw[0] : tv == 1 ? fw[1] : fw[2], gcw);
             if (HAS_V && c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
             const int shift = 2 * (2 - tv);
 #pragma unroll
@@ -721,7 +722,9 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
                 uint32_t x[6];
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
-                    const uint32_t w0 = r0[t * Wn + w], w1 = r1[t * Wn + w], wv = HAS_V ? rv[t * Wn + w] : m;
+                    const uint32_t w0 = r0[t * Wn + w], w1 = r1[t * Wn + w];
+                    uint32_t wv = 0xffffffffu;  // words of an unflagged cell were not fetched: all rows valid
+                    if (HAS_V && ((fw[t] >> (w / gcw)) & 1u)) wv = rv[t * Wn + w];
                     const uint32_t vm = HAS_V ? (wv & m) : m;
                     const uint32_t hi = vm & w1, lo = vm & ~w1;
                     cnt[t][PFA_C_T] += __popc(hi & w0);
@@ -809,7 +812,10 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
     const int Wq = a.s.Wq;
     const unsigned rec = (unsigned)Wq * 16u;  // one site record in one plane
     const int CPS = GW * m;                   // codon columns per slot
-    const unsigned slot_bytes = (unsigned)NPL * CPS * 3u * rec;  // [plane][site in slot][Wq] uint4
+    const int SPS = CPS * 3;                  // sites per slot
+    const unsigned slot_bytes = (unsigned)NPL * SPS * rec + (HAS_V ? (((unsigned)SPS * 4u + 15u) & ~15u) : 0u);  // pfa_slot_issue
+    const bool sparse = HAS_V && a.s.vflag != nullptr;  // fetch only the flagged cells of the v plane
+    const int gc = a.s.gc, gcw = a.s.gc * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);
     unsigned long long* smem = reinterpret_cast<unsigned long long*>(bars + NWARP * stages);  // [3] uniform + accumulators
     const int nacc = 3 + (a.acc_in_smem ? a.s.k * PFA_CDS_LEN : 0);
@@ -839,22 +845,44 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         const int j = sub + LPS * i;
         um[i] = j < Wq ? __ldg(a.s.umask + j) : make_uint4(0, 0, 0, 0);
     }
-    auto issue = [&](int64_t blk, int st) {  // lane 0: fetch block blk into slot st (or mark the slot empty)
-        if (blk < 0) return;
-        const int64_t c0 = blk * CPS;
-        const unsigned ncol = (unsigned)min((int64_t)CPS, a.ncf - c0);
-        pfa_mbar_expect_tx(&bar[st], NPL * ncol * 3u * rec);
+    int cell[ITER];  // the flag bit of each of this lane's chunks
 #pragma unroll
-        for (int p = 0; p < NPL; ++p)
-            pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * CPS * 3u * rec, planes[p] + (size_t)c0 * 3u * rec, ncol * 3u * rec, &bar[st]);
-    };
-    // blocks are claimed in chunks from a device-wide counter (PfaClaimer)
+    for (int i = 0; i < ITER; ++i) cell[i] = (sub + LPS * i) / gc;
+    // block distribution and the one-block-ahead validity flags: see pfa_site_scan_tma_kernel
     PfaClaimer claim;
     PfaBlockFifo inflight{-1, -1, -1, -1};
-    if (lane == 0) claim.init(a.s.work, nblk, nw);
+    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib;
+    const int64_t rounds = (nblk / nw) * 7 / 8;
+    int64_t round = 0;
+    if (lane == 0) claim.init(a.s.work, nblk - rounds * nw, nw);
+    auto next_block = [&]() -> long long {  // all lanes
+        if (round < rounds) return gw + (round++) * nw;
+        const long long b = pfa_bcast0(lane == 0 ? claim.next() : 0);
+        return b < 0 ? -1 : b + rounds * nw;
+    };
+    long long pend = next_block();
+    uint32_t pfl[PFA_VF_REGS];
+    auto load_flags = [&]() {
+#pragma unroll
+        for (int u = 0; u < PFA_VF_REGS; ++u) {
+            const int64_t s = pend * SPS + u * 32 + lane;
+            pfl[u] = (sparse && pend >= 0 && u * 32 + lane < SPS && s < a.ncf * 3) ? __ldg(a.s.vflag + s) : 0u;
+        }
+    };
+    load_flags();
+    auto issue_next = [&](int st) -> long long {  // all lanes: fetch `pend` into slot st, then look one block further ahead
+        const long long blk = pend;
+        if (blk >= 0) {
+            const int64_t c0 = blk * CPS;
+            pfa_slot_issue<HAS_V>(ring + (size_t)st * slot_bytes, &bar[st], planes[0], planes[1], planes[2], sparse, gc, c0 * 3,
+                                  3u * (unsigned)min((int64_t)CPS, a.ncf - c0), (unsigned)SPS, rec, Wq, pfl, lane);
+        }
+        pend = blk >= 0 ? next_block() : -1;
+        load_flags();
+        return blk;
+    };
     for (int j = 0; j < stages; ++j) {
-        const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);
-        if (lane == 0) issue(nb, j);
+        const long long nb = issue_next(j);
         if (j == 0) inflight.f0 = nb;
         else if (j == 1) inflight.f1 = nb;
         else if (j == 2) inflight.f2 = nb;
@@ -867,14 +895,8 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         if (blk < 0) break;
         pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
         const unsigned char* slot = ring + (size_t)st * slot_bytes;
-        auto refill = [&]() {  // see pfa_site_scan_tma_kernel
-            const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);  // the shuffle also brings the warp together
-            if (lane == 0) {
-                pfa_fence_proxy_async();
-                issue(nb, st);
-            }
-            inflight.push(nb, stages);
-        };
+        const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
+        auto refill = [&]() { inflight.push(issue_next(st), stages); };
         for (int t0 = 0; t0 < m; ++t0) {
             const int idx = t0 * GW + grp;  // codon column of this group inside the slot
             const int64_t cc = blk * CPS + idx;
@@ -884,6 +906,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)(idx * 3 + t) * rec);
                 const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(CPS * 3 + idx * 3 + t) * rec);
                 const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * CPS * 3 + idx * 3 + t) * rec);
+                const uint32_t fwt = sparse ? fa[idx * 3 + t] : 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < ITER; ++i) {
                     const int j = sub + LPS * i;
@@ -892,7 +915,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                     if (j < Wq && cc < a.ncf) {
                         x0[t][i] = q0[j];
                         x1[t][i] = q1[j];
-                        if (HAS_V) xv[t][i] = qv[j];
+                        if (HAS_V && ((fwt >> cell[i]) & 1u)) xv[t][i] = qv[j];
                     }
                 }
             }
@@ -921,9 +944,11 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                     const int leader = __ffs(rest) - 1;
                     const int vidx = t0 * GW + leader / LPS;
                     const unsigned fv = __shfl_sync(0xffffffffu, f, leader);
+                    const uint32_t fw3[3] = {sparse ? fa[vidx * 3] : 0xffffffffu, sparse ? fa[vidx * 3 + 1] : 0xffffffffu,
+                                             sparse ? fa[vidx * 3 + 2] : 0xffffffffu};
                     pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, reinterpret_cast<const uint32_t*>(slot + (size_t)(vidx * 3) * rec),
                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(CPS * 3 + vidx * 3) * rec),
-                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount);
+                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw);
                 }
                 if (t0 == m - 1 && vm) refill();
             } else {
@@ -1100,8 +1125,15 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
         int m = (int)std::max<int64_t>(1, 10000 / ((int64_t)gw * 3 * a->Wq * 16));
         if (const char* e = getenv("PFA_CDS_TMA_M")) m = std::max(1, atoi(e));
+        // validity flags: fetch only the flagged pieces of the v plane (see pfa_launch_site_scan)
+        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
+        if (sparse_v) {
+            args.s.vflag = a->vflag;
+            m = std::max(1, std::min(m, 32 * PFA_VF_REGS / (3 * gw)));
+        }
         auto dyn_for = [&](int mm) {
-            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16) + sizeof(uint64_t) * nwarp * tma_stages + smem +
+            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16 + (hv ? (((size_t)gw * mm * 12 + 15) & ~(size_t)15) : 0)) +
+                   sizeof(uint64_t) * nwarp * tma_stages + smem +
                    (lps >= 4 ? (size_t)nwarp * PFA_CDS_QFIELDS * 32 * sizeof(uint32_t) : 0);
         };
         while (m > 1 && dyn_for(m) > 220 * 1024) --m;

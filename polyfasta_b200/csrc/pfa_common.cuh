@@ -51,7 +51,11 @@ struct pfa_aln {
     uint4* planes = nullptr;  // one allocation: b0 | b1 | v
     uint4 *b0 = nullptr, *b1 = nullptr, *v = nullptr;
     size_t plane_bytes = 0;  // bytes of ONE plane (ns*Wq*16, padded to 256)
-    int has_invalid = 0;
+    int has_invalid = 0;  // bit 0: a row shows a symbol outside ACGT somewhere; bit 1: forced (benchmarks: read the v plane everywhere)
+    // validity flags, one 32-bit word per site: bit c is set when one of the chunks [c*gc, (c+1)*gc) of the site's v record holds
+    // a zero among the real rows.  Written by the encoders; the TMA scans fetch only flagged pieces of the v plane.
+    uint32_t* vflag = nullptr;
+    int gc = 1;  // chunks (16 bytes = 128 rows) per flag bit: ceil(Wq / 32)
     // exception list: sorted keys (site:32 | byte:8 | row:24), heads = first index of every distinct site
     unsigned long long* exc_keys = nullptr;
     int64_t n_exc = 0;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) pfa_encode_kernel(const uint8_t* __restri
                                                          uint32_t* __restrict__ b1, uint32_t* __restrict__ v, int Wn,
                                                          unsigned long long* __restrict__ exc_keys,
                                                          unsigned long long* __restrict__ exc_count, int64_t exc_cap,
-                                                         int* __restrict__ has_invalid, int vec_ok) {
+                                                         int* __restrict__ has_invalid, int vec_ok, uint32_t* __restrict__ vflag, int gc) {
     __shared__ uint8_t lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (uint8_t)classify_byte(i);
     __syncthreads();
@@ -83,9 +83,11 @@ __global__ void __launch_bounds__(256) pfa_encode_kernel(const uint8_t* __restri
         }
     }
     if (__any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(has_invalid, 1);
+    const uint32_t wlive = __ballot_sync(0xffffffffu, live);
     if (c0 + lane < cols) {
         const int64_t o = (site0 + c0 + lane) * (int64_t)Wn + w;
         b0[o] = my0; b1[o] = my1; v[o] = myv;
+        if (myv != wlive) atomicOr(vflag + site0 + c0 + lane, 1u << (int)((w >> 2) / gc));  // this 128-row chunk holds a non-ACGT symbol
     }
 }
 
@@ -99,7 +101,7 @@ int pfa_encode_chunk(pfa_aln* a, const uint8_t* d_text, int64_t ldt, int64_t col
     dim3 grid((unsigned)((groups + 7) / 8), (unsigned)((a->n + 31) / 32));
     pfa_encode_kernel<<<grid, 256, 0, st>>>(d_text, ldt, a->n, cols, site0, (uint32_t*)a->b0, (uint32_t*)a->b1,
                                                      (uint32_t*)a->v, a->Wq * 4, a->exc_keys, d_exc_count, exc_cap,
-                                                     d_has_invalid, vec_ok);
+                                                     d_has_invalid, vec_ok, a->vflag, a->gc);
     PFA_LAUNCH_CHECK(ctx);
     return PFA_OK;
 }
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* _
                                                                 const uint8_t* __restrict__ valid, int64_t ldv,
                                                                 int64_t n, int64_t cols, int64_t site0, uint32_t* __restrict__ b0,
                                                                 uint32_t* __restrict__ b1, uint32_t* __restrict__ v, int Wn,
-                                                                int* __restrict__ has_invalid) {
+                                                                int* __restrict__ has_invalid, uint32_t* __restrict__ vflag, int gc) {
     const int lane = threadIdx.x & 31;
     const int64_t sg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // group of 64 sites
     const int64_t w = blockIdx.y;
@@ -147,7 +149,10 @@ __global__ void __launch_bounds__(256) pfa_encode_packed_kernel(const uint8_t* _
         if (c < cols) {
             const int64_t o = (site0 + c) * (int64_t)Wn + w;
             b0[o] = my0; b1[o] = my1; v[o] = myv;
-            if (myv != wlive) any_invalid = true;
+            if (myv != wlive) {
+                any_invalid = true;
+                atomicOr(vflag + site0 + c, 1u << (int)((w >> 2) / gc));
+            }
         }
     }
     if (HAS_VALID && __any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(has_invalid, 1);
@@ -164,7 +169,7 @@ int pfa_encode_packed_chunk(pfa_aln* a, const uint8_t* d_packed, int64_t ldp, co
     dim3 grid((unsigned)((groups + 7) / 8), (unsigned)((a->n + 31) / 32));
 #define PFA_PACKED_LAUNCH(V_, D_)                                                                                     \
     pfa_encode_packed_kernel<V_, D_><<<grid, 256, 0, st>>>(d_packed, ldp, d_valid, ldv, a->n, cols, site0, (uint32_t*)a->b0,    \
-                                                           (uint32_t*)a->b1, (uint32_t*)a->v, a->Wq * 4, d_has_invalid)
+                                                           (uint32_t*)a->b1, (uint32_t*)a->v, a->Wq * 4, d_has_invalid, a->vflag, a->gc)
     if (d_valid && direct) PFA_PACKED_LAUNCH(true, true);
     else if (d_valid) PFA_PACKED_LAUNCH(true, false);
     else if (direct) PFA_PACKED_LAUNCH(false, true);
@@ -275,6 +280,56 @@ int pfa_synth_fill(pfa_aln* a, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_p
             (uint32_t*)a->b0 + off, (uint32_t*)a->b1 + off, (uint32_t*)a->v + off, site_hi - site_lo,
             a->col_begin + site_lo, a->n, a->Wq * 4, seed, p_seg_ppm, tri_ppm, mult);
         PFA_LAUNCH_CHECK(ctx);
+    }
+    return PFA_OK;
+}
+
+// sparse gaps poked into the planes of an alignment (benchmarks and tests of the validity flags): see pfa_synth_gap_bit
+__global__ void __launch_bounds__(256) pfa_poke_gaps_kernel(uint32_t* __restrict__ b0, uint32_t* __restrict__ b1, uint32_t* __restrict__ v,
+                                                            uint32_t* __restrict__ vflag, int gc, int64_t ns, int64_t col_begin, int64_t n, int Wn,
+                                                            uint64_t seed, uint32_t gap_ppm, int* __restrict__ any) {
+    const int nwords = (int)((n + 31) / 32);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t site = t / nwords;
+    const int w = (int)(t % nwords);
+    if (site >= ns) return;
+    const uint32_t bit = pfa_synth_gap_bit(seed, (uint64_t)(col_begin + site), (uint64_t)w, gap_ppm);
+    if (bit >= 32u || (int64_t)w * 32 + bit >= n) return;
+    const int64_t o = site * (int64_t)Wn + w;
+    b0[o] &= ~(1u << bit);
+    b1[o] &= ~(1u << bit);
+    v[o] &= ~(1u << bit);
+    atomicOr(vflag + site, 1u << ((w >> 2) / gc));
+    *any = 1;
+}
+
+extern "C" int pfa_aln_poke_gaps(pfa_aln* a, uint64_t seed, uint32_t gap_ppm) {
+    if (!a || gap_ppm > 31250u) return PFA_ERR_ARG;
+    pfa_ctx* ctx = a->ctx;
+    PFA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nwords = (a->n + 31) / 32;
+    if (a->ns == 0 || nwords == 0 || gap_ppm == 0) return PFA_OK;
+    int* d_any = nullptr;
+    PFA_CUDA(ctx, pfa_dmalloc(ctx, &d_any, sizeof(int)));
+    PFA_CUDA(ctx, cudaMemsetAsync(d_any, 0, sizeof(int), ctx->stream));
+    const int64_t sites_per_launch = std::max<int64_t>(1, ((int64_t)1 << 30) / nwords);
+    for (int64_t site_lo = 0; site_lo < a->ns; site_lo += sites_per_launch) {
+        const int64_t site_hi = std::min<int64_t>(a->ns, site_lo + sites_per_launch);
+        const int64_t cnt = (site_hi - site_lo) * nwords;
+        const int64_t off = site_lo * (int64_t)a->Wq * 4;
+        pfa_poke_gaps_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((uint32_t*)a->b0 + off, (uint32_t*)a->b1 + off, (uint32_t*)a->v + off,
+                                                                                   a->vflag + site_lo, a->gc, site_hi - site_lo, a->col_begin + site_lo,
+                                                                                   a->n, a->Wq * 4, seed, gap_ppm, d_any);
+        PFA_LAUNCH_CHECK(ctx);
+    }
+    int any = 0;
+    PFA_CUDA(ctx, cudaMemcpyAsync(&any, d_any, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pfa_dfree(ctx, d_any);
+    if (any) a->has_invalid |= 1;
+    if (a->rowmajor) {  // the pairwise kernel's transposed copy is stale
+        pfa_dfree(ctx, a->rowmajor);
+        a->rowmajor = nullptr;
     }
     return PFA_OK;
 }

@@ -346,12 +346,12 @@ __device__ __forceinline__ unsigned pfa_site_pass1(const uint4 (&x0)[ITER], cons
 template <bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_site_coop(const PfaSiteArgs& a, int64_t s, const uint32_t* w0, const uint32_t* w1, const uint32_t* wv,
                                               int Wn, int lane, unsigned long long* sm_SH, unsigned int* sm_sfs, uint32_t& S_mine,
-                                              unsigned long long& H_mine) {
+                                              unsigned long long& H_mine, uint32_t fw, int gcw) {
     const int k = MULTI ? a.k : 1;
     for (int q = 0; q < k; ++q) {
         const uint32_t* mq = reinterpret_cast<const uint32_t*>(MULTI ? a.masks + (int64_t)q * a.Wq : a.umask);
         uint32_t c[PFA_NCLASS];
-        pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c);
+        pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c, fw, gcw);
         const PfaSiteResult r = pfa_site_result(c, a.pop_n[q], 0u, 0ull);
         if (r.has_escape) continue;  // finished by pfa_escape_sites_kernel
         if (a.isvar && lane == 0) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
@@ -392,7 +392,9 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
     const int Wq = a.Wq;
     const unsigned rec = (unsigned)Wq * 16u;  // bytes of one site record in one plane
     const int SPS = GW * m;                   // sites per slot: m passes of the warp (narrow records: keeps a copy >= ~2 KB)
-    const unsigned slot_bytes = (unsigned)NPL * SPS * rec;  // [plane][site in slot][Wq] uint4
+    const unsigned slot_bytes = (unsigned)NPL * SPS * rec + (HAS_V ? (((unsigned)SPS * 4u + 15u) & ~15u) : 0u);  // pfa_slot_issue
+    const bool sparse = HAS_V && a.vflag != nullptr;  // fetch only the flagged cells of the v plane
+    const int gc = a.gc, gcw = a.gc * 4;
     unsigned char* ring_base = dyn;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);  // [warp][stage]
     unsigned long long* sm_SH = reinterpret_cast<unsigned long long*>(bars + NWARP * stages);
@@ -425,22 +427,46 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
         const int j = sub + LPS * i;
         um[i] = j < Wq ? __ldg(a.umask + j) : make_uint4(0, 0, 0, 0);
     }
-    auto issue = [&](int64_t blk, int st) {  // lane 0: fetch block blk into slot st (or mark the slot empty)
-        if (blk < 0) return;
-        const int64_t s0 = blk * SPS;
-        const unsigned nsite = (unsigned)min((int64_t)SPS, a.ns - s0);
-        pfa_mbar_expect_tx(&bar[st], NPL * nsite * rec);
+    int cell[ITER];  // the flag bit of each of this lane's chunks
 #pragma unroll
-        for (int p = 0; p < NPL; ++p)
-            pfa_bulk_load(ring + (size_t)st * slot_bytes + (size_t)p * SPS * rec, planes[p] + (size_t)s0 * rec, nsite * rec, &bar[st]);
-    };
-    // blocks are claimed in chunks from a device-wide counter (PfaClaimer): warps that meet few variable sites take more
+    for (int i = 0; i < ITER; ++i) cell[i] = (sub + LPS * i) / gc;
+    // The first 7/8 of the blocks are split statically (block gw + i nw is warp gw's i-th), the rest is claimed in chunks from
+    // a device-wide counter (PfaClaimer): warps that met few variable sites take more of it.
+    // `pend` is the block the NEXT refill will fetch, known one refill ahead so that its validity flags are in registers by then.
     PfaClaimer claim;
     PfaBlockFifo inflight{-1, -1, -1, -1};
-    if (lane == 0) claim.init(a.work, nblk, nw);
+    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib;
+    const int64_t rounds = (nblk / nw) * 7 / 8;  // static rounds of nw blocks
+    int64_t round = 0;
+    if (lane == 0) claim.init(a.work, nblk - rounds * nw, nw);
+    auto next_block = [&]() -> long long {  // all lanes
+        if (round < rounds) return gw + (round++) * nw;
+        const long long b = pfa_bcast0(lane == 0 ? claim.next() : 0);
+        return b < 0 ? -1 : b + rounds * nw;
+    };
+    long long pend = next_block();
+    uint32_t pfl[PFA_VF_REGS];
+    auto load_flags = [&]() {
+#pragma unroll
+        for (int u = 0; u < PFA_VF_REGS; ++u) {
+            const int64_t s = pend * SPS + u * 32 + lane;
+            pfl[u] = (sparse && pend >= 0 && u * 32 + lane < SPS && s < a.ns) ? __ldg(a.vflag + s) : 0u;
+        }
+    };
+    load_flags();
+    auto issue_next = [&](int st) -> long long {  // all lanes: fetch `pend` into slot st, then look one block further ahead
+        const long long blk = pend;
+        if (blk >= 0) {
+            const int64_t s0 = blk * SPS;
+            pfa_slot_issue<HAS_V>(ring + (size_t)st * slot_bytes, &bar[st], planes[0], planes[1], planes[2], sparse, gc, s0,
+                                  (unsigned)min((int64_t)SPS, a.ns - s0), (unsigned)SPS, rec, Wq, pfl, lane);
+        }
+        pend = blk >= 0 ? next_block() : -1;
+        load_flags();
+        return blk;
+    };
     for (int j = 0; j < stages; ++j) {
-        const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);
-        if (lane == 0) issue(nb, j);
+        const long long nb = issue_next(j);
         if (j == 0) inflight.f0 = nb;
         else if (j == 1) inflight.f1 = nb;
         else if (j == 2) inflight.f2 = nb;
@@ -453,20 +479,15 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
         if (blk < 0) break;
         pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
         const unsigned char* slot = ring + (size_t)st * slot_bytes;
-        auto refill = [&]() {
-            const long long nb = pfa_bcast0(lane == 0 ? claim.next() : 0);  // the shuffle also brings the warp together
-            if (lane == 0) {
-                pfa_fence_proxy_async();
-                issue(nb, st);
-            }
-            inflight.push(nb, stages);
-        };
+        const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
+        auto refill = [&]() { inflight.push(issue_next(st), stages); };
         for (int t = 0; t < m; ++t) {
             const int idx = t * GW + grp;  // site of this group inside the slot
             const int64_t s = blk * SPS + idx;
             const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
             const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
             const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
+            const uint32_t fw = sparse ? fa[idx] : 0xffffffffu;
             uint4 x0[ITER], x1[ITER], xv[ITER];
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
@@ -476,7 +497,7 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                 if (j < Wq && s < a.ns) {
                     x0[i] = q0[j];
                     x1[i] = q1[j];
-                    if (HAS_V) xv[i] = qv[j];
+                    if (HAS_V && ((fw >> cell[i]) & 1u)) xv[i] = qv[j];
                 }
             }
             if (COOP) {
@@ -491,7 +512,7 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                     pfa_site_coop<HAS_V, MULTI>(a, blk * SPS + vidx, reinterpret_cast<const uint32_t*>(slot + (size_t)vidx * rec),
                                                 reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec),
                                                 reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec), Wq * 4, lane, sm_SH,
-                                                sm_sfs, S_mine, H_mine);
+                                                sm_sfs, S_mine, H_mine, sparse ? fa[vidx] : 0xffffffffu, gcw);
                 }
                 if (t == m - 1 && vm) refill();
             } else {
@@ -592,8 +613,16 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
         int m = (int)std::max<int64_t>(1, 5000 / ((int64_t)gw * a->Wq * 16));
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
+        // validity flags: a shard with a few non-ACGT symbols fetches only the flagged pieces of its v plane (pfa_slot_issue);
+        // not when the validity plane is forced (benchmarks of the 3-plane worst case) or PFA_VFLAG=0
+        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
+        if (sparse_v) {
+            args.vflag = a->vflag;
+            m = std::min(m, 32 * PFA_VF_REGS / gw);
+        }
         auto dyn_for = [&](int mm) {
-            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * a->Wq * 16) + sizeof(uint64_t) * nwarp * tma_stages + smem;
+            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * a->Wq * 16 + (hv ? (((size_t)gw * mm * 4 + 15) & ~(size_t)15) : 0)) +
+                   sizeof(uint64_t) * nwarp * tma_stages + smem;
         };
         while (m > 1 && dyn_for(m) > 220 * 1024) --m;
         const size_t dyn = dyn_for(m);

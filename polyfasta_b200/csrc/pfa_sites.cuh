@@ -30,6 +30,8 @@ struct PfaSiteArgs {
     int k;
     int sfs_in_smem;
     int sfs_bins;  // total bins over all populations
+    const uint32_t* vflag;  // per-site validity flags (pfa_aln::vflag) or nullptr: fetch the whole v plane
+    int gc;                 // chunks per flag bit
     unsigned int* work;  // [2], zero between launches: next block to claim / CTAs done (TMA kernels, pfa_ctx_work)
     PfaXchgDev x;  // x.world > 0: the last block sums `out` over the column shards of all GPUs (pfa_xchg.cuh)
 };
@@ -148,22 +150,26 @@ __device__ __forceinline__ PfaSiteResult pfa_site_result(const uint32_t c[PFA_NC
 
 // class counts of one population at one site: w0 / w1 / wv point to the site's record in each plane (32-bit words, Wn of
 // them), mq to the population's row mask
+// fw / gcw: the site's validity flag word and the 32-bit words per flag bit -- words of an unflagged cell were not fetched
+// (pfa_slot_issue) and count as all valid; fw = ~0: every word of wv is there
 template <bool HAS_V>
 __device__ __forceinline__ void pfa_coop_counts(const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
                                                 const uint32_t* __restrict__ wv, const uint32_t* __restrict__ mq, int Wn, int lane,
-                                                uint32_t c[PFA_NCLASS]) {
+                                                uint32_t c[PFA_NCLASS], uint32_t fw = 0xffffffffu, int gcw = 1 << 20) {
 #pragma unroll
     for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
     for (int w = lane; w < Wn; w += 32) {
         const uint32_t m = __ldg(mq + w), x0 = w0[w], x1 = w1[w];
-        const uint32_t vm = HAS_V ? (wv[w] & m) : m;
+        uint32_t xv = 0xffffffffu;
+        if (HAS_V && ((fw >> (w / gcw)) & 1u)) xv = wv[w];
+        const uint32_t vm = HAS_V ? (xv & m) : m;
         const uint32_t hi = vm & x1, lo = vm & ~x1;
         c[PFA_C_T] += __popc(hi & x0);
         c[PFA_C_G] += __popc(hi & ~x0);
         c[PFA_C_C] += __popc(lo & x0);
         c[PFA_C_A] += __popc(lo & ~x0);
         if (HAS_V) {
-            const uint32_t im = ~wv[w] & m;
+            const uint32_t im = ~xv & m;
             const uint32_t ihi = im & x1;
             c[PFA_C_ESC] += __popc(ihi & x0);
             c[PFA_C_Q] += __popc(ihi & ~x0);
@@ -179,17 +185,17 @@ __device__ __forceinline__ void pfa_coop_counts(const uint32_t* __restrict__ w0,
 __device__ __forceinline__ bool pfa_flags_mono(unsigned f) { return ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u); }
 __device__ __forceinline__ bool pfa_flags_all_escape(unsigned f) { return (f & 1u) && (f & 4u) && !(f & 16u); }
 
-// ---- dynamic distribution of the blocks of a scan over the warps of the grid ------------------------------------------------
+// ---- distribution of the blocks of a scan over the warps of the grid --------------------------------------------------------
 // A static split (block b to warp b mod W) left ~7 % of the warp time idle at the end of K4: warps that meet more variable
-// columns finish later.  Claiming every block from one counter does not scale either (same-address atomics serialise in L2:
-// 5e6 claims took 10 ms on C4).  So warps claim CHUNKS of blocks whose size halves from phase to phase (guided
-// self-scheduling): with W warps, phase p hands out P = 4 W chunks of c = C0 >> p blocks each, C0 = blocks / (8 W); the last
-// blocks go out one by one.  ~4 W log2(C0) claims per launch, each prefetched one chunk ahead.  The chunks of a phase are
-// INTERLEAVED -- claim j of a phase takes blocks start + j, start + j + P, ... -- so that the warps of the grid keep reading one
-// contiguous window of the planes as they did under the static split.  Used by lane 0 of a warp.
+// columns finish later.  Claiming every block from one counter does not scale (same-address atomics serialise in L2: 5e6
+// claims took 10 ms on C4), and even chunked claims cost the memory-bound C4 scan 2 % (a warp-wide broadcast per block;
+// measured 3.59 -> 3.66 ms, interleaved chunks 3.68 ms).  So: the first 7/8 of the blocks keep the static split (no
+// communication at all), the last 1/8 is handed out dynamically in chunks of consecutive blocks whose size halves from
+// phase to phase (guided self-scheduling: with W warps, phase p gives out 4 W chunks of C0 >> p blocks, C0 = blocks / (8 W),
+// the last blocks go out one by one); each claim is prefetched one chunk ahead.  PfaClaimer is used by lane 0 of a warp.
 struct PfaClaimer {
     unsigned int* ctr;
-    long long nblk, P, C0, cur, remaining;
+    long long nblk, P, C0, cur, end;
     unsigned int pending;
     __device__ __forceinline__ void init(unsigned int* counter, long long blocks, long long warps) {
         ctr = counter;
@@ -197,18 +203,11 @@ struct PfaClaimer {
         P = 4 * warps;
         C0 = blocks / (8 * warps);
         if (C0 < 1) C0 = 1;
-        cur = remaining = 0;
+        cur = end = 0;
         pending = atomicAdd(ctr, 1u);
     }
     __device__ __forceinline__ long long next() {  // the next block of this warp, -1 when none is left
-        for (;;) {
-            if (remaining > 0) {
-                const long long b = cur;
-                cur += P;
-                --remaining;
-                if (b < nblk) return b;
-                remaining = 0;  // the rest of this chunk lies beyond the end
-            }
+        while (cur == end) {
             if (pending == 0xffffffffu) return -1;
             long long start = 0, c = C0, j = pending;
             while (c > 1 && j >= P) {
@@ -216,18 +215,16 @@ struct PfaClaimer {
                 j -= P;
                 c >>= 1;
             }
-            if (c == 1) {
-                start += (j / P) * P;
-                j %= P;
-            }
+            start += j * c;
             if (start >= nblk) {
                 pending = 0xffffffffu;
                 return -1;
             }
-            cur = start + j;
-            remaining = c;
+            cur = start;
+            end = start + c < nblk ? start + c : nblk;
             pending = atomicAdd(ctr, 1u);  // needed only when this chunk is used up
         }
+        return cur++;
     }
 };
 
@@ -281,5 +278,60 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
 }
 
+
+// ---- fetching one block of consecutive site records into a warp's shared-memory slot ------------------------------------------
+// Slot layout: [plane b0 | b1 | v][cap_sites][rec bytes], then cap_sites flag words.  Planes b0 and b1 always come whole, one
+// bulk copy each.  The v plane (HAS_V):
+//   * vflag == nullptr (dense): whole, a third bulk copy;
+//   * sparse: only the flagged cells of each site -- a cell = gc chunks of 16 bytes, one flag bit (pfa_aln::vflag) -- each with
+//     its own small bulk copy issued by the lane that holds the site's flag word; the flag words go into the slot so that the
+//     readers know which words of the v area are real (the others count as "all rows valid").  When more than a third of the
+//     cells of the block are flagged the whole range is fetched after all (flag words all ones).
+// All copies complete on the slot's mbarrier; lane 0 arms it last with the total byte count (bulk copies that finish before
+// the expect_tx only drive the transaction count negative for a moment; the phase cannot complete before lane 0 arrives).
+// Called by ALL lanes of the warp; fl[u] = flag word of site 32 u + lane of the block (sparse only).
+#define PFA_VF_REGS 4  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
+template <bool HAS_V>
+__device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* bar, const unsigned char* p0, const unsigned char* p1,
+                                               const unsigned char* pv, bool sparse, int gc, int64_t s0, unsigned nsite, unsigned cap_sites,
+                                               unsigned rec, int Wq, const uint32_t (&fl)[PFA_VF_REGS], int lane) {
+    pfa_fence_proxy_async();  // this lane's reads of the slot's previous contents come before the copies
+    unsigned vbytes = HAS_V ? nsite * rec : 0u;
+    bool whole_v = HAS_V;
+    if (HAS_V && sparse) {
+        uint32_t* fa = reinterpret_cast<uint32_t*>(slot + (size_t)3 * cap_sites * rec);
+        unsigned cells = 0;
+#pragma unroll
+        for (int u = 0; u < PFA_VF_REGS; ++u)
+            if ((unsigned)(u * 32 + lane) < nsite) cells += __popc(fl[u]);
+        cells = __reduce_add_sync(0xffffffffu, cells);
+        const unsigned ncell = (unsigned)((Wq + gc - 1) / gc);
+        whole_v = cells * 3u > nsite * ncell;
+        unsigned bytes = 0;
+#pragma unroll
+        for (int u = 0; u < PFA_VF_REGS; ++u) {
+            const unsigned si = (unsigned)(u * 32 + lane);
+            if (si < nsite) {
+                fa[si] = whole_v ? 0xffffffffu : fl[u];
+                if (!whole_v)
+                    for (uint32_t w = fl[u]; w; w &= w - 1) {
+                        const int c0 = (__ffs(w) - 1) * gc;
+                        const unsigned len = (unsigned)min(gc, Wq - c0) * 16u;
+                        pfa_bulk_load(slot + (size_t)2 * cap_sites * rec + (size_t)si * rec + (size_t)c0 * 16u, pv + (size_t)(s0 + si) * rec + (size_t)c0 * 16u, len, bar);
+                        bytes += len;
+                    }
+            }
+        }
+        bytes = __reduce_add_sync(0xffffffffu, bytes);
+        if (!whole_v) vbytes = bytes;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        pfa_mbar_expect_tx(bar, 2u * nsite * rec + vbytes);
+        pfa_bulk_load(slot, p0 + (size_t)s0 * rec, nsite * rec, bar);
+        pfa_bulk_load(slot + (size_t)cap_sites * rec, p1 + (size_t)s0 * rec, nsite * rec, bar);
+        if (whole_v) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
+    }
+}
 
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args);

@@ -63,6 +63,14 @@ PFA_HD uint32_t pfa_synth_base(const pfa_synth_site& s, uint64_t row, uint64_t n
     return s.anc;
 }
 
+// sparse gaps on top of the synthetic alignment: the 32-row word w of site `site` loses ONE row to '-' with probability
+// 32 * gap_ppm / 1e6 (i.e. gap_ppm gaps per million bases); returns the bit of that row or 32 for "none"
+PFA_HD uint32_t pfa_synth_gap_bit(uint64_t seed, uint64_t site, uint64_t w, uint32_t gap_ppm) {
+    const uint64_t h = pfa_mix64((seed * 0x9E3779B97F4A7C15ull + 0x5851F42D4C957F2Dull) ^ pfa_mix64(site * 1048583ull + w));
+    if ((h >> 8) % 1000000ull >= 32ull * gap_ppm) return 32u;
+    return (uint32_t)(h >> 40) & 31u;
+}
+
 inline uint64_t pfa_synth_multiplier(uint64_t n) {
     static const uint64_t primes[] = {7919, 7927, 7933, 7937, 7949, 7951, 7963, 7993, 8009, 8011, 8017, 8039};
     for (uint64_t p : primes)

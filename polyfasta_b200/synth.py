@@ -78,3 +78,25 @@ def expected_site_stats(seed, n, L, p_seg_ppm=50000, tri_ppm=10000, col_begin=0,
         second = cnt[1]
         np.add.at(sfs, second - 1, 1)
     return {"n": n, "S": S, "H": H, "sfs": sfs.tolist()}
+
+
+def poke_gaps(text, seed, gap_ppm, n=None, col_begin=0):
+    """numpy twin of pfa_aln_poke_gaps (pfa_synth_gap_bit): returns a copy of the uint8 text matrix [n][cols] with the same
+    cells turned into '-'"""
+    text = np.array(text, dtype=np.uint8, copy=True)
+    n = text.shape[0] if n is None else n
+    cols = text.shape[1]
+    nwords = (n + 31) // 32
+    u = np.uint64
+    with np.errstate(over="ignore"):
+        sites = np.arange(col_begin, col_begin + cols, dtype=np.uint64)[:, None]
+        w = np.arange(nwords, dtype=np.uint64)[None, :]
+        key = (u(seed) * u(0x9E3779B97F4A7C15) + u(0x5851F42D4C957F2D)) ^ mix64(sites * u(1048583) + w)
+        h = mix64(key)
+        hit = ((h >> u(8)) % u(1000000)) < u(32 * gap_ppm)
+        bit = ((h >> u(40)) & u(31)).astype(np.int64)
+    si, wi = np.nonzero(hit)
+    rows = wi * 32 + bit[si, wi]
+    ok = rows < n
+    text[rows[ok], si[ok]] = ord("-")
+    return text

@@ -755,3 +755,33 @@ def test_batch_codon_scan(ctx):
                 assert [got["poly_s"], got["poly_n"]] == ref, (n, L, q)
     batch.release()
     batch.close()
+
+
+@pytest.mark.parametrize("n,L,gap_ppm,k", [(2000, 60_000, 100, 2), (10_000, 6_000, 100, 1), (10_000, 3_000, 2_000, 2), (700, 50_001, 30, 3),
+                                          (4100, 9_000, 5, 2), (12_000, 3_003, 400, 1)])
+def test_sparse_validity_flags(ctx, monkeypatch, n, L, gap_ppm, k):
+    """alignments with a FEW gaps: the TMA scans fetch only the flagged 128-row pieces of the validity plane (per-site flag
+    words written by the encoders, pfa_slot_issue).  The gapped synthetic alignment is built twice -- on the device (generator +
+    pfa_aln_poke_gaps) and from the numpy twin's text through the encoder -- the planes must agree bit for bit, and K2 / K4 of
+    both must equal the C oracle on that text (gaps are alleles in the site scan, PolyFastA.py:256-258, and make a codon
+    unclean, :301).  With PFA_VFLAG=0 (whole validity plane fetched) the results must not change."""
+    seed = 11 + n
+    text = synth.poke_gaps(synth.text_matrix(seed, n, L), seed, gap_ppm)
+    assert (text == ord("-")).sum() > 0
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n // 2))][:k]
+    dev = pf.Alignment.synthetic(ctx, n, L, seed)
+    dev.poke_gaps(seed, gap_ppm)
+    host = pf.Alignment.from_rows(ctx, text)
+    assert dev.has_invalid and host.has_invalid
+    for pl in range(3):
+        assert np.array_equal(dev.plane(pl), host.plane(pl)), pl
+    res = []
+    for aln, flag in ((dev, "1"), (host, "1"), (host, "0")):
+        monkeypatch.setenv("PFA_VFLAG", flag)
+        aln.set_pops(pops)
+        res.append((aln.site_stats(want_isvar=True), aln.cds_stats(want_labels=True), ctx.last_kernel))
+    dev.free()
+    host.free()
+    for site, cds, _ in res:
+        _check_site_cds(site, cds, text, pops, (n, L, gap_ppm))
+    assert "HAS_V=1" in res[0][2]
