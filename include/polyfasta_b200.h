@@ -237,6 +237,9 @@ int pfa_batch_run_cds(pfa_batch* b, int jc);
 int pfa_batch_stage(pfa_batch* b);
 int pfa_batch_scan(pfa_batch* b, int jc, int cds);
 int pfa_batch_release(pfa_batch* b);
+/* measurement: device time (ms, CUDA events) of K2b and of K4b in the last scan; bases and plane bytes of the batch */
+int pfa_batch_kernel_ms(const pfa_batch* b, double* site_ms, double* cds_ms);
+int pfa_batch_shape(const pfa_batch* b, int64_t* bases, int64_t* plane_bytes /* one plane */);
 int pfa_batch_num_pops(const pfa_batch* b, int64_t locus);
 /* counts = {n, S, H}; sfs (optional) n/2 bins; fin (optional) the K5 output of that (locus, population) */
 int pfa_batch_result(const pfa_batch* b, int64_t locus, int pop, int64_t counts[3], int64_t* sfs, void* fin /* pfa_final_out* */);

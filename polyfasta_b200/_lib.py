@@ -27,7 +27,7 @@ EXPORTS = [
     "pfa_codon_class", "pfa_pairwise_device", "pfa_pairwise", "pfa_finalize", "pfa_cds_ssites",
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
     "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_synthetic", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_run_cds", "pfa_batch_stage", "pfa_batch_scan",
-    "pfa_batch_release", "pfa_batch_num_pops", "pfa_batch_result", "pfa_batch_result_cds",
+    "pfa_batch_release", "pfa_batch_kernel_ms", "pfa_batch_shape", "pfa_batch_num_pops", "pfa_batch_result", "pfa_batch_result_cds",
     "pfa_fasta_parse_files", "pfa_fasta_match_mask",
     "pfa_host_pack2", "pfa_host_pack2_rows", "pfa_host_pack3",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
@@ -136,6 +136,8 @@ def lib():
         "pfa_batch_stage": (c.c_int, [p]),
         "pfa_batch_scan": (c.c_int, [p, c.c_int, c.c_int]),
         "pfa_batch_release": (c.c_int, [p]),
+        "pfa_batch_kernel_ms": (c.c_int, [p, c.POINTER(c.c_double), c.POINTER(c.c_double)]),
+        "pfa_batch_shape": (c.c_int, [p, c.POINTER(i64), c.POINTER(i64)]),
         "pfa_batch_result_cds": (c.c_int, [p, i64, c.c_int, p, c.POINTER(c.c_double), p]),
         "pfa_batch_num_pops": (c.c_int, [p, i64]),
         "pfa_batch_result": (c.c_int, [p, i64, c.c_int, c.POINTER(i64), p, c.POINTER(FinalOut)]),

@@ -636,6 +636,18 @@ class Batch:
     def release(self):
         check(lib().pfa_batch_release(self._h), self.ctx.handle)
 
+    def kernel_ms(self):
+        """(site scan ms, codon scan ms) of the last scan, device time"""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        check(lib().pfa_batch_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b)), self.ctx.handle)
+        return a.value, b.value
+
+    def shape(self):
+        """(bases, bytes of one plane) of the batch"""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        check(lib().pfa_batch_shape(self._h, ctypes.byref(a), ctypes.byref(b)), self.ctx.handle)
+        return a.value, b.value
+
     def result_cds(self, locus, pop=0):
         """dict(nstops, missing, S_s, H_s, S_n, H_n, sum3_by_len, ssites, raw, poly_s, poly_n) of the codon scan"""
         raw = np.zeros(PFA_CDS_LEN, dtype=np.int64)

@@ -441,6 +441,9 @@ def devices_from_env():
     return [int(x) for x in spec.split(",") if x.strip() != ""]
 
 
+_SLOTS = {}
+
+
 def run_files(paths, cds, jc, popkeys, sink):
     """the per-file loop of PolyFastA.py:104-140 over sorted paths, in chunks; chunk i runs on device i mod G and the
     rows are emitted in the reference's order"""
@@ -450,14 +453,15 @@ def run_files(paths, cds, jc, popkeys, sink):
     chunks = [ps for _, ps in parallel.plan_units(paths, [_file_size(p) for p in paths], None, BATCH_FILES, BATCH_BYTES)]
     if len(chunks) > 1 and os.environ.get("POLYFASTA_DOUBLE_BUFFER", "1") != "0":
         devs = [d for d in devs for _ in (0, 1)]   # two slots per GPU: host staging of chunk i+1 overlaps the GPU pass of chunk i
-    state = {}
+    state = _SLOTS   # contexts and pinned staging buffers outlive one call (a process that runs several directories reuses them)
 
     def work(ci):
         slot = parallel.chunk_owner(ci, len(devs))   # one context + batch per listed device slot (a context is not re-entrant)
-        if slot not in state:
+        key = (slot, devs[slot])
+        if key not in state:
             ctx = api.Context(devs[slot])
-            state[slot] = (ctx, api.Batch(ctx))
-        ctx, batch = state[slot]
+            state[key] = (ctx, api.Batch(ctx))
+        ctx, batch = state[key]
         threads = max(1, (os.cpu_count() or 1) // len(devs))
         return process_chunk_native(ctx, batch, chunks[ci], jc, popkeys, threads, cds)
 

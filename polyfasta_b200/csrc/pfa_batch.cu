@@ -46,6 +46,8 @@ struct pfa_batch {
     std::vector<double> cds_ssites;       // [pops]
     std::vector<pfa_final_out> cds_fin;   // [pops][2]: synonymous, nonsynonymous
     bool ran = false, ran_cds = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around K2b and around K4b of the last scan
+    float site_ms = 0.f, cds_ms = 0.f;
     // device state between pfa_batch_stage and pfa_batch_release: the encoded planes of the whole batch and everything the
     // segmented kernels read
     struct Dev {
@@ -356,6 +358,7 @@ int pfa_batch_release(pfa_batch* b);
 int pfa_batch_destroy(pfa_batch* b) {
     if (!b) return PFA_OK;
     pfa_batch_release(b);
+    for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     if (b->h_text) cudaFreeHost(b->h_text);
     delete b;
     return PFA_OK;
@@ -825,6 +828,9 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
     uint4* p1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d.planes) + d.plane_bytes);
     uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<char*>(d.planes) + 2 * d.plane_bytes);
     PfaBatchArgs args{p0, p1, pv, d.masks, d.desc, d.pops, d.site_base, d.inv, d.out, b->n_sites, nloci, d.ctile_base, b->n_ctiles, d.cds_out, d.popn};
+    for (auto& ev : b->ev)
+        if (!ev) BR(cudaEventCreate(&ev));
+    BR(cudaEventRecord(b->ev[0], st));
     if (e == cudaSuccess && b->n_sites > 0) {
         int lps = 1;
         while (lps < 32 && (b->max_Wq + lps - 1) / lps > 4) lps *= 2;
@@ -846,8 +852,11 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
             e = cudaGetLastError();
         }
     }
+    BR(cudaEventRecord(b->ev[1], st));
+    BR(cudaEventRecord(b->ev[2], st));
     if (e == cudaSuccess && !rc && cds)
         rc = pfa_launch_batch_cds(ctx, args, b->max_Wq, d.keys, (long long)d.n_exc, (const long long*)d.heads, d.n_heads);
+    BR(cudaEventRecord(b->ev[3], st));
     if (e == cudaSuccess && !rc) {
         pfa_batch_final_in_kernel<<<(unsigned)((npops + 127) / 128), 128, 0, st>>>(d.pops, d.out, jc, npops, d.fin_in);
         ctx->launches++;
@@ -869,10 +878,32 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
             BR(cudaMemcpyAsync(b->cds_fin.data(), d.fin_out, sizeof(pfa_final_out) * 2 * (size_t)npops, cudaMemcpyDeviceToHost, st));
         }
         BR(cudaStreamSynchronize(st));
+        if (e == cudaSuccess) {
+            cudaEventElapsedTime(&b->site_ms, b->ev[0], b->ev[1]);
+            cudaEventElapsedTime(&b->cds_ms, b->ev[2], b->ev[3]);
+        }
     }
 #undef BR
     if (rc) return rc;
     if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "batched run failed: %s", cudaGetErrorString(e));
+    return PFA_OK;
+}
+
+/* device time of the segmented site scan (+ escape sites) and of the codon scan in the last pfa_batch_scan, ms (CUDA events) */
+int pfa_batch_kernel_ms(const pfa_batch* b, double* site_ms, double* cds_ms) {
+    if (!b) return PFA_ERR_ARG;
+    if (site_ms) *site_ms = b->site_ms;
+    if (cds_ms) *cds_ms = b->cds_ms;
+    return PFA_OK;
+}
+
+/* bases (rows x sites summed over the loci) and bytes of the planes of the staged batch */
+int pfa_batch_shape(const pfa_batch* b, int64_t* bases, int64_t* plane_bytes) {
+    if (!b) return PFA_ERR_ARG;
+    int64_t tot = 0;
+    for (const auto& e : b->entries) tot += (int64_t)e.n * e.L;
+    if (bases) *bases = tot;
+    if (plane_bytes) *plane_bytes = (int64_t)b->plane_u4 * 16;
     return PFA_OK;
 }
 

@@ -311,14 +311,10 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const Pf
 
 __device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 0 ? x.x : w == 1 ? x.y : w == 2 ? x.z : x.w; }
 
-// passes 1 and 2 of one codon column whose three site records are already in registers; shared by the register-resident
-// kernel (chunks loaded from global memory) and the TMA kernel (chunks read from the warp's shared-memory slot)
-template <int LPS, int ITER, bool HAS_V, bool MULTI>
-__device__ __forceinline__ void pfa_cds_process(const PfaCdsView& a, int64_t site0, const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER],
-                                                const uint4 (&xv)[3][ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
-                                                unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing, unsigned& u_sum3) {
-    constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask
-    // ---- pass 1 ----
+// pass 1 of one codon column whose three site records are in registers: 18 flag bits (6 per site), OR-reduced over the group
+template <int LPS, int ITER, bool HAS_V>
+__device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER],
+                                                  const uint4 (&um)[ITER], unsigned gmask) {
     unsigned f = 0;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
@@ -335,7 +331,17 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsView& a, int64_t sit
         }
         f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
     }
-    f = pfa_group_or<LPS>(f, gmask);
+    return pfa_group_or<LPS>(f, gmask);
+}
+
+// everything after pass 1 of one codon column whose three site records are in registers (f: the 18 flag bits of pass 1);
+// shared by the register-resident kernel, the TMA kernel's per-group path and the batched kernel
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
+__device__ __forceinline__ void pfa_cds_finish_regs(const PfaCdsView& a, int64_t site0, unsigned f, const uint4 (&x0)[3][ITER],
+                                                    const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER], const uint4 (&um)[ITER], int sub,
+                                                    unsigned gmask, int Wq, unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing,
+                                                    unsigned& u_sum3) {
+    constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask
     bool uniform = true, clean = true;
     int codon = 0;
 #pragma unroll
@@ -517,6 +523,15 @@ __device__ __forceinline__ void pfa_cds_process(const PfaCdsView& a, int64_t sit
                                                 : reinterpret_cast<unsigned long long*>(a.out + (int64_t)q * PFA_CDS_LEN);
         pfa_cds_contribute(P, cnt, a.pop_n[q], escd, escsq, dst, a.labels ? a.labels + (int64_t)q * a.ns : nullptr, site0);
     }
+}
+
+
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
+__device__ __forceinline__ void pfa_cds_process(const PfaCdsView& a, int64_t site0, const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER],
+                                                const uint4 (&xv)[3][ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
+                                                unsigned long long* sm_acc, unsigned& u_nstops, unsigned& u_missing, unsigned& u_sum3) {
+    const unsigned f = pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
+    pfa_cds_finish_regs<LPS, ITER, HAS_V, MULTI>(a, site0, f, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
 }
 
 // Register-resident variant (Wq <= 3*32 chunks): the three site records of a codon column are loaded once -- all
@@ -776,36 +791,13 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
     }
 }
 
-// pass 1 of one codon column whose three site records are in registers: 18 flag bits (6 per site), OR-reduced over the group
-template <int LPS, int ITER, bool HAS_V>
-__device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER],
-                                                  const uint4 (&um)[ITER], unsigned gmask) {
-    unsigned f = 0;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-            const uint4 m = um[i];
-            o0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
-            z0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
-            o1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
-            z1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
-            ov |= (xv[t][i].x & m.x) | (xv[t][i].y & m.y) | (xv[t][i].z & m.z) | (xv[t][i].w & m.w);
-            if (HAS_V) zv |= (~xv[t][i].x & m.x) | (~xv[t][i].y & m.y) | (~xv[t][i].z & m.z) | (~xv[t][i].w & m.w);
-        }
-        f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
-    }
-    return pfa_group_or<LPS>(f, gmask);
-}
-
 // TMA variant (see pfa_site_scan_tma_kernel): every warp owns shared-memory slots holding the site records of the codon
 // columns of m of its passes (3 * 32/LPS consecutive sites per pass), fed by one cp.async.bulk per plane.  Pass 1 runs per
 // group on registers; variable columns (LPS >= 4) are finished by the whole warp one at a time from the slot (pfa_cds_coop).
 template <int LPS, int ITER, bool HAS_V, bool MULTI, int NT>
 __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArgs a, int stages, int m) {
     extern __shared__ __align__(128) unsigned char dyn[];
-    constexpr bool COOP = LPS >= 4;
+    constexpr bool COOP = LPS >= 4;  // three site records per column: holding them through pass 2 spills (ptxas), the slot does not
     constexpr int GW = 32 / LPS;        // codon columns per warp pass
     constexpr int NPL = HAS_V ? 3 : 2;  // planes read
     constexpr int NWARP = NT / 32;
@@ -850,53 +842,44 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
     for (int i = 0; i < ITER; ++i) cell[i] = (sub + LPS * i) / gc;
     // block distribution and the one-block-ahead validity flags: see pfa_site_scan_tma_kernel
     PfaClaimer claim;
-    PfaBlockFifo inflight{-1, -1, -1, -1};
-    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib;
-    const int64_t rounds = (nblk / nw) * 7 / 8;
-    int64_t round = 0;
-    if (lane == 0) claim.init(a.s.work, nblk - rounds * nw, nw);
-    auto next_block = [&]() -> long long {  // all lanes
-        if (round < rounds) return gw + (round++) * nw;
-        const long long b = pfa_bcast0(lane == 0 ? claim.next() : 0);
-        return b < 0 ? -1 : b + rounds * nw;
+    const unsigned gw = blockIdx.x * NWARP + wib, nwu = gridDim.x * NWARP;
+    const unsigned rounds = (unsigned)(nblk / nwu) * 7u / 8u;  // static rounds of nwu blocks
+    unsigned round = 0;
+    if (lane == 0) claim.init(a.s.work, (unsigned)nblk - rounds * nwu, nwu);
+    auto next_block = [&]() -> int {  // all lanes
+        if (round < rounds) return (int)(gw + (round++) * nwu);
+        const int b = __shfl_sync(0xffffffffu, lane == 0 ? claim.next() : 0, 0);
+        return b < 0 ? -1 : b + (int)(rounds * nwu);
     };
-    long long pend = next_block();
+    int pend = next_block();
     uint32_t pfl[PFA_VF_REGS];
     auto load_flags = [&]() {
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u) {
-            const int64_t s = pend * SPS + u * 32 + lane;
+            const int64_t s = (int64_t)pend * SPS + u * 32 + lane;
             pfl[u] = (sparse && pend >= 0 && u * 32 + lane < SPS && s < a.ncf * 3) ? __ldg(a.s.vflag + s) : 0u;
         }
     };
     load_flags();
-    auto issue_next = [&](int st) -> long long {  // all lanes: fetch `pend` into slot st, then look one block further ahead
-        const long long blk = pend;
+    auto issue_next = [&]() -> int {  // all lanes: fetch `pend` into the warp's slot, then look one block further ahead
+        const int blk = pend;
         if (blk >= 0) {
-            const int64_t c0 = blk * CPS;
-            pfa_slot_issue<HAS_V>(ring + (size_t)st * slot_bytes, &bar[st], planes[0], planes[1], planes[2], sparse, gc, c0 * 3,
-                                  3u * (unsigned)min((int64_t)CPS, a.ncf - c0), (unsigned)SPS, rec, Wq, pfl, lane);
+            const int64_t c0 = (int64_t)blk * CPS;
+            pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, c0 * 3, 3u * (unsigned)min((int64_t)CPS, a.ncf - c0), (unsigned)SPS,
+                                  rec, Wq, pfl, lane);
         }
         pend = blk >= 0 ? next_block() : -1;
         load_flags();
         return blk;
     };
-    for (int j = 0; j < stages; ++j) {
-        const long long nb = issue_next(j);
-        if (j == 0) inflight.f0 = nb;
-        else if (j == 1) inflight.f1 = nb;
-        else if (j == 2) inflight.f2 = nb;
-        else inflight.f3 = nb;
-    }
+    int cur_blk = issue_next();
 
-    for (int64_t k = 0;; ++k) {
-        const int st = (int)(k % stages);
-        const int64_t blk = inflight.pop();
-        if (blk < 0) break;
-        pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
-        const unsigned char* slot = ring + (size_t)st * slot_bytes;
+    for (unsigned k = 0; cur_blk >= 0; ++k) {
+        const int64_t blk = cur_blk;
+        pfa_mbar_wait(bar, k & 1u);
+        const unsigned char* slot = ring;
         const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
-        auto refill = [&]() { inflight.push(issue_next(st), stages); };
+        auto refill = [&]() { cur_blk = issue_next(); };  // once per block, when the slot's last pass no longer needs it
         for (int t0 = 0; t0 < m; ++t0) {
             const int idx = t0 * GW + grp;  // codon column of this group inside the slot
             const int64_t cc = blk * CPS + idx;
@@ -952,9 +935,11 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 }
                 if (t0 == m - 1 && vm) refill();
             } else {
-                if (cc < a.ncf)
-                    pfa_cds_process<LPS, ITER, HAS_V, MULTI>(pfa_cds_view(a), cc * 3, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
+                // pass 1 has consumed every register loaded from the slot: refill it while the rest runs on registers
+                const unsigned f = pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
                 if (t0 == m - 1) refill();
+                if (cc < a.ncf)
+                    pfa_cds_finish_regs<LPS, ITER, HAS_V, MULTI>(pfa_cds_view(a), cc * 3, f, x0, x1, xv, um, sub, gmask, Wq, sm_acc, u_nstops, u_missing, u_sum3);
             }
         }
     }
@@ -1119,14 +1104,14 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     cudaStream_t st = ctx->stream;
     // TMA variant: per-warp shared-memory slots of ~5 KB per plane fed by cp.async.bulk (PFA_CDS_TMA=0 turns it off)
     int tma_stages = 1;
-    if (const char* e = getenv("PFA_CDS_TMA")) tma_stages = std::max(0, std::min(8, atoi(e)));
+    if (const char* e = getenv("PFA_CDS_TMA")) tma_stages = std::max(0, std::min(1, atoi(e)));  // 0: off; one slot per warp
     if (tma_stages > 0 && !generic && a->ns >= 3) {
         const int nt = iter >= 3 ? 256 : 512;
         const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
         int m = (int)std::max<int64_t>(1, 10000 / ((int64_t)gw * 3 * a->Wq * 16));
         if (const char* e = getenv("PFA_CDS_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: fetch only the flagged pieces of the v plane (see pfa_launch_site_scan)
-        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
+        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && a->Wq >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
         if (sparse_v) {
             args.s.vflag = a->vflag;
             m = std::max(1, std::min(m, 32 * PFA_VF_REGS / (3 * gw)));

@@ -108,12 +108,10 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
 // passes 1 and 2 of one site whose record chunks are already in registers (x0, x1, xv: the lane's ITER chunks of each plane;
 // um: its slice of the union mask).  Shared by the register-resident kernel (chunks loaded from global memory) and the
 // TMA kernel (chunks read from the warp's shared-memory ring).
-template <int LPS, int ITER, bool HAS_V, bool MULTI>
-__device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
-                                                 const uint4 (&xv)[ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
-                                                 unsigned long long* sm_SH, unsigned int* sm_sfs) {
-    constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask, lane 0 finishes the site at once
-    // ---- pass 1 on registers ----
+// pass 1 of one site whose chunks are in registers: the six presence flags, OR-reduced over the group
+template <int LPS, int ITER, bool HAS_V>
+__device__ __forceinline__ unsigned pfa_site_pass1(const uint4 (&x0)[ITER], const uint4 (&x1)[ITER], const uint4 (&xv)[ITER],
+                                                   const uint4 (&um)[ITER], unsigned gmask) {
     uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
@@ -125,10 +123,18 @@ __device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s
         ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
         if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
     }
-    unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
-    f = pfa_group_or<LPS>(f, gmask);
-    const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
-    const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
+    const unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+    return pfa_group_or<LPS>(f, gmask);
+}
+
+// pass 2 of one site on registers, given the flags of pass 1 (f, OR-reduced over the group): shared by the register-resident
+// kernel and the TMA kernel's per-group path
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
+__device__ __forceinline__ void pfa_site_finish_regs(const PfaSiteArgs& a, int64_t s, unsigned f, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
+                                                     const uint4 (&xv)[ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
+                                                     unsigned long long* sm_SH, unsigned int* sm_sfs) {
+    constexpr bool one_pop = !MULTI;  // one population: its mask is the union mask, lane 0 finishes the site at once
+    const bool mono = pfa_flags_mono(f), all_escape = pfa_flags_all_escape(f);
     if (mono && !all_escape) {
         if (a.isvar && sub == 0)
             for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
@@ -201,6 +207,17 @@ __device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s
         }
     }
     if (myq >= 0) finish(myq, mine);
+}
+
+
+// passes 1 and 2 of one site whose record chunks are already in registers (x0, x1, xv: the lane's ITER chunks of each plane;
+// um: its slice of the union mask)
+template <int LPS, int ITER, bool HAS_V, bool MULTI>
+__device__ __forceinline__ void pfa_site_process(const PfaSiteArgs& a, int64_t s, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
+                                                 const uint4 (&xv)[ITER], const uint4 (&um)[ITER], int sub, unsigned gmask, int Wq,
+                                                 unsigned long long* sm_SH, unsigned int* sm_sfs) {
+    const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
+    pfa_site_finish_regs<LPS, ITER, HAS_V, MULTI>(a, s, f, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
 }
 
 // Register-resident variant for Wq <= 5*32 chunks: every lane owns ITER fixed chunks of the site record, loads them
@@ -322,25 +339,6 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
     }
 }
 
-// pass 1 of one site whose chunks are in registers: the six presence flags, OR-reduced over the group
-template <int LPS, int ITER, bool HAS_V>
-__device__ __forceinline__ unsigned pfa_site_pass1(const uint4 (&x0)[ITER], const uint4 (&x1)[ITER], const uint4 (&xv)[ITER],
-                                                   const uint4 (&um)[ITER], unsigned gmask) {
-    uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
-#pragma unroll
-    for (int i = 0; i < ITER; ++i) {
-        const uint4 m = um[i];
-        o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
-        z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
-        o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
-        z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
-        ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
-        if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
-    }
-    const unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
-    return pfa_group_or<LPS>(f, gmask);
-}
-
 // second pass of ONE variable site by the whole warp (see pfa_sites.cuh): w0 / w1 / wv are the site's records in the warp's
 // shared-memory slot.  S and H of population q < 32 accumulate in the registers of lane q.
 template <bool HAS_V, bool MULTI>
@@ -384,7 +382,9 @@ __device__ __forceinline__ void pfa_site_coop(const PfaSiteArgs& a, int64_t s, c
 template <int LPS, int ITER, bool HAS_V, bool MULTI>
 __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSiteArgs a, int stages, int m) {
     constexpr int NT = 512;
-    constexpr bool COOP = LPS >= 4;
+    // whole-warp second pass for groups of 4-8 lanes; (half-)warp groups keep it on their registers -- unless the validity plane
+    // is read too: three planes held through pass 2 do not fit 128 registers (ptxas: 150-360 bytes of spills), the slot does
+    constexpr bool COOP = LPS >= 4 && (LPS <= 8 || HAS_V);
     extern __shared__ __align__(128) unsigned char dyn[];
     constexpr int GW = 32 / LPS;        // sites per warp pass
     constexpr int NPL = HAS_V ? 3 : 2;  // planes read
@@ -434,53 +434,44 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
     // a device-wide counter (PfaClaimer): warps that met few variable sites take more of it.
     // `pend` is the block the NEXT refill will fetch, known one refill ahead so that its validity flags are in registers by then.
     PfaClaimer claim;
-    PfaBlockFifo inflight{-1, -1, -1, -1};
-    const int64_t gw = (int64_t)blockIdx.x * NWARP + wib;
-    const int64_t rounds = (nblk / nw) * 7 / 8;  // static rounds of nw blocks
-    int64_t round = 0;
-    if (lane == 0) claim.init(a.work, nblk - rounds * nw, nw);
-    auto next_block = [&]() -> long long {  // all lanes
-        if (round < rounds) return gw + (round++) * nw;
-        const long long b = pfa_bcast0(lane == 0 ? claim.next() : 0);
-        return b < 0 ? -1 : b + rounds * nw;
+    const unsigned gw = blockIdx.x * NWARP + wib, nwu = gridDim.x * NWARP;
+    const unsigned rounds = (unsigned)(nblk / nwu) * 7u / 8u;  // static rounds of nwu blocks
+    unsigned round = 0;
+    if (lane == 0) claim.init(a.work, (unsigned)nblk - rounds * nwu, nwu);
+    auto next_block = [&]() -> int {  // all lanes
+        if (round < rounds) return (int)(gw + (round++) * nwu);
+        const int b = __shfl_sync(0xffffffffu, lane == 0 ? claim.next() : 0, 0);
+        return b < 0 ? -1 : b + (int)(rounds * nwu);
     };
-    long long pend = next_block();
+    int pend = next_block();
     uint32_t pfl[PFA_VF_REGS];
     auto load_flags = [&]() {
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u) {
-            const int64_t s = pend * SPS + u * 32 + lane;
+            const int64_t s = (int64_t)pend * SPS + u * 32 + lane;
             pfl[u] = (sparse && pend >= 0 && u * 32 + lane < SPS && s < a.ns) ? __ldg(a.vflag + s) : 0u;
         }
     };
     load_flags();
-    auto issue_next = [&](int st) -> long long {  // all lanes: fetch `pend` into slot st, then look one block further ahead
-        const long long blk = pend;
+    auto issue_next = [&]() -> int {  // all lanes: fetch `pend` into the warp's slot, then look one block further ahead
+        const int blk = pend;
         if (blk >= 0) {
-            const int64_t s0 = blk * SPS;
-            pfa_slot_issue<HAS_V>(ring + (size_t)st * slot_bytes, &bar[st], planes[0], planes[1], planes[2], sparse, gc, s0,
-                                  (unsigned)min((int64_t)SPS, a.ns - s0), (unsigned)SPS, rec, Wq, pfl, lane);
+            const int64_t s0 = (int64_t)blk * SPS;
+            pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, s0, (unsigned)min((int64_t)SPS, a.ns - s0), (unsigned)SPS, rec,
+                                  Wq, pfl, lane);
         }
         pend = blk >= 0 ? next_block() : -1;
         load_flags();
         return blk;
     };
-    for (int j = 0; j < stages; ++j) {
-        const long long nb = issue_next(j);
-        if (j == 0) inflight.f0 = nb;
-        else if (j == 1) inflight.f1 = nb;
-        else if (j == 2) inflight.f2 = nb;
-        else inflight.f3 = nb;
-    }
+    int cur_blk = issue_next();
 
-    for (int64_t k = 0;; ++k) {
-        const int st = (int)(k % stages);
-        const int64_t blk = inflight.pop();
-        if (blk < 0) break;
-        pfa_mbar_wait(&bar[st], (unsigned)((k / stages) & 1));
-        const unsigned char* slot = ring + (size_t)st * slot_bytes;
+    for (unsigned k = 0; cur_blk >= 0; ++k) {
+        const int64_t blk = cur_blk;
+        pfa_mbar_wait(bar, k & 1u);
+        const unsigned char* slot = ring;
         const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
-        auto refill = [&]() { inflight.push(issue_next(st), stages); };
+        auto refill = [&]() { cur_blk = issue_next(); };  // once per block, when the slot's last pass no longer needs it
         for (int t = 0; t < m; ++t) {
             const int idx = t * GW + grp;  // site of this group inside the slot
             const int64_t s = blk * SPS + idx;
@@ -516,8 +507,11 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                 }
                 if (t == m - 1 && vm) refill();
             } else {
-                if (s < a.ns) pfa_site_process<LPS, ITER, HAS_V, MULTI>(a, s, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
+                // pass 1 has consumed every register loaded from the slot: the slot can be refilled while the second pass (on
+                // registers) runs
+                const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
                 if (t == m - 1) refill();
+                if (s < a.ns) pfa_site_finish_regs<LPS, ITER, HAS_V, MULTI>(a, s, f, x0, x1, xv, um, sub, gmask, Wq, sm_SH, sm_sfs);
             }
         }
     }
@@ -605,7 +599,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     // stay on the register kernel.  ONE slot per warp: a second one puts more bytes in flight than the memory system likes
     // (7.0 -> 6.5 TB/s).  PFA_SITE_TMA=<slots> (0 = off), PFA_SITE_TMA_M (passes per slot).
     int tma_stages = 1;
-    if (const char* e = getenv("PFA_SITE_TMA")) tma_stages = std::max(0, std::min(16, atoi(e)));
+    if (const char* e = getenv("PFA_SITE_TMA")) tma_stages = std::max(0, std::min(1, atoi(e)));  // 0: off; one slot per warp
     bool use_tma = lps >= 4 || a->Wq <= 3;
     if (const char* e = getenv("PFA_SITE_TMA_MIN_LPS")) use_tma = lps >= std::max(1, atoi(e));
     if (tma_stages > 0 && !generic && use_tma) {
@@ -615,7 +609,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: a shard with a few non-ACGT symbols fetches only the flagged pieces of its v plane (pfa_slot_issue);
         // not when the validity plane is forced (benchmarks of the 3-plane worst case) or PFA_VFLAG=0
-        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
+        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && a->Wq >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
         if (sparse_v) {
             args.vflag = a->vflag;
             m = std::min(m, 32 * PFA_VF_REGS / gw);

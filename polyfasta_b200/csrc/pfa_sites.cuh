@@ -193,61 +193,40 @@ __device__ __forceinline__ bool pfa_flags_all_escape(unsigned f) { return (f & 1
 // communication at all), the last 1/8 is handed out dynamically in chunks of consecutive blocks whose size halves from
 // phase to phase (guided self-scheduling: with W warps, phase p gives out 4 W chunks of C0 >> p blocks, C0 = blocks / (8 W),
 // the last blocks go out one by one); each claim is prefetched one chunk ahead.  PfaClaimer is used by lane 0 of a warp.
-struct PfaClaimer {
+struct PfaClaimer {   // block numbers fit 32 bits (a shard has fewer than 2^31 sites)
     unsigned int* ctr;
-    long long nblk, P, C0, cur, end;
-    unsigned int pending;
-    __device__ __forceinline__ void init(unsigned int* counter, long long blocks, long long warps) {
+    unsigned nblk, P, C0, cur, end, pending;
+    __device__ __forceinline__ void init(unsigned int* counter, unsigned blocks, unsigned warps) {
         ctr = counter;
         nblk = blocks;
-        P = 4 * warps;
-        C0 = blocks / (8 * warps);
-        if (C0 < 1) C0 = 1;
-        cur = end = 0;
+        P = 4u * warps;
+        C0 = blocks / (8u * warps);
+        if (C0 < 1u) C0 = 1u;
+        cur = end = 0u;
         pending = atomicAdd(ctr, 1u);
     }
-    __device__ __forceinline__ long long next() {  // the next block of this warp, -1 when none is left
+    __device__ __forceinline__ int next() {  // the next block of this warp, -1 when none is left
         while (cur == end) {
             if (pending == 0xffffffffu) return -1;
-            long long start = 0, c = C0, j = pending;
-            while (c > 1 && j >= P) {
-                start += P * c;
+            unsigned long long start = 0;
+            unsigned c = C0, j = pending;
+            while (c > 1u && j >= P) {
+                start += (unsigned long long)P * c;
                 j -= P;
                 c >>= 1;
             }
-            start += j * c;
+            start += (unsigned long long)j * c;
             if (start >= nblk) {
                 pending = 0xffffffffu;
                 return -1;
             }
-            cur = start;
-            end = start + c < nblk ? start + c : nblk;
+            cur = (unsigned)start;
+            end = start + c < nblk ? (unsigned)start + c : nblk;
             pending = atomicAdd(ctr, 1u);  // needed only when this chunk is used up
         }
-        return cur++;
+        return (int)(cur++);
     }
 };
-
-// the blocks in flight of one warp, oldest first (one per slot of its ring, at most 4), kept identically in every lane
-struct PfaBlockFifo {
-    long long f0, f1, f2, f3;
-    __device__ __forceinline__ long long pop() {
-        const long long b = f0;
-        f0 = f1; f1 = f2; f2 = f3; f3 = -1;
-        return b;
-    }
-    __device__ __forceinline__ void push(long long b, int stages) {  // after a pop: stages - 1 blocks are in flight
-        if (stages == 1) f0 = b;
-        else if (stages == 2) f1 = b;
-        else if (stages == 3) f2 = b;
-        else f3 = b;
-    }
-};
-__device__ __forceinline__ long long pfa_bcast0(long long x) {
-    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(unsigned long long)x, 0);
-    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)((unsigned long long)x >> 32), 0);
-    return (long long)(((unsigned long long)hi << 32) | lo);
-}
 
 // ---- bulk copies (TMA) into shared memory completing on an mbarrier ------------------------------------------------------
 __device__ __forceinline__ uint32_t pfa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -290,12 +269,21 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
 // All copies complete on the slot's mbarrier; lane 0 arms it last with the total byte count (bulk copies that finish before
 // the expect_tx only drive the transaction count negative for a moment; the phase cannot complete before lane 0 arrives).
 // Called by ALL lanes of the warp; fl[u] = flag word of site 32 u + lane of the block (sparse only).
-#define PFA_VF_REGS 4  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
+#define PFA_VF_REGS 2  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
 template <bool HAS_V>
 __device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* bar, const unsigned char* p0, const unsigned char* p1,
                                                const unsigned char* pv, bool sparse, int gc, int64_t s0, unsigned nsite, unsigned cap_sites,
                                                unsigned rec, int Wq, const uint32_t (&fl)[PFA_VF_REGS], int lane) {
     pfa_fence_proxy_async();  // this lane's reads of the slot's previous contents come before the copies
+    if (!(HAS_V && sparse)) {   // whole planes: lane 0 alone
+        if (lane == 0) {
+            pfa_mbar_expect_tx(bar, (HAS_V ? 3u : 2u) * nsite * rec);
+            pfa_bulk_load(slot, p0 + (size_t)s0 * rec, nsite * rec, bar);
+            pfa_bulk_load(slot + (size_t)cap_sites * rec, p1 + (size_t)s0 * rec, nsite * rec, bar);
+            if (HAS_V) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
+        }
+        return;
+    }
     unsigned vbytes = HAS_V ? nsite * rec : 0u;
     bool whole_v = HAS_V;
     if (HAS_V && sparse) {
@@ -303,7 +291,7 @@ __device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* ba
         unsigned cells = 0;
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u)
-            if ((unsigned)(u * 32 + lane) < nsite) cells += __popc(fl[u]);
+            if ((unsigned)(u * 32) < nsite && (unsigned)(u * 32 + lane) < nsite) cells += __popc(fl[u]);
         cells = __reduce_add_sync(0xffffffffu, cells);
         const unsigned ncell = (unsigned)((Wq + gc - 1) / gc);
         whole_v = cells * 3u > nsite * ncell;
@@ -311,7 +299,7 @@ __device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* ba
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u) {
             const unsigned si = (unsigned)(u * 32 + lane);
-            if (si < nsite) {
+            if ((unsigned)(u * 32) < nsite && si < nsite) {
                 fa[si] = whole_v ? 0xffffffffu : fl[u];
                 if (!whole_v)
                     for (uint32_t w = fl[u]; w; w &= w - 1) {
