@@ -169,6 +169,7 @@ int pfa_codon_class(int codon);  /* id of the 3-char class of PolyFastA.py:324-3
 /* d_out: int64[k] sum_{i<j} d_ij per population; d_matrix (optional): int32[n][n] over all rows. */
 int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix /* host, optional */);
+/* d_matrix / matrix == NULL: only the sums; the n x n matrix is then never materialised (pairs are folded inside the tiles) */
 
 /* ---- column shards on several GPUs: the sum of the per-shard vectors, fused into the scan kernels ------------------------
  * an alignment split in contiguous column ranges, one process per GPU; every statistic is a sum of exact
@@ -201,6 +202,9 @@ int pfa_site_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_isva
 int pfa_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_labels);
 /* the same exchange on its own for a vector produced by another kernel (K3 pairwise sums): in place on d_buf */
 int pfa_xchg_allreduce(pfa_xchg* x, int64_t* d_buf, int64_t len);
+/* K3 over column shards: the per-population sums of this rank's shard, then the sum over all ranks (d_ij is additive over
+ * columns); d_out (device) = int64[k] of the whole alignment on every rank */
+int pfa_pairwise_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out);
 
 /* ---- batched path for many small loci: replaces the per-file loop of --dir mode (PolyFastA.py:93-94,104) ------------- */
 /* A batch is filled on the host (rows are copied into one pinned blob), then pfa_batch_run does ONE upload, three segmented
@@ -248,6 +252,12 @@ int pfa_batch_result(const pfa_batch* b, int64_t locus, int pop, int64_t counts[
 int pfa_batch_result_cds(const pfa_batch* b, int64_t locus, int pop, int64_t* cds, double* ssites, void* fin2 /* pfa_final_out[2] */);
 /* ingest helpers for --dir: parse many files with `threads` host threads (status[i] = PFA_OK / PFA_ERR_NOT_FASTA / ...), and
  * build the row mask of the headers containing `key` (PolyFastA.py:125); returns the number of matching rows */
+/* column-sharded runs over one large file: the rank that parsed it exports WHERE its rows are (a few bytes per row; 0 bytes =
+ * the file was not mapped in place, every rank parses for itself), the other ranks map the file and adopt the layout without
+ * scanning it */
+int64_t pfa_fasta_layout_bytes(const pfa_fasta* f);
+int pfa_fasta_export_layout(const pfa_fasta* f, void* buf, int64_t cap);
+int pfa_fasta_import_layout(const char* path, const void* buf, int64_t bytes, pfa_fasta** out);
 int pfa_fasta_parse_files(const char* const* paths, int count, int threads, pfa_fasta** out, int* status);
 int64_t pfa_fasta_match_mask(const pfa_fasta* f, const char* key, int64_t key_len, uint32_t* mask, int64_t mask_words);
 

@@ -28,10 +28,10 @@ EXPORTS = [
     "pfa_mask_words_for", "pfa_batch_create", "pfa_batch_destroy", "pfa_batch_clear", "pfa_batch_size", "pfa_batch_text_bytes",
     "pfa_batch_add", "pfa_batch_add_rows", "pfa_batch_add_synthetic", "pfa_batch_add_files", "pfa_batch_run", "pfa_batch_run_cds", "pfa_batch_stage", "pfa_batch_scan",
     "pfa_batch_release", "pfa_batch_kernel_ms", "pfa_batch_shape", "pfa_batch_num_pops", "pfa_batch_result", "pfa_batch_result_cds",
-    "pfa_fasta_parse_files", "pfa_fasta_match_mask",
+    "pfa_fasta_parse_files", "pfa_fasta_match_mask", "pfa_fasta_layout_bytes", "pfa_fasta_export_layout", "pfa_fasta_import_layout",
     "pfa_host_pack2", "pfa_host_pack2_rows", "pfa_host_pack3",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
-    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_set_timeout_ms", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce",
+    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_set_timeout_ms", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce", "pfa_pairwise_xchg",
 ]
 
 
@@ -131,6 +131,9 @@ def lib():
         "pfa_batch_add_files": (c.c_int, [p, c.POINTER(c.c_char_p), c.c_int, c.POINTER(c.c_char_p), c.c_int, c.c_int,
                                           c.POINTER(c.c_int), c.POINTER(i64), c.POINTER(i64), c.POINTER(i64)]),
         "pfa_ctx_last_kernel": (c.c_char_p, [p]),
+        "pfa_fasta_layout_bytes": (i64, [p]),
+        "pfa_fasta_export_layout": (c.c_int, [p, p, i64]),
+        "pfa_fasta_import_layout": (c.c_int, [c.c_char_p, p, i64, c.POINTER(p)]),
         "pfa_batch_run": (c.c_int, [p, c.c_int]),
         "pfa_batch_run_cds": (c.c_int, [p, c.c_int]),
         "pfa_batch_stage": (c.c_int, [p]),
@@ -159,6 +162,7 @@ def lib():
         "pfa_site_stats_xchg": (c.c_int, [p, p, p, p]),
         "pfa_cds_stats_xchg": (c.c_int, [p, p, p, p]),
         "pfa_xchg_allreduce": (c.c_int, [p, p, i64]),
+        "pfa_pairwise_xchg": (c.c_int, [p, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -147,6 +147,23 @@ class Fasta:
         check(rc)
         return cls(h)
 
+    def export_layout(self):
+        """where the rows of a large file parsed in place are (bytes), for the other ranks of a column-sharded run; None when
+        this file is not mapped in place"""
+        n = int(lib().pfa_fasta_layout_bytes(self._h))
+        if n == 0:
+            return None
+        buf = ctypes.create_string_buffer(n)
+        check(lib().pfa_fasta_export_layout(self._h, buf, n))
+        return buf.raw
+
+    @classmethod
+    def from_layout(cls, path, blob):
+        """map `path` and adopt the row layout another rank exported: no line scan, no byte of the file is read"""
+        h = ctypes.c_void_p()
+        rc = lib().pfa_fasta_import_layout(str(path).encode(), blob, len(blob), ctypes.byref(h))
+        return cls._wrap(rc, h, path)
+
     @property
     def handle(self):
         return self._h
@@ -410,6 +427,10 @@ class Alignment:
     def cds_stats_device(self, d_out_ptr, d_labels_ptr=None):
         check(lib().pfa_cds_stats_device(self.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_labels_ptr or 0)),
               self.ctx.handle)
+
+    def pairwise_xchg(self, xchg, d_out_ptr):
+        """K3 on this rank's column shard + the sum over all ranks: d_out (device int64[k]) = sums of the whole alignment"""
+        check(lib().pfa_pairwise_xchg(self.handle, xchg.handle, ctypes.c_void_p(d_out_ptr)), self.ctx.handle)
 
     def pairwise(self, want_matrix=False):
         """K3 -> (list of sum_{i<j} d_ij per population, optional int32 [n][n] matrix over all rows)"""

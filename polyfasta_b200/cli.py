@@ -164,6 +164,21 @@ class RankGroup:
         dist.all_gather_object(hosts, socket.gethostname())
         self.fused = self.world <= 16 and len(set(hosts)) == 1 and os.environ.get("POLYFASTA_HOST_ALLREDUCE", "0") != "1"
 
+    def parse_once(self, path, threads):
+        """a large file every rank needs: rank 0 parses it with all host threads and hands the others the row layout (a few bytes
+        per row); they map the file and adopt it.  Files that were not mapped in place are parsed by every rank."""
+        blob = [None]
+        fasta = None
+        if self.rank == 0:
+            fasta = api.parse_files([path], threads=max(threads, (os.cpu_count() or 1)))[0]
+            blob = [fasta.export_layout() if isinstance(fasta, api.Fasta) else None]
+        self.dist.broadcast_object_list(blob, src=0)
+        if self.rank == 0:
+            return fasta
+        if blob[0] is None:
+            return api.parse_files([path], threads=threads)[0]
+        return api.Fasta.from_layout(path, blob[0])
+
     def exchange(self, ctx, words):
         """an exchange of at least `words` int64 (collective: every rank asks for the same size at the same point)"""
         from . import parallel
@@ -492,7 +507,7 @@ def run_files_ranks(paths, cds, jc, popkeys, sink, group):
     mine, j = [], 0
     for ui, (kind, ps) in enumerate(units):
         if kind == "all":
-            fasta = api.parse_files(ps, threads=threads)[0]
+            fasta = group.parse_once(ps[0], threads)
             acts = process_chunk(ctx, None, [(ps[0], fasta)], cds, jc, popkeys, group=group)
             if group.rank == 0:
                 mine.append((ui, acts))

@@ -373,6 +373,16 @@ int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     return pfa_launch_pairwise(a, d_out, d_matrix);
 }
 
+/* column shards: d_ij is additive over columns, so the per-population sums of the shards of all ranks are summed by the
+ * same NVLink exchange as the scans (one extra launch of one block); d_out gets the whole alignment's sums on every rank */
+int pfa_pairwise_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out) {
+    if (!a || !x || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    int rc = pfa_launch_pairwise(a, d_out, nullptr);
+    if (rc) return rc;
+    return pfa_xchg_launch_only(x, d_out, a->k, d_out);
+}
+
 int pfa_pairwise(pfa_aln* a, int64_t* out, int32_t* matrix) {
     if (!a || !out) return PFA_ERR_ARG;
     return run_to_host(a, sizeof(int64_t) * (size_t)a->k, out, sizeof(int32_t) * (size_t)(a->n * a->n), matrix,

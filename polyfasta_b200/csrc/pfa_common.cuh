@@ -71,6 +71,7 @@ struct pfa_aln {
     std::vector<int64_t> site_off;  // offsets into the site result vector, size k+1
     // row-major copy for the pairwise kernel (built lazily): [plane][n][Wl] uint32, Wl = ceil(ns/32) padded to 4
     uint32_t* rowmajor = nullptr;
+    int rowmajor_planes = 0;  // 2: pure-ACGT shard (b0, b1), 3: with the validity plane
     int64_t Wl = 0;
 };
 

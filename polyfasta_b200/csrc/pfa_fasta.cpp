@@ -457,6 +457,88 @@ static int parse_big_file(const char* path, size_t size, pfa_fasta** out) {
     return PFA_ERR_IO;
 }
 
+// ---- layout of a file parsed in place, for the other ranks of a column-sharded run ----------------------------------------------
+// Every rank of a multi-GPU run needs the rows of the same large file, but only ONE has to find them: the line scan (and the
+// byte check) of a multi-GB file reads it once from the page cache, and eight ranks doing it at the same time fight for the
+// host's memory bandwidth, which the uploads need.  The rank that parsed exports where the rows are -- a few bytes per row --
+// and the others map the file and adopt that layout without reading a byte of it.
+static const uint64_t LAYOUT_MAGIC = 0x3159414c41465024ull;  // "$PFALAY1"
+
+int64_t pfa_fasta_layout_bytes(const pfa_fasta* f) {
+    if (!f || !f->in_place || !f->mapped_bytes) return 0;  // only files mapped in place can be adopted without a copy
+    const size_t n = (size_t)f->n;
+    return (int64_t)(8 * 6 + 8 * (n + 1) + 8 * n + 8 * (n + 1) + f->headers.size() + (f->wrap_w.empty() ? 0 : 8 * n));
+}
+
+int pfa_fasta_export_layout(const pfa_fasta* f, void* buf, int64_t cap) {
+    const int64_t need = pfa_fasta_layout_bytes(f);
+    if (!need || !buf || cap < need) return PFA_ERR_ARG;
+    unsigned char* p = static_cast<unsigned char*>(buf);
+    const size_t n = (size_t)f->n;
+    const uint64_t head[6] = {LAYOUT_MAGIC, (uint64_t)f->n, (uint64_t)f->seqlen, (uint64_t)f->data_bytes, (uint64_t)f->headers.size(),
+                              (uint64_t)(f->wrap_w.empty() ? 0 : 1)};
+    auto put = [&](const void* src, size_t bytes) {
+        memcpy(p, src, bytes);
+        p += bytes;
+    };
+    put(head, sizeof head);
+    put(f->row_off.data(), 8 * (n + 1));
+    put(f->row_len.data(), 8 * n);
+    put(f->header_off.data(), 8 * (n + 1));
+    put(f->headers.data(), f->headers.size());
+    if (!f->wrap_w.empty()) {
+        put(f->wrap_w.data(), 4 * n);
+        put(f->wrap_gap.data(), 4 * n);
+    }
+    return PFA_OK;
+}
+
+int pfa_fasta_import_layout(const char* path, const void* buf, int64_t bytes, pfa_fasta** out) {
+    if (!path || !buf || !out || bytes < 48) return PFA_ERR_ARG;
+    *out = nullptr;
+    const unsigned char* p = static_cast<const unsigned char*>(buf);
+    uint64_t head[6];
+    memcpy(head, p, sizeof head);
+    p += sizeof head;
+    if (head[0] != LAYOUT_MAGIC) return PFA_ERR_ARG;
+    const size_t n = (size_t)head[1], hbytes = (size_t)head[4];
+    const bool wrapped = head[5] != 0;
+    if ((uint64_t)bytes != 48 + 8 * (n + 1) + 8 * n + 8 * (n + 1) + hbytes + (wrapped ? 8 * n : 0)) return PFA_ERR_ARG;
+    struct stat st;
+    if (stat(path, &st) != 0 || (uint64_t)st.st_size != head[3]) return PFA_ERR_IO;  // not the file the layout describes
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return PFA_ERR_IO;
+    void* m = mmap(nullptr, (size_t)head[3], PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return PFA_ERR_IO;
+    pfa_fasta* f = new pfa_fasta();
+    f->n = (int64_t)n;
+    f->seqlen = (int64_t)head[2];
+    f->in_place = true;
+    f->data = static_cast<unsigned char*>(m);
+    f->data_bytes = f->mapped_bytes = (size_t)head[3];
+    auto get = [&](void* dst, size_t b) {
+        memcpy(dst, p, b);
+        p += b;
+    };
+    f->row_off.resize(n + 1);
+    f->row_len.resize(n);
+    f->header_off.resize(n + 1);
+    f->headers.resize(hbytes);
+    get(f->row_off.data(), 8 * (n + 1));
+    get(f->row_len.data(), 8 * n);
+    get(f->header_off.data(), 8 * (n + 1));
+    get(&f->headers[0], hbytes);
+    if (wrapped) {
+        f->wrap_w.resize(n);
+        f->wrap_gap.resize(n);
+        get(f->wrap_w.data(), 4 * n);
+        get(f->wrap_gap.data(), 4 * n);
+    }
+    *out = f;
+    return PFA_OK;
+}
+
 int pfa_fasta_parse_file(const char* path, pfa_fasta** out) {
     if (!out || !path) return PFA_ERR_ARG;
     *out = nullptr;

@@ -274,7 +274,8 @@ template <bool HAS_V>
 __device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* bar, const unsigned char* p0, const unsigned char* p1,
                                                const unsigned char* pv, bool sparse, int gc, int64_t s0, unsigned nsite, unsigned cap_sites,
                                                unsigned rec, int Wq, const uint32_t (&fl)[PFA_VF_REGS], int lane) {
-    pfa_fence_proxy_async();  // this lane's reads of the slot's previous contents come before the copies
+    __syncwarp();             // every lane has its last values of the slot's previous contents (consumed by pass 1) ...
+    pfa_fence_proxy_async();  // ... and those generic-proxy reads come before the async-proxy writes of the copies
     if (!(HAS_V && sparse)) {   // whole planes: lane 0 alone
         if (lane == 0) {
             pfa_mbar_expect_tx(bar, (HAS_V ? 3u : 2u) * nsite * rec);

@@ -785,3 +785,25 @@ def test_sparse_validity_flags(ctx, monkeypatch, n, L, gap_ppm, k):
     for site, cds, _ in res:
         _check_site_cds(site, cds, text, pops, (n, L, gap_ppm))
     assert "HAS_V=1" in res[0][2]
+
+
+@pytest.mark.parametrize("n,L", [(20, 300_000), (64, 200_000), (200, 100_000), (380, 60_000), (1100, 30_000)])
+def test_narrow_records_many_variable_sites(ctx, n, L):
+    """records handled by 1-2 lanes per site (every lane of a warp its own site, no shuffle inside a pass) with a third of the
+    sites variable, three populations: lanes leave the second pass at different times, and the refill of the warp's
+    shared-memory slot must wait for all of them (a missing warp barrier double-counted sites here)"""
+    rng = np.random.default_rng(n + L)
+    text = _random_text(rng, n, L, p_var=0.3, p_junk=0.0, lower=0.0)
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n))]
+    aln = pf.Alignment.from_rows(ctx, text)
+    aln.set_pops(pops)
+    for rep in range(3):
+        site = aln.site_stats()
+        cds = aln.cds_stats()
+        for q, rows in enumerate(pops):
+            want = co.site_stats(text, rows)
+            assert (site[q]["S"], site[q]["H"], site[q]["sfs"]) == (want["S"], want["H"], want["sfs"]), (n, L, q, rep)
+            wc = co.cds_stats(text, rows)
+            for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
+                assert cds[q][k] == wc[k], (n, L, q, k, rep)
+    aln.free()

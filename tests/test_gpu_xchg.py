@@ -95,7 +95,21 @@ def test_ranks_in_one_process(world, L):
         for r in range(world):
             assert np.array_equal(out_s[r].cpu().numpy(), want_s), (it, r)
             assert np.array_equal(out_c[r].cpu().numpy(), want_c), (it, r)
-    # a vector produced by another kernel (K3 sums), summed in place
+    # K3 over the column shards: the pairwise sums of every population, summed over the ranks, equal the whole alignment's
+    whole = pf.Alignment.from_rows(ctxs[0], text)
+    whole.set_pops(pops)
+    want_pw = whole.pairwise()
+    whole.free()
+    assert want_pw[1] == co.pairwise_sum(up, pops[1])
+    out_p = [torch.full((len(pops),), -1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        shards[r].pairwise_xchg(xs[r], out_p[r].data_ptr())
+    for c in ctxs:
+        c.sync()
+    for r in range(world):
+        assert out_p[r].cpu().tolist() == want_pw, r
+    # a vector produced by another kernel, summed in place
     bufs = [torch.arange(5, dtype=torch.int64, device="cuda") * (r + 1) for r in range(world)]
     torch.cuda.synchronize()
     for r in range(world):

@@ -303,3 +303,38 @@ def test_big_file_path_refuses_non_ascii_sequence_bytes(tmp_path, monkeypatch, m
         bad.write_bytes(body)
         with pytest.raises(ValueError):
             pf.Fasta.from_file(str(bad))
+
+
+def test_layout_export_import(tmp_path, monkeypatch):
+    """column-sharded runs parse a large file ONCE: the rank that parsed exports where the rows are, the others map the file and
+    adopt that layout without scanning it (pfa_fasta_export_layout / pfa_fasta_import_layout).  Rows on one line and rows
+    wrapped at a fixed width, headers of different lengths; a small file (not mapped in place) has no layout to export."""
+    import numpy as np
+    from polyfasta_b200 import api
+    rng = np.random.default_rng(5)
+    n, L = 37, 5000
+    rows = ["".join(rng.choice(list("ACGTacgtN-"), L)) for _ in range(n)]
+    for wrap in (0, 60):
+        path = tmp_path / ("big%d.fa" % wrap)
+        with open(path, "w") as f:
+            for i, r in enumerate(rows):
+                f.write(">pop%d_row%d%s\n" % (i % 2, i, "x" * (i % 5)))
+                if wrap:
+                    f.write("\n".join(r[o:o + wrap] for o in range(0, L, wrap)) + "\n")
+                else:
+                    f.write(r + "\n")
+        small = api.Fasta.from_file(str(path))
+        assert small.export_layout() is None
+        monkeypatch.setenv("PFA_BIG_FILE_MIN", "1")
+        big = api.Fasta.from_file(str(path))
+        blob = big.export_layout()
+        assert blob is not None and len(blob) < 40 * n + sum(len(h) for h in big.headers) + 100
+        twin = api.Fasta.from_layout(str(path), blob)
+        monkeypatch.delenv("PFA_BIG_FILE_MIN")
+        assert twin.headers == big.headers == small.headers and (twin.nseq, twin.seqlen) == (n, L)
+        for i in (0, 1, n // 2, n - 1):
+            assert twin.row(i) == small.row(i) == rows[i].upper()
+        with pytest.raises((OSError, Exception)):
+            api.Fasta.from_layout(str(path) + ".missing", blob)
+        for x in (small, big, twin):
+            x.close()
