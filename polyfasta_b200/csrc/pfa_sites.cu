@@ -108,20 +108,23 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_site_scan_kernel(const P
 // passes 1 and 2 of one site whose record chunks are already in registers (x0, x1, xv: the lane's ITER chunks of each plane;
 // um: its slice of the union mask).  Shared by the register-resident kernel (chunks loaded from global memory) and the
 // TMA kernel (chunks read from the warp's shared-memory ring).
-// pass 1 of one site whose chunks are in registers: the six presence flags, OR-reduced over the group
-template <int LPS, int ITER, bool HAS_V>
+// pass 1 of one site whose chunks are in registers: the six presence flags, OR-reduced over the group.
+// VALID_ONLY (with HAS_V): the flags of the two base planes look at the VALID rows only, so that "every valid row shows the same
+// base" can be told apart from real base variation (the gap-only fast path of the whole-warp second pass).
+template <int LPS, int ITER, bool HAS_V, bool VALID_ONLY = false>
 __device__ __forceinline__ unsigned pfa_site_pass1(const uint4 (&x0)[ITER], const uint4 (&x1)[ITER], const uint4 (&xv)[ITER],
                                                    const uint4 (&um)[ITER], unsigned gmask) {
     uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
-        const uint4 m = um[i];
+        uint4 m = um[i];
+        ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
+        if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
+        if (HAS_V && VALID_ONLY) m = make_uint4(m.x & xv[i].x, m.y & xv[i].y, m.z & xv[i].z, m.w & xv[i].w);
         o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
         z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
         o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
         z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
-        ov |= (xv[i].x & m.x) | (xv[i].y & m.y) | (xv[i].z & m.z) | (xv[i].w & m.w);
-        if (HAS_V) zv |= (~xv[i].x & m.x) | (~xv[i].y & m.y) | (~xv[i].z & m.z) | (~xv[i].w & m.w);
     }
     const unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
     return pfa_group_or<LPS>(f, gmask);
@@ -344,12 +347,16 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
 template <bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_site_coop(const PfaSiteArgs& a, int64_t s, const uint32_t* w0, const uint32_t* w1, const uint32_t* wv,
                                               int Wn, int lane, unsigned long long* sm_SH, unsigned int* sm_sfs, uint32_t& S_mine,
-                                              unsigned long long& H_mine, uint32_t fw, int gcw) {
+                                              unsigned long long& H_mine, uint32_t fw, int gcw, unsigned f) {
     const int k = MULTI ? a.k : 1;
+    // gap-only site: every valid row shows the same base and the few invalid rows sit in a handful of flagged cells
+    const bool gaps_only = HAS_V && pfa_flags_bases_mono(f) && __popc(fw) <= 6;
+    const int base = ((f & 4u) ? 2 : 0) | ((f & 1u) ? 1 : 0);
     for (int q = 0; q < k; ++q) {
         const uint32_t* mq = reinterpret_cast<const uint32_t*>(MULTI ? a.masks + (int64_t)q * a.Wq : a.umask);
         uint32_t c[PFA_NCLASS];
-        pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c, fw, gcw);
+        if (gaps_only) pfa_coop_counts_gaps(w0, w1, wv, mq, Wn, lane, c, fw, gcw, base, (uint32_t)a.pop_n[q]);
+        else pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c, fw, gcw);
         const PfaSiteResult r = pfa_site_result(c, a.pop_n[q], 0u, 0ull);
         if (r.has_escape) continue;  // finished by pfa_escape_sites_kernel
         if (a.isvar && lane == 0) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
@@ -492,18 +499,22 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                 }
             }
             if (COOP) {
-                const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
-                const bool var = s < a.ns && !(pfa_flags_mono(f) && !pfa_flags_all_escape(f));
+                // base-plane flags over the valid rows only: a site is done here iff all its rows are valid and show one base;
+                // anything with a non-ACGT row goes to the second pass (which has a short path for "gaps only")
+                const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V, true>(x0, x1, xv, um, gmask);
+                const bool var = s < a.ns && !(pfa_flags_bases_mono(f) && (f & 16u) && !(f & 32u));
                 if (a.isvar && sub == 0 && s < a.ns && !var)
                     for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
                 const unsigned vm = __ballot_sync(0xffffffffu, var && sub == 0);
                 if (t == m - 1 && !vm) refill();
                 for (unsigned rest = vm; rest; rest &= rest - 1) {
-                    const int vidx = t * GW + (__ffs(rest) - 1) / LPS;
+                    const int leader = __ffs(rest) - 1;
+                    const int vidx = t * GW + leader / LPS;
+                    const unsigned fv = __shfl_sync(0xffffffffu, f, leader);
                     pfa_site_coop<HAS_V, MULTI>(a, blk * SPS + vidx, reinterpret_cast<const uint32_t*>(slot + (size_t)vidx * rec),
                                                 reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec),
                                                 reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec), Wq * 4, lane, sm_SH,
-                                                sm_sfs, S_mine, H_mine, sparse ? fa[vidx] : 0xffffffffu, gcw);
+                                                sm_sfs, S_mine, H_mine, sparse ? fa[vidx] : 0xffffffffu, gcw, fv);
                 }
                 if (t == m - 1 && vm) refill();
             } else {

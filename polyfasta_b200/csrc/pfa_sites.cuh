@@ -181,9 +181,43 @@ __device__ __forceinline__ void pfa_coop_counts(const uint32_t* __restrict__ w0,
         if (HAS_V || i < 4) c[i] = __reduce_add_sync(0xffffffffu, c[i]);
 }
 
+// The same counts for a site whose rows, as far as they are VALID, all show one base (`base`) -- the site is on the second pass
+// only because some rows are not valid (a gap is an allele, PolyFastA.py:256-258).  Only the flagged cells of the validity
+// plane can hold those rows, so only they are read: a few words instead of the whole record.  nq = rows of the population.
+__device__ __forceinline__ void pfa_coop_counts_gaps(const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
+                                                     const uint32_t* __restrict__ wv, const uint32_t* __restrict__ mq, int Wn, int lane,
+                                                     uint32_t c[PFA_NCLASS], uint32_t fw, int gcw, int base, uint32_t nq) {
+    uint32_t cg = 0, cn = 0, cq = 0, ce = 0;
+    for (uint32_t cells = fw; cells; cells &= cells - 1) {
+        const int w = (__ffs(cells) - 1) * gcw + lane;
+        if (lane < gcw && w < Wn) {
+            const uint32_t im = ~wv[w] & __ldg(mq + w), x0 = w0[w], x1 = w1[w];
+            ce += __popc(im & x1 & x0);
+            cq += __popc(im & x1 & ~x0);
+            cn += __popc(im & ~x1 & x0);
+            cg += __popc(im & ~x1 & ~x0);
+        }
+    }
+    cg = __reduce_add_sync(0xffffffffu, cg);
+    cn = __reduce_add_sync(0xffffffffu, cn);
+    cq = __reduce_add_sync(0xffffffffu, cq);
+    ce = __reduce_add_sync(0xffffffffu, ce);
+#pragma unroll
+    for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+    c[PFA_C_N] = cn;
+    c[PFA_C_Q] = cq;
+    c[PFA_C_ESC] = ce;
+    const uint32_t valid = nq - (cg + cn + cq + ce);
+    c[PFA_C_A] = base == 0 ? valid : 0u;
+    c[PFA_C_C] = base == 1 ? valid : 0u;
+    c[PFA_C_G] = base == 2 ? valid : 0u;
+    c[PFA_C_T] = base == 3 ? valid : 0u;
+}
+
 // flags of pass 1 (bit 0/1: plane b0 shows a one / a zero among the rows of the union mask, 2/3: b1, 4/5: v)
 __device__ __forceinline__ bool pfa_flags_mono(unsigned f) { return ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u); }
 __device__ __forceinline__ bool pfa_flags_all_escape(unsigned f) { return (f & 1u) && (f & 4u) && !(f & 16u); }
+__device__ __forceinline__ bool pfa_flags_bases_mono(unsigned f) { return ((f & 3u) != 3u) && ((f & 12u) != 12u); }
 
 // ---- distribution of the blocks of a scan over the warps of the grid --------------------------------------------------------
 // A static split (block b to warp b mod W) left ~7 % of the warp time idle at the end of K4: warps that meet more variable
