@@ -267,6 +267,10 @@ class Env:
         torch.cuda.set_device(self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.cpus = host_threads()
+        if self.world > 1:
+            from polyfasta_b200 import parallel
+            parallel.bind_near_gpu(self.local_rank)   # pinned staging memory of this rank on the GPU's NUMA node
         self.ctx = pf.Context(self.local_rank)
         self.stream = torch.cuda.Stream()
         self.ctx.set_stream(self.stream.cuda_stream)
@@ -456,7 +460,7 @@ def run_c4(args, env):
             del d_text
             torch.cuda.empty_cache()
             h_out = torch.empty(out.numel(), dtype=torch.int64, pin_memory=True)
-            ctx.set_host_threads(max(1, host_threads() // world))   # the ranks of one box share its cores
+            ctx.set_host_threads(max(1, env.cpus // world))   # the ranks of one box share its cores
 
             def e2e_step():
                 a = pf.Alignment.from_host_ptr(ctx, h_text.data_ptr(), n, cols, ld)   # H2D (pinned, chunked) + K1
@@ -604,7 +608,7 @@ def run_c3(args, env):
             torch.cuda.empty_cache()
             h_site = torch.empty(d_site.numel(), dtype=torch.int64, pin_memory=True)
             h_cds = torch.empty(d_cds.numel(), dtype=torch.int64, pin_memory=True)
-            ctx.set_host_threads(max(1, host_threads() // world))
+            ctx.set_host_threads(max(1, env.cpus // world))
 
             def e2e_step():
                 a = pf.Alignment.from_host_ptr(ctx, h_text.data_ptr(), n, cols, ld)   # H2D (pinned, chunked) + K1 of this rank's columns

@@ -153,6 +153,9 @@ class RankGroup:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.device = int(os.environ.get("LOCAL_RANK", str(self.rank)))
+        self.host_cpus = os.cpu_count() or 1
+        from . import parallel
+        parallel.bind_near_gpu(self.device)
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("gloo", rank=self.rank, world_size=self.world)

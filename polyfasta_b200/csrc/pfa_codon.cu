@@ -861,25 +861,31 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         }
     };
     load_flags();
+    bool pend_v = HAS_V, cur_v = HAS_V;  // does the block in the slot (being fetched / being scanned) carry validity pieces?
     auto issue_next = [&]() -> int {  // all lanes: fetch `pend` into the warp's slot, then look one block further ahead
         const int blk = pend;
         if (blk >= 0) {
             const int64_t c0 = (int64_t)blk * CPS;
-            pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, c0 * 3, 3u * (unsigned)min((int64_t)CPS, a.ncf - c0), (unsigned)SPS,
-                                  rec, Wq, pfl, lane);
+            pend_v = pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, c0 * 3, 3u * (unsigned)min((int64_t)CPS, a.ncf - c0),
+                                           (unsigned)SPS, rec, Wq, pfl, lane);
         }
         pend = blk >= 0 ? next_block() : -1;
         load_flags();
         return blk;
     };
     int cur_blk = issue_next();
+    cur_v = pend_v;
 
     for (unsigned k = 0; cur_blk >= 0; ++k) {
         const int64_t blk = cur_blk;
+        const bool bv = cur_v;  // false: no row of this block's sites is invalid -- the two-plane code path
         pfa_mbar_wait(bar, k & 1u);
         const unsigned char* slot = ring;
         const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
-        auto refill = [&]() { cur_blk = issue_next(); };  // once per block, when the slot's last pass no longer needs it
+        auto refill = [&]() {  // once per block, when the slot's last pass no longer needs it
+            cur_blk = issue_next();
+            cur_v = pend_v;
+        };
         for (int t0 = 0; t0 < m; ++t0) {
             const int idx = t0 * GW + grp;  // codon column of this group inside the slot
             const int64_t cc = blk * CPS + idx;
@@ -889,7 +895,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)(idx * 3 + t) * rec);
                 const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(CPS * 3 + idx * 3 + t) * rec);
                 const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * CPS * 3 + idx * 3 + t) * rec);
-                const uint32_t fwt = sparse ? fa[idx * 3 + t] : 0xffffffffu;
+                const uint32_t fwt = !bv ? 0u : sparse ? fa[idx * 3 + t] : 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < ITER; ++i) {
                     const int j = sub + LPS * i;
@@ -903,7 +909,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 }
             }
             if (COOP) {
-                const unsigned f = pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
+                const unsigned f = (HAS_V && bv) ? pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask) : pfa_cds_pass1<LPS, ITER, false>(x0, x1, xv, um, gmask);
                 bool uniform = true, clean = true;
                 int codon = 0;
 #pragma unroll
@@ -927,8 +933,8 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                     const int leader = __ffs(rest) - 1;
                     const int vidx = t0 * GW + leader / LPS;
                     const unsigned fv = __shfl_sync(0xffffffffu, f, leader);
-                    const uint32_t fw3[3] = {sparse ? fa[vidx * 3] : 0xffffffffu, sparse ? fa[vidx * 3 + 1] : 0xffffffffu,
-                                             sparse ? fa[vidx * 3 + 2] : 0xffffffffu};
+                    const uint32_t fw3[3] = {!bv ? 0u : sparse ? fa[vidx * 3] : 0xffffffffu, !bv ? 0u : sparse ? fa[vidx * 3 + 1] : 0xffffffffu,
+                                             !bv ? 0u : sparse ? fa[vidx * 3 + 2] : 0xffffffffu};
                     pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, reinterpret_cast<const uint32_t*>(slot + (size_t)(vidx * 3) * rec),
                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(CPS * 3 + vidx * 3) * rec),
                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw);

@@ -460,32 +460,38 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
         }
     };
     load_flags();
+    bool pend_v = HAS_V, cur_v = HAS_V;  // does the block in the slot (being fetched / being scanned) carry validity pieces?
     auto issue_next = [&]() -> int {  // all lanes: fetch `pend` into the warp's slot, then look one block further ahead
         const int blk = pend;
         if (blk >= 0) {
             const int64_t s0 = (int64_t)blk * SPS;
-            pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, s0, (unsigned)min((int64_t)SPS, a.ns - s0), (unsigned)SPS, rec,
-                                  Wq, pfl, lane);
+            pend_v = pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, s0, (unsigned)min((int64_t)SPS, a.ns - s0),
+                                           (unsigned)SPS, rec, Wq, pfl, lane);
         }
         pend = blk >= 0 ? next_block() : -1;
         load_flags();
         return blk;
     };
     int cur_blk = issue_next();
+    cur_v = pend_v;
 
     for (unsigned k = 0; cur_blk >= 0; ++k) {
         const int64_t blk = cur_blk;
+        const bool bv = cur_v;  // false: no row of this block's sites is invalid -- the two-plane code path
         pfa_mbar_wait(bar, k & 1u);
         const unsigned char* slot = ring;
         const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
-        auto refill = [&]() { cur_blk = issue_next(); };  // once per block, when the slot's last pass no longer needs it
+        auto refill = [&]() {  // once per block, when the slot's last pass no longer needs it
+            cur_blk = issue_next();
+            cur_v = pend_v;
+        };
         for (int t = 0; t < m; ++t) {
             const int idx = t * GW + grp;  // site of this group inside the slot
             const int64_t s = blk * SPS + idx;
             const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
             const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
             const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
-            const uint32_t fw = sparse ? fa[idx] : 0xffffffffu;
+            const uint32_t fw = !bv ? 0u : sparse ? fa[idx] : 0xffffffffu;
             uint4 x0[ITER], x1[ITER], xv[ITER];
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
@@ -501,7 +507,8 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
             if (COOP) {
                 // base-plane flags over the valid rows only: a site is done here iff all its rows are valid and show one base;
                 // anything with a non-ACGT row goes to the second pass (which has a short path for "gaps only")
-                const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V, true>(x0, x1, xv, um, gmask);
+                const unsigned f = (HAS_V && bv) ? pfa_site_pass1<LPS, ITER, HAS_V, true>(x0, x1, xv, um, gmask)
+                                                 : pfa_site_pass1<LPS, ITER, false, false>(x0, x1, xv, um, gmask);
                 const bool var = s < a.ns && !(pfa_flags_bases_mono(f) && (f & 16u) && !(f & 32u));
                 if (a.isvar && sub == 0 && s < a.ns && !var)
                     for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                     pfa_site_coop<HAS_V, MULTI>(a, blk * SPS + vidx, reinterpret_cast<const uint32_t*>(slot + (size_t)vidx * rec),
                                                 reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec),
                                                 reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec), Wq * 4, lane, sm_SH,
-                                                sm_sfs, S_mine, H_mine, sparse ? fa[vidx] : 0xffffffffu, gcw, fv);
+                                                sm_sfs, S_mine, H_mine, !bv ? 0u : sparse ? fa[vidx] : 0xffffffffu, gcw, fv);
                 }
                 if (t == m - 1 && vm) refill();
             } else {

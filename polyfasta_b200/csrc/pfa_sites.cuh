@@ -304,20 +304,29 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
 // the expect_tx only drive the transaction count negative for a moment; the phase cannot complete before lane 0 arrives).
 // Called by ALL lanes of the warp; fl[u] = flag word of site 32 u + lane of the block (sparse only).
 #define PFA_VF_REGS 2  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
+// Returns true when the block's v area (or part of it) was fetched; false: the block holds no flagged cell (or the kernel reads no
+// validity plane at all) and its sites can be scanned as pure ACGT.
 template <bool HAS_V>
-__device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* bar, const unsigned char* p0, const unsigned char* p1,
+__device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* bar, const unsigned char* p0, const unsigned char* p1,
                                                const unsigned char* pv, bool sparse, int gc, int64_t s0, unsigned nsite, unsigned cap_sites,
                                                unsigned rec, int Wq, const uint32_t (&fl)[PFA_VF_REGS], int lane) {
     __syncwarp();             // every lane has its last values of the slot's previous contents (consumed by pass 1) ...
     pfa_fence_proxy_async();  // ... and those generic-proxy reads come before the async-proxy writes of the copies
-    if (!(HAS_V && sparse)) {   // whole planes: lane 0 alone
+    bool any_flag = HAS_V;
+    if (HAS_V && sparse) {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int u = 0; u < PFA_VF_REGS; ++u) mine |= fl[u];
+        any_flag = __any_sync(0xffffffffu, mine != 0u);
+    }
+    if (!(HAS_V && sparse) || !any_flag) {   // whole planes (or no validity piece at all): lane 0 alone
         if (lane == 0) {
-            pfa_mbar_expect_tx(bar, (HAS_V ? 3u : 2u) * nsite * rec);
+            pfa_mbar_expect_tx(bar, (any_flag ? 3u : 2u) * nsite * rec);
             pfa_bulk_load(slot, p0 + (size_t)s0 * rec, nsite * rec, bar);
             pfa_bulk_load(slot + (size_t)cap_sites * rec, p1 + (size_t)s0 * rec, nsite * rec, bar);
-            if (HAS_V) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
+            if (any_flag) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
         }
-        return;
+        return any_flag;
     }
     unsigned vbytes = HAS_V ? nsite * rec : 0u;
     bool whole_v = HAS_V;
@@ -355,6 +364,7 @@ __device__ __forceinline__ void pfa_slot_issue(unsigned char* slot, uint64_t* ba
         pfa_bulk_load(slot + (size_t)cap_sites * rec, p1 + (size_t)s0 * rec, nsite * rec, bar);
         if (whole_v) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
     }
+    return true;
 }
 
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args);

@@ -46,6 +46,37 @@ def chunk_owner(j, world):
     return j % world
 
 
+def bind_near_gpu(device):
+    """best effort: keep this process (and the ingest threads it starts) on the CPUs of the GPU's NUMA node, so that the pinned
+    staging buffers it allocates and packs are local to the PCIe root the uploads leave through.  One process per GPU on a
+    two-socket host otherwise reads half of its text across the socket link.  POLYFASTA_NUMA_BIND=0 turns it off.
+    Returns the CPU set now in force (or None when nothing was changed)."""
+    import os
+    if os.environ.get("POLYFASTA_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cur = os.sched_getaffinity(0)
+        new = cur & cpus
+        if not new or new == cur:
+            return None
+        os.sched_setaffinity(0, new)
+        return new
+    except Exception:
+        return None
+
+
 def connect_exchange(ctx, cap_words, group=None):
     """one api.Exchange per rank, connected over the ranks of `group`: the CUDA IPC handles of the symmetric buffers travel
     through all_gather_object (host plumbing); afterwards Alignment.site_stats_xchg / cds_stats_xchg sum the shard vectors

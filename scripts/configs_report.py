@@ -85,7 +85,8 @@ for i in range(nl):
     m[:, (i * 7) % 5000] = np.frombuffer(b"ACGT", dtype=np.uint8)[(np.arange(100) + i) % 4]   # every locus differs a little
     with open(os.path.join(tmp, "locus%06d.fa" % i), "wb") as f:
         f.write(b"".join(b">pop%d_ind%d\n" % (1 + r % 2, r) + m[r].tobytes() + b"\n" for r in range(100)))
-for extra, label in (([], "all rows"), (["-p", "pop1,pop2"], "-p pop1,pop2")):
+for extra, label in (([], "all rows"), (["-p", "pop1,pop2"], "-p pop1,pop2"), (["--cds"], "--cds (batched codon scan K4b)"),
+                     (["--cds", "-p", "pop1,pop2"], "--cds -p pop1,pop2")):
     t, out = cli_time(["-d", tmp, "--jc", "-s"] + extra, reps=2)
     emit("C5 --dir %d loci of 100 x 5000, %s" % (nl, label), wall_s=t, us_per_locus=t / nl * 1e6, bases_per_s=nl * 5e5 / t,
-         rows=len(out.strip().split("\n")), extrapolated_100k_loci_s=t / nl * 1e5)
+         rows=len(out.strip().split("\n")), first_row=out.strip().split("\n")[-1])
