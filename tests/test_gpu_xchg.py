@@ -214,8 +214,10 @@ def test_two_processes_two_gpus():
 def _cli_worker(rank, world, port, argv_list, shard_min, q):
     import io
     from contextlib import redirect_stdout
+    # PFA_BIG_FILE_MIN: the two large files are parsed in place (mapped), so rank 0 parses them once and the other rank adopts
+    # the exported row layout (RankGroup.parse_once)
     os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank), "MASTER_ADDR": "127.0.0.1",
-                       "MASTER_PORT": str(port)})
+                       "MASTER_PORT": str(port), "PFA_BIG_FILE_MIN": "1000000"})
     from polyfasta_b200 import cli
     cli.SHARD_MIN_BYTES = shard_min
     outs = []
@@ -246,8 +248,14 @@ def test_cli_under_two_ranks(tmp_path):
     with open(d / "file5_big.fa", "wb") as f:      # sorts between file5.fa and file6.fa
         for i in range(n):
             f.write((">indiv%d\n" % i).encode() + text[i].tobytes() + b"\n")
+    # a second large file whose length is not a multiple of 3: the trailing partial codon belongs to the LAST rank's shard
+    text2 = _random_text(rng, 45, 30001, p_junk=0.001)
+    with open(tmp_path / "odd_big.fa", "wb") as f:
+        for i in range(45):
+            f.write((">pop%d_%d\n" % (i % 2, i)).encode() + text2[i].tobytes() + b"\n")
     argvs = [["-d", str(d), "-p", "indiv1,indiv2,nobody", "--jc"], ["-d", str(d), "--cds", "--jc"],
-             ["-f", str(d / "file5_big.fa"), "--cds", "-p", "indiv1,indiv3"]]
+             ["-f", str(d / "file5_big.fa"), "--cds", "-p", "indiv1,indiv3"],
+             ["-f", str(tmp_path / "odd_big.fa"), "--cds", "--jc", "-p", "pop0,pop1"]]
     want = []
     for argv in argvs:
         buf = io.StringIO()
@@ -255,6 +263,7 @@ def test_cli_under_two_ranks(tmp_path):
             cli.main(argv)
         want.append(buf.getvalue())
     assert "file5_big.fa" in want[0] and want[2].count("\n") == 3
+    assert "not a multiple of 3: odd_big.fa" in want[3] and want[3].count("\n") == 4
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = _free_port()
