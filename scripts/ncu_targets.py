@@ -1,4 +1,4 @@
-"""Small fixed workloads for ncu captures.  usage: python scripts/ncu_targets.py k4|k3|k1
+"""Small fixed workloads for ncu captures.  usage: python scripts/ncu_targets.py k4|k3|k1|k2b
 k4: codon scan on the C3 shape (2000 x 3 Mb, 2 populations);  k3: pairwise 2000 rows x 100 kb;
 k1: one hybrid upload of 10000 x 200 kb pinned text (raw K1 + packed K1 kernels)"""
 import ctypes, os, sys
@@ -31,6 +31,15 @@ elif which == "k1":
         ctx.sync()
         print("k1", ctx.ingest_stats())
         a.free()
+elif which == "k2b":
+    # the batched site scan on the C5 shape: 2,500 resident loci of 100 x 5 kb
+    b = api.Batch(ctx)
+    for i in range(2500):
+        b.add_synthetic(100, 5000, 5 + i)
+    b.stage()
+    for _ in range(3):
+        b.scan(jc=True)
+    print("k2b", b.result(0)["S"], b.kernel_ms())
 else:
     a = pf.Alignment.synthetic(ctx, 2000, 100_000, 3)
     out = torch.zeros(1, dtype=torch.int64, device="cuda")
