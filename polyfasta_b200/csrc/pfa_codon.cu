@@ -1099,7 +1099,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
             int rc = launch_cds_escape(a, args);
             if (rc) return rc;
         }
-        int rc = pfa_xchg_fill(x, out_len, d_out, &args.s.x);
+        int rc = pfa_xchg_fill(x, out_len, d_out, &args.s.x, true);  // the TMA kernels run one CTA per SM
         if (rc) return rc;
     }
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;
@@ -1157,6 +1157,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
             return PFA_OK;
         }
     }
+    args.s.x.wide = 0;  // see pfa_launch_site_scan
 #define PFA_CDS_CASE(L_, I_)                                                                                          \
     if (lps == L_ && iter == I_) {                                                                                    \
         if (hv && multi) pfa_cds_scan_reg_kernel<L_, I_, true, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);       \

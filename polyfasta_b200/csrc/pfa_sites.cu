@@ -592,7 +592,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
             int rc = launch_escape_sites(a, args);
             if (rc) return rc;
         }
-        int rc = pfa_xchg_fill(x, out_len, d_out, &args.x);
+        int rc = pfa_xchg_fill(x, out_len, d_out, &args.x, true);  // the TMA kernels run one CTA per SM: all blocks may take part
         if (rc) return rc;
     }
     // lanes per site: the smallest power of two that leaves every lane at most 5 chunks
@@ -668,6 +668,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
             return PFA_OK;
         }
     }
+    args.x.wide = 0;  // several CTAs per SM, grids beyond the resident set: the last block alone runs the exchange
 #define PFA_REG_CASE(L_, I_)                                                                                          \
     if (lps == L_ && iter == I_) {                                                                                    \
         if (hv && multi) pfa_site_scan_reg_kernel<L_, I_, true, true><<<grid, PFA_SITE_THREADS, smem, st>>>(args);      \

@@ -20,6 +20,7 @@ struct pfa_xchg {
     unsigned int epoch = 0;  // exchanges LAUNCHED so far (pfa_xchg_commit): a call that fails before its launch leaves it alone
     int high_water = 0;
     unsigned long long timeout_ns = PFA_XCHG_TIMEOUT_NS;
+    bool distinct_devices = false;  // connected over CUDA IPC: every rank has a GPU of its own (the wide epilogue needs that)
     char* peer[PFA_XCHG_MAX_RANKS] = {};
     bool opened[PFA_XCHG_MAX_RANKS] = {};  // mapped with cudaIpcOpenMemHandle (to be closed)
 };
@@ -32,7 +33,9 @@ __global__ void __launch_bounds__(256) pfa_xchg_only_kernel(const PfaXchgDev x, 
     pfa_xchg_epilogue(x);
 }
 
-int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev) {
+// coresident: the kernel this exchange is compiled into is launched with at most one block per SM slot, so that all of its blocks
+// are resident together and may wait for one another (the TMA scans: one CTA per SM)
+int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev, bool coresident) {
     pfa_ctx* ctx = x->ctx;
     if (x->world <= 0) return pfa_fail(ctx, PFA_ERR_ARG, "exchange is not connected");
     if (len < 0 || len > x->cap) return pfa_fail(ctx, PFA_ERR_ARG, "exchange of %lld words exceeds the capacity %lld", (long long)len, (long long)x->cap);
@@ -42,6 +45,8 @@ int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev) {
     dev->epoch = x->epoch;
     dev->len = (int)len;
     dev->zero_len = x->high_water;
+    static const bool wide_off = getenv("PFA_XCHG_WIDE") && atoi(getenv("PFA_XCHG_WIDE")) == 0;
+    dev->wide = coresident && x->distinct_devices && x->world > 1 && !wide_off;
     dev->cap = x->cap;
     dev->timeout_ns = x->timeout_ns;
     dev->partial = x->partial;
@@ -61,7 +66,7 @@ void pfa_xchg_commit(pfa_xchg* x) { x->epoch++; }
 
 int pfa_xchg_launch_only(pfa_xchg* x, const int64_t* d_src, int64_t len, int64_t* d_out) {
     PfaXchgDev dev;
-    int rc = pfa_xchg_fill(x, len, d_out, &dev);
+    int rc = pfa_xchg_fill(x, len, d_out, &dev, false);
     if (rc) return rc;
     pfa_xchg_only_kernel<<<1, 256, 0, x->ctx->stream>>>(dev, d_src);
     PFA_LAUNCH_CHECK(x->ctx);
@@ -158,6 +163,7 @@ int pfa_xchg_connect(pfa_xchg* x, int rank, int world, const void* handles) {
     }
     x->rank = rank;
     x->world = world;
+    x->distinct_devices = true;
     return PFA_OK;
 }
 

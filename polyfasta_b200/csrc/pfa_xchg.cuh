@@ -22,6 +22,7 @@ struct PfaXchgDev {
     unsigned int epoch;  // exchanges completed before this launch
     int len;             // int64 words exchanged by this launch (<= cap)
     int zero_len;        // longest vector exchanged so far (>= len): that much of the idle slot is cleared
+    int wide;            // all blocks of the launch take part in the exchange (they are co-resident): see pfa_xchg_epilogue_wide
     int64_t cap;
     unsigned long long timeout_ns;  // how long the last block waits for the other ranks' flags before it gives up
     unsigned long long* partial;  // this rank's vector: the blocks add into it; zero at entry, zeroed again at exit
@@ -49,15 +50,100 @@ __device__ __forceinline__ unsigned int pfa_ld_acquire_sys(const unsigned int* p
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned int pfa_ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long pfa_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 
+// The exchange by ALL blocks of the launch (x.wide: the launch has at most one block per SM slot, so they are resident together;
+// ranks on distinct GPUs).  With one block doing everything, pushing 5,002 words to 8 ranks took 8.8 us and the whole epilogue
+// ~20 us of a 480 us step; here every block pushes, and later copies, 1/gridDim of the vector:
+//   barrier A (all blocks have added their share into x.partial)  ->  each block: clear its slice of the idle slot, push its
+//   slice to every rank, fence  ->  barrier B: the last block there raises the flags on all ranks  ->  every block waits for
+//   this rank's flag and copies its slice of the total to the caller's buffer  ->  the last block out resets the counters.
+// x.ticket[0], [2], [3] count the blocks at the three stages; spins give up after x.timeout_ns (status word).
+__device__ __forceinline__ void pfa_xchg_epilogue_wide(const PfaXchgDev& x) {
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned G = gridDim.x;
+    unsigned int* cnt_a = x.ticket;
+    unsigned int* cnt_b = x.ticket + 2;
+    unsigned int* cnt_c = x.ticket + 3;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(cnt_a, 1u);
+        const unsigned long long t0 = pfa_globaltimer();
+        while (pfa_ld_acquire_gpu(cnt_a) < G) {
+            if (pfa_globaltimer() - t0 > x.timeout_ns) {
+                *x.status = 1u;
+                break;
+            }
+        }
+        if (blockIdx.x == 0) x.stamps[0] = pfa_globaltimer();
+    }
+    __syncthreads();
+    const int slot = (int)(x.epoch & 1u);
+    const int per = (x.len + (int)G - 1) / (int)G, zper = (x.zero_len + (int)G - 1) / (int)G;
+    const int lo = min(x.len, (int)blockIdx.x * per), hi = min(x.len, lo + per);
+    unsigned long long* idle = pfa_xchg_acc(x.base[x.rank], slot ^ 1, x.cap);
+    for (int i = (int)blockIdx.x * zper + tid; i < min(x.zero_len, ((int)blockIdx.x + 1) * zper); i += nt) __stcg(idle + i, 0ull);
+    for (int i = lo + tid; i < hi; i += nt) {
+        const unsigned long long v = __ldcg(x.partial + i);
+        if (v) {
+            for (int p = 0; p < x.world; ++p) pfa_red_add_sys(pfa_xchg_acc(x.base[p], slot, x.cap) + i, v);
+            __stcg(x.partial + i, 0ull);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        if (blockIdx.x == 0) x.stamps[1] = x.stamps[2] = pfa_globaltimer();
+        s_flag = atomicAdd(cnt_b, 1u) == G - 1 ? 1 : 0;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_flag && tid < x.world) pfa_signal_sys(pfa_xchg_flag(x.base[tid], slot));  // every block's pushes are out and fenced
+    if (tid == 0) {
+        const unsigned int want = (x.epoch / 2u + 1u) * (unsigned int)x.world;
+        const unsigned int* mine = pfa_xchg_flag(x.base[x.rank], slot);
+        const unsigned long long t0 = pfa_globaltimer();
+        while ((int)(pfa_ld_acquire_sys(mine) - want) < 0) {
+            if (pfa_globaltimer() - t0 > x.timeout_ns) {
+                *x.status = 1u;
+                break;
+            }
+        }
+        if (blockIdx.x == 0) x.stamps[3] = pfa_globaltimer();
+    }
+    __syncthreads();
+    const unsigned long long* sum = pfa_xchg_acc(x.base[x.rank], slot, x.cap);
+    for (int i = lo + tid; i < hi; i += nt) x.out[i] = (int64_t)__ldcg(sum + i);
+    __syncthreads();
+    if (tid == 0) {
+        if (blockIdx.x == 0) x.stamps[4] = pfa_globaltimer();
+        __threadfence();
+        if (atomicAdd(cnt_c, 1u) == G - 1) {  // everybody is past the barriers: zero the counters for the next launch
+            *cnt_a = 0u;
+            *cnt_b = 0u;
+            *cnt_c = 0u;
+        }
+    }
+}
+
 // Called by EVERY thread of EVERY block at the very end of a scan kernel, after the block has added its share into
 // x.partial.  Returns in all blocks but the last one to arrive; that one runs the exchange.
 __device__ __forceinline__ void pfa_xchg_epilogue(const PfaXchgDev& x) {
+    if (x.wide) {
+        pfa_xchg_epilogue_wide(x);
+        return;
+    }
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
