@@ -27,6 +27,39 @@ struct PfaBatchEntry {
     std::vector<long long> pop_n;   // [k]
 };
 
+// result buffer in pinned host memory (the device-to-host copies of a scan run asynchronously at full PCIe speed; into
+// pageable vectors each of them was a staged, blocking copy: ~0.1 ms per batch of 2,500 loci)
+template <typename T>
+struct PfaPinned {
+    T* p = nullptr;
+    size_t cap = 0, n = 0;
+    bool assign(size_t count, const T& v) {  // false: out of pinned memory
+        if (count > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            const size_t want = std::max<size_t>(count + count / 4, 1024);
+            if (cudaHostAlloc(reinterpret_cast<void**>(&p), want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            cap = want;
+        }
+        n = count;
+        std::fill(p, p + count, v);
+        return true;
+    }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = n = 0;
+    }
+};
+
 struct pfa_batch {
     pfa_ctx* ctx = nullptr;
     std::vector<PfaBatchEntry> entries;
@@ -40,11 +73,11 @@ struct pfa_batch {
     int max_Wq = 0;
     long long n_ctiles = 0;
     // results (host)
-    std::vector<int64_t> out;
-    std::vector<pfa_final_out> fin;
-    std::vector<int64_t> cds_out;         // [pops][PFA_CDS_LEN] (codon scan)
-    std::vector<double> cds_ssites;       // [pops]
-    std::vector<pfa_final_out> cds_fin;   // [pops][2]: synonymous, nonsynonymous
+    PfaPinned<int64_t> out;
+    PfaPinned<pfa_final_out> fin;
+    PfaPinned<int64_t> cds_out;         // [pops][PFA_CDS_LEN] (codon scan)
+    PfaPinned<double> cds_ssites;       // [pops]
+    PfaPinned<pfa_final_out> cds_fin;   // [pops][2]: synonymous, nonsynonymous
     bool ran = false, ran_cds = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around K2b and around K4b of the last scan
     float site_ms = 0.f, cds_ms = 0.f;
@@ -374,6 +407,7 @@ int pfa_batch_destroy(pfa_batch* b) {
     if (!b) return PFA_OK;
     pfa_batch_release(b);
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+    b->out.release(); b->fin.release(); b->cds_out.release(); b->cds_ssites.release(); b->cds_fin.release();
     if (b->h_text) cudaFreeHost(b->h_text);
     delete b;
     return PFA_OK;
@@ -815,15 +849,14 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
     pfa_batch::Dev& d = b->dev;
     const int nloci = (int)b->desc.size();
     const long long npops = (long long)b->pops.size();
-    b->out.assign((size_t)b->out_len, 0);
-    b->fin.assign((size_t)npops, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
+    bool ok = b->out.assign((size_t)b->out_len, 0) && b->fin.assign((size_t)npops, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
     b->ran = true;
     b->ran_cds = cds != 0;
     if (cds) {
-        b->cds_out.assign((size_t)npops * PFA_CDS_LEN, 0);
-        b->cds_ssites.assign((size_t)npops, 0.0);
-        b->cds_fin.assign((size_t)npops * 2, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
+        ok = ok && b->cds_out.assign((size_t)npops * PFA_CDS_LEN, 0) && b->cds_ssites.assign((size_t)npops, 0.0) &&
+             b->cds_fin.assign((size_t)npops * 2, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
     }
+    if (!ok) return pfa_fail(ctx, PFA_ERR_NOMEM, "cannot pin the result buffers of the batch");
     if (nloci == 0) return PFA_OK;
     PFA_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
