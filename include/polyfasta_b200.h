@@ -200,6 +200,9 @@ int pfa_xchg_stamps(pfa_xchg* x, uint64_t out[8]);
  * by pfa_site_stats_device / pfa_cds_stats_device.  d_isvar / d_labels stay per shard. */
 int pfa_site_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_isvar);
 int pfa_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_labels);
+/* K2 + K4 with ONE exchange (what --cds needs per alignment): d_out = int64[pfa_site_len(a) + PFA_CDS_LEN * k], the site vector
+ * followed by the codon vectors of the whole alignment */
+int pfa_site_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_isvar, uint8_t* d_labels);
 /* the same exchange on its own for a vector produced by another kernel (K3 pairwise sums): in place on d_buf */
 int pfa_xchg_allreduce(pfa_xchg* x, int64_t* d_buf, int64_t len);
 /* K3 over column shards: the per-population sums of this rank's shard, then the sum over all ranks (d_ij is additive over

@@ -31,7 +31,7 @@ EXPORTS = [
     "pfa_fasta_parse_files", "pfa_fasta_match_mask", "pfa_fasta_layout_bytes", "pfa_fasta_export_layout", "pfa_fasta_import_layout",
     "pfa_host_pack2", "pfa_host_pack2_rows", "pfa_host_pack3",
     "pfa_xchg_create", "pfa_xchg_destroy", "pfa_xchg_capacity", "pfa_xchg_export", "pfa_xchg_connect", "pfa_xchg_base",
-    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_set_timeout_ms", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_xchg_allreduce", "pfa_pairwise_xchg",
+    "pfa_xchg_connect_ptrs", "pfa_xchg_status", "pfa_xchg_set_timeout_ms", "pfa_xchg_stamps", "pfa_site_stats_xchg", "pfa_cds_stats_xchg", "pfa_site_cds_stats_xchg", "pfa_xchg_allreduce", "pfa_pairwise_xchg",
 ]
 
 
@@ -162,6 +162,7 @@ def lib():
         "pfa_site_stats_xchg": (c.c_int, [p, p, p, p]),
         "pfa_cds_stats_xchg": (c.c_int, [p, p, p, p]),
         "pfa_xchg_allreduce": (c.c_int, [p, p, i64]),
+        "pfa_site_cds_stats_xchg": (c.c_int, [p, p, p, p, p]),
         "pfa_pairwise_xchg": (c.c_int, [p, p, p]),
     }
     for name, (res, args) in sig.items():

@@ -402,6 +402,11 @@ class Alignment:
         check(lib().pfa_cds_stats_xchg(self.handle, xchg.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_labels_ptr or 0)),
               self.ctx.handle)
 
+    def site_cds_stats_xchg(self, xchg, d_out_ptr, d_isvar_ptr=None, d_labels_ptr=None):
+        """K2 + K4 with ONE exchange: d_out (device int64[site_len + 71 k]) = the site vector, then the codon vectors"""
+        check(lib().pfa_site_cds_stats_xchg(self.handle, xchg.handle, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(d_isvar_ptr or 0),
+                                            ctypes.c_void_p(d_labels_ptr or 0)), self.ctx.handle)
+
     @staticmethod
     def unpack_cds(row):
         return {"nstops": int(row[0]), "missing": int(row[1]), "S_s": int(row[2]), "H_s": int(row[3]), "S_n": int(row[4]),

@@ -219,18 +219,25 @@ def sharded_alignment_rows(ctx, group, fasta, file, cds, jc, found):
         d_cds = torch.zeros(nc, dtype=torch.int64, device="cuda:%d" % ctx.device)
         torch.cuda.synchronize(ctx.device)
         if group.fused:
-            x = group.exchange(ctx, max(ns, nc))
+            x = group.exchange(ctx, ns + nc)
             # the ranks meet on the host AFTER their uploads (parse + ingest times differ by seconds on cold files), so the
             # wait inside the kernels only has to cover launch skew
             ctx.sync()
             group.dist.barrier()
-            aln.site_stats_xchg(x, d_site.data_ptr())
-            if cds:
-                aln.cds_stats_xchg(x, d_cds.data_ptr())
+            if cds:   # K2 leaves its vector in the exchange's buffer, K4's epilogue pushes both: ONE exchange per alignment
+                d_both = torch.zeros(ns + nc, dtype=torch.int64, device="cuda:%d" % ctx.device)
+                torch.cuda.synchronize(ctx.device)
+                aln.site_cds_stats_xchg(x, d_both.data_ptr())
+            else:
+                aln.site_stats_xchg(x, d_site.data_ptr())
             ctx.sync()
             if x.timed_out():
                 raise api.PolyFastaError(1, "a rank did not arrive at the exchange")
-            h_site, h_cds = d_site.cpu(), d_cds.cpu()
+            if cds:
+                h_both = d_both.cpu()
+                h_site, h_cds = h_both[:ns], h_both[ns:]
+            else:
+                h_site, h_cds = d_site.cpu(), d_cds.cpu()
         else:
             aln.site_stats_device(d_site.data_ptr())
             if cds:

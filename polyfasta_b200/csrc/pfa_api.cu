@@ -367,6 +367,19 @@ int pfa_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_label
     return pfa_launch_cds_scan(a, d_out, d_labels, x);
 }
 
+/* --cds over column shards with ONE exchange: the site scan leaves its vector in the exchange's buffer, the codon scan's
+ * epilogue pushes both.  d_out (device) = int64[pfa_site_len + PFA_CDS_LEN * k]: the site vector, then the codon vectors. */
+int pfa_site_cds_stats_xchg(pfa_aln* a, pfa_xchg* x, int64_t* d_out, uint8_t* d_isvar, uint8_t* d_labels) {
+    if (!a || !x || !d_out) return PFA_ERR_ARG;
+    PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));
+    int rc = pfa_launch_site_scan(a, nullptr, d_isvar, x, true);
+    if (rc) {
+        pfa_xchg_set_carry(x, 0);
+        return rc;
+    }
+    return pfa_launch_cds_scan(a, d_out, d_labels, x);
+}
+
 int pfa_pairwise_device(pfa_aln* a, int64_t* d_out, int32_t* d_matrix) {
     if (!a || !d_out) return PFA_ERR_ARG;
     PFA_CUDA(a->ctx, cudaSetDevice(a->ctx->device));

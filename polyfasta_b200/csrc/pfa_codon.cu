@@ -1072,14 +1072,19 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     const bool last = a->col_begin + a->ns == a->L_total;
     if (a->ns % 3 != 0 && !last) return pfa_fail(ctx, PFA_ERR_ARG, "cds scan: only the last shard may end inside a codon");
     const int64_t out_len = (int64_t)PFA_CDS_LEN * a->k;
+    // words the site scan left in the exchange's partial buffer (pfa_site_cds_stats_xchg): this scan's vector goes behind them
+    // and ONE exchange pushes both; d_out then receives [site vector | codon vector]
+    const int64_t carry = x ? pfa_xchg_carry(x) : 0;
+    if (x) pfa_xchg_set_carry(x, 0);
+    if (carry + out_len > (x ? pfa_xchg_cap(x) : carry + out_len)) return pfa_fail(ctx, PFA_ERR_ARG, "exchange buffer too small for both vectors");
     if (!x) PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
     if (d_labels && a->ns) PFA_CUDA(ctx, cudaMemsetAsync(d_labels, 0, (size_t)(a->k * a->ns), ctx->stream));
-    if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, out_len, d_out) : PFA_OK;
+    if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, carry + out_len, d_out) : PFA_OK;
     PfaCdsArgs args;
     unsigned int* work = nullptr;
     if (int rc = pfa_ctx_work(ctx, &work)) return rc;
     pfa_fill_site_args(a, nullptr, nullptr, &args.s);
-    args.out = x ? reinterpret_cast<int64_t*>(pfa_xchg_partial(x)) : d_out;
+    args.out = x ? reinterpret_cast<int64_t*>(pfa_xchg_partial(x)) + carry : d_out;
     args.labels = d_labels;
     args.ncf = a->ns / 3;
     args.has_partial = (a->ns % 3) != 0;
@@ -1099,7 +1104,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
             int rc = launch_cds_escape(a, args);
             if (rc) return rc;
         }
-        int rc = pfa_xchg_fill(x, out_len, d_out, &args.s.x, true);  // the TMA kernels run one CTA per SM
+        int rc = pfa_xchg_fill(x, carry + out_len, d_out, &args.s.x, true);  // the TMA kernels run one CTA per SM
         if (rc) return rc;
     }
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;

@@ -107,11 +107,15 @@ int pfa_synth_fill(pfa_aln* a, uint64_t seed, uint32_t p_seg_ppm, uint32_t tri_p
 struct pfa_xchg;
 struct PfaXchgDev;
 // x != nullptr: fused with the sum over the column shards of all ranks (pfa_xchg.cu); d_out receives the reduced vector
-int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg* x = nullptr);
+// defer (with x): the shard's vector stays in the exchange's partial buffer and travels with the next exchange (the codon scan's)
+int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg* x = nullptr, bool defer = false);
 int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg* x = nullptr);
 int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev, bool coresident = false);
 unsigned long long* pfa_xchg_partial(pfa_xchg* x);
 void pfa_xchg_commit(pfa_xchg* x);
+int64_t pfa_xchg_carry(const pfa_xchg* x);
+void pfa_xchg_set_carry(pfa_xchg* x, int64_t words);
+int64_t pfa_xchg_cap(const pfa_xchg* x);
 int pfa_xchg_launch_only(pfa_xchg* x, const int64_t* d_src, int64_t len, int64_t* d_out);
 int pfa_launch_pairwise(pfa_aln* a, int64_t* d_out, int32_t* d_matrix);
 int pfa_upload_codon_tables(pfa_ctx* ctx);

@@ -575,10 +575,15 @@ static int launch_escape_sites(pfa_aln* a, const PfaSiteArgs& args) {
     return PFA_OK;
 }
 
-int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg* x) {
+int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg* x, bool defer) {
     pfa_ctx* ctx = a->ctx;
     const int64_t out_len = a->site_off[a->k];
     if (!x) PFA_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)out_len, ctx->stream));
+    if (x && defer) {
+        if (pfa_xchg_carry(x) != 0 || out_len > pfa_xchg_cap(x)) return pfa_fail(ctx, PFA_ERR_ARG, "deferred exchange: buffer in use or too small");
+        pfa_xchg_set_carry(x, out_len);  // the next exchange pushes these words along
+        if (a->ns == 0 || a->n == 0) return PFA_OK;
+    }
     if (a->ns == 0 || a->n == 0) return x ? pfa_xchg_launch_only(x, nullptr, out_len, d_out) : PFA_OK;
     PfaSiteArgs args;
     unsigned int* work = nullptr;
@@ -592,8 +597,10 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
             int rc = launch_escape_sites(a, args);
             if (rc) return rc;
         }
-        int rc = pfa_xchg_fill(x, out_len, d_out, &args.x, true);  // the TMA kernels run one CTA per SM: all blocks may take part
-        if (rc) return rc;
+        if (!defer) {
+            int rc = pfa_xchg_fill(x, out_len, d_out, &args.x, true);  // the TMA kernels run one CTA per SM: all blocks may take part
+            if (rc) return rc;
+        }
     }
     // lanes per site: the smallest power of two that leaves every lane at most 5 chunks
     // (measured over n = 100 ... 10,000, scripts/probe_k2_shapes.py: fewer chunks per lane with more lanes per site, at
@@ -663,7 +670,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
 #undef PFA_TMA_LAUNCH
         if (launched) {
             PFA_LAUNCH_CHECK(ctx);
-            if (x) pfa_xchg_commit(x);
+            if (x && !defer) pfa_xchg_commit(x);
             if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
             return PFA_OK;
         }
@@ -698,7 +705,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     pfa_note_kernel(ctx, "%s<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d> grid=%u block=%d", generic ? "pfa_site_scan_kernel" : "pfa_site_scan_reg_kernel", lps, iter,
                     (int)hv, (int)multi, grid.x, PFA_SITE_THREADS);
     PFA_LAUNCH_CHECK(ctx);
-    if (x) pfa_xchg_commit(x);
+    if (x && !defer) pfa_xchg_commit(x);
     if (!x && a->n_exc_sites > 0) return launch_escape_sites(a, args);
     return PFA_OK;
 }

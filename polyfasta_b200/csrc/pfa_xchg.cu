@@ -20,7 +20,8 @@ struct pfa_xchg {
     unsigned int epoch = 0;  // exchanges LAUNCHED so far (pfa_xchg_commit): a call that fails before its launch leaves it alone
     int high_water = 0;
     unsigned long long timeout_ns = PFA_XCHG_TIMEOUT_NS;
-    bool distinct_devices = false;  // connected over CUDA IPC: every rank has a GPU of its own (the wide epilogue needs that)
+    bool distinct_devices = false;
+    int64_t carry = 0;  // words a scan has already left in `partial` for the NEXT exchange to push along (pfa_site_cds_stats_xchg)  // connected over CUDA IPC: every rank has a GPU of its own (the wide epilogue needs that)
     char* peer[PFA_XCHG_MAX_RANKS] = {};
     bool opened[PFA_XCHG_MAX_RANKS] = {};  // mapped with cudaIpcOpenMemHandle (to be closed)
 };
@@ -59,6 +60,9 @@ int pfa_xchg_fill(pfa_xchg* x, int64_t len, int64_t* d_out, PfaXchgDev* dev, boo
 }
 
 unsigned long long* pfa_xchg_partial(pfa_xchg* x) { return x->partial; }
+int64_t pfa_xchg_carry(const pfa_xchg* x) { return x->carry; }
+void pfa_xchg_set_carry(pfa_xchg* x, int64_t words) { x->carry = words; }
+int64_t pfa_xchg_cap(const pfa_xchg* x) { return x->cap; }
 
 // the kernel that carries exchange number x->epoch is in the stream: the next launch uses the other slot.  Called only
 // after a successful launch, so that an argument or launch error leaves this rank in step with its peers.

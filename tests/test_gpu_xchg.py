@@ -73,7 +73,7 @@ def test_ranks_in_one_process(world, L):
     assert [int(x) for x in want_c[api.PFA_CDS_LEN: api.PFA_CDS_LEN + 6]] == [wc[k] for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n")]
     if L < 3 * world:
         assert parallel.shard_columns(L, world, 0) == (0, 0)
-    xs = [api.Exchange(c, 1024) for c in ctxs]
+    xs = [api.Exchange(c, 2048) for c in ctxs]
     api.Exchange.connect_local(xs)
     shards = []
     for r in range(world):
@@ -95,6 +95,16 @@ def test_ranks_in_one_process(world, L):
         for r in range(world):
             assert np.array_equal(out_s[r].cpu().numpy(), want_s), (it, r)
             assert np.array_equal(out_c[r].cpu().numpy(), want_c), (it, r)
+    # K2 + K4 with ONE exchange (what --cds needs per alignment): [site vector | codon vectors]
+    out_b = [torch.full((len(want_s) + len(want_c),), -1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    for it in range(2):
+        for r in range(world):
+            shards[r].site_cds_stats_xchg(xs[r], out_b[r].data_ptr())
+        for c in ctxs:
+            c.sync()
+        for r in range(world):
+            assert np.array_equal(out_b[r].cpu().numpy(), np.concatenate([want_s, want_c])), (it, r)
     # K3 over the column shards: the pairwise sums of every population, summed over the ranks, equal the whole alignment's
     whole = pf.Alignment.from_rows(ctxs[0], text)
     whole.set_pops(pops)
