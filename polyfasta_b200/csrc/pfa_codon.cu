@@ -312,13 +312,27 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_cds_scan_kernel(const Pf
 __device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 0 ? x.x : w == 1 ? x.y : w == 2 ? x.z : x.w; }
 
 // pass 1 of one codon column whose three site records are in registers: 18 flag bits (6 per site), OR-reduced over the group
+// f2 (optional, with HAS_V): 4 more bits per site -- plane b0 / b1 shows a one / a zero among the VALID rows -- which tell a
+// column whose only "variation" is missing data (every valid row of a site shows the same base) from real base variation
 template <int LPS, int ITER, bool HAS_V>
 __device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER],
-                                                  const uint4 (&um)[ITER], unsigned gmask) {
-    unsigned f = 0;
+                                                  const uint4 (&um)[ITER], unsigned gmask, unsigned* f2_out = nullptr) {
+    unsigned f = 0, f2 = 0;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+        if (HAS_V && f2_out) {
+            uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                const uint4 m = make_uint4(um[i].x & xv[t][i].x, um[i].y & xv[t][i].y, um[i].z & xv[t][i].z, um[i].w & xv[t][i].w);
+                a0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
+                b0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
+                a1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
+                b1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
+            }
+            f2 |= ((a0 ? 1u : 0u) | (b0 ? 2u : 0u) | (a1 ? 4u : 0u) | (b1 ? 8u : 0u)) << (4 * t);
+        }
 #pragma unroll
         for (int i = 0; i < ITER; ++i) {
             const uint4 m = um[i];
@@ -331,6 +345,7 @@ __device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], co
         }
         f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
     }
+    if (HAS_V && f2_out) *f2_out = pfa_group_or<LPS>(f2, gmask);
     return pfa_group_or<LPS>(f, gmask);
 }
 
@@ -690,7 +705,54 @@ __device__ __forceinline__ uint32_t pfa_site_h32(const uint32_t c[PFA_NCLASS], u
 template <bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0, unsigned f, const uint32_t* r0, const uint32_t* r1,
                                              const uint32_t* rv, int Wn, int lane, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount,
-                                             const uint32_t (&fw)[3], int gcw) {
+                                             const uint32_t (&fw)[3], int gcw, unsigned f2) {
+    // Missing data only: at each of the three sites the valid rows show ONE base, and the rows that are not valid sit in a few
+    // flagged cells.  The rows valid at all three sites then carry one and the same codon: the presence mask has at most that
+    // one member (no labels), and only the flagged cells are read -- gaps aligned to codons and runs of N, the usual
+    // content of a real CDS alignment, no longer cost the peeling pass over the whole record.
+    const uint32_t fwu = fw[0] | fw[1] | fw[2];
+    bool gaps_only = HAS_V && __popc(fwu) <= 6;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const unsigned g = (f2 >> (4 * t)) & 15u;
+        gaps_only = gaps_only && ((g & 3u) != 3u) && ((g & 12u) != 12u);
+    }
+    if (gaps_only) {
+        int codon = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) codon = (codon << 2) | (((f2 >> (4 * t)) & 4u) ? 2 : 0) | (((f2 >> (4 * t)) & 1u) ? 1 : 0);
+        const int kq = MULTI ? a.s.k : 1;
+        for (int q = 0; q < kq; ++q) {
+            const uint32_t* mq = reinterpret_cast<const uint32_t*>(MULTI ? a.s.masks + (int64_t)q * a.s.Wq : a.s.umask);
+            uint32_t ninv = 0, nesc = 0;
+            for (uint32_t cells = fwu; cells; cells &= cells - 1) {
+                const int cell = __ffs(cells) - 1, w = cell * gcw + lane;
+                if (lane < gcw && w < Wn) {
+                    const uint32_t m = __ldg(mq + w);
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+                        if ((fw[t] >> cell) & 1u) {
+                            const uint32_t inv = ~rv[t * Wn + w] & m;
+                            any |= inv;
+                            nesc += __popc(inv & r1[t * Wn + w] & r0[t * Wn + w]);
+                        }
+                    ninv += __popc(any);
+                }
+            }
+            ninv = __reduce_add_sync(0xffffffffu, ninv);
+            nesc = __reduce_add_sync(0xffffffffu, nesc);
+            if (nesc) continue;  // finished by pfa_cds_escape_kernel
+            const unsigned long long P = (uint32_t)a.s.pop_n[q] > ninv ? 1ull << codon : 0ull;
+            pfa_cds_enqueue(qbuf, qcount, lane, P, 0u, 0u, 0u, q, (uint32_t)site0);
+            if (qcount == 32) {
+                pfa_cds_flush(qbuf, 32, lane, a.acc_in_smem ? sm_acc : reinterpret_cast<unsigned long long*>(a.out), a.labels, a.s.ns);
+                qcount = 0;
+                __syncwarp();
+            }
+        }
+        return;
+    }
     int nvar = 0, tv = 0, fixed = 0;
     bool fixed_valid = true;
 #pragma unroll
@@ -909,7 +971,9 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 }
             }
             if (COOP) {
-                const unsigned f = (HAS_V && bv) ? pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask) : pfa_cds_pass1<LPS, ITER, false>(x0, x1, xv, um, gmask);
+                unsigned f2 = 0xfffu;  // "bases vary" unless pass 1 finds otherwise
+                const unsigned f = (HAS_V && bv) ? pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask, sparse ? &f2 : nullptr)
+                                                 : pfa_cds_pass1<LPS, ITER, false>(x0, x1, xv, um, gmask);
                 bool uniform = true, clean = true;
                 int codon = 0;
 #pragma unroll
@@ -937,7 +1001,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                                              !bv ? 0u : sparse ? fa[vidx * 3 + 2] : 0xffffffffu};
                     pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, reinterpret_cast<const uint32_t*>(slot + (size_t)(vidx * 3) * rec),
                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(CPS * 3 + vidx * 3) * rec),
-                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw);
+                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, __shfl_sync(0xffffffffu, f2, leader));
                 }
                 if (t0 == m - 1 && vm) refill();
             } else {

@@ -807,3 +807,30 @@ def test_narrow_records_many_variable_sites(ctx, n, L):
             for k in ("nstops", "missing", "S_s", "H_s", "S_n", "H_n", "sum3_by_len"):
                 assert cds[q][k] == wc[k], (n, L, q, k, rep)
     aln.free()
+
+
+@pytest.mark.parametrize("n,L,k", [(2000, 60_000, 2), (5000, 9_000, 1), (700, 30_003, 3)])
+def test_missing_data_runs_in_cds(ctx, n, L, k):
+    """what a real CDS alignment holds: gaps aligned to codons, runs of N across codon borders, a few '?' and IUPAC codes, on top
+    of the base variation -- the codon scan's missing-data-only path (valid rows of every site show one base; only the flagged
+    cells are read) and the site scan's gap-only path against the C oracle"""
+    rng = np.random.default_rng(n + L + k)
+    text = synth.text_matrix(21, n, L).copy()
+    for _ in range(400):
+        r, c = int(rng.integers(0, n)), int(rng.integers(0, L // 3)) * 3
+        text[r, c: c + 3 * int(rng.integers(1, 4))] = ord("-")
+    for _ in range(150):
+        r, c = int(rng.integers(0, n)), int(rng.integers(0, L))
+        text[r, c: c + int(rng.integers(1, 12))] = ord("N")
+    rr, cc = rng.integers(0, n, 60), rng.integers(0, L, 60)
+    text[rr, cc] = np.frombuffer(b"?RY", dtype=np.uint8)[rng.integers(0, 3, 60)]
+    text[: n // 2, 300:306] = ord("-")      # a gap carried by half of the rows: more flagged cells than the short path takes
+    text[:, 600:603] = ord("-")             # a codon column nobody shows
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n // 2))][:k]
+    aln = pf.Alignment.from_rows(ctx, text)
+    assert aln.has_invalid
+    aln.set_pops(pops)
+    site = aln.site_stats(want_isvar=True)
+    cds = aln.cds_stats(want_labels=True)
+    aln.free()
+    _check_site_cds(site, cds, text, pops, (n, L, k))
