@@ -203,107 +203,170 @@ __global__ void __launch_bounds__(256) pfa_batch_encode_kernel(const uint8_t* __
     }
 }
 
+// pass 2 of one site of one locus on registers (class counts per population, group-reduced; the group's first lane books the
+// variable columns into the batch result vector)
+template <int LPS, int ITER>
+__device__ __forceinline__ void pfa_batch_site_pass2(const PfaBatchArgs& a, const PfaLocusDesc& d, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
+                                                     const uint4 (&xv)[ITER], int sub, unsigned gmask) {
+    const int Wq = d.Wq;
+    for (int q = 0; q < d.k; ++q) {
+        uint32_t c[PFA_NCLASS];
+#pragma unroll
+        for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+        const uint4* mq = a.masks + d.mask_off + (long long)q * Wq;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int j = sub + LPS * i;
+            const uint4 m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
+            const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
+                           w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w}, wv[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t vm = wv[w] & mm[w];
+                const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
+                c[PFA_C_T] += __popc(hi & w0[w]);
+                c[PFA_C_G] += __popc(hi & ~w0[w]);
+                c[PFA_C_C] += __popc(lo & w0[w]);
+                c[PFA_C_A] += __popc(lo & ~w0[w]);
+                const uint32_t im = ~wv[w] & mm[w];
+                const uint32_t ihi = im & w1[w];
+                c[PFA_C_ESC] += __popc(ihi & w0[w]);
+                c[PFA_C_Q] += __popc(ihi & ~w0[w]);
+                c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
+            }
+        }
+        if (LPS > 1) {
+#pragma unroll
+            for (int i = 0; i < PFA_NCLASS; ++i) c[i] = pfa_group_add<LPS>(c[i], gmask);
+        }
+        if (sub != 0) continue;
+        const PfaPopSlot ps = a.pops[d.pop_base + q];
+        const PfaSiteResult r = pfa_site_result(c, ps.n, 0u, 0ull);
+        if (r.has_escape || !r.isvar) continue;
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(a.out + ps.out_off);
+        atomicAdd(o, 1ull);
+        atomicAdd(o + 1, r.h);
+        if (r.sfs_bin >= 0) atomicAdd(o + 2 + r.sfs_bin, 1ull);
+    }
+}
+
 // K2b: a group of LPS lanes owns one site of one locus; same two passes as pfa_site_scan_reg_kernel, accumulators in global
 // memory (only variable columns touch them).  A warp walks CONTIGUOUS chunks of PFA_BATCH_SCHUNK sites, 32 / LPS at a time: its
 // loads stay coalesced and the locus of a site is found by one binary search per chunk plus a step forward now and then -- a
 // search per site (12 dependent loads for 2,500 loci) held this kernel at 1.3 TB/s on the C5 shape.
+// Records of one chunk handled by one lane (n <= 128 rows: LPS = ITER = 1, every lane of a warp its own site -- the shape of
+// C1, C2 and C5): with 5 % of the sites variable, four passes out of five met one or two of them and the warp ran the whole
+// second pass for those one or two lanes.  Here the variable sites go to a per-warp queue in shared memory (the 12 words of
+// the record + the locus) and the second pass runs when 32 are waiting: one lane each, all lanes busy.
 #define PFA_BATCH_SCHUNK 2048
+#define PFA_BQ_WORDS 13
 template <int LPS, int ITER>
 __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_batch_site_kernel(const PfaBatchArgs a) {
-    const int lane = threadIdx.x & 31;
+    constexpr bool QUEUE = LPS == 1 && ITER == 1;
+    __shared__ uint32_t sq[QUEUE ? PFA_SITE_THREADS / 32 : 1][QUEUE ? PFA_BQ_WORDS : 1][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane & (LPS - 1);
     const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
     constexpr int GW = 32 / LPS;
+    int qn = 0;  // entries waiting in this warp's queue (QUEUE)
+    auto drain = [&](int count) {  // second pass of the first `count` (<= 32) queue entries, one lane each
+        __syncwarp();
+        if (lane < count) {
+            uint4 y0[1], y1[1], yv[1];
+            y0[0] = make_uint4(sq[wib][0][lane], sq[wib][1][lane], sq[wib][2][lane], sq[wib][3][lane]);
+            y1[0] = make_uint4(sq[wib][4][lane], sq[wib][5][lane], sq[wib][6][lane], sq[wib][7][lane]);
+            yv[0] = make_uint4(sq[wib][8][lane], sq[wib][9][lane], sq[wib][10][lane], sq[wib][11][lane]);
+            const PfaLocusDesc dq = a.desc[sq[wib][12][lane]];
+            pfa_batch_site_pass2<1, 1>(a, dq, y0, y1, yv, 0, 1u << lane);
+        }
+        __syncwarp();
+    };
     const long long nchunks = (a.n_sites + PFA_BATCH_SCHUNK - 1) / PFA_BATCH_SCHUNK;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long ch = warp0; ch < nchunks; ch += nwarps) {
       const long long g_lo = ch * PFA_BATCH_SCHUNK, g_hi = min(a.n_sites, g_lo + PFA_BATCH_SCHUNK);
-      int li = pfa_find_locus(a.site_base, a.nloci, g_lo + lane / LPS);
+      int li = pfa_find_locus(a.site_base, a.nloci, min(g_lo + lane / LPS, a.n_sites - 1));
       PfaLocusDesc d = a.desc[li];
       long long next_base = a.site_base[li + 1];
-      for (long long g = g_lo + lane / LPS; g < g_hi; g += GW) {
-        if (g >= next_base) {  // the group has walked into a later locus
-            do {
-                ++li;
-                next_base = a.site_base[li + 1];
-            } while (g >= next_base);
-            d = a.desc[li];
-        }
-        const long long s = g - d.site_base;
-        const int Wq = d.Wq;
-        const bool hv = a.locus_invalid[li] != 0;
-        const uint4* um = a.masks + d.mask_off + (long long)d.k * Wq;
-        const uint4* p0 = a.b0 + d.plane_off + s * Wq;
-        const uint4* p1 = a.b1 + d.plane_off + s * Wq;
-        const uint4* pv = a.v + d.plane_off + s * Wq;
+      // QUEUE: every lane runs the same number of rounds (the ballots need the whole warp); lanes beyond the chunk idle
+      for (long long g = g_lo + lane / LPS; QUEUE ? (g - lane < g_hi) : (g < g_hi); g += GW) {
+        const bool active = g < g_hi;
+        bool var = false;
         uint4 x0[ITER], x1[ITER], xv[ITER], m[ITER];
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-            const int j = sub + LPS * i;
-            x0[i] = x1[i] = xv[i] = m[i] = make_uint4(0, 0, 0, 0);
-            if (j < Wq) {
-                m[i] = __ldg(um + j);
-                x0[i] = pfa_ld_stream(p0 + j);
-                x1[i] = pfa_ld_stream(p1 + j);
-                xv[i] = hv ? pfa_ld_stream(pv + j) : m[i];
+        if (active) {
+            if (g >= next_base) {  // the group has walked into a later locus
+                do {
+                    ++li;
+                    next_base = a.site_base[li + 1];
+                } while (g >= next_base);
+                d = a.desc[li];
             }
-        }
-        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-            o0 |= (x0[i].x & m[i].x) | (x0[i].y & m[i].y) | (x0[i].z & m[i].z) | (x0[i].w & m[i].w);
-            z0 |= (~x0[i].x & m[i].x) | (~x0[i].y & m[i].y) | (~x0[i].z & m[i].z) | (~x0[i].w & m[i].w);
-            o1 |= (x1[i].x & m[i].x) | (x1[i].y & m[i].y) | (x1[i].z & m[i].z) | (x1[i].w & m[i].w);
-            z1 |= (~x1[i].x & m[i].x) | (~x1[i].y & m[i].y) | (~x1[i].z & m[i].z) | (~x1[i].w & m[i].w);
-            ov |= (xv[i].x & m[i].x) | (xv[i].y & m[i].y) | (xv[i].z & m[i].z) | (xv[i].w & m[i].w);
-            zv |= (~xv[i].x & m[i].x) | (~xv[i].y & m[i].y) | (~xv[i].z & m[i].z) | (~xv[i].w & m[i].w);
-        }
-        unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
-        f = pfa_group_or<LPS>(f, gmask);
-        const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
-        const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
-        if (mono && !all_escape) continue;
-        for (int q = 0; q < d.k; ++q) {
-            uint32_t c[PFA_NCLASS];
-#pragma unroll
-            for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
-            const uint4* mq = a.masks + d.mask_off + (long long)q * Wq;
+            const long long s = g - d.site_base;
+            const int Wq = d.Wq;
+            const bool hv = a.locus_invalid[li] != 0;
+            const uint4* um = a.masks + d.mask_off + (long long)d.k * Wq;
+            const uint4* p0 = a.b0 + d.plane_off + s * Wq;
+            const uint4* p1 = a.b1 + d.plane_off + s * Wq;
+            const uint4* pv = a.v + d.plane_off + s * Wq;
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
                 const int j = sub + LPS * i;
-                const uint4 m4 = j < Wq ? __ldg(mq + j) : make_uint4(0, 0, 0, 0);
-                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
-                               w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w}, wv[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t vm = wv[w] & mm[w];
-                    const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
-                    c[PFA_C_T] += __popc(hi & w0[w]);
-                    c[PFA_C_G] += __popc(hi & ~w0[w]);
-                    c[PFA_C_C] += __popc(lo & w0[w]);
-                    c[PFA_C_A] += __popc(lo & ~w0[w]);
-                    const uint32_t im = ~wv[w] & mm[w];
-                    const uint32_t ihi = im & w1[w];
-                    c[PFA_C_ESC] += __popc(ihi & w0[w]);
-                    c[PFA_C_Q] += __popc(ihi & ~w0[w]);
-                    c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
+                x0[i] = x1[i] = xv[i] = m[i] = make_uint4(0, 0, 0, 0);
+                if (j < Wq) {
+                    m[i] = __ldg(um + j);
+                    x0[i] = pfa_ld_stream(p0 + j);
+                    x1[i] = pfa_ld_stream(p1 + j);
+                    xv[i] = hv ? pfa_ld_stream(pv + j) : m[i];
                 }
             }
-            if (LPS > 1) {
+            uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
 #pragma unroll
-                for (int i = 0; i < PFA_NCLASS; ++i) c[i] = pfa_group_add<LPS>(c[i], gmask);
+            for (int i = 0; i < ITER; ++i) {
+                o0 |= (x0[i].x & m[i].x) | (x0[i].y & m[i].y) | (x0[i].z & m[i].z) | (x0[i].w & m[i].w);
+                z0 |= (~x0[i].x & m[i].x) | (~x0[i].y & m[i].y) | (~x0[i].z & m[i].z) | (~x0[i].w & m[i].w);
+                o1 |= (x1[i].x & m[i].x) | (x1[i].y & m[i].y) | (x1[i].z & m[i].z) | (x1[i].w & m[i].w);
+                z1 |= (~x1[i].x & m[i].x) | (~x1[i].y & m[i].y) | (~x1[i].z & m[i].z) | (~x1[i].w & m[i].w);
+                ov |= (xv[i].x & m[i].x) | (xv[i].y & m[i].y) | (xv[i].z & m[i].z) | (xv[i].w & m[i].w);
+                zv |= (~xv[i].x & m[i].x) | (~xv[i].y & m[i].y) | (~xv[i].z & m[i].z) | (~xv[i].w & m[i].w);
             }
-            if (sub != 0) continue;
-            const PfaPopSlot ps = a.pops[d.pop_base + q];
-            const PfaSiteResult r = pfa_site_result(c, ps.n, 0u, 0ull);
-            if (r.has_escape || !r.isvar) continue;
-            unsigned long long* o = reinterpret_cast<unsigned long long*>(a.out + ps.out_off);
-            atomicAdd(o, 1ull);
-            atomicAdd(o + 1, r.h);
-            if (r.sfs_bin >= 0) atomicAdd(o + 2 + r.sfs_bin, 1ull);
+            unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u);
+            f = pfa_group_or<LPS>(f, gmask);
+            const bool mono = ((f & 3u) != 3u) && ((f & 12u) != 12u) && ((f & 48u) != 48u);
+            const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
+            var = !(mono && !all_escape);
+        }
+        if (QUEUE) {
+            const unsigned vm = __ballot_sync(0xffffffffu, var);
+            if (vm) {
+                if (var) {
+                    const int pos = qn + __popc(vm & ((1u << lane) - 1u));
+                    sq[wib][0][pos] = x0[0].x; sq[wib][1][pos] = x0[0].y; sq[wib][2][pos] = x0[0].z; sq[wib][3][pos] = x0[0].w;
+                    sq[wib][4][pos] = x1[0].x; sq[wib][5][pos] = x1[0].y; sq[wib][6][pos] = x1[0].z; sq[wib][7][pos] = x1[0].w;
+                    sq[wib][8][pos] = xv[0].x; sq[wib][9][pos] = xv[0].y; sq[wib][10][pos] = xv[0].z; sq[wib][11][pos] = xv[0].w;
+                    sq[wib][12][pos] = (uint32_t)li;
+                }
+                qn += __popc(vm);
+                if (qn >= 32) {
+                    drain(32);
+                    const int rest = qn - 32;  // move the entries behind the first 32 to the front
+                    uint32_t keep[PFA_BQ_WORDS];
+                    if (lane < rest)
+#pragma unroll
+                        for (int w = 0; w < PFA_BQ_WORDS; ++w) keep[w] = sq[wib][w][32 + lane];
+                    __syncwarp();
+                    if (lane < rest)
+#pragma unroll
+                        for (int w = 0; w < PFA_BQ_WORDS; ++w) sq[wib][w][lane] = keep[w];
+                    qn = rest;
+                    __syncwarp();
+                }
+            }
+        } else if (var) {
+            pfa_batch_site_pass2<LPS, ITER>(a, d, x0, x1, xv, sub, gmask);
         }
       }
     }
+    if (QUEUE && qn) drain(qn);
 }
 
 // sites with escape symbols: one warp per distinct (global) site of the sorted exception list
