@@ -338,3 +338,21 @@ def test_layout_export_import(tmp_path, monkeypatch):
             api.Fasta.from_layout(str(path) + ".missing", blob)
         for x in (small, big, twin):
             x.close()
+
+
+@pytest.mark.parametrize("workload,sample", [("c4", "500"), ("c3", "600"), ("c5", "4")])
+def test_bench_reference_arm_prints_one_json_line(workload, sample):
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) for every workload: one JSON line with the
+    contract's keys, no GPU needed"""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-sites", sample], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    lines = [ln for ln in p.stdout.strip().split("\n") if ln]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "bases/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
