@@ -670,7 +670,7 @@ def run_c5(args, env):
     rank, world = env.rank, env.world
     n, L, loci = args.n, args.sites, args.loci
     mine = [i for i in range(loci) if parallel.chunk_owner(i, world) == rank]   # locus i -> rank i mod world
-    per_batch = int(os.environ.get("PFA_BENCH_BATCH", "2500"))
+    per_batch = int(os.environ.get("PFA_BENCH_BATCH", "10000"))
     batches = []
     with torch.cuda.stream(stream):
         for b0 in range(0, len(mine), per_batch):

@@ -250,6 +250,22 @@ __device__ __forceinline__ void pfa_batch_site_pass2(const PfaBatchArgs& a, cons
     }
 }
 
+// second pass of the first `count` (<= 32) entries of a warp's queue (q: [PFA_BQ_WORDS][64] words), one lane each; a function of
+// its own so that its registers do not weigh on the streaming loop
+#define PFA_BQ_WORDS 13
+__device__ __noinline__ void pfa_batch_drain(const PfaBatchArgs& a, const uint32_t* q, int count, int lane) {
+    __syncwarp();
+    if (lane < count) {
+        uint4 y0[1], y1[1], yv[1];
+        y0[0] = make_uint4(q[0 * 64 + lane], q[1 * 64 + lane], q[2 * 64 + lane], q[3 * 64 + lane]);
+        y1[0] = make_uint4(q[4 * 64 + lane], q[5 * 64 + lane], q[6 * 64 + lane], q[7 * 64 + lane]);
+        yv[0] = make_uint4(q[8 * 64 + lane], q[9 * 64 + lane], q[10 * 64 + lane], q[11 * 64 + lane]);
+        const PfaLocusDesc dq = a.desc[q[12 * 64 + lane]];
+        pfa_batch_site_pass2<1, 1>(a, dq, y0, y1, yv, 0, 1u << lane);
+    }
+    __syncwarp();
+}
+
 // K2b: a group of LPS lanes owns one site of one locus; same two passes as pfa_site_scan_reg_kernel, accumulators in global
 // memory (only variable columns touch them).  A warp walks CONTIGUOUS chunks of PFA_BATCH_SCHUNK sites, 32 / LPS at a time: its
 // loads stay coalesced and the locus of a site is found by one binary search per chunk plus a step forward now and then -- a
@@ -259,9 +275,8 @@ __device__ __forceinline__ void pfa_batch_site_pass2(const PfaBatchArgs& a, cons
 // second pass for those one or two lanes.  Here the variable sites go to a per-warp queue in shared memory (the 12 words of
 // the record + the locus) and the second pass runs when 32 are waiting: one lane each, all lanes busy.
 #define PFA_BATCH_SCHUNK 2048
-#define PFA_BQ_WORDS 13
 template <int LPS, int ITER>
-__global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_batch_site_kernel(const PfaBatchArgs a) {
+__global__ void __launch_bounds__(PFA_SITE_THREADS, (LPS == 1 && ITER == 1) ? 3 : 1) pfa_batch_site_kernel(const PfaBatchArgs a) {
     constexpr bool QUEUE = LPS == 1 && ITER == 1;
     __shared__ uint32_t sq[QUEUE ? PFA_SITE_THREADS / 32 : 1][QUEUE ? PFA_BQ_WORDS : 1][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -269,18 +284,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_batch_site_kernel(const 
     const unsigned gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << (lane - sub));
     constexpr int GW = 32 / LPS;
     int qn = 0;  // entries waiting in this warp's queue (QUEUE)
-    auto drain = [&](int count) {  // second pass of the first `count` (<= 32) queue entries, one lane each
-        __syncwarp();
-        if (lane < count) {
-            uint4 y0[1], y1[1], yv[1];
-            y0[0] = make_uint4(sq[wib][0][lane], sq[wib][1][lane], sq[wib][2][lane], sq[wib][3][lane]);
-            y1[0] = make_uint4(sq[wib][4][lane], sq[wib][5][lane], sq[wib][6][lane], sq[wib][7][lane]);
-            yv[0] = make_uint4(sq[wib][8][lane], sq[wib][9][lane], sq[wib][10][lane], sq[wib][11][lane]);
-            const PfaLocusDesc dq = a.desc[sq[wib][12][lane]];
-            pfa_batch_site_pass2<1, 1>(a, dq, y0, y1, yv, 0, 1u << lane);
-        }
-        __syncwarp();
-    };
+    auto drain = [&](int count) { pfa_batch_drain(a, &sq[wib][0][0], count, lane); };
     const long long nchunks = (a.n_sites + PFA_BATCH_SCHUNK - 1) / PFA_BATCH_SCHUNK;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long ch = warp0; ch < nchunks; ch += nwarps) {
@@ -288,12 +292,80 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_batch_site_kernel(const 
       int li = pfa_find_locus(a.site_base, a.nloci, min(g_lo + lane / LPS, a.n_sites - 1));
       PfaLocusDesc d = a.desc[li];
       long long next_base = a.site_base[li + 1];
-      // QUEUE: every lane runs the same number of rounds (the ballots need the whole warp); lanes beyond the chunk idle
-      for (long long g = g_lo + lane / LPS; QUEUE ? (g - lane < g_hi) : (g < g_hi); g += GW) {
-        const bool active = g < g_hi;
+      if (QUEUE) {
+        // four sites per lane and round: all their loads are issued before the first is looked at (one 16-byte record per
+        // plane and site leaves little in flight otherwise: the kernel sat at 2 TB/s)
+        constexpr int UN = 2;
+        for (long long g0 = g_lo; g0 < g_hi; g0 += 32 * UN) {
+            uint4 y0[UN], y1[UN], yv[UN], ym[UN];
+            int yl[UN];
+            bool act[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const long long g = g0 + 32 * u + lane;
+                act[u] = g < g_hi;
+                y0[u] = y1[u] = yv[u] = ym[u] = make_uint4(0, 0, 0, 0);
+                yl[u] = li;
+                if (act[u]) {
+                    if (g >= next_base) {  // walked into a later locus
+                        do {
+                            ++li;
+                            next_base = a.site_base[li + 1];
+                        } while (g >= next_base);
+                        d = a.desc[li];
+                    }
+                    yl[u] = li;
+                    const long long o = d.plane_off + (g - d.site_base);  // Wq == 1
+                    ym[u] = __ldg(a.masks + d.mask_off + d.k);
+                    y0[u] = pfa_ld_stream(a.b0 + o);
+                    y1[u] = pfa_ld_stream(a.b1 + o);
+                    yv[u] = a.locus_invalid[li] ? pfa_ld_stream(a.v + o) : ym[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const uint4 m = ym[u];
+                const uint32_t o0 = (y0[u].x & m.x) | (y0[u].y & m.y) | (y0[u].z & m.z) | (y0[u].w & m.w);
+                const uint32_t z0 = (~y0[u].x & m.x) | (~y0[u].y & m.y) | (~y0[u].z & m.z) | (~y0[u].w & m.w);
+                const uint32_t o1 = (y1[u].x & m.x) | (y1[u].y & m.y) | (y1[u].z & m.z) | (y1[u].w & m.w);
+                const uint32_t z1 = (~y1[u].x & m.x) | (~y1[u].y & m.y) | (~y1[u].z & m.z) | (~y1[u].w & m.w);
+                const uint32_t ov = (yv[u].x & m.x) | (yv[u].y & m.y) | (yv[u].z & m.z) | (yv[u].w & m.w);
+                const uint32_t zv = (~yv[u].x & m.x) | (~yv[u].y & m.y) | (~yv[u].z & m.z) | (~yv[u].w & m.w);
+                const bool mono = !(o0 && z0) && !(o1 && z1) && !(ov && zv);
+                const bool all_escape = o0 && o1 && !ov;
+                const bool var = act[u] && !(mono && !all_escape);
+                const unsigned vm = __ballot_sync(0xffffffffu, var);
+                if (!vm) continue;
+                if (var) {
+                    const int pos = qn + __popc(vm & ((1u << lane) - 1u));
+                    sq[wib][0][pos] = y0[u].x; sq[wib][1][pos] = y0[u].y; sq[wib][2][pos] = y0[u].z; sq[wib][3][pos] = y0[u].w;
+                    sq[wib][4][pos] = y1[u].x; sq[wib][5][pos] = y1[u].y; sq[wib][6][pos] = y1[u].z; sq[wib][7][pos] = y1[u].w;
+                    sq[wib][8][pos] = yv[u].x; sq[wib][9][pos] = yv[u].y; sq[wib][10][pos] = yv[u].z; sq[wib][11][pos] = yv[u].w;
+                    sq[wib][12][pos] = (uint32_t)yl[u];
+                }
+                qn += __popc(vm);
+                if (qn >= 32) {
+                    drain(32);
+                    const int rest = qn - 32;  // move the entries behind the first 32 to the front
+                    uint32_t keep[PFA_BQ_WORDS];
+                    if (lane < rest)
+#pragma unroll
+                        for (int w = 0; w < PFA_BQ_WORDS; ++w) keep[w] = sq[wib][w][32 + lane];
+                    __syncwarp();
+                    if (lane < rest)
+#pragma unroll
+                        for (int w = 0; w < PFA_BQ_WORDS; ++w) sq[wib][w][lane] = keep[w];
+                    qn = rest;
+                    __syncwarp();
+                }
+            }
+        }
+        continue;
+      }
+      for (long long g = g_lo + lane / LPS; g < g_hi; g += GW) {
         bool var = false;
         uint4 x0[ITER], x1[ITER], xv[ITER], m[ITER];
-        if (active) {
+        {
             if (g >= next_base) {  // the group has walked into a later locus
                 do {
                     ++li;
@@ -335,35 +407,7 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS) pfa_batch_site_kernel(const 
             const bool all_escape = (f & 1u) && (f & 4u) && !(f & 16u);
             var = !(mono && !all_escape);
         }
-        if (QUEUE) {
-            const unsigned vm = __ballot_sync(0xffffffffu, var);
-            if (vm) {
-                if (var) {
-                    const int pos = qn + __popc(vm & ((1u << lane) - 1u));
-                    sq[wib][0][pos] = x0[0].x; sq[wib][1][pos] = x0[0].y; sq[wib][2][pos] = x0[0].z; sq[wib][3][pos] = x0[0].w;
-                    sq[wib][4][pos] = x1[0].x; sq[wib][5][pos] = x1[0].y; sq[wib][6][pos] = x1[0].z; sq[wib][7][pos] = x1[0].w;
-                    sq[wib][8][pos] = xv[0].x; sq[wib][9][pos] = xv[0].y; sq[wib][10][pos] = xv[0].z; sq[wib][11][pos] = xv[0].w;
-                    sq[wib][12][pos] = (uint32_t)li;
-                }
-                qn += __popc(vm);
-                if (qn >= 32) {
-                    drain(32);
-                    const int rest = qn - 32;  // move the entries behind the first 32 to the front
-                    uint32_t keep[PFA_BQ_WORDS];
-                    if (lane < rest)
-#pragma unroll
-                        for (int w = 0; w < PFA_BQ_WORDS; ++w) keep[w] = sq[wib][w][32 + lane];
-                    __syncwarp();
-                    if (lane < rest)
-#pragma unroll
-                        for (int w = 0; w < PFA_BQ_WORDS; ++w) sq[wib][w][lane] = keep[w];
-                    qn = rest;
-                    __syncwarp();
-                }
-            }
-        } else if (var) {
-            pfa_batch_site_pass2<LPS, ITER>(a, d, x0, x1, xv, sub, gmask);
-        }
+        if (var) pfa_batch_site_pass2<LPS, ITER>(a, d, x0, x1, xv, sub, gmask);
       }
     }
     if (QUEUE && qn) drain(qn);
