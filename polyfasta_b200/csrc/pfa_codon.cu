@@ -960,14 +960,14 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
                 const uint32_t fwt = !bv ? 0u : sparse ? fa[idx * 3 + t] : 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < ITER; ++i) {
+                    // unconditional loads: chunks beyond the record (j >= Wq) and columns beyond the end read whatever lies
+                    // there in the slot (the allocation is padded) -- every use is masked (the masks of those chunks are zero)
+                    // or dropped (cc >= ncf); 48 register clears and 12 predicates per pass less
                     const int j = sub + LPS * i;
-                    x0[t][i] = x1[t][i] = make_uint4(0, 0, 0, 0);
+                    x0[t][i] = q0[j];
+                    x1[t][i] = q1[j];
                     xv[t][i] = um[i];
-                    if (j < Wq && cc < a.ncf) {
-                        x0[t][i] = q0[j];
-                        x1[t][i] = q1[j];
-                        if (HAS_V && ((fwt >> cell[i]) & 1u)) xv[t][i] = qv[j];
-                    }
+                    if (HAS_V && ((fwt >> cell[i]) & 1u)) xv[t][i] = qv[j];
                 }
             }
             if (COOP) {
@@ -1193,7 +1193,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         }
         auto dyn_for = [&](int mm) {
             return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16 + (hv ? (((size_t)gw * mm * 12 + 15) & ~(size_t)15) : 0)) +
-                   sizeof(uint64_t) * nwarp * tma_stages + smem +
+                   sizeof(uint64_t) * nwarp * tma_stages + smem + 1024 /* unconditional chunk loads may run past the last record */ +
                    (lps >= 4 ? (size_t)nwarp * PFA_CDS_QFIELDS * 32 * sizeof(uint32_t) : 0);
         };
         while (m > 1 && dyn_for(m) > 220 * 1024) --m;

@@ -496,13 +496,12 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
                 const int j = sub + LPS * i;
-                x0[i] = x1[i] = make_uint4(0, 0, 0, 0);
+                // unconditional loads: chunks beyond the record and sites beyond the end read whatever lies there in the slot (the
+                // allocation is padded); every use is masked (those chunks' masks are zero) or dropped (s >= ns)
+                x0[i] = q0[j];
+                x1[i] = q1[j];
                 xv[i] = um[i];
-                if (j < Wq && s < a.ns) {
-                    x0[i] = q0[j];
-                    x1[i] = q1[j];
-                    if (HAS_V && ((fw >> cell[i]) & 1u)) xv[i] = qv[j];
-                }
+                if (HAS_V && ((fw >> cell[i]) & 1u)) xv[i] = qv[j];
             }
             if (COOP) {
                 // base-plane flags over the valid rows only: a site is done here iff all its rows are valid and show one base;
@@ -641,7 +640,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         }
         auto dyn_for = [&](int mm) {
             return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * a->Wq * 16 + (hv ? (((size_t)gw * mm * 4 + 15) & ~(size_t)15) : 0)) +
-                   sizeof(uint64_t) * nwarp * tma_stages + smem;
+                   sizeof(uint64_t) * nwarp * tma_stages + smem + 1024;  // + slack: unconditional chunk loads may run past the last record
         };
         while (m > 1 && dyn_for(m) > 220 * 1024) --m;
         const size_t dyn = dyn_for(m);
