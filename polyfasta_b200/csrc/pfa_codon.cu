@@ -13,6 +13,7 @@
 // only, that all three sites are monomorphic over the union of the populations -- then every population sees
 // the same single codon and the contribution is uniform.  Otherwise pass 2 builds the presence mask per
 // population by peeling distinct codons off each 32-row word, and counts the three columns with popcounts.
+#include <algorithm>
 #include <cstdlib>
 
 #include "pfa_batch.cuh"
@@ -53,6 +54,7 @@ struct PfaCdsArgs {
     int64_t ncf;       // complete codon columns in this shard
     int has_partial;   // the shard ends with a partial codon column (1 or 2 sites)
     int acc_in_smem;
+    int min_nq;        // rows of the smallest population
 };
 
 // what the per-column code needs to know about the alignment (or, on the batched path, about one locus of the batch)
@@ -318,6 +320,19 @@ template <int LPS, int ITER, bool HAS_V>
 __device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER],
                                                   const uint4 (&um)[ITER], unsigned gmask, unsigned* f2_out = nullptr) {
     unsigned f = 0, f2 = 0;
+    if (HAS_V && f2_out) {  // bit 12: a row valid at all three sites exists; bit 13: an escape row (not valid, both base bits set) exists
+        uint32_t cl = 0, es = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            cl |= (xv[0][i].x & xv[1][i].x & xv[2][i].x & um[i].x) | (xv[0][i].y & xv[1][i].y & xv[2][i].y & um[i].y) |
+                  (xv[0][i].z & xv[1][i].z & xv[2][i].z & um[i].z) | (xv[0][i].w & xv[1][i].w & xv[2][i].w & um[i].w);
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                es |= (~xv[t][i].x & x0[t][i].x & x1[t][i].x & um[i].x) | (~xv[t][i].y & x0[t][i].y & x1[t][i].y & um[i].y) |
+                      (~xv[t][i].z & x0[t][i].z & x1[t][i].z & um[i].z) | (~xv[t][i].w & x0[t][i].w & x1[t][i].w & um[i].w);
+        }
+        f2 |= (cl ? 1u << 12 : 0u) | (es ? 1u << 13 : 0u);
+    }
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
@@ -711,6 +726,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
     // one member (no labels), and only the flagged cells are read -- gaps aligned to codons and runs of N, the usual
     // content of a real CDS alignment, no longer cost the peeling pass over the whole record.
     const uint32_t fwu = fw[0] | fw[1] | fw[2];
+    const unsigned gcr = pfa_cell_rcp(gcw);
     bool gaps_only = HAS_V && __popc(fwu) <= 6;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
@@ -776,7 +792,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
             // exactly one site varies, the other two show one valid base: the clean codons are that fixed pair combined with
             // the bases present at the variable site, and only that position can carry a label
             uint32_t c[PFA_NCLASS];
-            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, rv + tv * Wn, mq, Wn, lane, c, tv == 0 ? fw[0] : tv == 1 ? fw[1] : fw[2], gcw);
+            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, rv + tv * Wn, mq, Wn, lane, c, tv == 0 ? fw[0] : tv == 1 ? fw[1] : fw[2], gcr);
             if (HAS_V && c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
             const int shift = 2 * (2 - tv);
 #pragma unroll
@@ -801,7 +817,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
                 for (int t = 0; t < 3; ++t) {
                     const uint32_t w0 = r0[t * Wn + w], w1 = r1[t * Wn + w];
                     uint32_t wv = 0xffffffffu;  // words of an unflagged cell were not fetched: all rows valid
-                    if (HAS_V && ((fw[t] >> (w / gcw)) & 1u)) wv = rv[t * Wn + w];
+                    if (HAS_V && ((fw[t] >> (((unsigned)w * gcr) >> 16)) & 1u)) wv = rv[t * Wn + w];
                     const uint32_t vm = HAS_V ? (wv & m) : m;
                     const uint32_t hi = vm & w1, lo = vm & ~w1;
                     cnt[t][PFA_C_T] += __popc(hi & w0);
@@ -849,6 +865,134 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
             pfa_cds_flush(qbuf, 32, lane, a.acc_in_smem ? sm_acc : reinterpret_cast<unsigned long long*>(a.out), a.labels, a.s.ns);
             qcount = 0;
             __syncwarp();
+        }
+    }
+}
+
+// One pass of a warp of the TMA kernel over GW codon columns of its slot (whole-warp second pass, LPS >= 4).  V = the block
+// carries validity pieces; blocks without a flagged cell run the two-plane instantiation as separate code (see
+// pfa_site_tma_pass).
+// Columns whose only "variation" is missing data -- at each of the three sites the valid rows show ONE base, no escape row --
+// are finished right here: the rows valid at all three sites carry one and the same codon, so as long as every population
+// keeps at least one such row the column contributes exactly what a monomorphic column does (stop test, syn-site sum of that
+// codon; no labels).  One population: "a clean row exists" is one more OR in pass 1; several: the number of rows that are
+// not valid somewhere in the column is compared with the smallest population.  Gaps aligned to codons and runs of N -- the
+// usual content of a real CDS alignment -- then cost nothing beyond pass 1.
+// bv selects pass 1 (runtime, per block); everything after pass 1 is ONE piece of code for both, with ONE call of `refill` (the
+// slot's last pass only, as soon as nothing reads the slot any more): the hot loop has to fit the instruction cache (see
+// pfa_site_scan_tma_kernel).
+template <int LPS, int ITER, bool HAS_V, bool MULTI, class Refill>
+__device__ __forceinline__ void pfa_cds_tma_pass(const PfaCdsArgs& a, const unsigned char* slot, int CPS, unsigned rec, int t0, int64_t blk,
+                                                 const uint4 (&um)[ITER], const int (&cell)[ITER], bool bv, bool sparse, int gcw, int lane,
+                                                 int sub, int grp, unsigned gmask, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount,
+                                                 unsigned& u_nstops, unsigned& u_missing, unsigned& u_sum3, bool last, Refill&& refill) {
+    constexpr int GW = 32 / LPS;
+    const int Wq = a.s.Wq, SPS = CPS * 3;
+    const int idx = t0 * GW + grp;  // codon column of this group inside the slot
+    const int64_t cc = blk * CPS + idx;
+    const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
+    uint4 x0[3][ITER], x1[3][ITER];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)(idx * 3 + t) * rec);
+        const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx * 3 + t) * rec);
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            // unconditional loads: chunks beyond the record (j >= Wq) and columns beyond the end read whatever lies there in
+            // the slot (the allocation is padded) -- every use is masked (the masks of those chunks are zero) or dropped
+            x0[t][i] = q0[sub + LPS * i];
+            x1[t][i] = q1[sub + LPS * i];
+        }
+    }
+    unsigned f, f2 = 0xfffu;  // f2: "bases vary" unless pass 1 finds otherwise
+    bool uniform = true, clean = true;
+    int codon = 0;
+    if (!(HAS_V && bv)) {
+        uint4 xv[3][ITER];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) xv[t][i] = um[i];
+        f = pfa_cds_pass1<LPS, ITER, false>(x0, x1, xv, um, gmask);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const unsigned ft = (f >> (6 * t)) & 63u;
+            uniform = uniform && pfa_flags_bases_mono(ft);
+            codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+        }
+    } else {
+        uint4 xv[3][ITER];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx * 3 + t) * rec);
+            const uint32_t fwt = sparse ? fa[idx * 3 + t] : 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < ITER; ++i) {
+                xv[t][i] = um[i];
+                if ((fwt >> cell[i]) & 1u) xv[t][i] = qv[sub + LPS * i];
+            }
+        }
+        f = pfa_cds_pass1<LPS, ITER, true>(x0, x1, xv, um, gmask, &f2);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const unsigned ft = (f >> (6 * t)) & 63u;
+            uniform = uniform && pfa_flags_mono(ft) && !pfa_flags_all_escape(ft);
+            clean = clean && (ft & 16u) && !(ft & 32u);
+            codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+        }
+        if (!uniform) {
+            bool gapcol = !((f2 >> 13) & 1u);  // no escape row
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const unsigned g = (f2 >> (4 * t)) & 15u;
+                gapcol = gapcol && ((g & 3u) != 3u) && ((g & 12u) != 12u);
+            }
+            if (gapcol) {  // group-uniform
+                bool every_pop_clean = ((f2 >> 12) & 1u) != 0u;  // one population: a row valid at all three sites exists
+                if (MULTI) {
+                    uint32_t inv = 0;
+#pragma unroll
+                    for (int i = 0; i < ITER; ++i) {
+                        inv += __popc(~(xv[0][i].x & xv[1][i].x & xv[2][i].x) & um[i].x) + __popc(~(xv[0][i].y & xv[1][i].y & xv[2][i].y) & um[i].y) +
+                               __popc(~(xv[0][i].z & xv[1][i].z & xv[2][i].z) & um[i].z) + __popc(~(xv[0][i].w & xv[1][i].w & xv[2][i].w) & um[i].w);
+                    }
+                    every_pop_clean = pfa_group_add<LPS>(inv, gmask) < (uint32_t)a.min_nq;
+                }
+                if (every_pop_clean || !MULTI) {
+                    uniform = true;
+                    clean = every_pop_clean;  // one population without a clean row: every codon is missing
+                    codon = 0;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) codon = (codon << 2) | (((f2 >> (4 * t)) & 4u) ? 2 : 0) | (((f2 >> (4 * t)) & 1u) ? 1 : 0);
+                }
+            }
+        }
+    }
+    // variable columns: the whole warp, one at a time, from the slot
+    for (unsigned rest = __ballot_sync(0xffffffffu, !uniform && sub == 0 && cc < a.ncf); rest; rest &= rest - 1) {
+        const int leader = __ffs(rest) - 1;
+        const int vidx = t0 * GW + leader / LPS;
+        const unsigned fv = __shfl_sync(0xffffffffu, f, leader), fv2 = __shfl_sync(0xffffffffu, f2, leader);
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(slot + (size_t)(vidx * 3) * rec);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx * 3) * rec);
+        uint32_t fw3[3] = {0u, 0u, 0u};
+        if (HAS_V && bv) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) fw3[t] = sparse ? fa[vidx * 3 + t] : 0xffffffffu;
+        }
+        if (HAS_V && (fw3[0] | fw3[1] | fw3[2]))
+            pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, r0, r1, reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx * 3) * rec),
+                                       Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, fv2);
+        else
+            pfa_cds_coop<false, MULTI>(a, (blk * CPS + vidx) * 3, fv, r0, r1, r0, Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, 0xfffu);
+    }
+    if (last) refill();
+    if (uniform && sub == 0 && cc < a.ncf) {  // the same single codon for every population
+        if (clean) {
+            u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
+            u_sum3 += c_syn3[codon];
+        } else {
+            u_missing += 3;
         }
     }
 }
@@ -943,68 +1087,31 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         const bool bv = cur_v;  // false: no row of this block's sites is invalid -- the two-plane code path
         pfa_mbar_wait(bar, k & 1u);
         const unsigned char* slot = ring;
-        const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
         auto refill = [&]() {  // once per block, when the slot's last pass no longer needs it
             cur_blk = issue_next();
             cur_v = pend_v;
         };
         for (int t0 = 0; t0 < m; ++t0) {
-            const int idx = t0 * GW + grp;  // codon column of this group inside the slot
-            const int64_t cc = blk * CPS + idx;
-            uint4 x0[3][ITER], x1[3][ITER], xv[3][ITER];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)(idx * 3 + t) * rec);
-                const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(CPS * 3 + idx * 3 + t) * rec);
-                const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * CPS * 3 + idx * 3 + t) * rec);
-                const uint32_t fwt = !bv ? 0u : sparse ? fa[idx * 3 + t] : 0xffffffffu;
-#pragma unroll
-                for (int i = 0; i < ITER; ++i) {
-                    // unconditional loads: chunks beyond the record (j >= Wq) and columns beyond the end read whatever lies
-                    // there in the slot (the allocation is padded) -- every use is masked (the masks of those chunks are zero)
-                    // or dropped (cc >= ncf); 48 register clears and 12 predicates per pass less
-                    const int j = sub + LPS * i;
-                    x0[t][i] = q0[j];
-                    x1[t][i] = q1[j];
-                    xv[t][i] = um[i];
-                    if (HAS_V && ((fwt >> cell[i]) & 1u)) xv[t][i] = qv[j];
-                }
-            }
             if (COOP) {
-                unsigned f2 = 0xfffu;  // "bases vary" unless pass 1 finds otherwise
-                const unsigned f = (HAS_V && bv) ? pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask, sparse ? &f2 : nullptr)
-                                                 : pfa_cds_pass1<LPS, ITER, false>(x0, x1, xv, um, gmask);
-                bool uniform = true, clean = true;
-                int codon = 0;
+                pfa_cds_tma_pass<LPS, ITER, HAS_V, MULTI>(a, slot, CPS, rec, t0, blk, um, cell, bv, sparse, gcw, lane, sub, grp, gmask, sm_acc, qbuf, qcount,
+                                                          u_nstops, u_missing, u_sum3, t0 == m - 1, refill);
+            } else {
+                const int idx = t0 * GW + grp;  // codon column of this group inside the slot
+                const int64_t cc = blk * CPS + idx;
+                uint4 x0[3][ITER], x1[3][ITER], xv[3][ITER];
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
-                    const unsigned ft = (f >> (6 * t)) & 63u;
-                    uniform = uniform && pfa_flags_mono(ft) && !pfa_flags_all_escape(ft);
-                    clean = clean && (ft & 16u) && !(ft & 32u);
-                    codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
-                }
-                if (uniform && sub == 0 && cc < a.ncf) {  // the same single codon for every population
-                    if (clean) {
-                        u_nstops += (unsigned)((c_stop_mask >> codon) & 1ull);
-                        u_sum3 += c_syn3[codon];
-                    } else {
-                        u_missing += 3;
+                    const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)(idx * 3 + t) * rec);
+                    const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(CPS * 3 + idx * 3 + t) * rec);
+                    const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * CPS * 3 + idx * 3 + t) * rec);
+#pragma unroll
+                    for (int i = 0; i < ITER; ++i) {
+                        const int j = sub + LPS * i;  // unconditional loads, see pfa_cds_tma_pass
+                        x0[t][i] = q0[j];
+                        x1[t][i] = q1[j];
+                        xv[t][i] = HAS_V ? qv[j] : um[i];
                     }
                 }
-                const unsigned vm = __ballot_sync(0xffffffffu, !uniform && sub == 0 && cc < a.ncf);
-                if (t0 == m - 1 && !vm) refill();
-                for (unsigned rest = vm; rest; rest &= rest - 1) {
-                    const int leader = __ffs(rest) - 1;
-                    const int vidx = t0 * GW + leader / LPS;
-                    const unsigned fv = __shfl_sync(0xffffffffu, f, leader);
-                    const uint32_t fw3[3] = {!bv ? 0u : sparse ? fa[vidx * 3] : 0xffffffffu, !bv ? 0u : sparse ? fa[vidx * 3 + 1] : 0xffffffffu,
-                                             !bv ? 0u : sparse ? fa[vidx * 3 + 2] : 0xffffffffu};
-                    pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, reinterpret_cast<const uint32_t*>(slot + (size_t)(vidx * 3) * rec),
-                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(CPS * 3 + vidx * 3) * rec),
-                                               reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * CPS * 3 + vidx * 3) * rec), Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, __shfl_sync(0xffffffffu, f2, leader));
-                }
-                if (t0 == m - 1 && vm) refill();
-            } else {
                 // pass 1 has consumed every register loaded from the slot: refill it while the rest runs on registers
                 const unsigned f = pfa_cds_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
                 if (t0 == m - 1) refill();
@@ -1153,11 +1260,13 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     args.ncf = a->ns / 3;
     args.has_partial = (a->ns % 3) != 0;
     args.acc_in_smem = (int64_t)a->k * PFA_CDS_LEN * 8 <= 40 * 1024;
+    args.min_nq = (int)*std::min_element(a->pop_n.begin(), a->pop_n.end());
     const size_t smem = 8 * (3 + (args.acc_in_smem ? (size_t)a->k * PFA_CDS_LEN : 0));
     int lps = 1;
     while (lps < 32 && (a->Wq + lps - 1) / lps > 2) lps *= 2;
     int iter = (a->Wq + lps - 1) / lps;
-    const bool hv = a->has_invalid != 0, multi = a->k > 1;
+    const bool probe_sparse = getenv("PFA_PROBE_SPARSE_V") != nullptr;  // measurement aid: the validity-aware kernel on a clean shard
+    const bool hv = a->has_invalid != 0 || probe_sparse, multi = a->k > 1;
     const bool generic = iter > 3 || getenv("PFA_GENERIC_SCAN") != nullptr;
     if (generic) {
         lps = 1;
@@ -1186,7 +1295,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         int m = (int)std::max<int64_t>(1, 10000 / ((int64_t)gw * 3 * a->Wq * 16));
         if (const char* e = getenv("PFA_CDS_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: fetch only the flagged pieces of the v plane (see pfa_launch_site_scan)
-        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && a->Wq >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
+        const bool sparse_v = (a->has_invalid == 1 || (probe_sparse && a->has_invalid == 0)) && lps >= 4 && a->Wq >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
         if (sparse_v) {
             args.s.vflag = a->vflag;
             m = std::max(1, std::min(m, 32 * PFA_VF_REGS / (3 * gw)));

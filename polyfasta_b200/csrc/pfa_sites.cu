@@ -130,6 +130,25 @@ __device__ __forceinline__ unsigned pfa_site_pass1(const uint4 (&x0)[ITER], cons
     return pfa_group_or<LPS>(f, gmask);
 }
 
+// pass 1 of a site of a block that carries validity pieces: mv = the lane's slice of "row belongs to the union AND is valid"
+// (um where the cell is not flagged).  Bits 0-3: the base planes over the valid rows, bit 5: some row is not valid.
+template <int LPS, int ITER>
+__device__ __forceinline__ unsigned pfa_site_pass1_valid(const uint4 (&x0)[ITER], const uint4 (&x1)[ITER], const uint4 (&mv)[ITER],
+                                                         const uint4 (&um)[ITER], unsigned gmask) {
+    uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, zv = 0;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const uint4 m = mv[i];
+        zv |= (um[i].x ^ m.x) | (um[i].y ^ m.y) | (um[i].z ^ m.z) | (um[i].w ^ m.w);
+        o0 |= (x0[i].x & m.x) | (x0[i].y & m.y) | (x0[i].z & m.z) | (x0[i].w & m.w);
+        z0 |= (~x0[i].x & m.x) | (~x0[i].y & m.y) | (~x0[i].z & m.z) | (~x0[i].w & m.w);
+        o1 |= (x1[i].x & m.x) | (x1[i].y & m.y) | (x1[i].z & m.z) | (x1[i].w & m.w);
+        z1 |= (~x1[i].x & m.x) | (~x1[i].y & m.y) | (~x1[i].z & m.z) | (~x1[i].w & m.w);
+    }
+    const unsigned f = (o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (zv ? 32u : 0u);
+    return pfa_group_or<LPS>(f, gmask);
+}
+
 // pass 2 of one site on registers, given the flags of pass 1 (f, OR-reduced over the group): shared by the register-resident
 // kernel and the TMA kernel's per-group path
 template <int LPS, int ITER, bool HAS_V, bool MULTI>
@@ -343,25 +362,22 @@ __global__ void __launch_bounds__(256) pfa_escape_sites_kernel(const PfaSiteArgs
 }
 
 // second pass of ONE variable site by the whole warp (see pfa_sites.cuh): w0 / w1 / wv are the site's records in the warp's
-// shared-memory slot.  S and H of population q < 32 accumulate in the registers of lane q.
-template <bool HAS_V, bool MULTI>
+// shared-memory slot.  S and H of population q < LPS accumulate in the registers of lane q (the lane with sub == q of the
+// first group: pfa_site_gap_finish uses the same registers for the lanes with sub == q of every group).
+template <int LPS, bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_site_coop(const PfaSiteArgs& a, int64_t s, const uint32_t* w0, const uint32_t* w1, const uint32_t* wv,
                                               int Wn, int lane, unsigned long long* sm_SH, unsigned int* sm_sfs, uint32_t& S_mine,
-                                              unsigned long long& H_mine, uint32_t fw, int gcw, unsigned f) {
+                                              unsigned long long& H_mine, uint32_t fw, unsigned gcr) {
     const int k = MULTI ? a.k : 1;
-    // gap-only site: every valid row shows the same base and the few invalid rows sit in a handful of flagged cells
-    const bool gaps_only = HAS_V && pfa_flags_bases_mono(f) && __popc(fw) <= 6;
-    const int base = ((f & 4u) ? 2 : 0) | ((f & 1u) ? 1 : 0);
     for (int q = 0; q < k; ++q) {
         const uint32_t* mq = reinterpret_cast<const uint32_t*>(MULTI ? a.masks + (int64_t)q * a.Wq : a.umask);
         uint32_t c[PFA_NCLASS];
-        if (gaps_only) pfa_coop_counts_gaps(w0, w1, wv, mq, Wn, lane, c, fw, gcw, base, (uint32_t)a.pop_n[q]);
-        else pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c, fw, gcw);
+        pfa_coop_counts<HAS_V>(w0, w1, wv, mq, Wn, lane, c, fw, gcr);
         const PfaSiteResult r = pfa_site_result(c, a.pop_n[q], 0u, 0ull);
         if (r.has_escape) continue;  // finished by pfa_escape_sites_kernel
         if (a.isvar && lane == 0) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)r.isvar;
         if (!r.isvar) continue;
-        if (q < 32) {
+        if (q < LPS) {
             if (lane == q) {
                 S_mine += 1u;
                 H_mine += r.h;
@@ -374,6 +390,65 @@ __device__ __forceinline__ void pfa_site_coop(const PfaSiteArgs& a, int64_t s, c
             if (a.sfs_in_smem) atomicAdd(&sm_sfs[a.sfs_off[q] + r.sfs_bin], 1u);
             else atomicAdd(reinterpret_cast<unsigned long long*>(a.out + a.out_off[q] + 2 + r.sfs_bin), 1ull);
         }
+    }
+}
+
+// A site whose VALID rows all show one base but which has rows that are not valid -- gaps, N, ? -- is a segregating site of the
+// reference (a gap is an allele, PolyFastA.py:256-258), and in an alignment with sparse gaps and many rows MOST sites are of this
+// kind (10,000 rows, one gap per 10^4 bases: 63 % of the sites).  Its statistics need only the numbers of gap / N / ? rows
+// per population, and those rows sit in the chunks of flagged cells, which the group already holds in registers: the
+// group finishes the site itself -- two packed popcount sums (pfa_site_gap_counts), one shuffle reduction and the arithmetic
+// (pfa_site_gap_apply) -- instead of queueing it for the whole warp.  H = n^2 - (valid^2 + gap^2 + N^2 + ?^2); no SFS bin
+// (fewer than two of A, C, G, T: getsfs skips the column).  Populations that hold an escape row here are left to
+// pfa_escape_sites_kernel, like everywhere else.
+template <int LPS, int ITER, bool MULTI>
+__device__ __forceinline__ void pfa_site_gap_counts(const PfaSiteArgs& a, int q, const uint4 (&x0)[ITER], const uint4 (&x1)[ITER],
+                                                    const uint4 (&mv)[ITER], const uint4 (&um)[ITER], const int (&cell)[ITER], uint32_t fw,
+                                                    int sub, uint32_t& pa, uint32_t& pb) {
+    pa = pb = 0u;  // (gap | N << 16), (? | escape << 16) among this lane's rows: a count is at most n <= 20,480
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        if (!((fw >> cell[i]) & 1u)) continue;  // rows that are not valid exist in flagged cells only
+        uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (MULTI) {
+            const int j = sub + LPS * i;
+            m4 = j < a.Wq ? __ldg(a.masks + (int64_t)q * a.Wq + j) : make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w},
+                       w1[4] = {x1[i].x, x1[i].y, x1[i].z, x1[i].w},
+                       iv[4] = {um[i].x ^ mv[i].x, um[i].y ^ mv[i].y, um[i].z ^ mv[i].z, um[i].w ^ mv[i].w};  // rows that are not valid
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t im = MULTI ? (iv[w] & m[w]) : iv[w];
+            if (im) {
+                pa += (uint32_t)__popc(im & ~w1[w] & ~w0[w]) | ((uint32_t)__popc(im & ~w1[w] & w0[w]) << 16);
+                pb += (uint32_t)__popc(im & w1[w] & ~w0[w]) | ((uint32_t)__popc(im & w1[w] & w0[w]) << 16);
+            }
+        }
+    }
+}
+
+template <int LPS>
+__device__ __forceinline__ void pfa_site_gap_apply(const PfaSiteArgs& a, int64_t s, int q, uint32_t pa, uint32_t pb, int sub, unsigned gmask,
+                                                   unsigned long long* sm_SH, uint32_t& S_mine, unsigned long long& H_mine) {
+    pa = pfa_group_add<LPS>(pa, gmask);
+    pb = pfa_group_add<LPS>(pb, gmask);
+    if (pb >> 16) return;  // escape rows: pfa_escape_sites_kernel counts this (site, population)
+    const uint32_t cg = pa & 0xffffu, cn = pa >> 16, cq = pb & 0xffffu;
+    const uint32_t nq = (uint32_t)a.pop_n[q], valid = nq - (cg + cn + cq);
+    const bool isvar = ((valid ? 1 : 0) + (cg ? 1 : 0) + (cn ? 1 : 0) + (cq ? 1 : 0)) > 1;
+    if (a.isvar && sub == 0) a.isvar[(int64_t)q * a.ns + s] = (uint8_t)isvar;
+    if (!isvar) return;
+    const unsigned long long h = (unsigned long long)nq * nq - ((unsigned long long)valid * valid + (unsigned long long)cg * cg +
+                                                                 (unsigned long long)cn * cn + (unsigned long long)cq * cq);
+    if (q < LPS) {
+        if (sub == q) {
+            S_mine += 1u;
+            H_mine += h;
+        }
+    } else if (sub == 0) {
+        atomicAdd(&sm_SH[2 * q], 1ull);
+        atomicAdd(&sm_SH[2 * q + 1], h);
     }
 }
 
@@ -401,7 +476,8 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
     const int SPS = GW * m;                   // sites per slot: m passes of the warp (narrow records: keeps a copy >= ~2 KB)
     const unsigned slot_bytes = (unsigned)NPL * SPS * rec + (HAS_V ? (((unsigned)SPS * 4u + 15u) & ~15u) : 0u);  // pfa_slot_issue
     const bool sparse = HAS_V && a.vflag != nullptr;  // fetch only the flagged cells of the v plane
-    const int gc = a.gc, gcw = a.gc * 4;
+    const int gc = a.gc;
+    const unsigned gcr = pfa_cell_rcp(a.gc * 4);
     unsigned char* ring_base = dyn;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);  // [warp][stage]
     unsigned long long* sm_SH = reinterpret_cast<unsigned long long*>(bars + NWARP * stages);
@@ -425,7 +501,7 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
     const int64_t nblk = (a.ns + SPS - 1) / SPS;                     // blocks of SPS consecutive sites
     const unsigned char* planes[3] = {reinterpret_cast<const unsigned char*>(a.b0), reinterpret_cast<const unsigned char*>(a.b1),
                                       reinterpret_cast<const unsigned char*>(a.v)};
-    uint32_t S_mine = 0;               // COOP: S and H of population `lane`
+    uint32_t S_mine = 0;               // COOP: S and H of population `sub`
     unsigned long long H_mine = 0ull;
 
     uint4 um[ITER];
@@ -480,50 +556,94 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
         const bool bv = cur_v;  // false: no row of this block's sites is invalid -- the two-plane code path
         pfa_mbar_wait(bar, k & 1u);
         const unsigned char* slot = ring;
-        const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
         auto refill = [&]() {  // once per block, when the slot's last pass no longer needs it
             cur_blk = issue_next();
             cur_v = pend_v;
         };
         for (int t = 0; t < m; ++t) {
-            const int idx = t * GW + grp;  // site of this group inside the slot
-            const int64_t s = blk * SPS + idx;
-            const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
-            const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
-            const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
-            const uint32_t fw = !bv ? 0u : sparse ? fa[idx] : 0xffffffffu;
-            uint4 x0[ITER], x1[ITER], xv[ITER];
-#pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const int j = sub + LPS * i;
+            if (COOP) {
+                // One pass over GW sites of the slot with the whole-warp second pass.  Blocks without a flagged cell run the
+                // two-plane pass 1 even in an alignment that has invalid rows somewhere.  What follows pass 1 is ONE piece of code
+                // for both: the kernel's hot loop has to fit the instruction cache (a version with the refill and the second pass
+                // inlined per path -- 7,000 instructions -- stalled 6 cycles per issue on instruction fetch, ncu r2w_k2g).
+                const int idx = t * GW + grp;  // site of this group inside the slot
+                const int64_t s = blk * SPS + idx;
+                const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
+                const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
+                const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
+                uint4 x0[ITER], x1[ITER];
                 // unconditional loads: chunks beyond the record and sites beyond the end read whatever lies there in the slot (the
                 // allocation is padded); every use is masked (those chunks' masks are zero) or dropped (s >= ns)
-                x0[i] = q0[j];
-                x1[i] = q1[j];
-                xv[i] = um[i];
-                if (HAS_V && ((fw >> cell[i]) & 1u)) xv[i] = qv[j];
-            }
-            if (COOP) {
-                // base-plane flags over the valid rows only: a site is done here iff all its rows are valid and show one base;
-                // anything with a non-ACGT row goes to the second pass (which has a short path for "gaps only")
-                const unsigned f = (HAS_V && bv) ? pfa_site_pass1<LPS, ITER, HAS_V, true>(x0, x1, xv, um, gmask)
-                                                 : pfa_site_pass1<LPS, ITER, false, false>(x0, x1, xv, um, gmask);
-                const bool var = s < a.ns && !(pfa_flags_bases_mono(f) && (f & 16u) && !(f & 32u));
-                if (a.isvar && sub == 0 && s < a.ns && !var)
-                    for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
-                const unsigned vm = __ballot_sync(0xffffffffu, var && sub == 0);
-                if (t == m - 1 && !vm) refill();
-                for (unsigned rest = vm; rest; rest &= rest - 1) {
-                    const int leader = __ffs(rest) - 1;
-                    const int vidx = t * GW + leader / LPS;
-                    const unsigned fv = __shfl_sync(0xffffffffu, f, leader);
-                    pfa_site_coop<HAS_V, MULTI>(a, blk * SPS + vidx, reinterpret_cast<const uint32_t*>(slot + (size_t)vidx * rec),
-                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec),
-                                                reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec), Wq * 4, lane, sm_SH,
-                                                sm_sfs, S_mine, H_mine, !bv ? 0u : sparse ? fa[vidx] : 0xffffffffu, gcw, fv);
+#pragma unroll
+                for (int i = 0; i < ITER; ++i) {
+                    x0[i] = q0[sub + LPS * i];
+                    x1[i] = q1[sub + LPS * i];
                 }
-                if (t == m - 1 && vm) refill();
+                bool var, gapsite = false;
+                uint32_t pa = 0, pb = 0;
+                if (!(HAS_V && bv)) {
+                    const unsigned f = pfa_site_pass1<LPS, ITER, false, false>(x0, x1, um, um, gmask);
+                    var = s < a.ns && !pfa_flags_bases_mono(f);
+                } else {
+                    const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
+                    const uint32_t fw = sparse ? fa[idx] : 0xffffffffu;
+                    uint4 mv[ITER];  // rows of the union that are valid
+#pragma unroll
+                    for (int i = 0; i < ITER; ++i) {
+                        mv[i] = um[i];
+                        if ((fw >> cell[i]) & 1u) {
+                            const uint4 v4 = qv[sub + LPS * i];
+                            mv[i] = make_uint4(um[i].x & v4.x, um[i].y & v4.y, um[i].z & v4.z, um[i].w & v4.w);
+                        }
+                    }
+                    // base-plane flags over the VALID rows: bases_mono = every valid row shows the same base
+                    const unsigned f = pfa_site_pass1_valid<LPS, ITER>(x0, x1, mv, um, gmask);
+                    const bool bmono = pfa_flags_bases_mono(f);
+                    var = s < a.ns && !bmono;
+                    gapsite = s < a.ns && bmono && (f & 32u);  // its valid rows show one base, but not all rows are valid
+                    if (gapsite) {
+                        if (!MULTI) {
+                            pfa_site_gap_counts<LPS, ITER, false>(a, 0, x0, x1, mv, um, cell, fw, sub, pa, pb);
+                        } else {
+                            for (int q = 0; q < a.k; ++q) {
+                                pfa_site_gap_counts<LPS, ITER, true>(a, q, x0, x1, mv, um, cell, fw, sub, pa, pb);
+                                pfa_site_gap_apply<LPS>(a, s, q, pa, pb, sub, gmask, sm_SH, S_mine, H_mine);
+                            }
+                        }
+                    }
+                }
+                if (a.isvar && sub == 0 && s < a.ns && !var && !gapsite)
+                    for (int q = 0; q < a.k; ++q) a.isvar[(int64_t)q * a.ns + s] = 0;
+                // variable sites: the whole warp, one at a time, from the slot
+                for (unsigned rest = __ballot_sync(0xffffffffu, var && sub == 0); rest; rest &= rest - 1) {
+                    const int vidx = t * GW + (__ffs(rest) - 1) / LPS;
+                    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(slot + (size_t)vidx * rec);
+                    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec);
+                    const uint32_t fwv = !(HAS_V && bv) ? 0u : sparse ? fa[vidx] : 0xffffffffu;
+                    if (HAS_V && fwv)
+                        pfa_site_coop<LPS, HAS_V, MULTI>(a, blk * SPS + vidx, r0, r1, reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec),
+                                                         Wq * 4, lane, sm_SH, sm_sfs, S_mine, H_mine, fwv, gcr);
+                    else
+                        pfa_site_coop<LPS, false, MULTI>(a, blk * SPS + vidx, r0, r1, r0, Wq * 4, lane, sm_SH, sm_sfs, S_mine, H_mine, 0u, 0u);
+                }
+                // the slot's last pass no longer needs it: fetch the next block; what is left of a gap site runs on registers
+                // while that block is on its way
+                if (t == m - 1) refill();
+                if (HAS_V && !MULTI && gapsite) pfa_site_gap_apply<LPS>(a, s, 0, pa, pb, sub, gmask, sm_SH, S_mine, H_mine);
             } else {
+                const int idx = t * GW + grp;  // site of this group inside the slot
+                const int64_t s = blk * SPS + idx;
+                const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
+                const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
+                const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
+                uint4 x0[ITER], x1[ITER], xv[ITER];
+#pragma unroll
+                for (int i = 0; i < ITER; ++i) {
+                    const int j = sub + LPS * i;  // unconditional loads, see pfa_site_tma_pass
+                    x0[i] = q0[j];
+                    x1[i] = q1[j];
+                    xv[i] = HAS_V ? qv[j] : um[i];
+                }
                 // pass 1 has consumed every register loaded from the slot: the slot can be refilled while the second pass (on
                 // registers) runs
                 const unsigned f = pfa_site_pass1<LPS, ITER, HAS_V>(x0, x1, xv, um, gmask);
@@ -532,9 +652,9 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
             }
         }
     }
-    if (COOP && lane < a.k && S_mine) {
-        atomicAdd(&sm_SH[2 * lane], (unsigned long long)S_mine);
-        atomicAdd(&sm_SH[2 * lane + 1], H_mine);
+    if (COOP && sub < a.k && S_mine) {  // population `sub`: whole-warp second passes (first group) and gap sites (every group)
+        atomicAdd(&sm_SH[2 * sub], (unsigned long long)S_mine);
+        atomicAdd(&sm_SH[2 * sub + 1], H_mine);
     }
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(a.work + 1, 1u) == gridDim.x - 1) {  // every CTA has made its last claim: reset for the next launch
@@ -610,7 +730,8 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     const size_t smem = sizeof(unsigned long long) * 2 * (size_t)a->k + (args.sfs_in_smem ? sizeof(unsigned int) * (size_t)args.sfs_bins : 0);
     const int64_t groups_per_block = PFA_SITE_THREADS / lps;
     int64_t blocks = (a->ns + groups_per_block - 1) / groups_per_block;
-    const bool hv = a->has_invalid != 0, multi = a->k > 1;
+    const bool probe_sparse = getenv("PFA_PROBE_SPARSE_V") != nullptr;  // measurement aid: the validity-aware kernel on a clean shard
+    const bool hv = a->has_invalid != 0 || probe_sparse, multi = a->k > 1;
     const bool generic = iter > 5 || getenv("PFA_GENERIC_SCAN") != nullptr;
     const int64_t max_blocks = (int64_t)ctx->sm_count * (generic ? 4 : 2);
     if (blocks > max_blocks) blocks = max_blocks;
@@ -633,7 +754,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: a shard with a few non-ACGT symbols fetches only the flagged pieces of its v plane (pfa_slot_issue);
         // not when the validity plane is forced (benchmarks of the 3-plane worst case) or PFA_VFLAG=0
-        const bool sparse_v = a->has_invalid == 1 && lps >= 4 && a->Wq >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
+        const bool sparse_v = (a->has_invalid == 1 || (probe_sparse && a->has_invalid == 0)) && lps >= 4 && a->Wq >= 4 && !(getenv("PFA_VFLAG") && atoi(getenv("PFA_VFLAG")) == 0);
         if (sparse_v) {
             args.vflag = a->vflag;
             m = std::min(m, 32 * PFA_VF_REGS / gw);

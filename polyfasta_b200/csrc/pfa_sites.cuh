@@ -150,18 +150,20 @@ __device__ __forceinline__ PfaSiteResult pfa_site_result(const uint32_t c[PFA_NC
 
 // class counts of one population at one site: w0 / w1 / wv point to the site's record in each plane (32-bit words, Wn of
 // them), mq to the population's row mask
-// fw / gcw: the site's validity flag word and the 32-bit words per flag bit -- words of an unflagged cell were not fetched
-// (pfa_slot_issue) and count as all valid; fw = ~0: every word of wv is there
+// fw / gcr: the site's validity flag word and the reciprocal of the 32-bit words per flag bit (pfa_cell_rcp; word w lies in
+// cell (w * gcr) >> 16 -- a division here cost 20 instructions per word) -- words of an unflagged cell were not fetched
+// (pfa_slot_issue) and count as all valid; fw = ~0, gcr = 0: every word of wv is there
+__host__ __device__ __forceinline__ unsigned pfa_cell_rcp(int gcw) { return (65536u + (unsigned)gcw - 1u) / (unsigned)gcw; }  // exact for w * gcw < 65536
 template <bool HAS_V>
 __device__ __forceinline__ void pfa_coop_counts(const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
                                                 const uint32_t* __restrict__ wv, const uint32_t* __restrict__ mq, int Wn, int lane,
-                                                uint32_t c[PFA_NCLASS], uint32_t fw = 0xffffffffu, int gcw = 1 << 20) {
+                                                uint32_t c[PFA_NCLASS], uint32_t fw = 0xffffffffu, unsigned gcr = 0u) {
 #pragma unroll
     for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
     for (int w = lane; w < Wn; w += 32) {
         const uint32_t m = __ldg(mq + w), x0 = w0[w], x1 = w1[w];
         uint32_t xv = 0xffffffffu;
-        if (HAS_V && ((fw >> (w / gcw)) & 1u)) xv = wv[w];
+        if (HAS_V && ((fw >> (((unsigned)w * gcr) >> 16)) & 1u)) xv = wv[w];
         const uint32_t vm = HAS_V ? (xv & m) : m;
         const uint32_t hi = vm & x1, lo = vm & ~x1;
         c[PFA_C_T] += __popc(hi & x0);
@@ -179,39 +181,6 @@ __device__ __forceinline__ void pfa_coop_counts(const uint32_t* __restrict__ w0,
 #pragma unroll
     for (int i = 0; i < PFA_NCLASS; ++i)
         if (HAS_V || i < 4) c[i] = __reduce_add_sync(0xffffffffu, c[i]);
-}
-
-// The same counts for a site whose rows, as far as they are VALID, all show one base (`base`) -- the site is on the second pass
-// only because some rows are not valid (a gap is an allele, PolyFastA.py:256-258).  Only the flagged cells of the validity
-// plane can hold those rows, so only they are read: a few words instead of the whole record.  nq = rows of the population.
-__device__ __forceinline__ void pfa_coop_counts_gaps(const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
-                                                     const uint32_t* __restrict__ wv, const uint32_t* __restrict__ mq, int Wn, int lane,
-                                                     uint32_t c[PFA_NCLASS], uint32_t fw, int gcw, int base, uint32_t nq) {
-    uint32_t cg = 0, cn = 0, cq = 0, ce = 0;
-    for (uint32_t cells = fw; cells; cells &= cells - 1) {
-        const int w = (__ffs(cells) - 1) * gcw + lane;
-        if (lane < gcw && w < Wn) {
-            const uint32_t im = ~wv[w] & __ldg(mq + w), x0 = w0[w], x1 = w1[w];
-            ce += __popc(im & x1 & x0);
-            cq += __popc(im & x1 & ~x0);
-            cn += __popc(im & ~x1 & x0);
-            cg += __popc(im & ~x1 & ~x0);
-        }
-    }
-    cg = __reduce_add_sync(0xffffffffu, cg);
-    cn = __reduce_add_sync(0xffffffffu, cn);
-    cq = __reduce_add_sync(0xffffffffu, cq);
-    ce = __reduce_add_sync(0xffffffffu, ce);
-#pragma unroll
-    for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
-    c[PFA_C_N] = cn;
-    c[PFA_C_Q] = cq;
-    c[PFA_C_ESC] = ce;
-    const uint32_t valid = nq - (cg + cn + cq + ce);
-    c[PFA_C_A] = base == 0 ? valid : 0u;
-    c[PFA_C_C] = base == 1 ? valid : 0u;
-    c[PFA_C_G] = base == 2 ? valid : 0u;
-    c[PFA_C_T] = base == 3 ? valid : 0u;
 }
 
 // flags of pass 1 (bit 0/1: plane b0 shows a one / a zero among the rows of the union mask, 2/3: b1, 4/5: v)
@@ -275,6 +244,15 @@ __device__ __forceinline__ void pfa_bulk_load(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(pfa_smem_u32(bar))
                  : "memory");
 }
+// 16 bytes global -> shared by the calling thread, asynchronously (LDGSTS; no TMA request)
+__device__ __forceinline__ void pfa_cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pfa_smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// the mbarrier's current phase also waits for the cp.async copies this thread has issued so far (the pending count goes up by
+// one now and down again when they have landed)
+__device__ __forceinline__ void pfa_cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(pfa_smem_u32(bar)) : "memory");
+}
 // orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) accesses
 __device__ __forceinline__ void pfa_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
@@ -296,12 +274,14 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
 // Slot layout: [plane b0 | b1 | v][cap_sites][rec bytes], then cap_sites flag words.  Planes b0 and b1 always come whole, one
 // bulk copy each.  The v plane (HAS_V):
 //   * vflag == nullptr (dense): whole, a third bulk copy;
-//   * sparse: only the flagged cells of each site -- a cell = gc chunks of 16 bytes, one flag bit (pfa_aln::vflag) -- each with
-//     its own small bulk copy issued by the lane that holds the site's flag word; the flag words go into the slot so that the
-//     readers know which words of the v area are real (the others count as "all rows valid").  When more than a third of the
-//     cells of the block are flagged the whole range is fetched after all (flag words all ones).
-// All copies complete on the slot's mbarrier; lane 0 arms it last with the total byte count (bulk copies that finish before
-// the expect_tx only drive the transaction count negative for a moment; the phase cannot complete before lane 0 arrives).
+//   * sparse: only the flagged cells of each site -- a cell = gc chunks of 16 bytes, one flag bit (pfa_aln::vflag) -- copied
+//     chunk by chunk with cp.async (LDGSTS) by the lane that holds the site's flag word, which then adds those copies to the
+//     slot's mbarrier (cp.async.mbarrier.arrive).  A small cp.async.bulk per cell, the first version, cost ~100 cycles of an
+//     SM-wide serial resource each: 0.46 ms for the 1.26e6 gap cells of a 10,000 x 2 Mb shard at one gap per 10^4 bases, more
+//     than fetching the whole plane.  The flag words go into the slot so that the readers know which words of the v area are
+//     real (the others count as "all rows valid").  When more than a third of the cells of the block are flagged the whole
+//     range is fetched after all (flag words all ones).
+// All copies complete on the slot's mbarrier; lane 0 arrives last, with the byte count of the bulk copies.
 // Called by ALL lanes of the warp; fl[u] = flag word of site 32 u + lane of the block (sparse only).
 #define PFA_VF_REGS 2  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
 // Returns true when the block's v area (or part of it) was fetched; false: the block holds no flagged cell (or the kernel reads no
@@ -328,7 +308,6 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
         }
         return any_flag;
     }
-    unsigned vbytes = HAS_V ? nsite * rec : 0u;
     bool whole_v = HAS_V;
     if (HAS_V && sparse) {
         uint32_t* fa = reinterpret_cast<uint32_t*>(slot + (size_t)3 * cap_sites * rec);
@@ -339,7 +318,7 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
         cells = __reduce_add_sync(0xffffffffu, cells);
         const unsigned ncell = (unsigned)((Wq + gc - 1) / gc);
         whole_v = cells * 3u > nsite * ncell;
-        unsigned bytes = 0;
+        bool issued = false;
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u) {
             const unsigned si = (unsigned)(u * 32 + lane);
@@ -347,19 +326,19 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
                 fa[si] = whole_v ? 0xffffffffu : fl[u];
                 if (!whole_v)
                     for (uint32_t w = fl[u]; w; w &= w - 1) {
-                        const int c0 = (__ffs(w) - 1) * gc;
-                        const unsigned len = (unsigned)min(gc, Wq - c0) * 16u;
-                        pfa_bulk_load(slot + (size_t)2 * cap_sites * rec + (size_t)si * rec + (size_t)c0 * 16u, pv + (size_t)(s0 + si) * rec + (size_t)c0 * 16u, len, bar);
-                        bytes += len;
+                        const int c0 = (__ffs(w) - 1) * gc, c1 = min(c0 + gc, Wq);
+                        unsigned char* dst = slot + (size_t)2 * cap_sites * rec + (size_t)si * rec;
+                        const unsigned char* src = pv + (size_t)(s0 + si) * rec;
+                        for (int c = c0; c < c1; ++c) pfa_cp_async16(dst + (size_t)c * 16u, src + (size_t)c * 16u);
+                        issued = true;
                     }
             }
         }
-        bytes = __reduce_add_sync(0xffffffffu, bytes);
-        if (!whole_v) vbytes = bytes;
+        if (issued) pfa_cp_async_arrive(bar);
     }
-    __syncwarp();
+    __syncwarp();  // the cp.async arrivals are registered before lane 0's own arrival can complete the phase
     if (lane == 0) {
-        pfa_mbar_expect_tx(bar, 2u * nsite * rec + vbytes);
+        pfa_mbar_expect_tx(bar, (whole_v ? 3u : 2u) * nsite * rec);
         pfa_bulk_load(slot, p0 + (size_t)s0 * rec, nsite * rec, bar);
         pfa_bulk_load(slot + (size_t)cap_sites * rec, p1 + (size_t)s0 * rec, nsite * rec, bar);
         if (whole_v) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
