@@ -244,15 +244,6 @@ __device__ __forceinline__ void pfa_bulk_load(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(pfa_smem_u32(bar))
                  : "memory");
 }
-// 16 bytes global -> shared by the calling thread, asynchronously (LDGSTS; no TMA request)
-__device__ __forceinline__ void pfa_cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pfa_smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-// the mbarrier's current phase also waits for the cp.async copies this thread has issued so far (the pending count goes up by
-// one now and down again when they have landed)
-__device__ __forceinline__ void pfa_cp_async_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(pfa_smem_u32(bar)) : "memory");
-}
 // orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) accesses
 __device__ __forceinline__ void pfa_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
@@ -274,14 +265,17 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
 // Slot layout: [plane b0 | b1 | v][cap_sites][rec bytes], then cap_sites flag words.  Planes b0 and b1 always come whole, one
 // bulk copy each.  The v plane (HAS_V):
 //   * vflag == nullptr (dense): whole, a third bulk copy;
-//   * sparse: only the flagged cells of each site -- a cell = gc chunks of 16 bytes, one flag bit (pfa_aln::vflag) -- copied
-//     chunk by chunk with cp.async (LDGSTS) by the lane that holds the site's flag word, which then adds those copies to the
-//     slot's mbarrier (cp.async.mbarrier.arrive).  A small cp.async.bulk per cell, the first version, cost ~100 cycles of an
-//     SM-wide serial resource each: 0.46 ms for the 1.26e6 gap cells of a 10,000 x 2 Mb shard at one gap per 10^4 bases, more
-//     than fetching the whole plane.  The flag words go into the slot so that the readers know which words of the v area are
-//     real (the others count as "all rows valid").  When more than a third of the cells of the block are flagged the whole
-//     range is fetched after all (flag words all ones).
-// All copies complete on the slot's mbarrier; lane 0 arrives last, with the byte count of the bulk copies.
+//   * sparse: only the flagged cells of each site -- a cell = gc chunks of 16 bytes, one flag bit (pfa_aln::vflag) -- each with
+//     its own small bulk copy issued by the lane that holds the site's flag word; the flag words go into the slot so that the
+//     readers know which words of the v area are real (the others count as "all rows valid").  When more than a third of the
+//     cells of the block are flagged the whole range is fetched after all (flag words all ones).
+//     (Measured alternatives, 10,000 x 2 Mb at one gap per 10^4 bases, 1.22 ms: the cells chunk by chunk with cp.async /
+//     LDGSTS added to the mbarrier with cp.async.mbarrier.arrive 1.32 ms -- three copies and nine scheduling no-ops per cell; the
+//     decisions taken before the warp waits for its block and lane 0's bulk copies issued first 1.42 ms.  With every other
+//     site flagged the kernel is bound by instruction issue (ncu r2x: 970 instructions per pass of two sites, 60 % issue
+//     utilisation with four warps per scheduler), not by bytes or by the copy engine.)
+// All copies complete on the slot's mbarrier; lane 0 arms it last with the total byte count (bulk copies that finish before
+// the expect_tx only drive the transaction count negative for a moment; the phase cannot complete before lane 0 arrives).
 // Called by ALL lanes of the warp; fl[u] = flag word of site 32 u + lane of the block (sparse only).
 #define PFA_VF_REGS 2  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
 // Returns true when the block's v area (or part of it) was fetched; false: the block holds no flagged cell (or the kernel reads no
@@ -308,6 +302,7 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
         }
         return any_flag;
     }
+    unsigned vbytes = HAS_V ? nsite * rec : 0u;
     bool whole_v = HAS_V;
     if (HAS_V && sparse) {
         uint32_t* fa = reinterpret_cast<uint32_t*>(slot + (size_t)3 * cap_sites * rec);
@@ -318,7 +313,7 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
         cells = __reduce_add_sync(0xffffffffu, cells);
         const unsigned ncell = (unsigned)((Wq + gc - 1) / gc);
         whole_v = cells * 3u > nsite * ncell;
-        bool issued = false;
+        unsigned bytes = 0;
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u) {
             const unsigned si = (unsigned)(u * 32 + lane);
@@ -326,19 +321,19 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
                 fa[si] = whole_v ? 0xffffffffu : fl[u];
                 if (!whole_v)
                     for (uint32_t w = fl[u]; w; w &= w - 1) {
-                        const int c0 = (__ffs(w) - 1) * gc, c1 = min(c0 + gc, Wq);
-                        unsigned char* dst = slot + (size_t)2 * cap_sites * rec + (size_t)si * rec;
-                        const unsigned char* src = pv + (size_t)(s0 + si) * rec;
-                        for (int c = c0; c < c1; ++c) pfa_cp_async16(dst + (size_t)c * 16u, src + (size_t)c * 16u);
-                        issued = true;
+                        const int c0 = (__ffs(w) - 1) * gc;
+                        const unsigned len = (unsigned)min(gc, Wq - c0) * 16u;
+                        pfa_bulk_load(slot + (size_t)2 * cap_sites * rec + (size_t)si * rec + (size_t)c0 * 16u, pv + (size_t)(s0 + si) * rec + (size_t)c0 * 16u, len, bar);
+                        bytes += len;
                     }
             }
         }
-        if (issued) pfa_cp_async_arrive(bar);
+        bytes = __reduce_add_sync(0xffffffffu, bytes);
+        if (!whole_v) vbytes = bytes;
     }
-    __syncwarp();  // the cp.async arrivals are registered before lane 0's own arrival can complete the phase
+    __syncwarp();
     if (lane == 0) {
-        pfa_mbar_expect_tx(bar, (whole_v ? 3u : 2u) * nsite * rec);
+        pfa_mbar_expect_tx(bar, 2u * nsite * rec + vbytes);
         pfa_bulk_load(slot, p0 + (size_t)s0 * rec, nsite * rec, bar);
         pfa_bulk_load(slot + (size_t)cap_sites * rec, p1 + (size_t)s0 * rec, nsite * rec, bar);
         if (whole_v) pfa_bulk_load(slot + (size_t)2 * cap_sites * rec, pv + (size_t)s0 * rec, nsite * rec, bar);
