@@ -49,6 +49,13 @@ struct PfaPinned {
         std::fill(p, p + count, v);
         return true;
     }
+    // room for `count` elements, contents unspecified (about to be overwritten by a device-to-host copy): zero-filling
+    // 4 MB of pinned results per 10,000-locus scan was 0.4 ms, as long as the scan kernel itself
+    bool resize(size_t count) {
+        if (count > cap && !assign(count, T())) return false;
+        n = count;
+        return true;
+    }
     T* data() { return p; }
     const T* data() const { return p; }
     T& operator[](size_t i) { return p[i]; }
@@ -98,6 +105,7 @@ struct pfa_batch {
         int64_t n_heads = 0;
         unsigned long long n_exc = 0;
         size_t plane_bytes = 0;
+        int any_invalid = 0;  // some locus of the batch holds a symbol outside A, C, G, T (count[1], read back with the exception count)
         bool staged = false;
     } dev;
 };
@@ -196,7 +204,10 @@ __global__ void __launch_bounds__(256) pfa_batch_encode_kernel(const uint8_t* __
                 exc_keys[slot] = ((unsigned long long)(d.site_base + c0 + s) << 32) | ((unsigned long long)up << 24) | (unsigned long long)row;
         }
     }
-    if (__any_sync(0xffffffffu, any_invalid) && lane == 0) atomicOr(locus_invalid + li, 1);
+    if (__any_sync(0xffffffffu, any_invalid) && lane == 0) {
+        atomicOr(locus_invalid + li, 1);
+        if (exc_count[1] == 0ull) atomicOr(exc_count + 1, 1ull);  // exc_count[1]: the batch holds a locus with invalid rows
+    }
     if (c0 + lane < d.L) {
         const long long o = (d.plane_off + (c0 + lane) * d.Wq) * 4 + w;
         b0[o] = my0; b1[o] = my1; v[o] = myv;
@@ -411,6 +422,122 @@ __global__ void __launch_bounds__(PFA_SITE_THREADS, (LPS == 1 && ITER == 1) ? 3 
       }
     }
     if (QUEUE && qn) drain(qn);
+}
+
+// K2b for batches in which EVERY locus fits one 128-row chunk (n <= 128: C1, C2, C5) -- the site records of the whole batch are
+// then one contiguous array of 16-byte entries per plane (plane offset == global site number), and the kernel is the site
+// scan's TMA design on it: one CTA of 512 threads per SM, every warp owns a shared-memory slot of PFA_BATCH_SLOT consecutive
+// sites per plane fed by one cp.async.bulk per plane on the slot's mbarrier, refilled as soon as the last of its sites sits in
+// registers.  pfa_batch_site_kernel's per-lane 16-byte loads left 50 KB per SM in flight (3.2 TB/s of padded bytes on the
+// C5 shape).  With 16-byte records a slot holds MANY sites and scanning it takes as long as fetching it (one slot per warp:
+// 4.7 TB/s), so every warp has two slots: one is scanned while the other is on its way.  HV = some locus of the batch holds a non-ACGT symbol: the validity plane is
+// fetched too (for every locus; the planes of a clean locus say "all rows valid").  Lanes walk the loci as before (one
+// binary search per slot, done while the slot's bytes are on their way); variable sites go to the warp's queue.
+#define PFA_BATCH_SLOT 128     // sites per slot, two planes
+#define PFA_BATCH_SLOT_HV 96   // sites per slot, three planes
+#define PFA_BATCH_STAGES 2     // slots per warp: one is scanned while the other is on its way
+template <bool HV>
+__global__ void __launch_bounds__(512, 1) pfa_batch_site_tma_kernel(const PfaBatchArgs a) {
+    constexpr int NW = 16, SB = HV ? PFA_BATCH_SLOT_HV : PFA_BATCH_SLOT, NPL = HV ? 3 : 2;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    constexpr int ST = PFA_BATCH_STAGES;
+    constexpr size_t SLOT_BYTES = (size_t)NPL * SB * 16;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NW * ST * SLOT_BYTES);  // [NW][ST]
+    uint32_t* sqs = reinterpret_cast<uint32_t*>(bars + NW * ST);                      // [NW][PFA_BQ_WORDS][64]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NW * ST; ++i) pfa_mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned char* ring = dyn + (size_t)wib * ST * SLOT_BYTES;
+    uint64_t* bar = bars + wib * ST;
+    uint32_t* sq = sqs + (size_t)wib * PFA_BQ_WORDS * 64;
+    // every warp scans a CONTIGUOUS range of slots: its lanes walk the loci forward from one slot to the next, with one binary
+    // search per warp (a search per slot -- 17 dependent loads -- took longer than the slot's bytes: ncu r2y, long scoreboard
+    // 4.5 cycles per issue)
+    const long long nblk = (a.n_sites + SB - 1) / SB;
+    const long long nw = (long long)gridDim.x * NW, per = (nblk + nw - 1) / nw;
+    long long blk = ((long long)blockIdx.x * NW + wib) * per;
+    const long long blk_hi = min(nblk, blk + per);
+    auto issue = [&](long long bnext, int stage) {  // all lanes
+        __syncwarp();             // every lane has consumed its last values of the slot ...
+        pfa_fence_proxy_async();  // ... and those generic-proxy reads come before the async-proxy writes of the copies
+        if (lane == 0 && bnext < blk_hi) {
+            const long long s0 = bnext * SB;
+            const unsigned bytes = (unsigned)min((long long)SB, a.n_sites - s0) * 16u;
+            unsigned char* dst = ring + (size_t)stage * SLOT_BYTES;
+            pfa_mbar_expect_tx(bar + stage, NPL * bytes);
+            pfa_bulk_load(dst, a.b0 + s0, bytes, bar + stage);
+            pfa_bulk_load(dst + (size_t)SB * 16, a.b1 + s0, bytes, bar + stage);
+            if (HV) pfa_bulk_load(dst + (size_t)2 * SB * 16, a.v + s0, bytes, bar + stage);
+        }
+    };
+    int qn = 0;  // entries waiting in this warp's queue
+#pragma unroll
+    for (int st = 0; st < ST; ++st) issue(blk + st, st);
+    // this lane's first site and its locus
+    int li = blk < blk_hi ? pfa_find_locus(a.site_base, a.nloci, min(blk * SB + lane, a.n_sites - 1)) : 0;
+    PfaLocusDesc d = a.desc[li];
+    long long next_base = a.site_base[li + 1];
+    uint4 m = __ldg(a.masks + d.mask_off + d.k);  // union of the locus' populations (Wq == 1)
+    for (unsigned k = 0; blk < blk_hi; ++k, ++blk) {
+        const long long g_lo = blk * SB, g_hi = min(a.n_sites, g_lo + SB);
+        const int stage = (int)(k % ST);
+        const uint4* slot = reinterpret_cast<const uint4*>(ring + (size_t)stage * SLOT_BYTES);
+        pfa_mbar_wait(bar + stage, (k / ST) & 1u);
+#pragma unroll 1
+        for (int r = 0; r < SB / 32; ++r) {
+            const long long g = g_lo + r * 32 + lane;
+            const bool act = g < g_hi;
+            if (act && g >= next_base) {  // walked into a later locus
+                do {
+                    ++li;
+                    next_base = a.site_base[li + 1];
+                } while (g >= next_base);
+                d = a.desc[li];
+                m = __ldg(a.masks + d.mask_off + d.k);
+            }
+            // sites beyond the end of the batch read what the slot held before: dropped (act)
+            const uint4 y0 = slot[r * 32 + lane], y1 = slot[SB + r * 32 + lane];
+            const uint4 yv = HV ? slot[2 * SB + r * 32 + lane] : m;
+            const uint32_t o0 = (y0.x & m.x) | (y0.y & m.y) | (y0.z & m.z) | (y0.w & m.w);
+            const uint32_t z0 = (~y0.x & m.x) | (~y0.y & m.y) | (~y0.z & m.z) | (~y0.w & m.w);
+            const uint32_t o1 = (y1.x & m.x) | (y1.y & m.y) | (y1.z & m.z) | (y1.w & m.w);
+            const uint32_t z1 = (~y1.x & m.x) | (~y1.y & m.y) | (~y1.z & m.z) | (~y1.w & m.w);
+            const uint32_t ov = (yv.x & m.x) | (yv.y & m.y) | (yv.z & m.z) | (yv.w & m.w);
+            const uint32_t zv = (~yv.x & m.x) | (~yv.y & m.y) | (~yv.z & m.z) | (~yv.w & m.w);
+            const bool mono = !(o0 && z0) && !(o1 && z1) && !(ov && zv);
+            const bool all_escape = o0 && o1 && !ov;
+            const bool var = act && !(mono && !all_escape);
+            const unsigned vm = __ballot_sync(0xffffffffu, var);  // every lane's record has been looked at
+            if (r == SB / 32 - 1) issue(blk + ST, stage);
+            if (!vm) continue;
+            if (var) {
+                const int pos = qn + __popc(vm & ((1u << lane) - 1u));
+                sq[0 * 64 + pos] = y0.x; sq[1 * 64 + pos] = y0.y; sq[2 * 64 + pos] = y0.z; sq[3 * 64 + pos] = y0.w;
+                sq[4 * 64 + pos] = y1.x; sq[5 * 64 + pos] = y1.y; sq[6 * 64 + pos] = y1.z; sq[7 * 64 + pos] = y1.w;
+                sq[8 * 64 + pos] = yv.x; sq[9 * 64 + pos] = yv.y; sq[10 * 64 + pos] = yv.z; sq[11 * 64 + pos] = yv.w;
+                sq[12 * 64 + pos] = (uint32_t)li;
+            }
+            qn += __popc(vm);
+            if (qn >= 32) {
+                pfa_batch_drain(a, sq, 32, lane);
+                const int rest = qn - 32;  // move the entries behind the first 32 to the front
+                uint32_t keep[PFA_BQ_WORDS];
+                if (lane < rest)
+#pragma unroll
+                    for (int w = 0; w < PFA_BQ_WORDS; ++w) keep[w] = sq[w * 64 + 32 + lane];
+                __syncwarp();
+                if (lane < rest)
+#pragma unroll
+                    for (int w = 0; w < PFA_BQ_WORDS; ++w) sq[w * 64 + lane] = keep[w];
+                qn = rest;
+                __syncwarp();
+            }
+        }
+    }
+    if (qn) pfa_batch_drain(a, sq, qn, lane);
 }
 
 // sites with escape symbols: one warp per distinct (global) site of the sorted exception list
@@ -870,7 +997,7 @@ int pfa_batch_stage(pfa_batch* b) {
     BR(pfa_dmalloc(ctx, &d.planes, 3 * d.plane_bytes));
     BR(pfa_dmalloc(ctx, &d.masks, sizeof(uint32_t) * std::max<size_t>(b->masks.size(), 4)));
     BR(pfa_dmalloc(ctx, &d.inv, sizeof(int) * (size_t)nloci));
-    BR(pfa_dmalloc(ctx, &d.count, sizeof(unsigned long long)));
+    BR(pfa_dmalloc(ctx, &d.count, 2 * sizeof(unsigned long long)));  // [0] exceptions, [1] any locus with invalid rows
     BR(pfa_dmalloc(ctx, &d.keys, sizeof(unsigned long long) * (size_t)cap));
     BR(pfa_dmalloc(ctx, &d.fin_in, sizeof(pfa_final_in) * 2 * (size_t)npops));
     BR(pfa_dmalloc(ctx, &d.fin_out, sizeof(pfa_final_out) * 2 * (size_t)npops));
@@ -890,7 +1017,8 @@ int pfa_batch_stage(pfa_batch* b) {
     BR(cudaMemcpyAsync(d.masks, b->masks.data(), sizeof(uint32_t) * b->masks.size(), cudaMemcpyHostToDevice, st));
     BR(cudaMemsetAsync(d.planes, 0, 3 * d.plane_bytes, st));
     BR(cudaMemsetAsync(d.inv, 0, sizeof(int) * (size_t)nloci, st));
-    BR(cudaMemsetAsync(d.count, 0, sizeof(unsigned long long), st));
+    BR(cudaMemsetAsync(d.count, 0, 2 * sizeof(unsigned long long), st));
+    d.any_invalid = 0;
     if (e == cudaSuccess && b->n_tiles > 0) {
         uint32_t* p0 = reinterpret_cast<uint32_t*>(d.planes);
         uint32_t* p1 = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d.planes) + d.plane_bytes);
@@ -901,10 +1029,12 @@ int pfa_batch_stage(pfa_batch* b) {
             ctx->launches++;
             e = cudaGetLastError();
             // exception list: one small synchronisation per batch
-            unsigned long long count = 0;
-            BR(cudaMemcpyAsync(&count, d.count, sizeof(count), cudaMemcpyDeviceToHost, st));
+            unsigned long long counts[2] = {0, 0};
+            BR(cudaMemcpyAsync(counts, d.count, sizeof(counts), cudaMemcpyDeviceToHost, st));
             BR(cudaStreamSynchronize(st));
             if (e != cudaSuccess) break;
+            const unsigned long long count = counts[0];
+            d.any_invalid = counts[1] != 0;
             d.n_exc = count;
             if ((long long)count <= cap) break;
             // more symbols outside ACGT-N? than the list was sized for (dense IUPAC codes, '.', '*' ...: every character is an
@@ -917,7 +1047,7 @@ int pfa_batch_stage(pfa_batch* b) {
             d.keys = nullptr;
             cap = (long long)count;
             BR(pfa_dmalloc(ctx, &d.keys, sizeof(unsigned long long) * (size_t)cap));
-            BR(cudaMemsetAsync(d.count, 0, sizeof(unsigned long long), st));
+            BR(cudaMemsetAsync(d.count, 0, 2 * sizeof(unsigned long long), st));
         }
         if (e == cudaSuccess && !rc && d.n_exc > 0) rc = pfa_sort_exceptions(ctx, &d.keys, (int64_t)d.n_exc, &d.heads, &d.n_heads);
     }
@@ -956,15 +1086,16 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
     pfa_batch::Dev& d = b->dev;
     const int nloci = (int)b->desc.size();
     const long long npops = (long long)b->pops.size();
-    bool ok = b->out.assign((size_t)b->out_len, 0) && b->fin.assign((size_t)npops, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
-    b->ran = true;
-    b->ran_cds = cds != 0;
-    if (cds) {
-        ok = ok && b->cds_out.assign((size_t)npops * PFA_CDS_LEN, 0) && b->cds_ssites.assign((size_t)npops, 0.0) &&
-             b->cds_fin.assign((size_t)npops * 2, pfa_final_out{0.0, 0.0, 0.0, 1, 1});
-    }
+    // every element of these is written by the copies at the end of the scan (an empty batch has none)
+    bool ok = b->out.resize((size_t)b->out_len) && b->fin.resize((size_t)npops);
+    b->ran = b->ran_cds = false;  // results become readable when the scan has succeeded
+    if (cds) ok = ok && b->cds_out.resize((size_t)npops * PFA_CDS_LEN) && b->cds_ssites.resize((size_t)npops) && b->cds_fin.resize((size_t)npops * 2);
     if (!ok) return pfa_fail(ctx, PFA_ERR_NOMEM, "cannot pin the result buffers of the batch");
-    if (nloci == 0) return PFA_OK;
+    if (nloci == 0) {
+        b->ran = true;
+        b->ran_cds = cds != 0;
+        return PFA_OK;
+    }
     PFA_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc = PFA_OK;
@@ -990,6 +1121,23 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
         int lps = 1;
         while (lps < 32 && (b->max_Wq + lps - 1) / lps > 4) lps *= 2;
         const int iter = (b->max_Wq + lps - 1) / lps;
+        // every locus in one 128-row chunk: the TMA variant (PFA_BATCH_TMA=0 turns it off)
+        const bool tma = b->max_Wq == 1 && b->plane_u4 == b->n_sites && !(getenv("PFA_BATCH_TMA") && atoi(getenv("PFA_BATCH_TMA")) == 0);
+        if (tma) {
+            const bool hv = d.any_invalid != 0;
+            const int sb = hv ? PFA_BATCH_SLOT_HV : PFA_BATCH_SLOT;
+            const size_t dyn = (size_t)16 * PFA_BATCH_STAGES * (hv ? 3 : 2) * sb * 16 + 16 * PFA_BATCH_STAGES * sizeof(uint64_t) + (size_t)16 * PFA_BQ_WORDS * 64 * sizeof(uint32_t);
+            const long long nblk = (b->n_sites + sb - 1) / sb;
+            const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, (nblk + 15) / 16);
+            if (hv) {
+                BR(cudaFuncSetAttribute(pfa_batch_site_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                if (e == cudaSuccess) pfa_batch_site_tma_kernel<true><<<grid, 512, dyn, st>>>(args);
+            } else {
+                BR(cudaFuncSetAttribute(pfa_batch_site_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                if (e == cudaSuccess) pfa_batch_site_tma_kernel<false><<<grid, 512, dyn, st>>>(args);
+            }
+        } else
+        {
         const long long chunks = (b->n_sites + PFA_BATCH_SCHUNK - 1) / PFA_BATCH_SCHUNK;   // one warp per chunk at a time
         long long blocks = (chunks + PFA_SITE_THREADS / 32 - 1) / (PFA_SITE_THREADS / 32);
         blocks = std::min<long long>(std::max<long long>(blocks, 1), (long long)ctx->sm_count * 8);
@@ -999,6 +1147,7 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
         PFA_B_CASE(8, 3) PFA_B_CASE(8, 4) PFA_B_CASE(16, 3) PFA_B_CASE(16, 4) PFA_B_CASE(32, 3) PFA_B_CASE(32, 4)
         rc = pfa_fail(ctx, PFA_ERR_ARG, "batched path: a locus has too many sequences (Wq=%d); use the single-alignment path", b->max_Wq);
 #undef PFA_B_CASE
+        }
         ctx->launches++;
         e = cudaGetLastError();
         if (e == cudaSuccess && !rc && d.n_heads > 0) {
@@ -1042,6 +1191,8 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
 #undef BR
     if (rc) return rc;
     if (e != cudaSuccess) return pfa_fail(ctx, PFA_ERR_CUDA, "batched run failed: %s", cudaGetErrorString(e));
+    b->ran = true;
+    b->ran_cds = cds != 0;
     return PFA_OK;
 }
 
