@@ -721,6 +721,37 @@ def test_batch_many_short_rows(ctx, tmp_path):
     batch.close()
 
 
+@pytest.mark.parametrize("p_junk", [0.0, 0.01])
+def test_batch_of_narrow_loci_tma_scan(ctx, monkeypatch, p_junk):
+    """every locus of the batch has at most 128 rows: the batched site scan runs as pfa_batch_site_tma_kernel on the contiguous
+    site records of the whole batch (slots of 128 / 96 sites that span many tiny loci, loci that span many slots, empty loci, a
+    last slot that is not full; with non-ACGT symbols the validity plane travels too).  Against the C oracle, and the per-lane
+    kernel (PFA_BATCH_TMA=0) must book the same numbers."""
+    rng = np.random.default_rng(77 + int(p_junk * 100))
+    shapes = [(100, 5000), (3, 1), (128, 700), (20, 0), (64, 33), (5, 2), (2, 129), (90, 4097), (128, 95), (17, 640), (1, 50)] + \
+             [(int(rng.integers(2, 129)), int(rng.integers(1, 60))) for _ in range(40)]
+    loci = []
+    for i, (n, L) in enumerate(shapes):
+        text = _random_text(rng, n, L, p_junk=p_junk, p_var=0.1) if L else np.zeros((n, 0), dtype=np.uint8)
+        pops = None if i % 3 else [p for p in (list(range(0, n, 2)), list(range(n // 2, n)), list(range(n))) if p]
+        loci.append((text, pops))
+    results = []
+    for tma in ("1", "0"):
+        monkeypatch.setenv("PFA_BATCH_TMA", tma)
+        batch = pf.api.Batch(ctx)
+        idx = [batch.add_rows(text, pops) for text, pops in loci]
+        batch.run(jc=False)
+        results.append([[batch.result(i, q, want_sfs=True) for q in range(len(pops or [0]))] for i, (text, pops) in zip(idx, loci)])
+        batch.close()
+    for (text, pops), got_tma, got_lane in zip(loci, *results):
+        n, L = text.shape
+        up = _upper(text)
+        for q, rows in enumerate(pops or [list(range(n))]):
+            want = co.site_stats(up, rows) if L else {"S": 0, "H": 0, "sfs": [0] * (len(rows) // 2)}
+            for got in (got_tma[q], got_lane[q]):
+                assert (got["n"], got["S"], got["H"], got["sfs"]) == (len(rows), want["S"], want["H"], want["sfs"]), (n, L, q)
+
+
 def test_batch_codon_scan(ctx):
     """K4b: the segmented codon scan of the batched --dir --cds path == the single-alignment K4 == the C oracle, for loci of
     mixed shapes (lengths not divisible by 3, shorter than a codon, more rows than one tile column handles), populations and
@@ -758,7 +789,7 @@ def test_batch_codon_scan(ctx):
 
 
 @pytest.mark.parametrize("n,L,gap_ppm,k", [(2000, 60_000, 100, 2), (10_000, 6_000, 100, 1), (10_000, 3_000, 2_000, 2), (700, 50_001, 30, 3),
-                                          (4100, 9_000, 5, 2), (12_000, 3_003, 400, 1)])
+                                          (4100, 9_000, 5, 2), (12_000, 3_003, 400, 1), (2000, 30_000, 100, 6), (10_000, 6_000, 10, 3)])
 def test_sparse_validity_flags(ctx, monkeypatch, n, L, gap_ppm, k):
     """alignments with a FEW gaps: the TMA scans fetch only the flagged 128-row pieces of the validity plane (per-site flag
     words written by the encoders, pfa_slot_issue).  The gapped synthetic alignment is built twice -- on the device (generator +
@@ -768,7 +799,8 @@ def test_sparse_validity_flags(ctx, monkeypatch, n, L, gap_ppm, k):
     seed = 11 + n
     text = synth.poke_gaps(synth.text_matrix(seed, n, L), seed, gap_ppm)
     assert (text == ord("-")).sum() > 0
-    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n // 2))][:k]
+    # six populations on groups of four lanes: the gap sites of populations 4 and 5 go through shared-memory atomics
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n // 2)), list(range(1, n, 3)), list(range(n // 2, n)), list(range(5, n, 7))][:k]
     dev = pf.Alignment.synthetic(ctx, n, L, seed)
     dev.poke_gaps(seed, gap_ppm)
     host = pf.Alignment.from_rows(ctx, text)
@@ -809,7 +841,7 @@ def test_narrow_records_many_variable_sites(ctx, n, L):
     aln.free()
 
 
-@pytest.mark.parametrize("n,L,k", [(2000, 60_000, 2), (5000, 9_000, 1), (700, 30_003, 3)])
+@pytest.mark.parametrize("n,L,k", [(2000, 60_000, 2), (5000, 9_000, 1), (700, 30_003, 3), (2000, 30_000, 3), (10_000, 6_000, 2)])
 def test_missing_data_runs_in_cds(ctx, n, L, k):
     """what a real CDS alignment holds: gaps aligned to codons, runs of N across codon borders, a few '?' and IUPAC codes, on top
     of the base variation -- the codon scan's missing-data-only path (valid rows of every site show one base; only the flagged
@@ -826,6 +858,14 @@ def test_missing_data_runs_in_cds(ctx, n, L, k):
     text[rr, cc] = np.frombuffer(b"?RY", dtype=np.uint8)[rng.integers(0, 3, 60)]
     text[: n // 2, 300:306] = ord("-")      # a gap carried by half of the rows: more flagged cells than the short path takes
     text[:, 600:603] = ord("-")             # a codon column nobody shows
+    # gap-only columns are settled in pass 1 when every population keeps a clean row; here no row is clean (first half
+    # misses site 900, second half site 901) although each site shows one base among its valid rows, ...
+    text[:, 900:903] = np.frombuffer(b"ACG", dtype=np.uint8)
+    text[: n // 2, 900] = ord("-")
+    text[n // 2:, 901] = ord("N")
+    # ... and here the third population (rows n/3 .. n/2) loses all its rows while the others keep theirs
+    text[:, 1200:1203] = np.frombuffer(b"TGA", dtype=np.uint8)
+    text[n // 3: n // 2, 1201] = ord("-")
     pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n // 2))][:k]
     aln = pf.Alignment.from_rows(ctx, text)
     assert aln.has_invalid
