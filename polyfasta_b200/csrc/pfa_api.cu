@@ -457,6 +457,36 @@ int pfa_ctx_work(pfa_ctx* ctx, unsigned int** out) {
     return PFA_OK;
 }
 
+// number of sites of the shard whose validity flag word is not zero (counted once per alignment, one small synchronisation;
+// the TMA scans size the validity area of their slots from it)
+__global__ void pfa_count_flagged_kernel(const uint32_t* __restrict__ vflag, int64_t ns, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += (int64_t)gridDim.x * blockDim.x) c += vflag[i] != 0u;
+    c = __reduce_add_sync(0xffffffffu, (unsigned)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int pfa_aln_flagged_sites(pfa_aln* a, int64_t* out) {
+    if (a->vflag_sites < 0) {
+        pfa_ctx* ctx = a->ctx;
+        unsigned long long* d = nullptr;
+        unsigned long long h = 0;
+        PFA_CUDA(ctx, pfa_dmalloc(ctx, &d, sizeof(unsigned long long)));
+        PFA_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+        if (a->ns > 0 && a->vflag) {
+            const unsigned blocks = (unsigned)std::min<int64_t>((a->ns + 255) / 256, (int64_t)ctx->sm_count * 8);
+            pfa_count_flagged_kernel<<<blocks, 256, 0, ctx->stream>>>(a->vflag, a->ns, d);
+            PFA_LAUNCH_CHECK(ctx);
+        }
+        PFA_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        PFA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pfa_dfree(ctx, d);
+        a->vflag_sites = (int64_t)h;
+    }
+    *out = a->vflag_sites;
+    return PFA_OK;
+}
+
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args) {
     memset(&args->x, 0, sizeof args->x);
     args->work = a->ctx->d_work;
@@ -473,6 +503,7 @@ void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaS
     args->ns = a->ns;
     args->vflag = nullptr;  // the launchers switch the sparse validity fetch on
     args->gc = a->gc;
+    args->vs = 0;
     args->Wq = a->Wq;
     args->k = a->k;
     int64_t bins = 0;

@@ -715,11 +715,12 @@ __device__ __forceinline__ uint32_t pfa_site_h32(const uint32_t c[PFA_NCLASS], u
 }
 
 // second pass of ONE variable codon column by the whole warp (pfa_sites.cuh): r0 / r1 / rv point to the record of the
-// column's first site in the warp's shared-memory slot (32-bit words; the next site follows Wn words later); f = the 18
+// column's first site in the warp's shared-memory slot (32-bit words; the next site follows Wn words later), rv[t] to the
+// validity record of site t (pfa_slot_vrec: the three need not be neighbours); f = the 18
 // flag bits of pass 1 (6 per site)
 template <bool HAS_V, bool MULTI>
 __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0, unsigned f, const uint32_t* r0, const uint32_t* r1,
-                                             const uint32_t* rv, int Wn, int lane, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount,
+                                             const uint32_t* const (&rv)[3], int Wn, int lane, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount,
                                              const uint32_t (&fw)[3], int gcw, unsigned f2) {
     // Missing data only: at each of the three sites the valid rows show ONE base, and the rows that are not valid sit in a few
     // flagged cells.  The rows valid at all three sites then carry one and the same codon: the presence mask has at most that
@@ -749,7 +750,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
 #pragma unroll
                     for (int t = 0; t < 3; ++t)
                         if ((fw[t] >> cell) & 1u) {
-                            const uint32_t inv = ~rv[t * Wn + w] & m;
+                            const uint32_t inv = ~rv[t][w] & m;
                             any |= inv;
                             nesc += __popc(inv & r1[t * Wn + w] & r0[t * Wn + w]);
                         }
@@ -792,7 +793,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
             // exactly one site varies, the other two show one valid base: the clean codons are that fixed pair combined with
             // the bases present at the variable site, and only that position can carry a label
             uint32_t c[PFA_NCLASS];
-            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, rv + tv * Wn, mq, Wn, lane, c, tv == 0 ? fw[0] : tv == 1 ? fw[1] : fw[2], gcr);
+            pfa_coop_counts<HAS_V>(r0 + tv * Wn, r1 + tv * Wn, tv == 0 ? rv[0] : tv == 1 ? rv[1] : rv[2], mq, Wn, lane, c, tv == 0 ? fw[0] : tv == 1 ? fw[1] : fw[2], gcr);
             if (HAS_V && c[PFA_C_ESC]) continue;  // finished by pfa_cds_escape_kernel
             const int shift = 2 * (2 - tv);
 #pragma unroll
@@ -817,7 +818,7 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
                 for (int t = 0; t < 3; ++t) {
                     const uint32_t w0 = r0[t * Wn + w], w1 = r1[t * Wn + w];
                     uint32_t wv = 0xffffffffu;  // words of an unflagged cell were not fetched: all rows valid
-                    if (HAS_V && ((fw[t] >> (((unsigned)w * gcr) >> 16)) & 1u)) wv = rv[t * Wn + w];
+                    if (HAS_V && ((fw[t] >> (((unsigned)w * gcr) >> 16)) & 1u)) wv = rv[t][w];
                     const uint32_t vm = HAS_V ? (wv & m) : m;
                     const uint32_t hi = vm & w1, lo = vm & ~w1;
                     cnt[t][PFA_C_T] += __popc(hi & w0);
@@ -883,14 +884,15 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
 // pfa_site_scan_tma_kernel).
 template <int LPS, int ITER, bool HAS_V, bool MULTI, class Refill>
 __device__ __forceinline__ void pfa_cds_tma_pass(const PfaCdsArgs& a, const unsigned char* slot, int CPS, unsigned rec, int t0, int64_t blk,
-                                                 const uint4 (&um)[ITER], const int (&cell)[ITER], bool bv, bool sparse, int gcw, int lane,
+                                                 const uint4 (&um)[ITER], const int (&cell)[ITER], bool bv, bool sparse, unsigned VS, int gcw, int lane,
                                                  int sub, int grp, unsigned gmask, unsigned long long* sm_acc, uint32_t* qbuf, int& qcount,
                                                  unsigned& u_nstops, unsigned& u_missing, unsigned& u_sum3, bool last, Refill&& refill) {
     constexpr int GW = 32 / LPS;
     const int Wq = a.s.Wq, SPS = CPS * 3;
     const int idx = t0 * GW + grp;  // codon column of this group inside the slot
     const int64_t cc = blk * CPS + idx;
-    const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
+    const uint32_t* fa = pfa_slot_flags(slot, (unsigned)SPS, VS, rec);  // flag words of the slot's sites (sparse)
+    const unsigned char* gv = reinterpret_cast<const unsigned char*>(a.s.v);
     uint4 x0[3][ITER], x1[3][ITER];
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
@@ -924,8 +926,9 @@ __device__ __forceinline__ void pfa_cds_tma_pass(const PfaCdsArgs& a, const unsi
         uint4 xv[3][ITER];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx * 3 + t) * rec);
             const uint32_t fwt = sparse ? fa[idx * 3 + t] : 0xffffffffu;
+            const uint4* qv = reinterpret_cast<const uint4*>(
+                pfa_slot_vrec(slot, (unsigned)SPS, VS, rec, sparse, idx * 3 + t, gv + (size_t)((cc < a.ncf ? cc : 0) * 3 + t) * rec));
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
                 xv[t][i] = um[i];
@@ -980,11 +983,16 @@ __device__ __forceinline__ void pfa_cds_tma_pass(const PfaCdsArgs& a, const unsi
 #pragma unroll
             for (int t = 0; t < 3; ++t) fw3[t] = sparse ? fa[vidx * 3 + t] : 0xffffffffu;
         }
-        if (HAS_V && (fw3[0] | fw3[1] | fw3[2]))
-            pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, r0, r1, reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx * 3) * rec),
-                                       Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, fv2);
-        else
-            pfa_cds_coop<false, MULTI>(a, (blk * CPS + vidx) * 3, fv, r0, r1, r0, Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, 0xfffu);
+        const uint32_t* rv3[3] = {r0, r0, r0};
+        if (HAS_V && (fw3[0] | fw3[1] | fw3[2])) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                rv3[t] = reinterpret_cast<const uint32_t*>(
+                    pfa_slot_vrec(slot, (unsigned)SPS, VS, rec, sparse, vidx * 3 + t, gv + (size_t)((blk * CPS + vidx) * 3 + t) * rec));
+            pfa_cds_coop<HAS_V, MULTI>(a, (blk * CPS + vidx) * 3, fv, r0, r1, rv3, Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, fv2);
+        } else {
+            pfa_cds_coop<false, MULTI>(a, (blk * CPS + vidx) * 3, fv, r0, r1, rv3, Wq * 4, lane, sm_acc, qbuf, qcount, fw3, gcw, 0xfffu);
+        }
     }
     if (last) refill();
     if (uniform && sub == 0 && cc < a.ncf) {  // the same single codon for every population
@@ -1011,7 +1019,8 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
     const unsigned rec = (unsigned)Wq * 16u;  // one site record in one plane
     const int CPS = GW * m;                   // codon columns per slot
     const int SPS = CPS * 3;                  // sites per slot
-    const unsigned slot_bytes = (unsigned)NPL * SPS * rec + (HAS_V ? (((unsigned)SPS * 4u + 15u) & ~15u) : 0u);  // pfa_slot_issue
+    const unsigned VS = HAS_V ? (a.s.vs > 0 ? (unsigned)a.s.vs : (unsigned)SPS) : 0u;  // validity records per slot (pfa_slot_issue)
+    const unsigned slot_bytes = (unsigned)pfa_slot_bytes(HAS_V, (unsigned)SPS, VS, rec);
     const bool sparse = HAS_V && a.s.vflag != nullptr;  // fetch only the flagged cells of the v plane
     const int gc = a.s.gc, gcw = a.s.gc * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + (size_t)NWARP * stages * slot_bytes);
@@ -1073,7 +1082,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         if (blk >= 0) {
             const int64_t c0 = (int64_t)blk * CPS;
             pend_v = pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, c0 * 3, 3u * (unsigned)min((int64_t)CPS, a.ncf - c0),
-                                           (unsigned)SPS, rec, Wq, pfl, lane);
+                                           (unsigned)SPS, VS, rec, Wq, pfl, lane);
         }
         pend = blk >= 0 ? next_block() : -1;
         load_flags();
@@ -1093,7 +1102,7 @@ __global__ void __launch_bounds__(NT, 1) pfa_cds_scan_tma_kernel(const PfaCdsArg
         };
         for (int t0 = 0; t0 < m; ++t0) {
             if (COOP) {
-                pfa_cds_tma_pass<LPS, ITER, HAS_V, MULTI>(a, slot, CPS, rec, t0, blk, um, cell, bv, sparse, gcw, lane, sub, grp, gmask, sm_acc, qbuf, qcount,
+                pfa_cds_tma_pass<LPS, ITER, HAS_V, MULTI>(a, slot, CPS, rec, t0, blk, um, cell, bv, sparse, VS, gcw, lane, sub, grp, gmask, sm_acc, qbuf, qcount,
                                                           u_nstops, u_missing, u_sum3, t0 == m - 1, refill);
             } else {
                 const int idx = t0 * GW + grp;  // codon column of this group inside the slot
@@ -1291,7 +1300,7 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
     if (const char* e = getenv("PFA_CDS_TMA")) tma_stages = std::max(0, std::min(1, atoi(e)));  // 0: off; one slot per warp
     if (tma_stages > 0 && !generic && a->ns >= 3) {
         const int nt = iter >= 3 ? 256 : 512;
-        const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
+        const int gw = 32 / lps, nwarp = nt / 32;
         int m = (int)std::max<int64_t>(1, 10000 / ((int64_t)gw * 3 * a->Wq * 16));
         if (const char* e = getenv("PFA_CDS_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: fetch only the flagged pieces of the v plane (see pfa_launch_site_scan)
@@ -1300,13 +1309,25 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
             args.s.vflag = a->vflag;
             m = std::max(1, std::min(m, 32 * PFA_VF_REGS / (3 * gw)));
         }
+        // sparse validity: the fewer sites are flagged, the smaller the slots' v area and the more passes per slot (see
+        // pfa_launch_site_scan); 2,000 rows: two passes per slot as in the pure-ACGT kernel instead of one
+        int64_t flagged_sites = 0;
+        if (sparse_v)
+            if (int rc = pfa_aln_flagged_sites(a, &flagged_sites)) return rc;
+        int v_div = 1;  // v area = sites per slot / v_div records (at least one codon column)
+        if (sparse_v && !(getenv("PFA_VCOMPACT") && atoi(getenv("PFA_VCOMPACT")) == 0))
+            v_div = flagged_sites * 64 <= a->ns ? 8 : flagged_sites * 16 <= a->ns ? 4 : flagged_sites * 4 <= a->ns ? 2 : 1;
+        if (sparse_v && getenv("PFA_VDIV")) v_div = std::max(1, std::min(8, atoi(getenv("PFA_VDIV"))));  // tests: force a small v area
+        if (v_div > 1 && !getenv("PFA_CDS_TMA_M")) m = std::max(1, std::min(m + (m + 1) / 2, 32 * PFA_VF_REGS / (3 * gw)));
+        auto vs_for = [&](int mm) { return hv ? std::max(3, 3 * gw * mm / v_div) : 0; };
         auto dyn_for = [&](int mm) {
-            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * 3 * a->Wq * 16 + (hv ? (((size_t)gw * mm * 12 + 15) & ~(size_t)15) : 0)) +
+            return (size_t)nwarp * tma_stages * pfa_slot_bytes(hv, (unsigned)(3 * gw * mm), (unsigned)vs_for(mm), (unsigned)a->Wq * 16u) +
                    sizeof(uint64_t) * nwarp * tma_stages + smem + 1024 /* unconditional chunk loads may run past the last record */ +
                    (lps >= 4 ? (size_t)nwarp * PFA_CDS_QFIELDS * 32 * sizeof(uint32_t) : 0);
         };
-        while (m > 1 && dyn_for(m) > 220 * 1024) --m;
+        while (m > 1 && dyn_for(m) > PFA_TMA_SMEM_MAX) --m;
         const size_t dyn = dyn_for(m);
+        args.s.vs = vs_for(m);
         const int64_t per_cta = (int64_t)gw * m * nwarp;
         const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (std::max<int64_t>(args.ncf, 1) + per_cta - 1) / per_cta);
         bool launched = false;
@@ -1314,10 +1335,10 @@ int pfa_launch_cds_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_labels, pfa_xchg*
         {                                                                                                                 \
             cudaFuncSetAttribute(pfa_cds_scan_tma_kernel<L_, I_, V_, M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
             pfa_cds_scan_tma_kernel<L_, I_, V_, M_, N_><<<tgrid, N_, dyn, st>>>(args, tma_stages, m);                      \
-            pfa_note_kernel(ctx, "pfa_cds_scan_tma_kernel<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d,NT=%d> grid=%u slots=%d passes_per_slot=%d", L_, I_, (int)V_, (int)M_, N_, tgrid, tma_stages, m); \
+            pfa_note_kernel(ctx, "pfa_cds_scan_tma_kernel<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d,NT=%d> grid=%u slots=%d passes_per_slot=%d v_records_per_slot=%d", L_, I_, (int)V_, (int)M_, N_, tgrid, tma_stages, m, args.s.vs); \
         }
 #define PFA_CDS_TMA_CASE(L_, I_, N_)                                                                                    \
-        if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
+        if (!launched && lps == L_ && iter == I_ && dyn <= PFA_TMA_SMEM_MAX) {                                                  \
             if (hv && multi) PFA_CDS_TMA_LAUNCH(L_, I_, true, true, N_)                                                   \
             else if (hv) PFA_CDS_TMA_LAUNCH(L_, I_, true, false, N_)                                                      \
             else if (multi) PFA_CDS_TMA_LAUNCH(L_, I_, false, true, N_)                                                   \

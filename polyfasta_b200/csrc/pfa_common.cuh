@@ -55,6 +55,7 @@ struct pfa_aln {
     // validity flags, one 32-bit word per site: bit c is set when one of the chunks [c*gc, (c+1)*gc) of the site's v record holds
     // a zero among the real rows.  Written by the encoders; the TMA scans fetch only flagged pieces of the v plane.
     uint32_t* vflag = nullptr;
+    int64_t vflag_sites = -1;  // sites with a flag word != 0 (-1: not counted yet; pfa_aln_flagged_sites)
     int gc = 1;  // chunks (16 bytes = 128 rows) per flag bit: ceil(Wq / 32)
     // exception list: sorted keys (site:32 | byte:8 | row:24), heads = first index of every distinct site
     unsigned long long* exc_keys = nullptr;

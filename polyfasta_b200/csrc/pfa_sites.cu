@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
     const int Wq = a.Wq;
     const unsigned rec = (unsigned)Wq * 16u;  // bytes of one site record in one plane
     const int SPS = GW * m;                   // sites per slot: m passes of the warp (narrow records: keeps a copy >= ~2 KB)
-    const unsigned slot_bytes = (unsigned)NPL * SPS * rec + (HAS_V ? (((unsigned)SPS * 4u + 15u) & ~15u) : 0u);  // pfa_slot_issue
+    const unsigned VS = HAS_V ? (a.vs > 0 ? (unsigned)a.vs : (unsigned)SPS) : 0u;  // validity records per slot (pfa_slot_issue)
+    const unsigned slot_bytes = (unsigned)pfa_slot_bytes(HAS_V, (unsigned)SPS, VS, rec);
     const bool sparse = HAS_V && a.vflag != nullptr;  // fetch only the flagged cells of the v plane
     const int gc = a.gc;
     const unsigned gcr = pfa_cell_rcp(a.gc * 4);
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
         if (blk >= 0) {
             const int64_t s0 = (int64_t)blk * SPS;
             pend_v = pfa_slot_issue<HAS_V>(ring, bar, planes[0], planes[1], planes[2], sparse, gc, s0, (unsigned)min((int64_t)SPS, a.ns - s0),
-                                           (unsigned)SPS, rec, Wq, pfl, lane);
+                                           (unsigned)SPS, VS, rec, Wq, pfl, lane);
         }
         pend = blk >= 0 ? next_block() : -1;
         load_flags();
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                 const int64_t s = blk * SPS + idx;
                 const uint4* q0 = reinterpret_cast<const uint4*>(slot + (size_t)idx * rec);
                 const uint4* q1 = reinterpret_cast<const uint4*>(slot + (size_t)(SPS + idx) * rec);
-                const uint32_t* fa = reinterpret_cast<const uint32_t*>(slot + (size_t)3 * SPS * rec);  // flag words of the slot's sites (sparse)
+                const uint32_t* fa = pfa_slot_flags(slot, (unsigned)SPS, VS, rec);  // flag words of the slot's sites (sparse)
                 uint4 x0[ITER], x1[ITER];
                 // unconditional loads: chunks beyond the record and sites beyond the end read whatever lies there in the slot (the
                 // allocation is padded); every use is masked (those chunks' masks are zero) or dropped (s >= ns)
@@ -585,8 +586,9 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                     const unsigned f = pfa_site_pass1<LPS, ITER, false, false>(x0, x1, um, um, gmask);
                     var = s < a.ns && !pfa_flags_bases_mono(f);
                 } else {
-                    const uint4* qv = reinterpret_cast<const uint4*>(slot + (size_t)(2 * SPS + idx) * rec);
                     const uint32_t fw = sparse ? fa[idx] : 0xffffffffu;
+                    const uint4* qv = reinterpret_cast<const uint4*>(
+                        pfa_slot_vrec(slot, (unsigned)SPS, VS, rec, sparse, idx, planes[2] + (size_t)(s < a.ns ? s : 0) * rec));
                     uint4 mv[ITER];  // rows of the union that are valid
 #pragma unroll
                     for (int i = 0; i < ITER; ++i) {
@@ -621,7 +623,8 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                     const uint32_t* r1 = reinterpret_cast<const uint32_t*>(slot + (size_t)(SPS + vidx) * rec);
                     const uint32_t fwv = !(HAS_V && bv) ? 0u : sparse ? fa[vidx] : 0xffffffffu;
                     if (HAS_V && fwv)
-                        pfa_site_coop<LPS, HAS_V, MULTI>(a, blk * SPS + vidx, r0, r1, reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * SPS + vidx) * rec),
+                        pfa_site_coop<LPS, HAS_V, MULTI>(a, blk * SPS + vidx, r0, r1,
+                                                         reinterpret_cast<const uint32_t*>(pfa_slot_vrec(slot, (unsigned)SPS, VS, rec, sparse, vidx, planes[2] + (size_t)(blk * SPS + vidx) * rec)),
                                                          Wq * 4, lane, sm_SH, sm_sfs, S_mine, H_mine, fwv, gcr);
                     else
                         pfa_site_coop<LPS, false, MULTI>(a, blk * SPS + vidx, r0, r1, r0, Wq * 4, lane, sm_SH, sm_sfs, S_mine, H_mine, 0u, 0u);
@@ -749,7 +752,7 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     if (const char* e = getenv("PFA_SITE_TMA_MIN_LPS")) use_tma = lps >= std::max(1, atoi(e));
     if (tma_stages > 0 && !generic && use_tma) {
         const int nt = 512;
-        const int planes = hv ? 3 : 2, gw = 32 / lps, nwarp = nt / 32;
+        const int gw = 32 / lps, nwarp = nt / 32;
         int m = (int)std::max<int64_t>(1, 5000 / ((int64_t)gw * a->Wq * 16));
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: a shard with a few non-ACGT symbols fetches only the flagged pieces of its v plane (pfa_slot_issue);
@@ -759,12 +762,25 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
             args.vflag = a->vflag;
             m = std::min(m, 32 * PFA_VF_REGS / gw);
         }
+        // sparse validity: the fewer sites are flagged, the smaller the slots' v area (a half, a quarter of a plane) and the more
+        // shared memory goes into passes per slot -- with two passes per slot the validity-aware kernel runs a clean or nearly
+        // clean 10,000-row shard as fast as the pure-ACGT kernel (0.73 against 0.77 ms with one; scripts/probe_gaps5.py)
+        int64_t flagged_sites = 0;
+        if (sparse_v)
+            if (int rc = pfa_aln_flagged_sites(a, &flagged_sites)) return rc;
+        int v_div = 1;  // v area = sites per slot / v_div records
+        if (sparse_v && !(getenv("PFA_VCOMPACT") && atoi(getenv("PFA_VCOMPACT")) == 0))
+            v_div = flagged_sites * 16 <= a->ns ? 4 : flagged_sites * 4 <= a->ns ? 2 : 1;
+        if (sparse_v && getenv("PFA_VDIV")) v_div = std::max(1, std::min(8, atoi(getenv("PFA_VDIV"))));  // tests: force a small v area
+        if (v_div > 1 && !getenv("PFA_SITE_TMA_M")) m = std::min(2 * m, 32 * PFA_VF_REGS / gw);
+        auto vs_for = [&](int mm) { return hv ? std::max(1, gw * mm / v_div) : 0; };
         auto dyn_for = [&](int mm) {
-            return (size_t)nwarp * tma_stages * ((size_t)planes * gw * mm * a->Wq * 16 + (hv ? (((size_t)gw * mm * 4 + 15) & ~(size_t)15) : 0)) +
+            return (size_t)nwarp * tma_stages * pfa_slot_bytes(hv, (unsigned)(gw * mm), (unsigned)vs_for(mm), (unsigned)a->Wq * 16u) +
                    sizeof(uint64_t) * nwarp * tma_stages + smem + 1024;  // + slack: unconditional chunk loads may run past the last record
         };
-        while (m > 1 && dyn_for(m) > 220 * 1024) --m;
+        while (m > 1 && dyn_for(m) > PFA_TMA_SMEM_MAX) --m;
         const size_t dyn = dyn_for(m);
+        args.vs = vs_for(m);
         const int64_t per_cta = (int64_t)gw * m * nwarp;
         const unsigned tgrid = (unsigned)std::min<int64_t>(ctx->sm_count, (a->ns + per_cta - 1) / per_cta);
         bool launched = false;
@@ -772,10 +788,10 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         {                                                                                                                 \
             cudaFuncSetAttribute(pfa_site_scan_tma_kernel<L_, I_, V_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
             pfa_site_scan_tma_kernel<L_, I_, V_, M_><<<tgrid, nt, dyn, st>>>(args, tma_stages, m);                         \
-            pfa_note_kernel(ctx, "pfa_site_scan_tma_kernel<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d> grid=%u block=%d slots=%d passes_per_slot=%d", L_, I_, (int)V_, (int)M_, tgrid, nt, tma_stages, m); \
+            pfa_note_kernel(ctx, "pfa_site_scan_tma_kernel<LPS=%d,ITER=%d,HAS_V=%d,MULTI=%d> grid=%u block=%d slots=%d passes_per_slot=%d v_records_per_slot=%d", L_, I_, (int)V_, (int)M_, tgrid, nt, tma_stages, m, args.vs); \
         }
 #define PFA_TMA_CASE(L_, I_)                                                                                            \
-        if (!launched && lps == L_ && iter == I_ && dyn <= 220 * 1024) {                                                  \
+        if (!launched && lps == L_ && iter == I_ && dyn <= PFA_TMA_SMEM_MAX) {                                                  \
             if (hv && multi) PFA_TMA_LAUNCH(L_, I_, true, true)                                                           \
             else if (hv) PFA_TMA_LAUNCH(L_, I_, true, false)                                                              \
             else if (multi) PFA_TMA_LAUNCH(L_, I_, false, true)                                                           \

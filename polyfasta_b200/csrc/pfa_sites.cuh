@@ -32,6 +32,7 @@ struct PfaSiteArgs {
     int sfs_bins;  // total bins over all populations
     const uint32_t* vflag;  // per-site validity flags (pfa_aln::vflag) or nullptr: fetch the whole v plane
     int gc;                 // chunks per flag bit
+    int vs;                 // validity records per slot of the TMA kernels (pfa_slot_issue); 0: as many as sites
     unsigned int* work;  // [2], zero between launches: next block to claim / CTAs done (TMA kernels, pfa_ctx_work)
     PfaXchgDev x;  // x.world > 0: the last block sums `out` over the column shards of all GPUs (pfa_xchg.cuh)
 };
@@ -262,13 +263,18 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
 
 
 // ---- fetching one block of consecutive site records into a warp's shared-memory slot ------------------------------------------
-// Slot layout: [plane b0 | b1 | v][cap_sites][rec bytes], then cap_sites flag words.  Planes b0 and b1 always come whole, one
-// bulk copy each.  The v plane (HAS_V):
-//   * vflag == nullptr (dense): whole, a third bulk copy;
+// Slot layout: [plane b0: cap_sites records | b1: cap_sites records | v: vs records], then cap_sites flag words and cap_sites
+// rank bytes (HAS_V).  Planes b0 and b1 always come whole, one bulk copy each.  The v plane (HAS_V):
+//   * vflag == nullptr (dense; vs == cap_sites): whole, a third bulk copy;
 //   * sparse: only the flagged cells of each site -- a cell = gc chunks of 16 bytes, one flag bit (pfa_aln::vflag) -- each with
-//     its own small bulk copy issued by the lane that holds the site's flag word; the flag words go into the slot so that the
-//     readers know which words of the v area are real (the others count as "all rows valid").  When more than a third of the
-//     cells of the block are flagged the whole range is fetched after all (flag words all ones).
+//     its own small bulk copy issued by the lane that holds the site's flag word.  The v area holds the records of the FLAGGED
+//     sites side by side (rank = number of flagged sites before it in the block): an alignment with few flagged sites gets a
+//     v area of a quarter of a plane (vs = cap_sites / 4, chosen at launch from the density of vflag) and spends the shared
+//     memory on more passes per slot instead.  The flag words and ranks go into the slot so that the readers know which
+//     words of which record are real (the others count as "all rows valid").  A flagged site beyond the v area (rank >= vs:
+//     rare by construction) gets rank 0xff and is read from global memory when it is scanned (pfa_slot_vrec).  With a full v
+//     area (vs == cap_sites), when more than a third of the cells of the block are flagged the whole range is fetched after
+//     all (flag words all ones, rank = site).
 //     (Measured alternatives, 10,000 x 2 Mb at one gap per 10^4 bases, 1.22 ms: the cells chunk by chunk with cp.async /
 //     LDGSTS added to the mbarrier with cp.async.mbarrier.arrive 1.32 ms -- three copies and nine scheduling no-ops per cell; the
 //     decisions taken before the warp waits for its block and lane 0's bulk copies issued first 1.42 ms.  With every other
@@ -278,12 +284,36 @@ __device__ __forceinline__ void pfa_mbar_wait(uint64_t* bar, unsigned parity) {
 // the expect_tx only drive the transaction count negative for a moment; the phase cannot complete before lane 0 arrives).
 // Called by ALL lanes of the warp; fl[u] = flag word of site 32 u + lane of the block (sparse only).
 #define PFA_VF_REGS 2  // sparse validity: at most 32 * PFA_VF_REGS sites per slot
+#define PFA_TMA_SMEM_MAX ((size_t)226 * 1024)  // dynamic shared memory of a TMA scan CTA (227 KB per block on sm_100, 128 bytes static)
+__host__ __device__ __forceinline__ unsigned pfa_slot_meta_bytes(unsigned cap_sites) {  // flag words + rank bytes
+    return ((cap_sites * 4u + 15u) & ~15u) + ((cap_sites + 15u) & ~15u);
+}
+__host__ __device__ __forceinline__ size_t pfa_slot_bytes(bool has_v, unsigned cap_sites, unsigned vs, unsigned rec) {
+    return (size_t)(2u * cap_sites + (has_v ? vs : 0u)) * rec + (has_v ? pfa_slot_meta_bytes(cap_sites) : 0u);
+}
+__device__ __forceinline__ uint32_t* pfa_slot_flags(unsigned char* slot, unsigned cap_sites, unsigned vs, unsigned rec) {
+    return reinterpret_cast<uint32_t*>(slot + (size_t)(2u * cap_sites + vs) * rec);
+}
+__device__ __forceinline__ const uint32_t* pfa_slot_flags(const unsigned char* slot, unsigned cap_sites, unsigned vs, unsigned rec) {
+    return reinterpret_cast<const uint32_t*>(slot + (size_t)(2u * cap_sites + vs) * rec);
+}
+__device__ __forceinline__ const uint8_t* pfa_slot_ranks(const unsigned char* slot, unsigned cap_sites, unsigned vs, unsigned rec) {
+    return slot + (size_t)(2u * cap_sites + vs) * rec + ((cap_sites * 4u + 15u) & ~15u);
+}
+// the validity record of site idx of the slot (a generic pointer: shared or global memory); gsite = that site's record in the
+// v plane in global memory
+__device__ __forceinline__ const unsigned char* pfa_slot_vrec(const unsigned char* slot, unsigned cap_sites, unsigned vs, unsigned rec, bool sparse,
+                                                              int idx, const unsigned char* gsite) {
+    if (!sparse) return slot + (size_t)(2u * cap_sites + (unsigned)idx) * rec;
+    const unsigned rk = pfa_slot_ranks(slot, cap_sites, vs, rec)[idx];
+    return rk == 0xffu ? gsite : slot + (size_t)(2u * cap_sites + rk) * rec;
+}
 // Returns true when the block's v area (or part of it) was fetched; false: the block holds no flagged cell (or the kernel reads no
 // validity plane at all) and its sites can be scanned as pure ACGT.
 template <bool HAS_V>
 __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* bar, const unsigned char* p0, const unsigned char* p1,
                                                const unsigned char* pv, bool sparse, int gc, int64_t s0, unsigned nsite, unsigned cap_sites,
-                                               unsigned rec, int Wq, const uint32_t (&fl)[PFA_VF_REGS], int lane) {
+                                               unsigned vs, unsigned rec, int Wq, const uint32_t (&fl)[PFA_VF_REGS], int lane) {
     __syncwarp();             // every lane has its last values of the slot's previous contents (consumed by pass 1) ...
     pfa_fence_proxy_async();  // ... and those generic-proxy reads come before the async-proxy writes of the copies
     bool any_flag = HAS_V;
@@ -305,25 +335,32 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
     unsigned vbytes = HAS_V ? nsite * rec : 0u;
     bool whole_v = HAS_V;
     if (HAS_V && sparse) {
-        uint32_t* fa = reinterpret_cast<uint32_t*>(slot + (size_t)3 * cap_sites * rec);
+        uint32_t* fa = pfa_slot_flags(slot, cap_sites, vs, rec);
+        uint8_t* ra = const_cast<uint8_t*>(pfa_slot_ranks(slot, cap_sites, vs, rec));
         unsigned cells = 0;
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u)
             if ((unsigned)(u * 32) < nsite && (unsigned)(u * 32 + lane) < nsite) cells += __popc(fl[u]);
         cells = __reduce_add_sync(0xffffffffu, cells);
         const unsigned ncell = (unsigned)((Wq + gc - 1) / gc);
-        whole_v = cells * 3u > nsite * ncell;
-        unsigned bytes = 0;
+        whole_v = vs == cap_sites && cells * 3u > nsite * ncell;
+        unsigned bytes = 0, base = 0;
 #pragma unroll
         for (int u = 0; u < PFA_VF_REGS; ++u) {
             const unsigned si = (unsigned)(u * 32 + lane);
-            if ((unsigned)(u * 32) < nsite && si < nsite) {
+            const bool live = (unsigned)(u * 32) < nsite && si < nsite;
+            const unsigned flagged = __ballot_sync(0xffffffffu, live && fl[u] != 0u);
+            const unsigned rank = base + (unsigned)__popc(flagged & ((1u << lane) - 1u));
+            base += (unsigned)__popc(flagged);
+            if (live) {
+                const bool resident = whole_v || (fl[u] != 0u && rank < vs);
                 fa[si] = whole_v ? 0xffffffffu : fl[u];
-                if (!whole_v)
+                ra[si] = (uint8_t)(whole_v ? si : resident ? rank : 0xffu);
+                if (!whole_v && resident)
                     for (uint32_t w = fl[u]; w; w &= w - 1) {
                         const int c0 = (__ffs(w) - 1) * gc;
                         const unsigned len = (unsigned)min(gc, Wq - c0) * 16u;
-                        pfa_bulk_load(slot + (size_t)2 * cap_sites * rec + (size_t)si * rec + (size_t)c0 * 16u, pv + (size_t)(s0 + si) * rec + (size_t)c0 * 16u, len, bar);
+                        pfa_bulk_load(slot + (size_t)(2u * cap_sites + rank) * rec + (size_t)c0 * 16u, pv + (size_t)(s0 + si) * rec + (size_t)c0 * 16u, len, bar);
                         bytes += len;
                     }
             }
@@ -342,3 +379,4 @@ __device__ __forceinline__ bool pfa_slot_issue(unsigned char* slot, uint64_t* ba
 }
 
 void pfa_fill_site_args(const pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, PfaSiteArgs* args);
+int pfa_aln_flagged_sites(pfa_aln* a, int64_t* out);

@@ -819,6 +819,26 @@ def test_sparse_validity_flags(ctx, monkeypatch, n, L, gap_ppm, k):
     assert "HAS_V=1" in res[0][2]
 
 
+@pytest.mark.parametrize("n,L,gap_ppm,k", [(2000, 30_000, 300, 2), (10_000, 4_002, 100, 1), (5000, 9_000, 50, 3)])
+def test_validity_area_overflow(ctx, monkeypatch, n, L, gap_ppm, k):
+    """the slots of the sparse-validity scans hold the validity records of a FRACTION of their sites (sized from the density
+    of flagged sites); flagged sites beyond that are read from global memory when they are scanned.  Forced here: an eighth of
+    the sites (PFA_VDIV=8) on alignments in which a third to most of the sites hold a gap -- most flagged sites overflow."""
+    seed = 5 + n
+    text = synth.poke_gaps(synth.text_matrix(seed, n, L), seed, gap_ppm)
+    pops = [list(range(n)), list(range(0, n, 2)), list(range(n // 3, n // 2))][:k]
+    aln = pf.Alignment.from_rows(ctx, text)
+    aln.set_pops(pops)
+    res = []
+    for vdiv in ("8", "2", "1"):
+        monkeypatch.setenv("PFA_VDIV", vdiv)
+        res.append((aln.site_stats(want_isvar=True), aln.cds_stats(want_labels=True)))
+        assert "v_records_per_slot" in ctx.last_kernel
+    aln.free()
+    for site, cds in res:
+        _check_site_cds(site, cds, text, pops, (n, L, gap_ppm))
+
+
 @pytest.mark.parametrize("n,L", [(20, 300_000), (64, 200_000), (200, 100_000), (380, 60_000), (1100, 30_000)])
 def test_narrow_records_many_variable_sites(ctx, n, L):
     """records handled by 1-2 lanes per site (every lane of a warp its own site, no shuffle inside a pass) with a third of the
