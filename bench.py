@@ -692,6 +692,7 @@ def run_c5(args, env):
         elapsed_ms, _, launches, clocks = env.timed_steps(args, step)
         # the segmented site kernel is timed inside the library (CUDA events around it, pfa_batch_kernel_ms)
         kernel_ms = env.max_over_ranks(sum(ms_acc[-args.steps:]) / args.steps)
+        kernel_name = ctx.last_kernel or "pfa_batch_site_kernel"
     my_bases = n * L * len(mine)
     value = n * L * loci * args.steps / (elapsed_ms * 1e-3)
     algo_bytes = my_bases * 2 / 8.0
@@ -784,7 +785,7 @@ def run_c5(args, env):
            "loci_per_gpu": len(mine), "loci_per_resident_batch": per_batch, "planes_read": 2, "seed": "%d + locus" % C5_SEED,
            "record_layout": "n = 100 rows in 128-bit records: the planes hold 1.28 x the algorithmic bytes"}
     return {"value": value, "elapsed_ms": elapsed_ms, "scaling": "strong", "config": cfg,
-            "roofline": roofline("pfa_batch_site_kernel<LPS=1,ITER=1> (segmented over %d loci per launch)" % per_batch, kernel_ms, algo_bytes,
+            "roofline": roofline("%s (segmented over %d loci per launch)" % (kernel_name, per_batch), kernel_ms, algo_bytes,
                                  traffic_for("C5 n=%d sites=%d" % (n, L))),
             "e2e": e2e, "launches": launches, "clocks": clocks, "parity": parity,
             "result": {"locus0": {"S": first["S"], "H": first["H"], "poly": list(first["poly"])}}}

@@ -425,7 +425,16 @@ def process_chunk_native(ctx, batch, paths, jc, popkeys, threads, cds=False):
             break
     t2 = time.perf_counter()
     if pending:
-        batch.run(jc, cds)
+        if os.environ.get("POLYFASTA_TIMING"):  # the three steps of Batch.run, timed one by one
+            ta = time.perf_counter()
+            batch.stage()
+            tb = time.perf_counter()
+            batch.scan(jc, cds)
+            tc = time.perf_counter()
+            batch.release()
+            print("  gpu run: stage %.1f ms, scan %.1f ms, release %.1f ms" % ((tb - ta) * 1e3, (tc - tb) * 1e3, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
+        else:
+            batch.run(jc, cds)
         t3 = time.perf_counter()
         for pos, locus, q, file, seqlen, label, n in pending:
             if cds:

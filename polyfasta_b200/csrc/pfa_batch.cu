@@ -1121,8 +1121,13 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
         int lps = 1;
         while (lps < 32 && (b->max_Wq + lps - 1) / lps > 4) lps *= 2;
         const int iter = (b->max_Wq + lps - 1) / lps;
-        // every locus in one 128-row chunk: the TMA variant (PFA_BATCH_TMA=0 turns it off)
-        const bool tma = b->max_Wq == 1 && b->plane_u4 == b->n_sites && !(getenv("PFA_BATCH_TMA") && atoi(getenv("PFA_BATCH_TMA")) == 0);
+        // every locus in one 128-row chunk: the TMA variant (PFA_BATCH_TMA=0 turns it off, =1 forces it).  Not for small batches:
+        // its CTAs take a whole SM's shared memory, and in the --dir loop (chunks of 512 loci, two staging slots per GPU) a
+        // scan then waits until the other slot's encode kernel has left the SMs -- 0.2 -> 2.4 ms per scan on average, 24 -> 33 us
+        // per locus end to end (the per-lane kernel needs 0.2 ms for such a chunk either way)
+        const char* tma_env = getenv("PFA_BATCH_TMA");
+        const bool tma = b->max_Wq == 1 && b->plane_u4 == b->n_sites && !(tma_env && atoi(tma_env) == 0) &&
+                         (b->n_sites >= ((long long)16 << 20) || (tma_env && atoi(tma_env) == 1));
         if (tma) {
             const bool hv = d.any_invalid != 0;
             const int sb = hv ? PFA_BATCH_SLOT_HV : PFA_BATCH_SLOT;
@@ -1136,6 +1141,7 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
                 BR(cudaFuncSetAttribute(pfa_batch_site_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
                 if (e == cudaSuccess) pfa_batch_site_tma_kernel<false><<<grid, 512, dyn, st>>>(args);
             }
+            pfa_note_kernel(ctx, "pfa_batch_site_tma_kernel<HV=%d> grid=%u block=512 slots=%d sites_per_slot=%d", (int)hv, grid, PFA_BATCH_STAGES, sb);
         } else
         {
         const long long chunks = (b->n_sites + PFA_BATCH_SCHUNK - 1) / PFA_BATCH_SCHUNK;   // one warp per chunk at a time
@@ -1147,6 +1153,7 @@ int pfa_batch_scan(pfa_batch* b, int jc, int cds) {
         PFA_B_CASE(8, 3) PFA_B_CASE(8, 4) PFA_B_CASE(16, 3) PFA_B_CASE(16, 4) PFA_B_CASE(32, 3) PFA_B_CASE(32, 4)
         rc = pfa_fail(ctx, PFA_ERR_ARG, "batched path: a locus has too many sequences (Wq=%d); use the single-alignment path", b->max_Wq);
 #undef PFA_B_CASE
+        if (!rc) pfa_note_kernel(ctx, "pfa_batch_site_kernel<LPS=%d,ITER=%d> grid=%u block=%d", lps, iter, (unsigned)blocks, PFA_SITE_THREADS);
         }
         ctx->launches++;
         e = cudaGetLastError();

@@ -753,7 +753,8 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
     if (tma_stages > 0 && !generic && use_tma) {
         const int nt = 512;
         const int gw = 32 / lps, nwarp = nt / 32;
-        int m = (int)std::max<int64_t>(1, 5000 / ((int64_t)gw * a->Wq * 16));
+        const int64_t pass_bytes = (int64_t)gw * a->Wq * 16;  // one pass of a warp, per plane
+        int m = (int)std::max<int64_t>(1, (5000 + pass_bytes / 2) / pass_bytes);  // nearest to 5 KB (C4: 2 x 2.5 KB, 3.49 ms; 1 x: 3.55)
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: a shard with a few non-ACGT symbols fetches only the flagged pieces of its v plane (pfa_slot_issue);
         // not when the validity plane is forced (benchmarks of the 3-plane worst case) or PFA_VFLAG=0

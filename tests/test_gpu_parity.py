@@ -736,7 +736,7 @@ def test_batch_of_narrow_loci_tma_scan(ctx, monkeypatch, p_junk):
         pops = None if i % 3 else [p for p in (list(range(0, n, 2)), list(range(n // 2, n)), list(range(n))) if p]
         loci.append((text, pops))
     results = []
-    for tma in ("1", "0"):
+    for tma in ("1", "0"):   # 1: forced (small batches take the per-lane kernel by default)
         monkeypatch.setenv("PFA_BATCH_TMA", tma)
         batch = pf.api.Batch(ctx)
         idx = [batch.add_rows(text, pops) for text, pops in loci]
