@@ -870,6 +870,40 @@ __device__ __forceinline__ void pfa_cds_coop(const PfaCdsArgs& a, int64_t site0,
     }
 }
 
+// pass 1 of a codon column that has flagged cells: mv[t] = the lane's slice of "row of the union AND valid at site t" (the
+// site scan's formulation, pfa_site_pass1_valid: everything follows from that one mask per site).  Per site t, six bits at
+// 6 t in the layout of pfa_cds_pass1: bits 0-3 the base planes over the VALID rows, bit 4 some row is valid, bit 5 some row is
+// not.  Bit 18: a row valid at all three sites exists; bit 19: an escape row (not valid, both base bits set) exists.
+template <int LPS, int ITER>
+__device__ __forceinline__ unsigned pfa_cds_pass1_valid(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&mv)[3][ITER],
+                                                        const uint4 (&um)[ITER], unsigned gmask) {
+    unsigned f = 0;
+    uint32_t cl = 0, es = 0;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i)
+        cl |= (mv[0][i].x & mv[1][i].x & mv[2][i].x) | (mv[0][i].y & mv[1][i].y & mv[2][i].y) | (mv[0][i].z & mv[1][i].z & mv[2][i].z) |
+              (mv[0][i].w & mv[1][i].w & mv[2][i].w);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const uint4 m = mv[t][i];
+            const uint4 iv = make_uint4(um[i].x ^ m.x, um[i].y ^ m.y, um[i].z ^ m.z, um[i].w ^ m.w);  // rows that are not valid
+            zv |= iv.x | iv.y | iv.z | iv.w;
+            ov |= m.x | m.y | m.z | m.w;
+            es |= (iv.x & x0[t][i].x & x1[t][i].x) | (iv.y & x0[t][i].y & x1[t][i].y) | (iv.z & x0[t][i].z & x1[t][i].z) | (iv.w & x0[t][i].w & x1[t][i].w);
+            o0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
+            z0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
+            o1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
+            z1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
+        }
+        f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
+    }
+    f |= (cl ? 1u << 18 : 0u) | (es ? 1u << 19 : 0u);
+    return pfa_group_or<LPS>(f, gmask);
+}
+
 // One pass of a warp of the TMA kernel over GW codon columns of its slot (whole-warp second pass, LPS >= 4).  V = the block
 // carries validity pieces; blocks without a flagged cell run the two-plane instantiation as separate code (see
 // pfa_site_tma_pass).
@@ -906,10 +940,17 @@ __device__ __forceinline__ void pfa_cds_tma_pass(const PfaCdsArgs& a, const unsi
             x1[t][i] = q1[sub + LPS * i];
         }
     }
-    unsigned f, f2 = 0xfffu;  // f2: "bases vary" unless pass 1 finds otherwise
+    unsigned f, f2 = 0xfffu;  // f2: the base planes over the valid rows, four bits per site ("bases vary" unless pass 1 finds otherwise)
     bool uniform = true, clean = true;
     int codon = 0;
-    if (!(HAS_V && bv)) {
+    // the flag words of this column's sites: a column without a flagged cell runs the two-plane pass 1 even inside a block that
+    // carries validity pieces (group-uniform branch; in a sparse alignment most columns of a flagged block are clean)
+    uint32_t fwg[3] = {0u, 0u, 0u};
+    if (HAS_V && bv && cc < a.ncf) {  // a column beyond the end of the shard (last block) has no flag words in the slot
+#pragma unroll
+        for (int t = 0; t < 3; ++t) fwg[t] = sparse ? fa[idx * 3 + t] : 0xffffffffu;
+    }
+    if (!(HAS_V && bv) || !(fwg[0] | fwg[1] | fwg[2])) {
         uint4 xv[3][ITER];
 #pragma unroll
         for (int t = 0; t < 3; ++t)
@@ -923,53 +964,51 @@ __device__ __forceinline__ void pfa_cds_tma_pass(const PfaCdsArgs& a, const unsi
             codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
         }
     } else {
-        uint4 xv[3][ITER];
+        uint4 mv[3][ITER];  // rows of the union that are valid at site t
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            const uint32_t fwt = sparse ? fa[idx * 3 + t] : 0xffffffffu;
             const uint4* qv = reinterpret_cast<const uint4*>(
                 pfa_slot_vrec(slot, (unsigned)SPS, VS, rec, sparse, idx * 3 + t, gv + (size_t)((cc < a.ncf ? cc : 0) * 3 + t) * rec));
 #pragma unroll
             for (int i = 0; i < ITER; ++i) {
-                xv[t][i] = um[i];
-                if ((fwt >> cell[i]) & 1u) xv[t][i] = qv[sub + LPS * i];
+                mv[t][i] = um[i];
+                if ((fwg[t] >> cell[i]) & 1u) {
+                    const uint4 v4 = qv[sub + LPS * i];
+                    mv[t][i] = make_uint4(um[i].x & v4.x, um[i].y & v4.y, um[i].z & v4.z, um[i].w & v4.w);
+                }
             }
         }
-        f = pfa_cds_pass1<LPS, ITER, true>(x0, x1, xv, um, gmask, &f2);
+        f = pfa_cds_pass1_valid<LPS, ITER>(x0, x1, mv, um, gmask);
+        bool bases_mono = true, some_invalid = false;
+        f2 = 0u;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const unsigned ft = (f >> (6 * t)) & 63u;
-            uniform = uniform && pfa_flags_mono(ft) && !pfa_flags_all_escape(ft);
-            clean = clean && (ft & 16u) && !(ft & 32u);
+            bases_mono = bases_mono && pfa_flags_bases_mono(ft);
+            some_invalid = some_invalid || (ft & 32u);
             codon = (codon << 2) | ((ft & 4u) ? 2 : 0) | ((ft & 1u) ? 1 : 0);
+            f2 |= (ft & 15u) << (4 * t);
         }
-        if (!uniform) {
-            bool gapcol = !((f2 >> 13) & 1u);  // no escape row
+        // at every site the valid rows show ONE base and no row is an escape: as long as every population keeps a row valid at
+        // all three sites the column contributes what a monomorphic column does
+        uniform = false;
+        if (bases_mono && !((f >> 19) & 1u)) {  // group-uniform
+            bool every_pop_clean = !some_invalid || ((f >> 18) & 1u);  // one population: a clean row exists
+            if (MULTI && some_invalid) {
+                uint32_t inv = 0;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const unsigned g = (f2 >> (4 * t)) & 15u;
-                gapcol = gapcol && ((g & 3u) != 3u) && ((g & 12u) != 12u);
+                for (int i = 0; i < ITER; ++i) {
+                    inv += __popc(~(mv[0][i].x & mv[1][i].x & mv[2][i].x) & um[i].x) + __popc(~(mv[0][i].y & mv[1][i].y & mv[2][i].y) & um[i].y) +
+                           __popc(~(mv[0][i].z & mv[1][i].z & mv[2][i].z) & um[i].z) + __popc(~(mv[0][i].w & mv[1][i].w & mv[2][i].w) & um[i].w);
+                }
+                every_pop_clean = pfa_group_add<LPS>(inv, gmask) < (uint32_t)a.min_nq;
             }
-            if (gapcol) {  // group-uniform
-                bool every_pop_clean = ((f2 >> 12) & 1u) != 0u;  // one population: a row valid at all three sites exists
-                if (MULTI) {
-                    uint32_t inv = 0;
-#pragma unroll
-                    for (int i = 0; i < ITER; ++i) {
-                        inv += __popc(~(xv[0][i].x & xv[1][i].x & xv[2][i].x) & um[i].x) + __popc(~(xv[0][i].y & xv[1][i].y & xv[2][i].y) & um[i].y) +
-                               __popc(~(xv[0][i].z & xv[1][i].z & xv[2][i].z) & um[i].z) + __popc(~(xv[0][i].w & xv[1][i].w & xv[2][i].w) & um[i].w);
-                    }
-                    every_pop_clean = pfa_group_add<LPS>(inv, gmask) < (uint32_t)a.min_nq;
-                }
-                if (every_pop_clean || !MULTI) {
-                    uniform = true;
-                    clean = every_pop_clean;  // one population without a clean row: every codon is missing
-                    codon = 0;
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) codon = (codon << 2) | (((f2 >> (4 * t)) & 4u) ? 2 : 0) | (((f2 >> (4 * t)) & 1u) ? 1 : 0);
-                }
+            if (every_pop_clean || !MULTI) {
+                uniform = true;
+                clean = every_pop_clean;  // one population without a clean row: every codon is missing
             }
         }
+        f &= 0x3ffffu;  // the whole-warp pass reads the six bits per site
     }
     // variable columns: the whole warp, one at a time, from the slot
     for (unsigned rest = __ballot_sync(0xffffffffu, !uniform && sub == 0 && cc < a.ncf); rest; rest &= rest - 1) {

@@ -586,7 +586,8 @@ __global__ void __launch_bounds__(512, 1) pfa_site_scan_tma_kernel(const PfaSite
                     const unsigned f = pfa_site_pass1<LPS, ITER, false, false>(x0, x1, um, um, gmask);
                     var = s < a.ns && !pfa_flags_bases_mono(f);
                 } else {
-                    const uint32_t fw = sparse ? fa[idx] : 0xffffffffu;
+                    // a site beyond the end of the shard (last block) has no flag word in the slot: what lies there is stale
+                    const uint32_t fw = s >= a.ns ? 0u : sparse ? fa[idx] : 0xffffffffu;
                     const uint4* qv = reinterpret_cast<const uint4*>(
                         pfa_slot_vrec(slot, (unsigned)SPS, VS, rec, sparse, idx, planes[2] + (size_t)(s < a.ns ? s : 0) * rec));
                     uint4 mv[ITER];  // rows of the union that are valid

@@ -306,7 +306,7 @@ __device__ __forceinline__ const unsigned char* pfa_slot_vrec(const unsigned cha
                                                               int idx, const unsigned char* gsite) {
     if (!sparse) return slot + (size_t)(2u * cap_sites + (unsigned)idx) * rec;
     const unsigned rk = pfa_slot_ranks(slot, cap_sites, vs, rec)[idx];
-    return rk == 0xffu ? gsite : slot + (size_t)(2u * cap_sites + rk) * rec;
+    return rk >= vs ? gsite : slot + (size_t)(2u * cap_sites + rk) * rec;  // 0xff: not in the v area
 }
 // Returns true when the block's v area (or part of it) was fetched; false: the block holds no flagged cell (or the kernel reads no
 // validity plane at all) and its sites can be scanned as pure ACGT.

@@ -54,9 +54,9 @@ elif which == "k1":
         print("k1", ctx.ingest_stats())
         a.free()
 elif which == "k2b":
-    # the batched site scan on the C5 shape: 2,500 resident loci of 100 x 5 kb
+    # the batched site scan on the C5 shape: 4,000 resident loci of 100 x 5 kb
     b = api.Batch(ctx)
-    for i in range(2500):
+    for i in range(4000):
         b.add_synthetic(100, 5000, 5 + i)
     b.stage()
     for _ in range(3):
