@@ -318,36 +318,11 @@ __device__ __forceinline__ uint32_t pfa_u4(const uint4& x, int w) { return w == 
 // column whose only "variation" is missing data (every valid row of a site shows the same base) from real base variation
 template <int LPS, int ITER, bool HAS_V>
 __device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], const uint4 (&x1)[3][ITER], const uint4 (&xv)[3][ITER],
-                                                  const uint4 (&um)[ITER], unsigned gmask, unsigned* f2_out = nullptr) {
-    unsigned f = 0, f2 = 0;
-    if (HAS_V && f2_out) {  // bit 12: a row valid at all three sites exists; bit 13: an escape row (not valid, both base bits set) exists
-        uint32_t cl = 0, es = 0;
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-            cl |= (xv[0][i].x & xv[1][i].x & xv[2][i].x & um[i].x) | (xv[0][i].y & xv[1][i].y & xv[2][i].y & um[i].y) |
-                  (xv[0][i].z & xv[1][i].z & xv[2][i].z & um[i].z) | (xv[0][i].w & xv[1][i].w & xv[2][i].w & um[i].w);
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-                es |= (~xv[t][i].x & x0[t][i].x & x1[t][i].x & um[i].x) | (~xv[t][i].y & x0[t][i].y & x1[t][i].y & um[i].y) |
-                      (~xv[t][i].z & x0[t][i].z & x1[t][i].z & um[i].z) | (~xv[t][i].w & x0[t][i].w & x1[t][i].w & um[i].w);
-        }
-        f2 |= (cl ? 1u << 12 : 0u) | (es ? 1u << 13 : 0u);
-    }
+                                                  const uint4 (&um)[ITER], unsigned gmask) {
+    unsigned f = 0;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         uint32_t o0 = 0, z0 = 0, o1 = 0, z1 = 0, ov = 0, zv = 0;
-        if (HAS_V && f2_out) {
-            uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-#pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const uint4 m = make_uint4(um[i].x & xv[t][i].x, um[i].y & xv[t][i].y, um[i].z & xv[t][i].z, um[i].w & xv[t][i].w);
-                a0 |= (x0[t][i].x & m.x) | (x0[t][i].y & m.y) | (x0[t][i].z & m.z) | (x0[t][i].w & m.w);
-                b0 |= (~x0[t][i].x & m.x) | (~x0[t][i].y & m.y) | (~x0[t][i].z & m.z) | (~x0[t][i].w & m.w);
-                a1 |= (x1[t][i].x & m.x) | (x1[t][i].y & m.y) | (x1[t][i].z & m.z) | (x1[t][i].w & m.w);
-                b1 |= (~x1[t][i].x & m.x) | (~x1[t][i].y & m.y) | (~x1[t][i].z & m.z) | (~x1[t][i].w & m.w);
-            }
-            f2 |= ((a0 ? 1u : 0u) | (b0 ? 2u : 0u) | (a1 ? 4u : 0u) | (b1 ? 8u : 0u)) << (4 * t);
-        }
 #pragma unroll
         for (int i = 0; i < ITER; ++i) {
             const uint4 m = um[i];
@@ -360,7 +335,6 @@ __device__ __forceinline__ unsigned pfa_cds_pass1(const uint4 (&x0)[3][ITER], co
         }
         f |= ((o0 ? 1u : 0u) | (z0 ? 2u : 0u) | (o1 ? 4u : 0u) | (z1 ? 8u : 0u) | (ov ? 16u : 0u) | (zv ? 32u : 0u)) << (6 * t);
     }
-    if (HAS_V && f2_out) *f2_out = pfa_group_or<LPS>(f2, gmask);
     return pfa_group_or<LPS>(f, gmask);
 }
 

@@ -755,7 +755,14 @@ int pfa_launch_site_scan(pfa_aln* a, int64_t* d_out, uint8_t* d_isvar, pfa_xchg*
         const int nt = 512;
         const int gw = 32 / lps, nwarp = nt / 32;
         const int64_t pass_bytes = (int64_t)gw * a->Wq * 16;  // one pass of a warp, per plane
-        int m = (int)std::max<int64_t>(1, (5000 + pass_bytes / 2) / pass_bytes);  // nearest to 5 KB (C4: 2 x 2.5 KB, 3.49 ms; 1 x: 3.55)
+        // passes per slot: ~5 KB per plane.  Rounded to the nearest when every warp still gets >= 512 blocks (C4 on one GPU, two
+        // passes of 2.5 KB: 3.46 ms against 3.55 with one), else rounded down: on a 1.25 Mb shard of C4 (one of 8 GPUs) the larger
+        // blocks cost 4 % (0.476 against 0.458 ms), at 5 Mb they break even
+        int m = (int)std::max<int64_t>(1, 5000 / pass_bytes);
+        {
+            const int64_t m_near = std::max<int64_t>(1, (5000 + pass_bytes / 2) / pass_bytes);
+            if (m_near > m && a->ns / ((int64_t)gw * m_near * nwarp * ctx->sm_count) >= 512) m = (int)m_near;
+        }
         if (const char* e = getenv("PFA_SITE_TMA_M")) m = std::max(1, atoi(e));
         // validity flags: a shard with a few non-ACGT symbols fetches only the flagged pieces of its v plane (pfa_slot_issue);
         // not when the validity plane is forced (benchmarks of the 3-plane worst case) or PFA_VFLAG=0
