@@ -266,13 +266,54 @@ __device__ __forceinline__ void pfa_batch_site_pass2(const PfaBatchArgs& a, cons
 #define PFA_BQ_WORDS 13
 __device__ __noinline__ void pfa_batch_drain(const PfaBatchArgs& a, const uint32_t* q, int count, int lane) {
     __syncwarp();
+    const unsigned act = __ballot_sync(0xffffffffu, lane < count);
     if (lane < count) {
         uint4 y0[1], y1[1], yv[1];
         y0[0] = make_uint4(q[0 * 64 + lane], q[1 * 64 + lane], q[2 * 64 + lane], q[3 * 64 + lane]);
         y1[0] = make_uint4(q[4 * 64 + lane], q[5 * 64 + lane], q[6 * 64 + lane], q[7 * 64 + lane]);
         yv[0] = make_uint4(q[8 * 64 + lane], q[9 * 64 + lane], q[10 * 64 + lane], q[11 * 64 + lane]);
-        const PfaLocusDesc dq = a.desc[q[12 * 64 + lane]];
-        pfa_batch_site_pass2<1, 1>(a, dq, y0, y1, yv, 0, 1u << lane);
+        const int li = (int)q[12 * 64 + lane];
+        const PfaLocusDesc dq = a.desc[li];
+        if (__match_any_sync(act, li) == act) {
+            // the waiting sites are neighbours and nearly always belong to ONE locus: the lanes add up S and H (n <= 128 rows:
+            // H of a site < 2^15) and one lane books them -- two atomics per population instead of two per site on the same
+            // two words
+            for (int p = 0; p < dq.k; ++p) {
+                const uint4 m4 = __ldg(a.masks + dq.mask_off + p);
+                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w}, w0[4] = {y0[0].x, y0[0].y, y0[0].z, y0[0].w},
+                               w1[4] = {y1[0].x, y1[0].y, y1[0].z, y1[0].w}, wv[4] = {yv[0].x, yv[0].y, yv[0].z, yv[0].w};
+                uint32_t c[PFA_NCLASS];
+#pragma unroll
+                for (int i = 0; i < PFA_NCLASS; ++i) c[i] = 0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t vm = wv[w] & mm[w];
+                    const uint32_t hi = vm & w1[w], lo = vm & ~w1[w];
+                    c[PFA_C_T] += __popc(hi & w0[w]);
+                    c[PFA_C_G] += __popc(hi & ~w0[w]);
+                    c[PFA_C_C] += __popc(lo & w0[w]);
+                    c[PFA_C_A] += __popc(lo & ~w0[w]);
+                    const uint32_t im = ~wv[w] & mm[w];
+                    const uint32_t ihi = im & w1[w];
+                    c[PFA_C_ESC] += __popc(ihi & w0[w]);
+                    c[PFA_C_Q] += __popc(ihi & ~w0[w]);
+                    c[PFA_C_N] += __popc(im & ~w1[w] & w0[w]);
+                }
+                const PfaPopSlot ps = a.pops[dq.pop_base + p];
+                const PfaSiteResult r = pfa_site_result(c, ps.n, 0u, 0ull);
+                const bool ok = !r.has_escape && r.isvar;
+                const unsigned nS = (unsigned)__popc(__ballot_sync(act, ok));
+                const unsigned hsum = __reduce_add_sync(act, ok ? (unsigned)r.h : 0u);
+                unsigned long long* o = reinterpret_cast<unsigned long long*>(a.out + ps.out_off);
+                if (nS && lane == __ffs(act) - 1) {
+                    atomicAdd(o, (unsigned long long)nS);
+                    atomicAdd(o + 1, (unsigned long long)hsum);
+                }
+                if (ok && r.sfs_bin >= 0) atomicAdd(o + 2 + r.sfs_bin, 1ull);
+            }
+        } else {
+            pfa_batch_site_pass2<1, 1>(a, dq, y0, y1, yv, 0, 1u << lane);
+        }
     }
     __syncwarp();
 }
